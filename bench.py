@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- autoregressive field-steps/sec for DPOT-Small 128^2 (BASELINE.json config C2).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores (oracle port)
+
+One "step" = one 10-step autoregressive rollout (evaluate.py:192-208) of a batch of 32 synthetic
+128x128x10x4 fields on each GPU = 320 field-steps per GPU per step.  Multi-GPU = independent
+replicas (the rollout has no exchange step): weak scaling, no collective on the data path.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, N_AR, MODEL = 32, 10, "S"
+FLOP_PER_FIELD_STEP = 15.07e9      # algorithmic forward FLOPs of DPOT-S @128^2
+METRIC = "autoregressive field-steps/sec, DPOT-S 128x128 (10 frames in -> 1 out), fp32"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_leg(nthreads: int, B: int, steps: int, warmup: int):
+    """The reference algorithm on the host cores: the numpy oracle port (the reference itself is a
+    Python/PyTorch program that cannot travel to the GPU box).  Returns (field-steps/s, ms/step)."""
+    from oracle import dpot_oracle as O
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=nthreads)
+    except Exception:  # pragma: no cover
+        import contextlib
+        ctx = contextlib.nullcontext()
+    cfg = O.zoo_cfg(MODEL)
+    params = O.make_params(cfg, seed=0)
+    x = O.make_input(cfg, B, seed=0)
+    with ctx:
+        for _ in range(warmup):
+            O.dpot_forward(x, params, cfg)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.dpot_forward(x, params, cfg)
+        dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = 2
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    fs, ms = cpu_reference_leg(cores, B, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fs, "unit": "field-steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DPOT-{MODEL} 128x128x10x4 forward, bounded sample B={B} per step", "batch": B},
+        "cpu_baseline": {"value": fs, "unit": "field-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} forwards of B={B} (numpy/BLAS oracle port of models/dpot.py)"},
+        "e2e": {"value": fs, "unit": "field-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [s.strip() for s in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dpot_b200 import _lib, ops
+    from dpot_b200.models.dpot import DPOTNet
+    from dpot_b200.rollout import RolloutEngine
+    from oracle import dpot_oracle as O   # synthetic weights/inputs + the cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the dpot_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    cfg = O.zoo_cfg(MODEL)
+    model = DPOTNet(**cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_params(cfg, seed=0).items()})
+    model = model.to(dev).eval()
+    if args.engine is not None:
+        model.gemm_engine = args.engine
+
+    # synthetic inputs: NBUF distinct batches so that consecutive steps never find their input in L2
+    NBUF = 4
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host = [torch.randn((BATCH, 128, 128, 10, 4), generator=g).pin_memory() for _ in range(NBUF)]
+    devbuf = [h.to(dev) for h in host]
+    eng = RolloutEngine(model, BATCH, N_AR, device=dev)
+    host_out = torch.empty((BATCH, 128, 128, N_AR, 4)).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(s):
+        eng.run(devbuf[s % NBUF])
+
+    def step_e2e(s):
+        pred = eng.run(host[s % NBUF], non_blocking=True)   # H2D of this step's inputs from pinned memory
+        host_out.copy_(pred, non_blocking=True)               # D2H of this step's result
+        torch.cuda.current_stream().synchronize()
+
+    for s in range(args.warmup):
+        step_resident(s)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.dpot_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.dpot_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    for s in range(min(args.warmup, 2)):
+        step_e2e(s)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    fs_per_step = BATCH * N_AR * world
+    value = fs_per_step * args.steps / (ms * 1e-3)
+    e2e = fs_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel: the channel-MLP GEMM (M=B*256, N=K=1024), timed alone
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        M, N, K = BATCH * 256, 1024, 1024
+        nrot = 6  # rotate operands: > 126 MB L2 in total
+        As = [torch.randn((M, K), device=dev) for _ in range(nrot)]
+        Ws = [torch.randn((N, K), device=dev) / 32 for _ in range(nrot)]
+        Cs = [torch.empty((M, N), device=dev) for _ in range(nrot)]
+        bias = torch.randn(N, device=dev)
+        eng_id = model.gemm_engine
+        for i in range(nrot):
+            ops.gemm(As[i], Ws[i], bias=bias, act="gelu", out=Cs[i], engine=eng_id)
+        torch.cuda.synchronize()
+        reps = 30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            ops.gemm(As[i % nrot], Ws[i % nrot], bias=bias, act="gelu", out=Cs[i % nrot], engine=eng_id)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / reps
+        ach = 2.0 * M * N * K / t / 1e12
+        tc = bool(lib.dpot_tc_available()) and eng_id != 1
+        roof = {"bound": "tensor", "kernel": "channel-MLP GEMM M=8192 N=1024 K=1024 (bias+GELU epilogue)",
+                "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
+                "traffic": None, "peak_source": pk["src"] + ", dense bf16 cuBLAS burst",
+                "engine": "tcgen05 3xTF32" if tc else "fp32 CUDA cores (SIMT)",
+                "frac_of_3xtf32_equiv_peak": ach / (pk["bf16"] / 6.0),
+                "note": "fp32 parity needs 3 TF32 MMAs per product: effective ceiling = bf16 peak / 6",
+                "whole_step_algorithmic_tflops": FLOP_PER_FIELD_STEP * value / world / 1e12}
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cb_fs, _ = cpu_reference_leg(cores, 2, 3, 1)
+        in_bytes = BATCH * 128 * 128 * 10 * 4 * 4
+        out_bytes = BATCH * 128 * 128 * N_AR * 4 * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": "field-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"DPOT-{MODEL} (30.8M) 10->1 autoregressive rollout, 128x128x10x4, batch {BATCH}/GPU, "
+                                   f"{N_AR} AR steps per bench step, no_grad",
+                       "batch_per_gpu": BATCH, "ar_steps": N_AR, "field_steps_per_step": fs_per_step,
+                       "l2_policy": f"{NBUF} distinct input batches rotated ({NBUF * in_bytes / 2**20:.0f} MiB > 126 MB L2)",
+                       "parallelism": f"replicas x{world} (no data-path collective)"},
+            "e2e": {"value": e2e, "unit": "field-steps/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": {"value": cb_fs, "unit": "field-steps/s", "cores": cores, "kind": "port",
+                             "sample": "3 forwards of B=2 DPOT-S 128^2 (numpy/BLAS oracle port), rank 0"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", type=int, default=None, help="force GEMM engine: 1 = SIMT fp32, 2 = tcgen05")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,37 @@
+// ABI plumbing: version, error string, device probe.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+
+namespace dpot {
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+}  // namespace dpot
+
+extern "C" int dpot_abi_version(void) { return DPOT_ABI_VERSION; }
+extern "C" const char* dpot_last_error_string(void) { return dpot::g_err; }
+
+extern "C" long long dpot_launch_count(void) { return dpot::g_launches.load(); }
+
+extern "C" int dpot_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return (major == 10 && minor == 0) ? 1 : 0;
+}

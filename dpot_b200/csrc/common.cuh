@@ -1,0 +1,94 @@
+// Shared device/host helpers for libdpot_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/dpot_b200.h"
+
+namespace dpot {
+
+// ---- error plumbing (thread-local message, no exceptions across the ABI) -------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+void count_launch();   // kernels launched by this library since load (dpot_launch_count)
+
+#define DPOT_REQUIRE(cond, code, ...)              \
+  do {                                             \
+    if (!(cond)) {                                 \
+      ::dpot::set_error(__VA_ARGS__);              \
+      return (code);                               \
+    }                                              \
+  } while (0)
+
+#define DPOT_CUDA(call)                                             \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return ::dpot::cuda_fail(e__, #call);   \
+  } while (0)
+
+#define DPOT_LAUNCH_CHECK(name)                                     \
+  do {                                                              \
+    ::dpot::count_launch();                                         \
+    cudaError_t e__ = cudaGetLastError();                           \
+    if (e__ != cudaSuccess) return ::dpot::cuda_fail(e__, name);    \
+  } while (0)
+
+#define DPOT_CALL(expr)            \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != 0) return rc__;    \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- activations: ACTIVATION table of models/dpot.py:19 (torch module defaults) --------------
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case DPOT_ACT_GELU:  // nn.GELU() exact erf form
+      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case DPOT_ACT_TANH: return tanhf(x);
+    case DPOT_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case DPOT_ACT_RELU: return fmaxf(x, 0.0f);
+    case DPOT_ACT_LEAKY_RELU: return x > 0.0f ? x : 0.1f * x;
+    case DPOT_ACT_SOFTPLUS: return x > 20.0f ? x : log1pf(expf(x));
+    case DPOT_ACT_ELU: return x > 0.0f ? x : expm1f(x);
+    case DPOT_ACT_SILU: return x / (1.0f + expf(-x));
+    default: return x;
+  }
+}
+
+// derivative d act(x)/dx, used by the backward kernels
+__device__ __forceinline__ float act_grad(float x, int act) {
+  switch (act) {
+    case DPOT_ACT_GELU: {
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+      return cdf + x * pdf;
+    }
+    case DPOT_ACT_TANH: { float t = tanhf(x); return 1.0f - t * t; }
+    case DPOT_ACT_SIGMOID: { float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f - s); }
+    case DPOT_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
+    case DPOT_ACT_LEAKY_RELU: return x > 0.0f ? 1.0f : 0.1f;
+    case DPOT_ACT_SOFTPLUS: return x > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-x));
+    case DPOT_ACT_ELU: return x > 0.0f ? 1.0f : expf(x);
+    case DPOT_ACT_SILU: { float s = 1.0f / (1.0f + expf(-x)); return s * (1.0f + x * (1.0f - s)); }
+    default: return 1.0f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace dpot

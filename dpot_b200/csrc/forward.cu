@@ -1,0 +1,244 @@
+// Whole-model inference forward (DPOTNet.forward under no_grad, models/dpot.py:364-403):
+// host-side orchestration of the kernels of this library on one stream.  No allocation, no
+// synchronisation: packed weights and the activation workspace are caller-provided arenas.
+#include "common.cuh"
+#include <string.h>
+
+namespace dpot {
+
+struct Dims {
+  int P, C, Co, T, To, nb, E, old, depth, hid, ncls, h, n, mid, K0, Kp, bs, km1, km2, NP;
+};
+
+static int make_dims(const dpot_config* c, Dims& d) {
+  DPOT_REQUIRE(c != nullptr, DPOT_E_BADARG, "null config");
+  DPOT_REQUIRE(c->patch_size > 0 && c->img_size > 0 && c->img_size % c->patch_size == 0, DPOT_E_BADARG,
+               "img_size %d must be a multiple of patch_size %d", c->img_size, c->patch_size);
+  DPOT_REQUIRE(c->n_blocks > 0 && c->embed_dim % c->n_blocks == 0, DPOT_E_BADARG, "embed_dim %% n_blocks != 0");
+  DPOT_REQUIRE(c->embed_dim % 8 == 0, DPOT_E_BADARG, "embed_dim must be divisible by the 8 GroupNorm groups");
+  d.P = c->patch_size; d.C = c->in_channels; d.Co = c->out_channels; d.T = c->in_timesteps; d.To = c->out_timesteps;
+  d.nb = c->n_blocks; d.E = c->embed_dim; d.old = c->out_layer_dim; d.depth = c->depth; d.hid = c->hidden_dim;
+  d.ncls = c->n_cls; d.h = c->img_size / c->patch_size; d.n = d.h * d.h;
+  d.mid = d.Co * d.P + 3;                       // models/dpot.py:278
+  d.K0 = d.P * d.P * d.C;
+  d.Kp = (int)round_up((int64_t)d.T * d.mid, 32);
+  d.bs = d.E / d.nb;
+  d.km1 = c->modes < d.h ? c->modes : d.h;       // python slicing clamps, models/dpot.py:70-94
+  d.km2 = c->modes < d.h / 2 + 1 ? c->modes : d.h / 2 + 1;
+  d.NP = d.P * d.P * d.old;
+  DPOT_REQUIRE(d.km1 >= 1, DPOT_E_BADARG, "modes must be >= 1");
+  DPOT_REQUIRE(d.h == 2 || d.h == 4 || d.h == 8 || d.h == 16 || d.h == 32, DPOT_E_UNSUPPORTED,
+               "latent grid img_size/patch_size = %d unsupported (power of two in [2,32])", d.h);
+  return 0;
+}
+
+static inline int64_t slot(int64_t n) { return round_up(n, 64); }  // 256 B granules
+
+struct Packed {
+  int64_t W0p, rowbias0, WeffT, bias_eff, blocks, blk_stride, Wc1, bc1, Wc2, bc2, WtT, bias_t, total;
+};
+static Packed packed_layout(const Dims& d) {
+  Packed L; int64_t o = 0;
+  L.W0p = o; o += slot((int64_t)d.mid * d.K0);
+  L.rowbias0 = o; o += slot((int64_t)d.n * d.T * d.mid);
+  L.WeffT = o; o += slot((int64_t)d.E * d.Kp);
+  L.bias_eff = o; o += slot((int64_t)d.n * d.E + (int64_t)d.E * d.E);  // + Wsum scratch
+  L.blocks = o;
+  int64_t b = 0;
+  L.Wc1 = b; b += slot((int64_t)d.nb * 4 * d.bs * d.bs);
+  L.bc1 = b; b += slot(2 * d.E);
+  L.Wc2 = b; b += slot((int64_t)d.nb * 4 * d.bs * d.bs);
+  L.bc2 = b; b += slot(2 * d.E);
+  L.blk_stride = b; o += b * d.depth;
+  L.WtT = o; o += slot((int64_t)d.NP * d.E);
+  L.bias_t = o; o += slot(d.NP);
+  L.total = o;
+  return L;
+}
+
+struct Work {
+  int64_t z1, lat0, lat1, f, hid, S, O1, sc1, sh1, sc2, sh2, st1, st2, Y1, Y2, tok, c1, c2, musig, asc, ash, smu, ssg, total;
+};
+static Work work_layout(const Dims& d, const dpot_config* c, int B) {
+  Work L; int64_t o = 0;
+  const int64_t Mt = (int64_t)B * d.n, Ms = (int64_t)B * d.km1 * d.km2;
+  L.z1 = o; o += slot(Mt * d.Kp);
+  L.lat0 = o; o += slot(Mt * d.E);
+  L.lat1 = o; o += slot(Mt * d.E);
+  L.f = o; o += slot(Mt * d.E);
+  L.hid = o; o += slot(Mt * d.hid);
+  L.S = o; o += slot(Ms * 2 * d.E);
+  L.O1 = o; o += slot(Ms * 2 * d.E);
+  L.sc1 = o; o += slot((int64_t)B * d.E);
+  L.sh1 = o; o += slot((int64_t)B * d.E);
+  L.sc2 = o; o += slot((int64_t)B * d.E);
+  L.sh2 = o; o += slot((int64_t)B * d.E);
+  L.st1 = o; o += slot((int64_t)B * 8 * 2 * 2);   // doubles
+  L.st2 = o; o += slot((int64_t)B * 8 * 2 * 2);
+  L.Y1 = o; o += slot(Mt * d.NP);
+  const bool fused_tail = (d.old == 4 || d.old == 8 || d.old == 16 || d.old == 32);
+  L.Y2 = o; o += fused_tail ? 0 : slot(Mt * d.NP);
+  L.tok = o; o += slot((int64_t)B * d.E);
+  L.c1 = o; o += slot((int64_t)B * d.E);
+  L.c2 = o; o += slot((int64_t)B * d.E);
+  L.musig = o; o += c->normalize ? slot((int64_t)B * 2 * d.C) : 0;
+  L.asc = o; o += c->normalize ? slot((int64_t)B * d.K0) : 0;
+  L.ash = o; o += c->normalize ? slot((int64_t)B * d.K0) : 0;
+  L.smu = o; o += c->normalize ? slot((int64_t)B * d.E) : 0;
+  L.ssg = o; o += c->normalize ? slot((int64_t)B * d.E) : 0;
+  L.total = o;
+  return L;
+}
+
+static dpot_gemm_args gemm_args(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int M,
+                                int N, int K, const float* bias, int act, int engine) {
+  dpot_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.act = act; g.batch = 1; g.engine = engine; g.a_mode = DPOT_A_PLAIN;
+  return g;
+}
+
+}  // namespace dpot
+
+using namespace dpot;
+
+extern "C" int64_t dpot_packed_floats(const dpot_config* cfg) {
+  Dims d;
+  if (make_dims(cfg, d) != 0) return -1;
+  return packed_layout(d).total;
+}
+
+extern "C" int64_t dpot_workspace_floats(const dpot_config* cfg, int32_t B) {
+  Dims d;
+  if (make_dims(cfg, d) != 0 || B <= 0) return -1;
+  return work_layout(d, cfg, B).total;
+}
+
+extern "C" int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm, float* packed, void* stream) {
+  Dims d;
+  DPOT_CALL(make_dims(cfg, d));
+  DPOT_REQUIRE(prm && packed && prm->blocks, DPOT_E_BADARG, "dpot_pack_weights: null pointer");
+  const Packed L = packed_layout(d);
+  DPOT_CALL(dpot_pack_patch(prm->pe0_w, prm->pe0_b, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h,
+                            d.T, packed + L.W0p, packed + L.rowbias0, stream));
+  DPOT_CALL(dpot_fold_timeagg(prm->pe2_w, prm->pe2_b, prm->pos_embed, prm->tagg_w, prm->temb, d.T, d.E, d.mid, d.n,
+                              d.Kp, packed + L.WeffT, packed + L.bias_eff, stream));
+  for (int i = 0; i < d.depth; ++i) {
+    float* base = packed + L.blocks + (int64_t)i * L.blk_stride;
+    const dpot_block_params& b = prm->blocks[i];
+    DPOT_CALL(dpot_pack_afno(b.w1, b.b1, d.nb, d.bs, base + L.Wc1, base + L.bc1, stream));
+    DPOT_CALL(dpot_pack_afno(b.w2, b.b2, d.nb, d.bs, base + L.Wc2, base + L.bc2, stream));
+  }
+  DPOT_CALL(dpot_pack_out(prm->out0_w, prm->out0_b, d.E, d.old, d.P, packed + L.WtT, packed + L.bias_t, stream));
+  return 0;
+}
+
+extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
+                            int32_t B, float* y, float* cls, float* ws, int32_t engine, void* stream) {
+  Dims d;
+  DPOT_CALL(make_dims(cfg, d));
+  DPOT_REQUIRE(prm && packed && x && y && ws && prm->blocks && B > 0, DPOT_E_BADARG, "dpot_forward: null pointer / bad B");
+  const Packed PL = packed_layout(d);
+  const Work WL = work_layout(d, cfg, B);
+  cudaStream_t st = as_stream(stream);
+  const int Mt = B * d.n, Ms = B * d.km1 * d.km2, act = cfg->act, R = cfg->img_size;
+  const int groups = 8;
+
+  // ---- input normalisation (normalize=True only), models/dpot.py:366-370
+  if (cfg->normalize) {
+    DPOT_CALL(dpot_input_stats(x, B, (int64_t)R * R * d.T * d.C, d.C, d.P * d.P, ws + WL.musig, ws + WL.asc, ws + WL.ash, stream));
+    dpot_gemm_args g = gemm_args(ws + WL.musig, 2 * d.C, prm->mu_w, 2 * d.C, ws + WL.smu, d.E, B, d.E, 2 * d.C, prm->mu_b, DPOT_ACT_NONE, engine);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(ws + WL.musig, 2 * d.C, prm->sigma_w, 2 * d.C, ws + WL.ssg, d.E, B, d.E, 2 * d.C, prm->sigma_b, DPOT_ACT_NONE, engine);
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+
+  // ---- PatchEmbed conv0 + act as an im2col GEMM, coordinate channels folded into rowbias0
+  if (d.Kp != d.T * d.mid) DPOT_CUDA(cudaMemsetAsync(ws + WL.z1, 0, sizeof(float) * (size_t)Mt * d.Kp, st));
+  {
+    dpot_gemm_args g = gemm_args(x, 0, packed + PL.W0p, d.K0, ws + WL.z1, d.mid, Mt * d.T, d.mid, d.K0, nullptr, act, engine);
+    g.a_mode = DPOT_A_PATCH; g.pX = R; g.pY = R; g.pT = d.T; g.pC = d.C; g.pP = d.P;
+    g.rowbias = packed + PL.rowbias0; g.rowbias_period = d.n * d.T; g.ldrb = d.mid;
+    g.c_group = d.T; g.c_group_stride = d.Kp;
+    if (cfg->normalize) { g.a_scale = ws + WL.asc; g.a_shift = ws + WL.ash; g.a_rows_per_sample = d.n * d.T; }
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+  // ---- folded (conv 1x1 + pos_embed + TimeAggregator) GEMM (+ AdaIN), models/dpot.py:201,378-387
+  float* lat = ws + WL.lat0;
+  float* lat_next = ws + WL.lat1;
+  {
+    dpot_gemm_args g = gemm_args(ws + WL.z1, d.Kp, packed + PL.WeffT, d.Kp, lat, d.E, Mt, d.E, d.Kp, nullptr, DPOT_ACT_NONE, engine);
+    g.rowbias = packed + PL.bias_eff; g.rowbias_period = d.n; g.ldrb = d.E;
+    if (cfg->normalize) { g.c_scale = ws + WL.ssg; g.c_shift = ws + WL.smu; g.c_rows_per_sample = d.n; }
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+
+  // ---- blocks, models/dpot.py:165-180
+  double* st1 = reinterpret_cast<double*>(ws + WL.st1);
+  double* st2 = reinterpret_cast<double*>(ws + WL.st2);
+  for (int i = 0; i < d.depth; ++i) {
+    const dpot_block_params& bp = prm->blocks[i];
+    const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
+    DPOT_CALL(dpot_gn_stats(lat, B, d.n, d.E, groups, st1, stream));
+    DPOT_CALL(dpot_gn_finalize(st1, bp.norm1_w, bp.norm1_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc1, ws + WL.sh1, stream));
+    DPOT_CALL(dpot_afno_fft_fwd(lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.S, stream));
+    {
+      dpot_gemm_args g = gemm_args(ws + WL.S, 2 * d.E, pk + PL.Wc1, 2 * d.bs, ws + WL.O1, 2 * d.E, Ms, 2 * d.bs, 2 * d.bs, pk + PL.bc1, act, engine);
+      g.batch = d.nb; g.strideA = 2 * d.bs; g.strideW = (int64_t)4 * d.bs * d.bs; g.strideC = 2 * d.bs; g.strideBias = 2 * d.bs;
+      DPOT_CALL(dpot_gemm(&g, stream));
+      g.A = ws + WL.O1; g.W = pk + PL.Wc2; g.C = ws + WL.S; g.bias = pk + PL.bc2; g.act = DPOT_ACT_NONE;
+      DPOT_CALL(dpot_gemm(&g, stream));
+    }
+    DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
+    DPOT_CALL(dpot_afno_fft_inv(ws + WL.S, lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.f, st2, groups, stream));
+    DPOT_CALL(dpot_gn_finalize(st2, bp.norm2_w, bp.norm2_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc2, ws + WL.sh2, stream));
+    {
+      dpot_gemm_args g = gemm_args(ws + WL.f, d.E, bp.fc1_w, d.E, ws + WL.hid, d.hid, Mt, d.hid, d.E, bp.fc1_b, act, engine);
+      g.a_scale = ws + WL.sc2; g.a_shift = ws + WL.sh2; g.a_rows_per_sample = d.n;
+      DPOT_CALL(dpot_gemm(&g, stream));
+      g = gemm_args(ws + WL.hid, d.hid, bp.fc2_w, d.hid, lat_next, d.E, Mt, d.E, d.hid, bp.fc2_b, DPOT_ACT_NONE, engine);
+      g.residual = lat; g.ldr = d.E;
+      DPOT_CALL(dpot_gemm(&g, stream));
+    }
+    float* t = lat; lat = lat_next; lat_next = t;
+  }
+
+  // ---- classification head, models/dpot.py:394-395
+  if (cls) {
+    DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, stream));
+    dpot_gemm_args g = gemm_args(ws + WL.tok, d.E, prm->cls0_w, d.E, ws + WL.c1, d.E, B, d.E, d.E, prm->cls0_b, act, engine);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(ws + WL.c1, d.E, prm->cls2_w, d.E, ws + WL.c2, d.E, B, d.E, d.E, prm->cls2_b, act, engine);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(ws + WL.c2, d.E, prm->cls4_w, d.E, cls, d.ncls, B, d.ncls, d.E, prm->cls4_b, DPOT_ACT_NONE, engine);
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+
+  // ---- output head, models/dpot.py:315-321,397-401
+  {
+    dpot_gemm_args g = gemm_args(lat, d.E, packed + PL.WtT, d.E, ws + WL.Y1, d.NP, Mt, d.NP, d.E, packed + PL.bias_t, act, engine);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    const float* mu = cfg->normalize ? ws + WL.musig : nullptr;
+    const int nout = d.Co * d.To;
+    const bool fused_tail = (d.old == 4 || d.old == 8 || d.old == 16 || d.old == 32);
+    // musig is [B, 2C] = [mu | sigma]; the tail indexes [b*Co + c], so it needs C == Co and a compact copy
+    if (cfg->normalize) DPOT_REQUIRE(d.C == d.Co, DPOT_E_UNSUPPORTED, "normalize=True needs in_channels == out_channels");
+    const float* mu_c = nullptr; const float* sg_c = nullptr;
+    if (mu) {
+      // compact [B,C] views: reuse the (now free) smu/ssg buffers
+      float* mc = ws + WL.smu; float* sc = ws + WL.ssg;
+      DPOT_CUDA(cudaMemcpy2DAsync(mc, sizeof(float) * d.C, mu, sizeof(float) * 2 * d.C, sizeof(float) * d.C, B, cudaMemcpyDeviceToDevice, st));
+      DPOT_CUDA(cudaMemcpy2DAsync(sc, sizeof(float) * d.C, mu + d.C, sizeof(float) * 2 * d.C, sizeof(float) * d.C, B, cudaMemcpyDeviceToDevice, st));
+      mu_c = mc; sg_c = sc;
+    }
+    if (fused_tail) {
+      DPOT_CALL(dpot_out_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+    } else {
+      g = gemm_args(ws + WL.Y1, d.old, prm->out2_w, d.old, ws + WL.Y2, d.old, Mt * d.P * d.P, d.old, d.old, prm->out2_b, act, engine);
+      DPOT_CALL(dpot_gemm(&g, stream));
+      DPOT_CALL(dpot_out_tail(ws + WL.Y2, nullptr, nullptr, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,48 @@
+// dpot_gemm: argument validation and engine dispatch (see include/dpot_b200.h).
+#include "common.cuh"
+#include "gemm_common.cuh"
+
+using namespace dpot;
+
+extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
+  DPOT_REQUIRE(a != nullptr, DPOT_E_BADARG, "dpot_gemm: null args");
+  DPOT_REQUIRE(a->A && a->W && a->C, DPOT_E_BADARG, "dpot_gemm: null A/W/C");
+  DPOT_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, DPOT_E_BADARG, "dpot_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  DPOT_REQUIRE(a->batch >= 1, DPOT_E_BADARG, "dpot_gemm: batch must be >= 1");
+  DPOT_REQUIRE(a->act >= DPOT_ACT_NONE && a->act <= DPOT_ACT_SILU, DPOT_E_BADARG, "dpot_gemm: bad act %d", a->act);
+  DPOT_REQUIRE(!a->rowbias || a->rowbias_period > 0, DPOT_E_BADARG, "dpot_gemm: rowbias needs a period");
+  DPOT_REQUIRE((a->a_scale == nullptr) == (a->a_shift == nullptr), DPOT_E_BADARG, "dpot_gemm: a_scale/a_shift must come together");
+  DPOT_REQUIRE(!a->a_scale || a->a_rows_per_sample > 0, DPOT_E_BADARG, "dpot_gemm: a_rows_per_sample");
+  DPOT_REQUIRE((a->c_scale == nullptr) == (a->c_shift == nullptr), DPOT_E_BADARG, "dpot_gemm: c_scale/c_shift must come together");
+  DPOT_REQUIRE(!a->c_scale || a->c_rows_per_sample > 0, DPOT_E_BADARG, "dpot_gemm: c_rows_per_sample");
+  DPOT_REQUIRE(a->a_mode == DPOT_A_PLAIN || a->a_mode == DPOT_A_PATCH, DPOT_E_BADARG, "dpot_gemm: bad a_mode");
+  if (a->M == 0) return 0;
+
+  GemmDev p;
+  p.A = a->A; p.lda = a->lda; p.W = a->W; p.ldw = a->ldw; p.C = a->C; p.ldc = a->ldc;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = a->bias; p.rowbias = a->rowbias; p.rb_period = a->rowbias_period; p.ldrb = a->ldrb;
+  p.residual = a->residual; p.ldr = a->ldr; p.act = a->act;
+  p.a_scale = a->a_scale; p.a_shift = a->a_shift; p.a_rps = a->a_rows_per_sample;
+  p.c_scale = a->c_scale; p.c_shift = a->c_shift; p.c_rps = a->c_rows_per_sample;
+  p.c_group = a->c_group; p.c_group_stride = a->c_group_stride;
+  p.sA = a->strideA; p.sW = a->strideW; p.sC = a->strideC; p.sBias = a->strideBias;
+  p.a_mode = a->a_mode; p.pX = a->pX; p.pY = a->pY; p.pT = a->pT; p.pC = a->pC; p.pP = a->pP;
+  p.ph = p.pw = 0;
+  if (a->a_mode == DPOT_A_PATCH) {
+    DPOT_REQUIRE(a->pP > 0 && a->pX % a->pP == 0 && a->pY % a->pP == 0, DPOT_E_BADARG, "dpot_gemm: patch geometry");
+    p.ph = a->pX / a->pP; p.pw = a->pY / a->pP;
+    DPOT_REQUIRE(a->K == a->pP * a->pP * a->pC, DPOT_E_BADARG, "dpot_gemm: patch K must be P*P*C");
+    DPOT_REQUIRE(a->M % (p.ph * p.pw * a->pT) == 0, DPOT_E_BADARG, "dpot_gemm: patch M must be B*h*w*T");
+    DPOT_REQUIRE(a->batch == 1, DPOT_E_BADARG, "dpot_gemm: patch mode is not batched");
+  }
+  cudaStream_t st = as_stream(stream);
+  int engine = a->engine;
+  if (engine == DPOT_GEMM_AUTO) engine = gemm_tc_supports(p, a->batch) ? DPOT_GEMM_TC : DPOT_GEMM_SIMT;
+  if (engine == DPOT_GEMM_TC) {
+    DPOT_REQUIRE(gemm_tc_supports(p, a->batch), DPOT_E_UNSUPPORTED,
+                 "dpot_gemm: tcgen05 engine does not take this problem (M=%d N=%d K=%d)", a->M, a->N, a->K);
+    return gemm_tc_launch(p, a->batch, st);
+  }
+  return gemm_simt_launch(p, a->batch, st);
+}

@@ -1,0 +1,70 @@
+// Device-side view of dpot_gemm_args and the A-prologue / C-epilogue shared by both engines.
+#pragma once
+#include "common.cuh"
+
+namespace dpot {
+
+struct GemmDev {
+  const float* A; int64_t lda;
+  const float* W; int64_t ldw;
+  float* C; int64_t ldc;
+  int M, N, K;
+  const float* bias;
+  const float* rowbias; int rb_period; int64_t ldrb;
+  const float* residual; int64_t ldr;
+  int act;
+  const float* a_scale; const float* a_shift; int a_rps;
+  const float* c_scale; const float* c_shift; int c_rps;
+  int c_group; int64_t c_group_stride;
+  int64_t sA, sW, sC, sBias;
+  int a_mode, pX, pY, pT, pC, pP, ph, pw;
+};
+
+// im2col address of PatchEmbed conv0 (models/dpot.py:199,375): row m = (b,p,q,t), k = (u,v,c)
+__device__ __forceinline__ int64_t patch_offset(const GemmDev& p, int m, int k) {
+  const int t = m % p.pT; int r = m / p.pT;
+  const int q = r % p.pw; r /= p.pw;
+  const int pp = r % p.ph; const int b = r / p.ph;
+  const int c = k % p.pC; const int uv = k / p.pC;
+  const int v = uv % p.pP, u = uv / p.pP;
+  return ((((int64_t)b * p.pX + pp * p.pP + u) * p.pY + q * p.pP + v) * p.pT + t) * p.pC + c;
+}
+
+__device__ __forceinline__ float gemm_load_a(const GemmDev& p, const float* __restrict__ A, int m, int k) {
+  if (m >= p.M || k >= p.K) return 0.f;
+  float v = (p.a_mode == DPOT_A_PLAIN) ? A[(int64_t)m * p.lda + k] : A[patch_offset(p, m, k)];
+  if (p.a_scale) {
+    const int64_t o = (int64_t)(m / p.a_rps) * p.K + k;
+    v = fmaf(v, p.a_scale[o], p.a_shift[o]);
+  }
+  return v;
+}
+
+__device__ __forceinline__ float gemm_epilogue_value(const GemmDev& p, const float* __restrict__ bias, int m, int n,
+                                                     float v) {
+  if (bias) v += bias[n];
+  if (p.rowbias) v += p.rowbias[(int64_t)(m % p.rb_period) * p.ldrb + n];
+  v = act_apply(v, p.act);
+  if (p.c_scale) {
+    const int64_t o = (int64_t)(m / p.c_rps) * p.N + n;
+    v = fmaf(v, p.c_scale[o], p.c_shift[o]);
+  }
+  if (p.residual) v += p.residual[(int64_t)m * p.ldr + n];
+  return v;
+}
+
+__device__ __forceinline__ int64_t gemm_c_offset(const GemmDev& p, int m) {
+  return p.c_group ? (int64_t)(m / p.c_group) * p.c_group_stride + (int64_t)(m % p.c_group) * p.ldc
+                   : (int64_t)m * p.ldc;
+}
+
+__device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, float* __restrict__ C,
+                                                    const float* __restrict__ bias, int m, int n, float v) {
+  C[gemm_c_offset(p, m) + n] = gemm_epilogue_value(p, bias, m, n, v);
+}
+
+int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st);
+int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st);   // tcgen05 engine
+bool gemm_tc_supports(const GemmDev& p, int batch);
+
+}  // namespace dpot

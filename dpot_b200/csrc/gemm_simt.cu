@@ -1,0 +1,160 @@
+// fp32 CUDA-core GEMM engine (DPOT_GEMM_SIMT): the exact-fp32 path of dpot_gemm.
+// It serves (a) every contraction on shapes the tcgen05 engine does not take (tiny test
+// configs, K or N not tile friendly) and (b) as the numerics cross-check of the tensor-core
+// engine.  Register-tiled 128x64x16, 256 threads, 8x4 outputs per thread, register prefetch
+// of the next K-slab.  See include/dpot_b200.h for the epilogue contract.
+#include "common.cuh"
+#include "gemm_common.cuh"
+
+namespace dpot {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4, NT = 256;
+constexpr int AS_LD = BM + 4, WS_LD = BN + 4;
+
+template <bool VEC>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
+  __shared__ __align__(16) float As[BK][AS_LD];
+  __shared__ __align__(16) float Ws[BK][WS_LD];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int bz = blockIdx.z;
+  const float* __restrict__ A = p.A + bz * p.sA;
+  const float* __restrict__ W = p.W + bz * p.sW;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // register staging for the next slab
+  float ra[8], rw[4];
+
+  auto load_slab = [&](int k0) {
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = tid + j * NT;
+        const int row = idx >> 2, kq = idx & 3;
+        const int m = m0 + row, k = k0 + kq * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M && k < p.K) {
+          v = *reinterpret_cast<const float4*>(A + (int64_t)m * p.lda + k);
+          if (p.a_scale) {
+            const int64_t o = (int64_t)(m / p.a_rps) * p.K + k;
+            const float4 s = *reinterpret_cast<const float4*>(p.a_scale + o);
+            const float4 h = *reinterpret_cast<const float4*>(p.a_shift + o);
+            v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y);
+            v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+          }
+        }
+        ra[j * 4 + 0] = v.x; ra[j * 4 + 1] = v.y; ra[j * 4 + 2] = v.z; ra[j * 4 + 3] = v.w;
+      }
+      {
+        const int row = tid >> 2, kq = tid & 3;
+        const int n = n0 + row, k = k0 + kq * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < p.N && k < p.K) v = *reinterpret_cast<const float4*>(W + (int64_t)n * p.ldw + k);
+        rw[0] = v.x; rw[1] = v.y; rw[2] = v.z; rw[3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = tid + j * NT;
+        const int row = idx / BK, kk = idx % BK;
+        ra[j] = gemm_load_a(p, A, m0 + row, k0 + kk);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tid + j * NT;
+        const int row = idx / BK, kk = idx % BK;
+        const int n = n0 + row, k = k0 + kk;
+        rw[j] = (n < p.N && k < p.K) ? W[(int64_t)n * p.ldw + k] : 0.f;
+      }
+    }
+  };
+  auto store_slab = [&]() {
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = tid + j * NT;
+        const int row = idx >> 2, kq = idx & 3;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) As[kq * 4 + e][row] = ra[j * 4 + e];
+      }
+      const int row = tid >> 2, kq = tid & 3;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Ws[kq * 4 + e][row] = rw[e];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = tid + j * NT;
+        As[idx % BK][idx / BK] = ra[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tid + j * NT;
+        Ws[idx % BK][idx / BK] = rw[j];
+      }
+    }
+  };
+
+  const int nk = (p.K + BK - 1) / BK;
+  load_slab(0);
+  for (int kb = 0; kb < nk; ++kb) {
+    store_slab();
+    __syncthreads();
+    if (kb + 1 < nk) load_slab((kb + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * TN]);
+      const float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float w[TN] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------
+  float* __restrict__ C = p.C + bz * p.sC;
+  const float* bias = p.bias ? p.bias + bz * p.sBias : nullptr;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= p.N) continue;
+      gemm_epilogue_store(p, C, bias, m, n, acc[i][j]);
+    }
+  }
+}
+
+}  // namespace
+
+int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM), (unsigned)batch);
+  DPOT_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, DPOT_E_BADARG, "dpot_gemm: grid too large (M=%d batch=%d)", p.M, batch);
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.A) % 16 == 0) && (reinterpret_cast<uintptr_t>(p.W) % 16 == 0) &&
+                       (p.lda % 4 == 0) && (p.ldw % 4 == 0) && (p.K % 4 == 0) && (p.sA % 4 == 0) && (p.sW % 4 == 0) &&
+                       (!p.a_scale || (reinterpret_cast<uintptr_t>(p.a_scale) % 16 == 0 &&
+                                       reinterpret_cast<uintptr_t>(p.a_shift) % 16 == 0));
+  if (p.a_mode == DPOT_A_PLAIN && aligned)
+    gemm_simt_kernel<true><<<grid, NT, 0, st>>>(p);
+  else
+    gemm_simt_kernel<false><<<grid, NT, 0, st>>>(p);
+  DPOT_LAUNCH_CHECK("gemm_simt_kernel");
+  return 0;
+}
+
+}  // namespace dpot

@@ -1,0 +1,180 @@
+"""Torch-tensor wrappers over the C ABI (one python function per entry point of
+include/dpot_b200.h).  These only marshal pointers/shapes and enqueue on the current CUDA stream;
+every arithmetic operation happens inside libdpot_b200.so.  There is no fallback: a CPU tensor
+or a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, ACT_NONE, GEMM_AUTO, GemmArgs, check, ptr
+
+GROUPS = 8  # torch.nn.GroupNorm(8, width), models/dpot.py:142,152
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("dpot_b200: tensors must be float32 CUDA tensors (the hot path has no CPU fallback); "
+                               f"got device={t.device} dtype={t.dtype}")
+
+
+def act_id(act) -> int:
+    if act is None:
+        return ACT_NONE
+    if isinstance(act, int):
+        return act
+    return ACT_IDS[act]
+
+
+def gemm(A: torch.Tensor, W: torch.Tensor, *, bias=None, act=None, residual=None, rowbias=None,
+         a_scale=None, a_shift=None, a_rows_per_sample=0, c_scale=None, c_shift=None, c_rows_per_sample=0,
+         out: Optional[torch.Tensor] = None, engine: int = GEMM_AUTO) -> torch.Tensor:
+    """C = act(A' @ W.T + bias + rowbias[m % period]) * c_scale + c_shift + residual; A[M,K], W[N,K]."""
+    _need_cuda(A, W, bias, residual, rowbias, a_scale, a_shift, c_scale, c_shift, out)
+    assert A.dim() == 2 and W.dim() == 2 and A.shape[1] == W.shape[1]
+    assert A.stride(1) == 1 and W.stride(1) == 1
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.ldw, g.C, g.ldc = ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(out), out.stride(0)
+    g.M, g.N, g.K = M, N, K
+    g.bias = ptr(bias)
+    if rowbias is not None:
+        g.rowbias, g.rowbias_period, g.ldrb = ptr(rowbias), rowbias.shape[0], rowbias.stride(0)
+    if residual is not None:
+        g.residual, g.ldr = ptr(residual), residual.stride(0)
+    g.act = act_id(act)
+    if a_scale is not None:
+        g.a_scale, g.a_shift, g.a_rows_per_sample = ptr(a_scale), ptr(a_shift), a_rows_per_sample
+    if c_scale is not None:
+        g.c_scale, g.c_shift, g.c_rows_per_sample = ptr(c_scale), ptr(c_shift), c_rows_per_sample
+    g.batch, g.engine, g.a_mode = 1, engine, _lib.A_PLAIN
+    check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm")
+    return out
+
+
+def gemm_batched_cols(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, nb: int, *, act=None,
+                      out: Optional[torch.Tensor] = None, engine: int = GEMM_AUTO) -> torch.Tensor:
+    """Block-diagonal GEMM of the AFNO spectral MLP: A[M, nb*k], W[nb, n, k], bias[nb, n] -> C[M, nb*n]."""
+    _need_cuda(A, W, bias, out)
+    M = A.shape[0]
+    _, n, k = W.shape
+    assert A.shape[1] == nb * k and W.is_contiguous() and bias.is_contiguous() and A.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, nb * n), device=A.device, dtype=torch.float32)
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.ldw, g.C, g.ldc = ptr(A), A.stride(0), ptr(W), k, ptr(out), out.stride(0)
+    g.M, g.N, g.K = M, n, k
+    g.bias, g.act = ptr(bias), act_id(act)
+    g.batch, g.strideA, g.strideW, g.strideC, g.strideBias = nb, k, n * k, n, n
+    g.engine, g.a_mode = engine, _lib.A_PLAIN
+    check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(batched)")
+    return out
+
+
+def patch_gemm(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: int, act, Kp: int, *,
+               a_scale=None, a_shift=None, engine: int = GEMM_AUTO) -> torch.Tensor:
+    """PatchEmbed conv0 + act as an im2col GEMM: x[B,X,Y,T,C] -> z1[B*n, Kp] (column t*mid+m)."""
+    _need_cuda(x, W0p, rowbias0, a_scale, a_shift)
+    B, X, Y, T, Cc = x.shape
+    assert x.is_contiguous()
+    mid, K0 = W0p.shape
+    h, w = X // P, Y // P
+    z1 = torch.zeros((B * h * w, Kp), device=x.device, dtype=torch.float32)
+    g = GemmArgs()
+    g.A, g.W, g.ldw, g.C, g.ldc = ptr(x), ptr(W0p), K0, ptr(z1), mid
+    g.M, g.N, g.K = B * h * w * T, mid, K0
+    g.rowbias, g.rowbias_period, g.ldrb = ptr(rowbias0), h * w * T, mid
+    g.act = act_id(act)
+    g.c_group, g.c_group_stride = T, Kp
+    if a_scale is not None:
+        g.a_scale, g.a_shift, g.a_rows_per_sample = ptr(a_scale), ptr(a_shift), h * w * T
+    g.batch, g.engine = 1, engine
+    g.a_mode, g.pX, g.pY, g.pT, g.pC, g.pP = _lib.A_PATCH, X, Y, T, Cc, P
+    check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(patch)")
+    return z1
+
+
+def gn_stats(x: torch.Tensor, B: int, n: int, groups: int = GROUPS) -> torch.Tensor:
+    _need_cuda(x)
+    E = x.shape[-1]
+    stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float64)
+    check(_lib.load().dpot_gn_stats(ptr(x), B, n, E, groups, ptr(stats), _stream()), "dpot_gn_stats")
+    return stats
+
+
+def gn_finalize(stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, eps: float = 1e-5):
+    B, groups, _ = stats.shape
+    E = gamma.numel()
+    scale = torch.empty((B, E), device=stats.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    check(_lib.load().dpot_gn_finalize(ptr(stats), ptr(gamma), ptr(beta), B, n, E, groups, eps, ptr(scale), ptr(shift),
+                                       _stream()), "dpot_gn_finalize")
+    return scale, shift
+
+
+def afno_fft_fwd(a, scale, shift, B, h, nb, km1, km2):
+    _need_cuda(a, scale, shift)
+    E = a.shape[-1]
+    S = torch.empty((B * km1 * km2, 2 * E), device=a.device, dtype=torch.float32)
+    check(_lib.load().dpot_afno_fft_fwd(ptr(a), ptr(scale), ptr(shift), B, h, E, nb, km1, km2, ptr(S), _stream()),
+          "dpot_afno_fft_fwd")
+    return S
+
+
+def afno_fft_inv(O2, a, scale, shift, B, h, nb, km1, km2, want_stats=True, groups: int = GROUPS):
+    _need_cuda(O2, a, scale, shift)
+    E = a.shape[-1]
+    f = torch.empty_like(a)
+    stats = torch.zeros((B, groups, 2), device=a.device, dtype=torch.float64) if want_stats else None
+    check(_lib.load().dpot_afno_fft_inv(ptr(O2), ptr(a), ptr(scale), ptr(shift), B, h, E, nb, km1, km2, ptr(f),
+                                        ptr(stats), groups, _stream()), "dpot_afno_fft_inv")
+    return f, stats
+
+
+def pack_afno(w: torch.Tensor, b: torch.Tensor):
+    _need_cuda(w, b)
+    _, nb, bs, _ = w.shape
+    Wc = torch.empty((nb, 2 * bs, 2 * bs), device=w.device, dtype=torch.float32)
+    bc = torch.empty((nb, 2 * bs), device=w.device, dtype=torch.float32)
+    check(_lib.load().dpot_pack_afno(ptr(w.contiguous()), ptr(b.contiguous()), nb, bs, ptr(Wc), ptr(bc), _stream()),
+          "dpot_pack_afno")
+    return Wc, bc
+
+
+def window_advance(xx, im, xx_next, pred=None, step=0):
+    _need_cuda(xx, im, xx_next, pred)
+    B, X, Y, T, Cc = xx.shape
+    Tb = im.shape[-2]
+    Ttot = pred.shape[-2] if pred is not None else 0
+    check(_lib.load().dpot_window_advance(ptr(xx), ptr(im), ptr(xx_next), ptr(pred), B * X * Y, T, Tb, Cc, Ttot, step,
+                                          _stream()), "dpot_window_advance")
+    return xx_next
+
+
+def adam_step_multi(params, grads, ms, vs, vmaxs, steps, *, lr, beta1, beta2, eps, weight_decay, decoupled,
+                    grad_scale=1.0):
+    n = len(params)
+    if n == 0:
+        return
+    _need_cuda(*params, *grads, *ms, *vs)
+    VP = C.c_void_p * n
+    pa = VP(*[p.data_ptr() for p in params])
+    ga = VP(*[g.data_ptr() for g in grads])
+    ma = VP(*[m.data_ptr() for m in ms])
+    va = VP(*[v.data_ptr() for v in vs])
+    xa = VP(*[x.data_ptr() for x in vmaxs]) if vmaxs else None
+    na = (C.c_int64 * n)(*[p.numel() for p in params])
+    sa = (C.c_int32 * n)(*steps)
+    check(_lib.load().dpot_adam_step_multi(pa, ga, ma, va, xa, na, n, lr, beta1, beta2, eps, weight_decay, sa,
+                                           1 if decoupled else 0, grad_scale, _stream()), "dpot_adam_step_multi")

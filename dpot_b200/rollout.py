@@ -1,0 +1,44 @@
+"""Pipelined autoregressive rollout (the loop of evaluate.py:192-208 / train_temporal.py:262-272
+under no_grad): im = model(xx); pred[..., t] = im; xx = cat(xx[..., T_bundle:, :], im).
+
+Everything is enqueued on one CUDA stream without host synchronisation: the window is advanced by
+a kernel into a ping-pong buffer (no torch.cat allocation per step) which also scatters the new
+frame into the preallocated prediction tensor."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class RolloutEngine:
+    def __init__(self, model, batch: int, n_steps: int, device=None):
+        self.model = model
+        self.n_steps = n_steps
+        dev = device or next(model.parameters()).device
+        R, T, Cc = model.img_size, model.in_timesteps, model.in_channels
+        Tb, Co = model.out_timesteps, model.out_channels
+        if Co != Cc:
+            raise ValueError("autoregressive rollout needs out_channels == in_channels")
+        self.win = [torch.empty((batch, R, R, T, Cc), device=dev), torch.empty((batch, R, R, T, Cc), device=dev)]
+        self.im = torch.empty((batch, R, R, Tb, Co), device=dev)
+        self.pred = torch.empty((batch, R, R, n_steps * Tb, Co), device=dev)
+
+    @torch.no_grad()
+    def run(self, xx: torch.Tensor, non_blocking: bool = True) -> torch.Tensor:
+        """xx[B,X,Y,T,C] (host-pinned or device) -> pred[B,X,Y,n_steps*T_bundle,C] on the device."""
+        eng = self.model.engine()
+        self.win[0].copy_(xx, non_blocking=non_blocking)
+        cur = 0
+        for s in range(self.n_steps):
+            eng.forward(self.win[cur], out=self.im, want_cls=False)
+            ops.window_advance(self.win[cur], self.im, self.win[1 - cur], self.pred, step=s)
+            cur = 1 - cur
+        return self.pred
+
+
+def rollout(model, xx: torch.Tensor, n_steps: int, engine: Optional[RolloutEngine] = None) -> torch.Tensor:
+    eng = engine or RolloutEngine(model, xx.shape[0], n_steps, device=xx.device if xx.is_cuda else None)
+    return eng.run(xx)

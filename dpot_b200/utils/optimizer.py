@@ -1,0 +1,139 @@
+"""B200-native drop-in for the reference's ``utils/optimizer.py``.
+
+``Adam`` / ``AdamW`` keep the reference's constructor arguments, ``param_groups`` and per-parameter
+state layout (``step`` python int, ``exp_avg``, ``exp_avg_sq``[, ``max_exp_avg_sq``]) -- see
+utils/optimizer.py:55-164 and :217-334 -- so ``optimizer.state_dict()`` round-trips with the
+reference.  The update itself (utils/optimizer.py:9-52, :170-212) is ONE fused multi-tensor
+kernel of libdpot_b200.so per 32 tensors instead of ~8 elementwise kernels per tensor.
+The reference's ``grad * grad.conj()`` only differs from ``grad**2`` for complex parameters;
+no parameter of the reference is complex (models/dpot.py:45-48), complex tensors raise here.
+
+``Lamb`` (utils/optimizer.py:359-499) is off the hot path (no config selects it); it is kept as a
+small plain-torch optimizer so that ``from utils.optimizer import Adam, Lamb`` keeps working.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.optim.optimizer import Optimizer
+
+from .. import ops
+
+
+class _FusedAdamBase(Optimizer):
+    _decoupled = False
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if not 0.0 <= weight_decay:
+            raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+        self.grad_scale = 1.0  # set to 1/world_size to fold the DDP average into the step
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:
+            group.setdefault('amsgrad', False)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps, gs, ms, vs, xs, steps = [], [], [], [], [], []
+            beta1, beta2 = group['betas']
+            for p in group['params']:
+                if p.grad is None:  # skipped exactly like the reference (:123)
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError('Adam does not support sparse gradients, please consider SparseAdam instead')
+                if p.is_complex():
+                    raise RuntimeError('dpot_b200 Adam: complex parameters are not supported (the reference has none)')
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise RuntimeError('dpot_b200 Adam: parameters must be float32 CUDA tensors (no CPU fallback)')
+                st = self.state[p]
+                if len(st) == 0:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if group['amsgrad']:
+                        st['max_exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st['step'] += 1
+                g = p.grad
+                if not (p.is_contiguous() and g.is_contiguous()):
+                    raise RuntimeError('dpot_b200 Adam: parameters and gradients must be contiguous')
+                ps.append(p); gs.append(g); ms.append(st['exp_avg']); vs.append(st['exp_avg_sq'])
+                if group['amsgrad']:
+                    xs.append(st['max_exp_avg_sq'])
+                steps.append(int(st['step']))
+            ops.adam_step_multi(ps, gs, ms, vs, xs if group['amsgrad'] else None, steps, lr=float(group['lr']),
+                                beta1=beta1, beta2=beta2, eps=group['eps'], weight_decay=group['weight_decay'],
+                                decoupled=self._decoupled, grad_scale=self.grad_scale)
+        return loss
+
+
+class Adam(_FusedAdamBase):
+    """Adam with L2-coupled weight decay, reference utils/optimizer.py:55-164 + adam() :9-52."""
+    _decoupled = False
+
+
+class AdamW(_FusedAdamBase):
+    """AdamW (decoupled decay), reference utils/optimizer.py:217-334 + adamw() :170-212."""
+    _decoupled = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
+
+
+class Lamb(Optimizer):
+    """Layer-wise adaptive moments (reference utils/optimizer.py:359-499).  Plain torch: not on the
+    hot path (no shipped config uses --opt lamb)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0, clamp_value=10, adam=False,
+                 debias=False):
+        if lr <= 0.0 or eps < 0.0 or weight_decay < 0 or clamp_value < 0.0:
+            raise ValueError("Invalid Lamb hyper-parameter")
+        if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
+            raise ValueError("Invalid beta parameter: {}".format(betas))
+        self.clamp_value, self.adam, self.debias = clamp_value, adam, debias
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            b1, b2 = group['betas']
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p)
+                    st['exp_avg_sq'] = torch.zeros_like(p)
+                st['step'] += 1
+                m, v, g = st['exp_avg'], st['exp_avg_sq'], p.grad
+                m.mul_(b1).add_(g, alpha=1 - b1)
+                v.mul_(b2).addcmul_(g, g.conj(), value=1 - b2)
+                corr = math.sqrt(1 - b2 ** st['step']) / (1 - b1 ** st['step']) if self.debias else 1
+                w_norm = torch.norm(p).clamp(0, self.clamp_value)
+                upd = m / v.sqrt().add(group['eps'])
+                if group['weight_decay'] != 0:
+                    upd.add_(p, alpha=group['weight_decay'])
+                u_norm = torch.norm(upd)
+                trust = 1 if (w_norm == 0 or u_norm == 0) else w_norm / u_norm
+                st['weight_norm'], st['adam_norm'], st['trust_ratio'] = w_norm, u_norm, trust
+                if self.adam:
+                    trust = 1
+                p.add_(upd, alpha=-group['lr'] * corr * trust)
+        return loss

@@ -1,0 +1,225 @@
+/*
+ * dpot_b200.h -- C ABI of libdpot_b200.so: the B200 (sm_100a) implementation of the DPOT
+ * autoregressive Fourier-operator hot path (forward / backward / optimizer step).
+ *
+ * The reference (HaoZhongkai/DPOT) is pure Python on this path and has no FFI of its own;
+ * each entry point below therefore names the reference *Python* interface (file:line under
+ * /root/reference) whose arithmetic it replaces.  The Python binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md (dpot_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *  - plain C: pointers, ints, floats; no torch / C++ types.  `stream` is a cudaStream_t
+ *    passed as void* (NULL = legacy default stream).
+ *  - every device pointer is BORROWED for the duration of the stream-ordered work enqueued by
+ *    the call; the library never allocates or frees device memory and never synchronises,
+ *    so every entry point is CUDA-graph capturable and re-entrant.
+ *  - return value: 0 = ok; >0 = cudaError_t; <0 = argument error (DPOT_E_*).  The message
+ *    of the last failure on the calling thread: dpot_last_error_string().
+ *  - all tensors are fp32 and contiguous unless a leading-dimension argument says otherwise.
+ *  - latent tensors are token-major ("NHWC"): a[B*n, E], n = h*w latent cells, row = b*n + p*w + q.
+ */
+#ifndef DPOT_B200_H_
+#define DPOT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPOT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DPOT_API __attribute__((visibility("default")))
+#else
+#define DPOT_API
+#endif
+
+/* argument-error codes */
+#define DPOT_E_BADARG   (-1)
+#define DPOT_E_UNSUPPORTED (-2)
+#define DPOT_E_ALIGN    (-3)
+
+/* activation ids, order of ACTIVATION in models/dpot.py:19 */
+enum {
+  DPOT_ACT_NONE = -1,
+  DPOT_ACT_GELU = 0, DPOT_ACT_TANH = 1, DPOT_ACT_SIGMOID = 2, DPOT_ACT_RELU = 3,
+  DPOT_ACT_LEAKY_RELU = 4, DPOT_ACT_SOFTPLUS = 5, DPOT_ACT_ELU = 6, DPOT_ACT_SILU = 7
+};
+
+/* GEMM engines */
+enum { DPOT_GEMM_AUTO = 0, DPOT_GEMM_SIMT = 1, DPOT_GEMM_TC = 2 };
+
+DPOT_API int         dpot_abi_version(void);
+DPOT_API const char* dpot_last_error_string(void);
+/* 1 if the tcgen05 engine can serve this device (sm_100) */
+DPOT_API int         dpot_device_supported(void);
+/* number of CUDA kernels this library has launched in this process (all threads) */
+DPOT_API long long   dpot_launch_count(void);
+/* 1 if the tcgen05 3xTF32 GEMM engine is compiled in and the current device can run it */
+DPOT_API int         dpot_tc_available(void);
+
+/* ------------------------------------------------------------------------------------------
+ * The dense-contraction engine.  C = epilogue( A' * W^T ), fp32 in / fp32 out.
+ *   A'[m,k] = A[m,k] * a_scale[s,k] + a_shift[s,k]   (s = m / a_rows_per_sample; tables optional)
+ *   v       = sum_k A'[m,k] W[n,k] + bias[n] + rowbias[(m % rowbias_period), n]
+ *   v       = act(v)
+ *   v       = v * c_scale[s', n] + c_shift[s', n]      (s' = m / c_rows_per_sample; optional)
+ *   C[m,n]  = v + residual[m,n]
+ * A is [M,K] row-major (or the im2col view of a field, see a_mode), W is [N,K] row-major --
+ * the layout torch keeps Conv2d(1x1)/Linear weights in.  `batch` independent problems are
+ * addressed by the stride* fields (block-diagonal AFNO weights).
+ * Replaces: torch.einsum / Conv2d(1x1) / Linear / ConvTranspose2d call sites
+ * models/dpot.py:72-94 (AFNO block MLP), :157-161 (channel MLP), :198-202 (PatchEmbed),
+ * :228-232 (TimeAggregator), :303-309 (cls head), :315-321 (out layer).
+ * ---------------------------------------------------------------------------------------- */
+enum { DPOT_A_PLAIN = 0, DPOT_A_PATCH = 1 };
+
+typedef struct dpot_gemm_args {
+  const float* A;  int64_t lda;          /* DPOT_A_PLAIN: [M,K]; DPOT_A_PATCH: field x[B,X,Y,T,C] */
+  const float* W;  int64_t ldw;          /* [N,K] */
+  float*       C;  int64_t ldc;
+  int32_t M, N, K;
+  const float* bias;                     /* [N] or NULL */
+  const float* rowbias; int32_t rowbias_period; int64_t ldrb;   /* [period, N] or NULL */
+  const float* residual; int64_t ldr;    /* [M,N] or NULL (may alias C) */
+  int32_t act;                           /* DPOT_ACT_* */
+  const float* a_scale; const float* a_shift; int32_t a_rows_per_sample;  /* [*,K] tables or NULL */
+  const float* c_scale; const float* c_shift; int32_t c_rows_per_sample;  /* [*,N] tables or NULL */
+  /* output row remap: row m is stored at C + (m / c_group) * c_group_stride + (m % c_group) * ldc;
+     c_group = 0 disables it */
+  int32_t c_group; int64_t c_group_stride;
+  int32_t batch; int64_t strideA, strideW, strideC, strideBias;
+  /* DPOT_A_PATCH geometry: row m = (b, p, q, t), k = (u, v, c):
+     A[m,k] = x[b, p*P+u, q*P+v, t, c]   (PatchEmbed im2col, models/dpot.py:199,375) */
+  int32_t a_mode, pX, pY, pT, pC, pP;
+  int32_t engine;                        /* DPOT_GEMM_* */
+} dpot_gemm_args;
+
+DPOT_API int dpot_gemm(const dpot_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm pieces (torch.nn.GroupNorm(8,E), models/dpot.py:142,152,167,175).
+ * stats[B, groups, 2] are double (sum, sum of squares) over the (E/groups)*n values of a group.
+ * dpot_gn_stats zeroes `stats` itself.  dpot_gn_finalize turns them into per-(sample, channel)
+ * affine tables: scale = rstd*gamma, shift = beta - mean*rstd*gamma, consumed by the
+ * a_scale/a_shift prologue of dpot_gemm and by the AFNO spectral kernels.
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_gn_stats(const float* x, int32_t B, int32_t n, int32_t E, int32_t groups, double* stats, void* stream);
+DPOT_API int dpot_gn_finalize(const double* stats, const float* gamma, const float* beta, int32_t B, int32_t n,
+                     int32_t E, int32_t groups, float eps, float* scale, float* shift, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * AFNO2D spectral transforms (models/dpot.py:59 rfft2 ortho, :102 irfft2 ortho, :106 skip).
+ * fwd:  n1 = a*scale+shift (GroupNorm-1 applied on load); S = rfft2_ortho(n1) restricted to the kept
+ *       modes k1<km1, k2<km2, written as S[(b,k1,k2), kappa, {re[bs] | im[bs]}]  (row length 2E).
+ * inv:  f = irfft2_ortho(O2 zero-padded to [h, h/2+1]) + n1, c2r ignoring Im of k2 in {0, h/2};
+ *       also accumulates GroupNorm-2 statistics of f into stats_out[B,groups,2] (must be zeroed
+ *       by the caller; NULL to skip).
+ * h must be a power of two in [2, 32].
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_afno_fft_fwd(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
+                      int32_t E, int32_t nb, int32_t km1, int32_t km2, float* S, void* stream);
+DPOT_API int dpot_afno_fft_inv(const float* O2, const float* a, const float* scale, const float* shift, int32_t B,
+                      int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, float* f,
+                      double* stats_out, int32_t groups, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing (run when weights change, not per step).
+ * ---------------------------------------------------------------------------------------- */
+/* AFNO2D w[2,nb,bs,bs] ("bio": in,out), b[2,nb,bs]  (models/dpot.py:45-48)  ->
+   real block form Wc[nb, 2bs(out), 2bs(in)] with [re|im] halves, bc[nb, 2bs]. */
+DPOT_API int dpot_pack_afno(const float* w, const float* b, int32_t nb, int32_t bs, float* Wc, float* bc, void* stream);
+/* PatchEmbed conv0 weight [mid, C+3, P, P] (models/dpot.py:199) -> W0p[mid, (u,v,c<C)] and the
+   coordinate-channel contribution rowbias0[(p,q,t), mid] = b0 + sum_uv W0[:,C..C+2,u,v]*grid
+   (get_grid_3d, models/dpot.py:350-360; gx/gy/gt are the fp32 linspace tables). */
+DPOT_API int dpot_pack_patch(const float* w0, const float* b0, const float* gx, const float* gy, const float* gt,
+                    int32_t mid, int32_t C, int32_t P, int32_t h, int32_t w, int32_t T,
+                    float* W0p, float* rowbias0, void* stream);
+/* Fold PatchEmbed conv 1x1 (W2[E,mid], b2[E]) + pos_embed[E,n] + TimeAggregator (w[T,E,E],
+   temb[T,E] = cos(t*gamma) or ones) (models/dpot.py:201,378,228-232) into
+   WeffT[E, Kp] (Kp >= T*mid, zero padded; column t*mid+m) and bias_eff[n, E].  The bias_eff
+   buffer must hold n*E + E*E floats (the tail is scratch for sum_t temb*w).  */
+DPOT_API int dpot_fold_timeagg(const float* W2, const float* b2, const float* pos, const float* w, const float* temb,
+                      int32_t T, int32_t E, int32_t mid, int32_t n, int32_t Kp,
+                      float* WeffT, float* bias_eff, void* stream);
+/* ConvTranspose2d weight [E, old, P, P], bias[old] (models/dpot.py:316) ->
+   WtT[(u,v,o), E], bias_t[(u,v,o)]. */
+DPOT_API int dpot_pack_out(const float* wt, const float* bt, int32_t E, int32_t old, int32_t P,
+                  float* WtT, float* bias_t, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Output head tail (models/dpot.py:317-321, 397-401): per pixel
+ *   y1 = act(Y0[(b,p,q), (u,v,:)]) (act already applied by the GEMM epilogue), y2 = act(W2 y1 + b2),
+ *   y3 = W4 y2 + b4 -> out[b, p*P+u, q*P+v, to, c]  (x sigma + mu when denorm tables are given).
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_out_tail(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4,
+                  int32_t B, int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act,
+                  const float* mu, const float* sigma, int32_t Co, float* out, void* stream);
+/* spatial mean a[B*n,E] -> tok[B,E]  (models/dpot.py:394) */
+DPOT_API int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E, float* tok, void* stream);
+/* per (sample, channel) mean and unbiased std + 1e-6 over (X,Y,T)  (models/dpot.py:367);
+   writes musig[B, 2C] = [mu | sigma] and the im2col prologue tables a_scale/a_shift[B, P*P*C]. */
+DPOT_API int dpot_input_stats(const float* x, int32_t B, int64_t per_sample, int32_t C, int32_t PP,
+                     float* musig, float* a_scale, float* a_shift, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Autoregressive window advance (train_temporal.py:219, evaluate.py:208):
+ *   xx_next = cat(xx[..., Tb:, :], im) on xx[B,X,Y,T,C], im[B,X,Y,Tb,C]; also copies im into
+ *   pred[..., step*Tb:(step+1)*Tb, :] of pred[B,X,Y,Ttot,C] when pred != NULL.
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_window_advance(const float* xx, const float* im, float* xx_next, float* pred, int64_t npix,
+                        int32_t T, int32_t Tb, int32_t C, int32_t Ttot, int32_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer: adam()/adamw() of utils/optimizer.py:9-52 / :170-212 on one flat tensor.
+ * step = 1-based count after the increment; decoupled = 0 (Adam, L2-coupled decay) or 1 (AdamW);
+ * vmax = amsgrad buffer or NULL; grad_scale multiplies the gradient first (1/world for DDP).
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                   int32_t decoupled, float grad_scale, void* stream);
+/* multi-tensor form: `count` tensors described by parallel host arrays */
+DPOT_API int dpot_adam_step_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
+                         float* const* vmax, const int64_t* n, int32_t count, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, const int32_t* steps,
+                         int32_t decoupled, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-model inference forward: DPOTNet.forward under no_grad (models/dpot.py:364-403).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dpot_config {
+  int32_t img_size, patch_size, in_channels, out_channels, in_timesteps, out_timesteps;
+  int32_t n_blocks, embed_dim, out_layer_dim, depth, modes, hidden_dim, n_cls;
+  int32_t normalize, act, time_agg;      /* time_agg: 0 = 'mlp', 1 = 'exp_mlp' */
+} dpot_config;
+
+typedef struct dpot_block_params {
+  const float *norm1_w, *norm1_b, *w1, *b1, *w2, *b2, *norm2_w, *norm2_b;
+  const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} dpot_block_params;
+
+typedef struct dpot_params {             /* reference state_dict tensors, SURVEY.md appendix A */
+  const float *pos_embed, *pe0_w, *pe0_b, *pe2_w, *pe2_b;
+  const float *tagg_w, *tagg_gamma;
+  const float *cls0_w, *cls0_b, *cls2_w, *cls2_b, *cls4_w, *cls4_b;
+  const float *out0_w, *out0_b, *out2_w, *out2_b, *out4_w, *out4_b;
+  const float *mu_w, *mu_b, *sigma_w, *sigma_b;           /* scale_feats_* (normalize only) */
+  const dpot_block_params* blocks;                        /* host array [depth] */
+  const float *grid_x, *grid_y, *grid_t;                  /* fp32 linspace(0,1,n) tables on device */
+  const float *temb;                                      /* [T,E] cos(t*gamma) (ones for 'mlp') */
+} dpot_params;
+
+/* number of floats of the packed-weight arena / the per-call workspace */
+DPOT_API int64_t dpot_packed_floats(const dpot_config* cfg);
+DPOT_API int64_t dpot_workspace_floats(const dpot_config* cfg, int32_t B);
+/* derive every packed weight from the raw parameters (weights changed -> call again) */
+DPOT_API int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm, float* packed, void* stream);
+/* x[B,X,Y,T,C] -> y[B,X,Y,To,Co], cls[B,n_cls] (cls may be NULL) */
+DPOT_API int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
+                 int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPOT_B200_H_ */

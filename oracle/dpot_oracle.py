@@ -159,7 +159,12 @@ def afno2d(x: np.ndarray, p: Params, prefix: str, n_blocks: int, modes: int, act
     km = modes
     Fk = F[:, :km, :km]
     fr, fi = Fk.real.astype(x.dtype), Fk.imag.astype(x.dtype)
-    mm = lambda a, wgt: np.einsum("...bi,bio->...bo", a, wgt, optimize=True).astype(x.dtype)
+
+    def mm(a, wgt):  # einsum('...bi,bio->...bo') as a BLAS batched matmul over the nb blocks
+        lead = a.shape[:-2]
+        r = np.matmul(np.ascontiguousarray(a.reshape(-1, n_blocks, bs).transpose(1, 0, 2)), wgt)
+        return np.ascontiguousarray(r.transpose(1, 0, 2)).reshape(*lead, n_blocks, bs).astype(x.dtype)
+
     o1r = activation(mm(fr, w1[0]) - mm(fi, w1[1]) + b1[0], act)  # :72-76
     o1i = activation(mm(fi, w1[0]) + mm(fr, w1[1]) + b1[1], act)  # :78-82
     o2r = mm(o1r, w2[0]) - mm(o1i, w2[1]) + b2[0]  # :84-88

@@ -1,0 +1,142 @@
+"""CPU-only checks of the host side: ABI surface, drop-in schema, constructor errors, loud failure."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dpot_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from dpot_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "dpot_b200.h")).read()
+    declared = set(re.findall(r"DPOT_API[^;(]*?\b(dpot_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dpot_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.dpot_abi_version() == 1
+
+
+def test_ctypes_struct_sizes_match_header():
+    """Sizes of the mirrored structs, checked against a tiny C program compiled from the header."""
+    import subprocess
+    import tempfile
+    from dpot_b200 import _lib
+    src = '#include <stdio.h>\n#include "dpot_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(dpot_gemm_args),' \
+          'sizeof(dpot_config), sizeof(dpot_block_params), sizeof(dpot_params));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
+    import ctypes as C
+    got = [C.sizeof(_lib.GemmArgs), C.sizeof(_lib.Config), C.sizeof(_lib.BlockParams), C.sizeof(_lib.Params)]
+    assert [int(v) for v in out] == got
+
+
+@pytest.mark.parametrize("name", ["Ti", "S"])
+def test_state_dict_schema_matches_appendix_a(name):
+    from dpot_b200.models.dpot import DPOTNet
+    cfg = O.zoo_cfg(name, img_size=64 if name == "Ti" else 128)
+    m = DPOTNet(**cfg)
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert got == O.param_shapes(cfg)
+
+
+def test_normalize_schema_and_attrs():
+    from dpot_b200.models.dpot import DPOTNet
+    cfg = O.make_cfg(img_size=32, patch_size=4, in_channels=3, out_channels=3, in_timesteps=5, out_timesteps=2,
+                     n_blocks=4, embed_dim=32, out_layer_dim=16, depth=2, modes=3, mlp_ratio=2, n_cls=5, normalize=True)
+    m = DPOTNet(**cfg)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == O.param_shapes(cfg)
+    for attr in ("in_channels", "out_channels", "in_timesteps", "out_timesteps", "n_blocks", "modes", "num_features",
+                 "embed_dim", "mlp_ratio", "latent_size", "normalize", "time_agg", "n_cls", "mixing_type",
+                 "patch_embed", "pos_embed", "blocks", "time_agg_layer", "cls_head", "out_layer", "scale_feats_mu"):
+        assert hasattr(m, attr), attr
+    assert "pos_embed" in m.extra_repr()
+    assert m.latent_size == (8, 8)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_drop_in_against_reference_module():
+    """Same seed -> identical initial weights; strict state-dict loading both ways; same repr lines."""
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    try:
+        import importlib
+        ref = importlib.import_module("models.dpot")
+    finally:
+        sys.path.remove(REF)
+    from dpot_b200.models import dpot as ours
+    kw = dict(img_size=32, patch_size=4, in_channels=3, out_channels=3, in_timesteps=5, out_timesteps=2, n_blocks=4,
+              embed_dim=32, out_layer_dim=16, depth=2, modes=3, mlp_ratio=2, n_cls=5, normalize=True)
+    torch.manual_seed(0)
+    a = ref.DPOTNet(**kw)
+    torch.manual_seed(0)
+    b = ours.DPOTNet(**kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    b.load_state_dict(sa, strict=True)
+    a.load_state_dict(sb, strict=True)
+    assert a.extra_repr() == b.extra_repr()
+    for name in ("AFNO2D", "Block", "PatchEmbed", "TimeAggregator", "DPOTNet", "ACTIVATION", "resize_pos_embed",
+                 "checkpoint_filter_fn", "Mlp"):
+        assert hasattr(ours, name)
+    import inspect
+    assert str(inspect.signature(ref.DPOTNet.__init__)) == str(inspect.signature(ours.DPOTNet.__init__))
+    assert str(inspect.signature(ref.AFNO2D.__init__)) == str(inspect.signature(ours.AFNO2D.__init__))
+    assert str(inspect.signature(ref.Block.__init__)) == str(inspect.signature(ours.Block.__init__))
+
+
+def test_constructor_rejects_unbuilt_configs_loudly():
+    from dpot_b200.models.dpot import DPOTNet
+    with pytest.raises(NotImplementedError):
+        DPOTNet(img_size=224, patch_size=16)  # latent 14x14 is not a power of two
+    with pytest.raises(KeyError):
+        DPOTNet(img_size=32, patch_size=4, act="swish")
+
+
+def test_no_cpu_fallback():
+    from dpot_b200.models.dpot import DPOTNet
+    m = DPOTNet(img_size=16, patch_size=4, in_channels=2, out_channels=2, in_timesteps=3, embed_dim=16, depth=1,
+                n_blocks=2, out_layer_dim=8, n_cls=3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 16, 16, 3, 2))
+
+
+def test_optimizer_state_layout_and_errors():
+    from dpot_b200.utils.optimizer import Adam, AdamW, Lamb
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = Adam([p], lr=1e-3, betas=(0.9, 0.9), weight_decay=1e-6)
+    assert opt.param_groups[0]["lr"] == 1e-3 and opt.param_groups[0]["amsgrad"] is False
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()  # CPU parameter: no fallback
+    with pytest.raises(ValueError):
+        AdamW([p], lr=-1.0)
+    q = torch.nn.Parameter(torch.ones(3))
+    lamb = Lamb([q], lr=1e-2)
+    q.grad = torch.ones(3)
+    lamb.step()
+    assert set(lamb.state[q]) >= {"step", "exp_avg", "exp_avg_sq", "trust_ratio"}
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under dpot_b200/ may reference it."""
+    for dp, _, files in os.walk(os.path.join(ROOT, "dpot_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("oracle/", "oracle/") or f == "build.py" or "import oracle" not in txt
+                assert "from oracle" not in txt and "import oracle" not in txt, os.path.join(dp, f)

@@ -1,0 +1,195 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden outputs of the reference
+and against the numpy oracle.  Tolerance: rel-L2 <= 1e-5 in fp32 (BASELINE.json north_star)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dpot_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+FWD = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(G, "fwd_*.npz")))
+TOL = 1e-5
+
+
+def build_model(cfg, params):
+    from dpot_b200.models.dpot import DPOTNet
+    m = DPOTNet(**cfg)
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()}, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("engine", [1, 0], ids=["simt", "auto"])
+@pytest.mark.parametrize("name", FWD)
+def test_forward_and_rollout_match_reference_golden(name, engine):
+    from dpot_b200.rollout import rollout
+    z = np.load(os.path.join(G, f"fwd_{name}.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    params = O.make_params(cfg, seed=0)
+    x = O.make_input(cfg, int(z["B"]), seed=0, kind=str(z["kind"]))
+    m = build_model(cfg, params)
+    m.gemm_engine = engine
+    with torch.no_grad():
+        y, cls = m(torch.from_numpy(x).cuda())
+        pred = rollout(m, torch.from_numpy(x).cuda(), int(z["nsteps"]))
+    torch.cuda.synchronize()
+    assert y.shape == z["y"].shape and y.is_contiguous()
+    assert O.rel_l2(y.cpu().numpy(), z["y"]) < TOL
+    assert O.rel_l2(cls.cpu().numpy(), z["cls"]) < TOL
+    assert O.rel_l2(pred.cpu().numpy(), z["pred"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["tiny_trunc", "tiny_norm_tanh_mlp", "smoke_20"])
+def test_forward_matches_fp64_oracle(name):
+    """Against the float64 oracle the CUDA fp32 path must sit at the fp32 noise floor."""
+    z = np.load(os.path.join(G, f"fwd_{name}.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    params = O.make_params(cfg, seed=3)
+    x = O.make_input(cfg, 2, seed=3)
+    yo, co = O.dpot_forward(x.astype(np.float64), O.cast_params(params, np.float64), cfg)
+    m = build_model(cfg, params)
+    with torch.no_grad():
+        y, cls = m(torch.from_numpy(x).cuda())
+    assert O.rel_l2(y.cpu().numpy(), yo) < 3e-6
+    assert O.rel_l2(cls.cpu().numpy(), co) < 3e-6
+
+
+def test_afno2d_module_delta():
+    """AFNO2D(x) - x per module with re-scaled weights, incl. real mode truncation (SURVEY finding 3)."""
+    from dpot_b200.models.dpot import AFNO2D
+    z = np.load(os.path.join(G, "afno2d.npz"))
+    for tag in sorted({k.split(".")[0] for k in z.files}):
+        E, nb, H, modes = [int(v) for v in z[f"{tag}.meta"]]
+        f = AFNO2D(width=E, num_blocks=nb, channel_first=True, modes=modes)
+        f.load_state_dict({k: torch.from_numpy(z[f"{tag}.{k}"]) for k in ("w1", "b1", "w2", "b2")})
+        f = f.cuda()
+        x = torch.from_numpy(z[f"{tag}.x"]).cuda()
+        with torch.no_grad():
+            y = f(x)
+        assert O.rel_l2((y - x).cpu().numpy(), z[f"{tag}.delta"]) < TOL, tag
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 7), (130, 70, 33), (257, 64, 128), (64, 200, 20)])
+def test_gemm_engine_matches_numpy(shape):
+    from dpot_b200 import ops
+    M, N, K = shape
+    rng = np.random.default_rng(M * 1000 + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    ref = O.activation(A.astype(np.float64) @ W.T.astype(np.float64) + b, "gelu") + R
+    out = ops.gemm(torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda(), bias=torch.from_numpy(b).cuda(), act="gelu",
+                   residual=torch.from_numpy(R).cuda(), engine=1)
+    assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
+
+
+def test_module_forwards_match_oracle():
+    """Standalone Block / PatchEmbed / TimeAggregator forwards (the reference exports these names)."""
+    from dpot_b200.models.dpot import Block, PatchEmbed, TimeAggregator
+    rng = np.random.default_rng(11)
+    cfg = O.make_cfg(img_size=32, patch_size=4, in_channels=3, out_channels=3, in_timesteps=5, n_blocks=4,
+                     embed_dim=32, out_layer_dim=16, depth=1, modes=32, mlp_ratio=2)
+    p = O.make_params(cfg, seed=5)
+    blk = Block(width=32, n_blocks=4, mlp_ratio=2, modes=32, double_skip=False)
+    sd = {k[len("blocks.0."):]: torch.from_numpy(v) for k, v in p.items() if k.startswith("blocks.0.")}
+    blk.load_state_dict(sd)
+    blk = blk.cuda()
+    x = rng.standard_normal((2, 32, 8, 8)).astype(np.float32)
+    with torch.no_grad():
+        y = blk(torch.from_numpy(x).cuda())
+    want = O.block(x.astype(np.float64), O.cast_params(p, np.float64), 0, cfg)
+    assert O.rel_l2(y.cpu().numpy(), want) < 3e-6
+    pe = PatchEmbed(img_size=32, patch_size=4, in_chans=6, embed_dim=15, out_dim=32)
+    pe.load_state_dict({k[len("patch_embed."):]: torch.from_numpy(v) for k, v in p.items() if k.startswith("patch_embed.")})
+    pe = pe.cuda()
+    xf = rng.standard_normal((3, 6, 32, 32)).astype(np.float32)
+    with torch.no_grad():
+        z = pe(torch.from_numpy(xf).cuda())
+    want = O.patch_embed(xf.astype(np.float64), O.cast_params(p, np.float64), 4, "gelu")
+    assert O.rel_l2(z.cpu().numpy(), want) < 3e-6
+    ta = TimeAggregator(3, 5, 32, "exp_mlp")
+    ta.load_state_dict({"w": torch.from_numpy(p["time_agg_layer.w"]), "gamma": torch.from_numpy(p["time_agg_layer.gamma"])})
+    ta = ta.cuda()
+    xt = rng.standard_normal((2, 8, 8, 5, 32)).astype(np.float32)
+    with torch.no_grad():
+        a = ta(torch.from_numpy(xt).cuda())
+    want = O.time_aggregate(xt, p, "exp_mlp")
+    assert O.rel_l2(a.cpu().numpy(), want) < 1e-5
+
+
+def test_adam_matches_reference_golden():
+    from dpot_b200.utils.optimizer import Adam, AdamW
+    z = np.load(os.path.join(G, "adam.npz"))
+    for tag, cls in [("adam", Adam), ("adam_wd0", Adam), ("adam_ams", Adam), ("adamw", AdamW), ("adamw_ams", AdamW)]:
+        kw = json.loads(str(z[f"{tag}.kw"]))
+        kw["betas"] = tuple(kw["betas"])
+        p = torch.nn.Parameter(torch.from_numpy(z["p0"].copy()).cuda())
+        opt = cls([p], lr=1e-3, eps=1e-8, **kw)
+        for s in range(z["grads"].shape[0]):
+            opt.param_groups[0]["lr"] = float(z["lrs"][s])
+            p.grad = torch.from_numpy(z["grads"][s].copy()).cuda()
+            opt.step()
+            np.testing.assert_allclose(p.detach().cpu().numpy(), z[f"{tag}.p"][s], rtol=3e-6, atol=3e-7,
+                                       err_msg=f"{tag} step {s}")
+        st = opt.state[p]
+        assert st["step"] == z["grads"].shape[0]
+        np.testing.assert_allclose(st["exp_avg"].cpu().numpy(), z[f"{tag}.m"], rtol=3e-6, atol=1e-7)
+        np.testing.assert_allclose(st["exp_avg_sq"].cpu().numpy(), z[f"{tag}.v"], rtol=3e-6, atol=1e-7)
+
+
+def test_adam_multi_tensor_many_shapes():
+    """91+ tensors of ragged sizes (incl. empty and odd) in one step == per-tensor oracle."""
+    from dpot_b200.utils.optimizer import Adam
+    rng = np.random.default_rng(0)
+    sizes = [0, 1, 3, 4, 5, 1023, 4096, 4097] + [int(s) for s in rng.integers(1, 20000, size=90)]
+    ps = [torch.nn.Parameter(torch.from_numpy(rng.standard_normal(s).astype(np.float32)).cuda()) for s in sizes]
+    p0 = [p.detach().cpu().numpy().copy() for p in ps]
+    gs = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+    opt = Adam(ps, lr=2e-3, betas=(0.9, 0.9), weight_decay=1e-6)
+    for p, g in zip(ps, gs):
+        p.grad = torch.from_numpy(g).cuda()
+    opt.step()
+    opt.step()
+    for p, a, g in zip(ps, p0, gs):
+        m = np.zeros_like(a); v = np.zeros_like(a)
+        for s in (1, 2):
+            O.adam_step(a, g.copy(), m, v, s, lr=2e-3, beta1=0.9, beta2=0.9, eps=1e-8, weight_decay=1e-6)
+        np.testing.assert_allclose(p.detach().cpu().numpy(), a, rtol=3e-6, atol=3e-7)
+
+
+def test_full_size_batch_properties():
+    """BASELINE config C2 (DPOT-S, 128^2, B=32): sample 0 equals the committed B=1 golden, and a batch
+    permutation permutes the outputs (samples are independent end to end)."""
+    z = np.load(os.path.join(G, "fwd_c2_s128.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    params = O.make_params(cfg, seed=0)
+    B = 32
+    x = O.make_input(cfg, B, seed=0)
+    m = build_model(cfg, params)
+    xt = torch.from_numpy(x).cuda()
+    with torch.no_grad():
+        y, cls = m(xt)
+        perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+        y2, cls2 = m(xt[perm].contiguous())
+    assert O.rel_l2(y[0:1].cpu().numpy(), z["y"]) < TOL
+    assert O.rel_l2(cls[0:1].cpu().numpy(), z["cls"]) < TOL
+    assert torch.equal(y[perm], y2) or O.rel_l2(y2.cpu().numpy(), y[perm].cpu().numpy()) < 1e-6
+    assert O.rel_l2(cls2.cpu().numpy(), cls[perm].cpu().numpy()) < 1e-6
+
+
+def test_window_advance_and_rollout_buffers():
+    from dpot_b200 import ops
+    rng = np.random.default_rng(2)
+    xx = torch.from_numpy(rng.standard_normal((2, 8, 8, 5, 3)).astype(np.float32)).cuda()
+    im = torch.from_numpy(rng.standard_normal((2, 8, 8, 2, 3)).astype(np.float32)).cuda()
+    nxt = torch.empty_like(xx)
+    pred = torch.zeros((2, 8, 8, 6, 3), device="cuda")
+    ops.window_advance(xx, im, nxt, pred, step=1)
+    want = torch.cat((xx[..., 2:, :], im), dim=-2)
+    assert torch.equal(nxt, want)
+    assert torch.equal(pred[..., 2:4, :], im) and pred[..., :2, :].abs().sum() == 0
