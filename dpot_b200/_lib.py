@@ -66,7 +66,7 @@ class Params(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/dpot_b200.h declares
-_i32, _i64, _f, _p = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+_i32, _i64, _f, _d, _p = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 SIGNATURES = {
     "dpot_abi_version": (C.c_int, []),
     "dpot_last_error_string": (C.c_char_p, []),
@@ -86,8 +86,8 @@ SIGNATURES = {
     "dpot_spatial_mean": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "dpot_input_stats": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p]),
     "dpot_window_advance": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
-    "dpot_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i32, _i32, _f, _p]),
-    "dpot_adam_step_multi": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _f, _f, _f, _f, _f, _p, _i32, _f, _p]),
+    "dpot_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _d, _i32, _i32, _d, _p]),
+    "dpot_adam_step_multi": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _p, _i32, _d, _p]),
     "dpot_packed_floats": (C.c_int64, [C.POINTER(Config)]),
     "dpot_workspace_floats": (C.c_int64, [C.POINTER(Config), _i32]),
     "dpot_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p]),

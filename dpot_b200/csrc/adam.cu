@@ -83,16 +83,17 @@ __global__ void __launch_bounds__(ADAM_NT) adam_multi_kernel(const MultiArgs a, 
 using namespace dpot;
 
 extern "C" int dpot_adam_step_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
-                                    float* const* vmax, const int64_t* n, int32_t count, float lr, float beta1,
-                                    float beta2, float eps, float weight_decay, const int32_t* steps,
-                                    int32_t decoupled, float grad_scale, void* stream) {
+                                    float* const* vmax, const int64_t* n, int32_t count, double lr, double beta1,
+                                    double beta2, double eps, double weight_decay, const int32_t* steps,
+                                    int32_t decoupled, double grad_scale, void* stream) {
   DPOT_REQUIRE(count >= 0, DPOT_E_BADARG, "dpot_adam_step_multi: negative count");
   if (count == 0) return 0;
   DPOT_REQUIRE(p && g && m && v && n && steps, DPOT_E_BADARG, "dpot_adam_step_multi: null array");
   AdamConst c;
-  c.beta1 = beta1; c.beta2 = beta2; c.one_m_beta1 = 1.0f - beta1; c.one_m_beta2 = 1.0f - beta2;
-  c.eps = eps; c.wd = weight_decay; c.decay_mul = (float)(1.0 - (double)lr * (double)weight_decay);
-  c.grad_scale = grad_scale; c.decoupled = decoupled;
+  c.beta1 = (float)beta1; c.beta2 = (float)beta2;
+  c.one_m_beta1 = (float)(1.0 - beta1); c.one_m_beta2 = (float)(1.0 - beta2);  // python-float arithmetic, then fp32
+  c.eps = (float)eps; c.wd = (float)weight_decay; c.decay_mul = (float)(1.0 - lr * weight_decay);
+  c.grad_scale = (float)grad_scale; c.decoupled = decoupled;
   cudaStream_t st = as_stream(stream);
   for (int t0 = 0; t0 < count; t0 += MT_MAX) {
     MultiArgs a;
@@ -107,9 +108,9 @@ extern "C" int dpot_adam_step_multi(float* const* p, const float* const* g, floa
       a.blk_start[k] = blk;
       blk += (int)ceil_div(n[t], ADAM_PER_BLOCK);
       // bias corrections in double like the python floats of the reference (:33-34,50)
-      const double bc1 = 1.0 - pow((double)beta1, (double)steps[t]);
-      const double bc2 = 1.0 - pow((double)beta2, (double)steps[t]);
-      a.step_size[k] = (float)((double)lr / bc1);
+      const double bc1 = 1.0 - pow(beta1, (double)steps[t]);
+      const double bc2 = 1.0 - pow(beta2, (double)steps[t]);
+      a.step_size[k] = (float)(lr / bc1);
       a.sqrt_bc2[k] = (float)sqrt(bc2);
     }
     a.blk_start[a.count] = blk;
@@ -120,9 +121,9 @@ extern "C" int dpot_adam_step_multi(float* const* p, const float* const* g, floa
   return 0;
 }
 
-extern "C" int dpot_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr,
-                              float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                              int32_t decoupled, float grad_scale, void* stream) {
+extern "C" int dpot_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, double lr,
+                              double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                              int32_t decoupled, double grad_scale, void* stream) {
   float* pp[1] = {p}; const float* gg[1] = {g}; float* mm[1] = {m}; float* vv[1] = {v}; float* xx[1] = {vmax};
   int64_t nn[1] = {n}; int32_t ss[1] = {step};
   return dpot_adam_step_multi(pp, gg, mm, vv, vmax ? xx : nullptr, nn, 1, lr, beta1, beta2, eps, weight_decay, ss,

@@ -1,13 +1,438 @@
-// tcgen05 / TMEM / TMA 3xTF32 GEMM engine (DPOT_GEMM_TC).  Placeholder until the engine lands.
+// tcgen05 / TMEM / TMA GEMM engine with fp32-faithful numerics (3xTF32 split), DPOT_GEMM_TC.
+//
+//   C[m,n] = epilogue( sum_k A'[m,k] W[n,k] )            (contract: include/dpot_b200.h)
+//
+// Formulation.  The weight tile is the UMMA "A" operand (M = 128 output channels n) and the
+// activation tile the UMMA "B" operand (N = BA <= 256 tokens m), both K-major in shared memory,
+// so the accumulator lives TRANSPOSED in TMEM: lane = n, column = m.  An epilogue warp then
+// holds 32 consecutive output channels of one token per register index, i.e. every global
+// store / residual / row-bias access is one coalesced 128 B line.
+//
+// fp32 parity on tensor cores: x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact);
+//   D += W_hi*X_hi + W_lo*X_hi + W_hi*X_lo   (fp32 accumulate in TMEM; the lo*lo term is < 2^-22)
+// Raw fp32 tiles arrive by TMA (128B-swizzled); four converter warps split them IN PLACE
+// (hi overwrites the raw tile, lo goes to a twin buffer at the same swizzled offsets) and apply
+// the optional per-(sample,k) affine of the A operand (GroupNorm-apply fused into the load).
+// Loading raw fp32 and splitting on chip keeps L2->SM traffic at 1.0x instead of 2x.
+//
+// Warp roles (512 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer            warp 1      MMA issuer (one elected lane)
+//   warp 2      TMEM allocator          warp 3      spare
+//   warps 4-11  epilogue (TMEM -> regs -> global), 2 warps per TMEM lane quarter
+//   warps 12-15 converters (hi/lo split + affine)
+// Pipelines: smem ring (full -> converted -> empty, 2 stages of 96 KB) and a 2-deep TMEM
+// accumulator ring (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of i+1.
 #include "common.cuh"
 #include "gemm_common.cuh"
 
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace dpot {
-bool gemm_tc_supports(const GemmDev&, int) { return false; }
-int gemm_tc_launch(const GemmDev&, int, cudaStream_t) {
-  set_error("tcgen05 engine not built");
-  return DPOT_E_UNSUPPORTED;
+namespace {
+
+constexpr int TN = 128;            // weight rows (output channels) per tile  = UMMA M
+constexpr int TM_MAX = 256;        // activation rows (tokens) per tile       = UMMA N
+constexpr int BK = 32;             // fp32 elements per k-block = one 128 B swizzle row
+constexpr int STAGES = 2;
+constexpr int NTHREADS = 512;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, CONV_WARP0 = 12, CONV_THREADS = 128;
+
+constexpr uint32_t P_BYTES = TN * 128;          // 16 KB
+constexpr uint32_t Q_BYTES = TM_MAX * 128;      // 32 KB
+constexpr uint32_t OFF_P_HI = 0, OFF_P_LO = P_BYTES, OFF_Q_HI = 2 * P_BYTES, OFF_Q_LO = 2 * P_BYTES + Q_BYTES;
+constexpr uint32_t STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;   // 96 KB
+constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;        // + barriers + alignment slack
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must fail loudly (trap -> CUDA error), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > 20000000u) { printf("dpot gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset  bits [16,30): unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   bits [32,46): 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                            // descriptor version   bits [46,48)
+  d |= (uint64_t)2 << 61;                            // layout: SWIZZLE_128B bits [61,64)
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+struct TcParams {
+  GemmDev g;
+  int BA;            // activation rows per tile (UMMA N), multiple of 16, <= 256
+  int n_tiles, m_tiles, total_tiles, kblocks;
+};
+
+// hi/lo split of one 16 B chunk at swizzled offset `off` of a tile; optional affine
+__device__ __forceinline__ void split_chunk(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, bool affine,
+                                            const float* __restrict__ sc, const float* __restrict__ sh) {
+  float4 v = *reinterpret_cast<float4*>(tile_hi + off);
+  if (affine) {
+    const float4 s = *reinterpret_cast<const float4*>(sc);
+    const float4 h = *reinterpret_cast<const float4*>(sh);
+    v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+  }
+  float4 hi, lo;
+  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+  *reinterpret_cast<float4*>(tile_hi + off) = hi;
+  *reinterpret_cast<float4*>(tile_lo + off) = lo;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  // barrier map: [0,2) full  [2,4) converted  [4,6) empty  [6,8) tmem_full  [8,10) tmem_empty ; [10] tmem base
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int which, int idx) -> uint32_t { return bar0 + 8u * (which * 2 + idx); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemmDev& g = P.g;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapA);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(BAR(0, s), 1);
+      mbar_init(BAR(1, s), CONV_THREADS);
+      mbar_init(BAR(2, s), 1);
+      mbar_init(BAR(3, s), 1);
+      mbar_init(BAR(4, s), EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int KB = P.kblocks;
+  const uint32_t stage_tx = P_BYTES + (uint32_t)P.BA * 128u;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
+        const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(BAR(2, s), ph ^ 1);
+          mbar_expect_tx(BAR(0, s), stage_tx);
+          const uint32_t sb = smem_u32(smem + (uint32_t)s * STAGE_BYTES);
+          tma_load_3d(sb + OFF_P_HI, &mapW, BAR(0, s), kb * BK, nt * TN, bz);       // dims (k, n, batch)
+          tma_load_3d(sb + OFF_Q_HI, &mapA, BAR(0, s), kb * BK, bz, mt * P.BA);     // dims (k, batch, m)
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc((uint32_t)P.BA);
+      int s = 0; uint32_t ph = 0; int lt = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1; const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(BAR(4, acc), aph ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TM_MAX;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(BAR(1, s), ph);               // TMA landed AND converters finished the split
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + (uint32_t)s * STAGE_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 8; ++k4) {
+            const uint64_t p_hi = make_smem_desc(sb + OFF_P_HI + k4 * 32);
+            const uint64_t p_lo = make_smem_desc(sb + OFF_P_LO + k4 * 32);
+            const uint64_t q_hi = make_smem_desc(sb + OFF_Q_HI + k4 * 32);
+            const uint64_t q_lo = make_smem_desc(sb + OFF_Q_LO + k4 * 32);
+            umma_tf32(d_tmem, p_hi, q_hi, idesc, (kb | k4) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, p_lo, q_hi, idesc, 1u);
+            umma_tf32(d_tmem, p_hi, q_lo, idesc, 1u);
+          }
+          umma_commit(BAR(2, s));                 // stage reusable once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(BAR(3, acc));                 // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= CONV_WARP0) {
+    // ================================ converters ==================================
+    const int ct = threadIdx.x - CONV_WARP0 * 32;     // 0..127
+    const bool affine = g.a_scale != nullptr;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int mt = tile % P.m_tiles;
+      const int m0 = mt * P.BA;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(BAR(0, s), ph);
+        uint8_t* sb = smem + (uint32_t)s * STAGE_BYTES;
+        // weight tile: row ct
+        {
+          const uint32_t rbase = (uint32_t)ct * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t cp = (uint32_t)(j + lane) & 7u;     // rotate chunks across lanes: conflict-free
+            split_chunk(sb + OFF_P_HI, sb + OFF_P_LO, rbase + cp * 16u, false, nullptr, nullptr);
+          }
+        }
+        // activation tile: rows ct and ct+128
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int r = ct + half * 128;
+          if (r < P.BA) {
+            const uint32_t rbase = (uint32_t)r * 128u;
+            const int m = m0 + r;
+            const bool aff = affine && m < g.M;
+            const int64_t tbl = aff ? (int64_t)(m / g.a_rps) * g.K + (int64_t)kb * BK : 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t cp = (uint32_t)(j + lane) & 7u;
+              const uint32_t cl = cp ^ ((uint32_t)r & 7u);       // logical 16 B chunk held at physical chunk cp
+              split_chunk(sb + OFF_Q_HI, sb + OFF_Q_LO, rbase + cp * 16u, aff,
+                          aff ? g.a_scale + tbl + cl * 4 : nullptr, aff ? g.a_shift + tbl + cl * 4 : nullptr);
+            }
+          }
+        }
+        fence_proxy_async();                      // generic-proxy writes -> visible to the UMMA (async proxy)
+        mbar_arrive(BAR(1, s));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================================ epilogue ====================================
+    const int ew = warp - EPI_WARP0;                  // 0..7
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may read
+    const int cpar = ew >> 2;                         // this warp takes the 32-column chunks of parity cpar
+    const int nchunks = (P.BA + 31) / 32;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+      const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
+      const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
+      const int acc = lt & 1; const uint32_t aph = (lt >> 1) & 1;
+      const int n = nt * TN + quarter * 32 + lane;
+      const bool n_ok = n < g.N;
+      float* __restrict__ C = g.C + (int64_t)bz * g.sC;
+      const float* bias = g.bias ? g.bias + (int64_t)bz * g.sBias : nullptr;
+      const float bias_n = (bias && n_ok) ? bias[n] : 0.f;
+      mbar_wait(BAR(3, acc), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)acc * TM_MAX + ((uint32_t)(quarter * 32) << 16);
+      for (int ci = cpar; ci < nchunks; ci += 2) {
+        const int c0 = ci * 32;
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int cmax = min(32, P.BA - c0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = mt * P.BA + c0 + j;
+          if (j < cmax && m < g.M && n_ok) {
+            float v = __uint_as_float(r[j]) + bias_n;
+            if (g.rowbias) v += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
+            v = act_apply(v, g.act);
+            if (g.c_scale) {
+              const int64_t o = (int64_t)(m / g.c_rps) * g.N + n;
+              v = fmaf(v, g.c_scale[o], g.c_shift[o]);
+            }
+            if (g.residual) v += g.residual[(int64_t)m * g.ldr + n];
+            C[gemm_c_offset(g, m) + n] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(4, acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 3-D fp32 tensor map, 128B swizzle.  dims/strides fastest-first; strides in bytes for dims 1,2.
+int encode_map(CUtensorMap* out, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+               uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn enc = get_encode();
+  DPOT_REQUIRE(enc != nullptr, DPOT_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DPOT_REQUIRE(r == CUDA_SUCCESS, DPOT_E_BADARG,
+               "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)", (int)r,
+               (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1,
+               (unsigned long long)s2, b0, b1, b2);
+  return 0;
+}
+
+bool device_ok() {
+  static int ok = -1;
+  if (ok < 0) ok = dpot_device_supported();
+  return ok == 1;
+}
+
+}  // namespace
+
+bool gemm_tc_supports(const GemmDev& p, int batch) {
+  if (!device_ok() || get_encode() == nullptr) return false;
+  if (p.a_mode != DPOT_A_PLAIN) return false;
+  if (p.K < BK || p.K % BK != 0) return false;
+  if (p.M < 64 || p.N < 32) return false;                       // tiny problems stay on the SIMT engine
+  if (p.lda % 4 || p.ldw % 4) return false;
+  if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W)) % 16) return false;
+  if (p.a_scale && ((reinterpret_cast<uintptr_t>(p.a_scale) | reinterpret_cast<uintptr_t>(p.a_shift)) % 16)) return false;
+  if (batch > 1) {
+    if (p.sA <= 0 || p.sW <= 0 || p.sA % 4 || p.sW % 4) return false;
+    if (p.lda % p.sA != 0) return false;           // tensor-map strides ascending multiples: (k, batch, m)
+    if (p.sW % p.ldw != 0 || p.sW < (int64_t)p.N * p.ldw) return false;   // (k, n, batch)
+  }
+  return true;
+}
+
+int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
+  TcParams P;
+  P.g = p;
+  P.BA = p.M >= TM_MAX ? TM_MAX : (int)round_up(p.M, 16);
+  P.n_tiles = (int)ceil_div(p.N, TN);
+  P.m_tiles = (int)ceil_div(p.M, P.BA);
+  P.total_tiles = P.n_tiles * P.m_tiles * batch;
+  P.kblocks = p.K / BK;
+
+  alignas(64) CUtensorMap mapW, mapA;
+  const uint64_t sWb = batch > 1 ? (uint64_t)p.sW * 4 : (uint64_t)p.ldw * 4 * (uint64_t)p.N;
+  DPOT_CALL(encode_map(&mapW, p.W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 4, sWb, BK, TN, 1));
+  const uint64_t sAb = batch > 1 ? (uint64_t)p.sA * 4 : (uint64_t)p.lda * 4;
+  DPOT_CALL(encode_map(&mapA, p.A, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 4, BK, 1,
+                       (uint32_t)P.BA));
+
+  static int sm_count = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int dev = 0;
+    DPOT_CUDA(cudaGetDevice(&dev));
+    DPOT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = P.total_tiles < sm_count ? P.total_tiles : sm_count;
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mapW, mapA, P);
+  DPOT_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
 }  // namespace dpot
 
-extern "C" int dpot_tc_available(void) { return 0; }
+extern "C" int dpot_tc_available(void) { return (dpot::device_ok() && dpot::get_encode() != nullptr) ? 1 : 0; }

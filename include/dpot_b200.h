@@ -175,15 +175,17 @@ DPOT_API int dpot_window_advance(const float* xx, const float* im, float* xx_nex
  * Optimizer: adam()/adamw() of utils/optimizer.py:9-52 / :170-212 on one flat tensor.
  * step = 1-based count after the increment; decoupled = 0 (Adam, L2-coupled decay) or 1 (AdamW);
  * vmax = amsgrad buffer or NULL; grad_scale multiplies the gradient first (1/world for DDP).
+ * Hyper-parameters are doubles: the reference derives 1-beta, lr/(1-beta1^t), sqrt(1-beta2^t) as
+ * python floats (doubles) and only then rounds to fp32.
  * ---------------------------------------------------------------------------------------- */
-DPOT_API int dpot_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                   int32_t decoupled, float grad_scale, void* stream);
+DPOT_API int dpot_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                   int32_t decoupled, double grad_scale, void* stream);
 /* multi-tensor form: `count` tensors described by parallel host arrays */
 DPOT_API int dpot_adam_step_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
-                         float* const* vmax, const int64_t* n, int32_t count, float lr, float beta1,
-                         float beta2, float eps, float weight_decay, const int32_t* steps,
-                         int32_t decoupled, float grad_scale, void* stream);
+                         float* const* vmax, const int64_t* n, int32_t count, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, const int32_t* steps,
+                         int32_t decoupled, double grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-model inference forward: DPOTNet.forward under no_grad (models/dpot.py:364-403).

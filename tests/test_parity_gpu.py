@@ -88,6 +88,28 @@ def test_gemm_engine_matches_numpy(shape):
     assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
 
 
+@pytest.mark.parametrize("shape", [(256, 128, 32), (300, 200, 96), (144, 256, 64), (1024, 512, 1024), (8192, 1024, 352)])
+def test_tcgen05_engine_matches_fp64(shape):
+    """3xTF32 on tcgen05 must sit at fp32-level error (SURVEY: 1xTF32 = 2.9e-4, 3xTF32 = 3.4e-7)."""
+    from dpot_b200 import _lib, ops
+    if not _lib.load().dpot_tc_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    sc = (1 + 0.1 * rng.standard_normal((M // 8 + 1, K))).astype(np.float32)
+    sh = (0.1 * rng.standard_normal((M // 8 + 1, K))).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).cuda()
+    out = ops.gemm(t(A), t(W), bias=t(b), act="gelu", residual=t(R), a_scale=t(sc), a_shift=t(sh),
+                   a_rows_per_sample=8, engine=2)
+    Ap = A.astype(np.float64) * np.repeat(sc, 8, 0)[:M] + np.repeat(sh, 8, 0)[:M]
+    ref = O.activation(Ap @ W.T.astype(np.float64) + b, "gelu") + R
+    assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
+
+
 def test_module_forwards_match_oracle():
     """Standalone Block / PatchEmbed / TimeAggregator forwards (the reference exports these names)."""
     from dpot_b200.models.dpot import Block, PatchEmbed, TimeAggregator
