@@ -8,27 +8,28 @@
 // holds 32 consecutive output channels of one token per register index, i.e. every global
 // store / residual / row-bias access is one coalesced 128 B line.
 //
-// fp32 parity on tensor cores: x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact);
-//   D += W_hi*X_hi + W_lo*X_hi + W_hi*X_lo   (fp32 accumulate in TMEM; the lo*lo term is < 2^-22)
-// Raw fp32 tiles arrive by TMA (128B-swizzled); four converter warps split them IN PLACE
-// (hi overwrites the raw tile, lo goes to a twin buffer at the same swizzled offsets) and apply
-// the optional per-(sample,k) affine of the A operand (GroupNorm-apply fused into the load).
-// Loading raw fp32 and splitting on chip keeps L2->SM traffic at 1.0x instead of 2x.
+// fp32 parity on tensor cores, two ingredients (both measured on B200):
+//  (1) 3xTF32: x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact);
+//        D += W_hi*X_hi + W_lo*X_hi + W_hi*X_lo      (the lo*lo term is < 2^-22)
+//      Raw fp32 tiles arrive by TMA (128B-swizzled); four converter warps split them IN PLACE
+//      (hi overwrites the raw tile, lo goes to a twin buffer at the same swizzled offsets) and apply
+//      the optional per-(sample,k) affine of the A operand (GroupNorm-apply fused into the load).
+//  (2) short accumulation chains: the tensor core truncates (round-toward-zero) on every
+//      accumulate into TMEM, a bias of ~2e-8 per MMA that grows linearly with the chain (7e-6 at
+//      K=1024).  The MMA issuer therefore accumulates only `flush` k-blocks in TMEM, ping-ponging
+//      two 256-column buffers, and the epilogue warps add each partial sum into fp32 REGISTER
+//      accumulators with round-to-nearest.
 //
-// Warp roles (512 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (512 threads, 1 CTA / SM, persistent over tiles; setmaxnreg moves registers to the
+// epilogue warpgroups):
 //   warp 0      TMA producer            warp 1      MMA issuer (one elected lane)
 //   warp 2      TMEM allocator          warp 3      spare
-//   warps 4-11  epilogue (TMEM -> regs -> global), 2 warps per TMEM lane quarter
+//   warps 4-11  epilogue: TMEM partial sums -> register accumulators -> fused epilogue -> global
 //   warps 12-15 converters (hi/lo split + affine)
-// Pipelines: smem ring (full -> converted -> empty, 2 stages of 96 KB) and a 2-deep TMEM
-// accumulator ring (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of i+1.
 #include "common.cuh"
 #include "gemm_common.cuh"
 
 #include <cuda.h>
-#include <map>
-#include <mutex>
-#include <tuple>
 
 namespace dpot {
 namespace {
@@ -73,7 +74,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // bounded wait: a protocol bug must fail loudly (trap -> CUDA error), never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-    if (it > 20000000u) { printf("dpot gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (it > 20000000u) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -120,6 +121,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -145,33 +157,46 @@ struct TcParams {
   GemmDev g;
   int BA;            // activation rows per tile (UMMA N), multiple of 16, <= 256
   int n_tiles, m_tiles, total_tiles, kblocks;
+  int flush;         // k-blocks accumulated inside TMEM before the partial sum is flushed to registers
 };
 
-// hi/lo split of one 16 B chunk at swizzled offset `off` of a tile; optional affine
-__device__ __forceinline__ void split_chunk(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, bool affine,
-                                            const float* __restrict__ sc, const float* __restrict__ sh) {
-  float4 v = *reinterpret_cast<float4*>(tile_hi + off);
-  if (affine) {
-    const float4 s = *reinterpret_cast<const float4*>(sc);
-    const float4 h = *reinterpret_cast<const float4*>(sh);
-    v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+// Split one 128 B operand row (8 swizzled 16 B chunks) into hi (in place) and lo (twin tile).
+// All 8 loads are issued before the first use; chunk order is rotated by lane so that a
+// quarter-warp touches 8 distinct 16 B bank groups (row pitch is 128 B).
+template <bool AFFINE>
+__device__ __forceinline__ void split_row(uint32_t row_hi, uint32_t lo_delta, int lane, uint32_t rsw,
+                                          const float* __restrict__ sc, const float* __restrict__ sh) {
+  float4 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = lds128(row_hi + (((uint32_t)(j + lane) & 7u) << 4));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t cp = (uint32_t)(j + lane) & 7u;
+    float4 x = v[j];
+    if (AFFINE) {
+      const uint32_t cl = cp ^ rsw;                 // logical k-chunk stored at physical chunk cp
+      const float4 s = __ldg(reinterpret_cast<const float4*>(sc) + cl);
+      const float4 h = __ldg(reinterpret_cast<const float4*>(sh) + cl);
+      x.x = fmaf(x.x, s.x, h.x); x.y = fmaf(x.y, s.y, h.y); x.z = fmaf(x.z, s.z, h.z); x.w = fmaf(x.w, s.w, h.w);
+    }
+    float4 hi, lo;
+    hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+    lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+    sts128(row_hi + (cp << 4), hi);
+    sts128(row_hi + lo_delta + (cp << 4), lo);
   }
-  float4 hi, lo;
-  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-  *reinterpret_cast<float4*>(tile_hi + off) = hi;
-  *reinterpret_cast<float4*>(tile_lo + off) = lo;
 }
 
+// ACT_MODE: 0 = no activation, 1 = GELU (erf), 2 = runtime switch over the other activations
+template <int ACT_MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  // barrier map: [0,2) full  [2,4) converted  [4,6) empty  [6,8) tmem_full  [8,10) tmem_empty ; [10] tmem base
-  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 1024 B aligned (128B swizzle atom)
+  // barrier map: [0,2) full  [2,4) converted  [4,6) empty  [6,8) tmem_full  [8,10) tmem_empty ; then tmem base slot
+  const uint32_t bar0 = smem0 + BAR_OFF;
   auto BAR = [&](int which, int idx) -> uint32_t { return bar0 + 8u * (which * 2 + idx); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const uint32_t tmem_slot = bar0 + 8u * 10;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmDev& g = P.g;
@@ -190,97 +215,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int KB = P.kblocks;
+  const int F = P.flush;
   const uint32_t stage_tx = P_BYTES + (uint32_t)P.BA * 128u;
 
-  if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (elect_one()) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
-        const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(BAR(2, s), ph ^ 1);
-          mbar_expect_tx(BAR(0, s), stage_tx);
-          const uint32_t sb = smem_u32(smem + (uint32_t)s * STAGE_BYTES);
-          tma_load_3d(sb + OFF_P_HI, &mapW, BAR(0, s), kb * BK, nt * TN, bz);       // dims (k, n, batch)
-          tma_load_3d(sb + OFF_Q_HI, &mapA, BAR(0, s), kb * BK, bz, mt * P.BA);     // dims (k, batch, m)
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+  if (warp < 4) {
+    reg_dec<56>();
+    if (warp == 0) {
+      // ================================ TMA producer ================================
+      if (elect_one()) {
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
+          const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(BAR(2, s), ph ^ 1);
+            mbar_expect_tx(BAR(0, s), stage_tx);
+            const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
+            tma_load_3d(sb + OFF_P_HI, &mapW, BAR(0, s), kb * BK, nt * TN, bz);       // dims (k, n, batch)
+            tma_load_3d(sb + OFF_Q_HI, &mapA, BAR(0, s), kb * BK, bz, mt * P.BA);     // dims (k, batch, m)
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc((uint32_t)P.BA);
-      int s = 0; uint32_t ph = 0; int lt = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1; const uint32_t aph = (lt >> 1) & 1;
-        mbar_wait(BAR(4, acc), aph ^ 1);          // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TM_MAX;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(BAR(1, s), ph);               // TMA landed AND converters finished the split
-          tc_fence_after();
-          const uint32_t sb = smem_u32(smem + (uint32_t)s * STAGE_BYTES);
+    } else if (warp == 1) {
+      // ================================ MMA issuer ==================================
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc((uint32_t)P.BA);
+        int s = 0; uint32_t ph = 0; uint32_t gc = 0;       // gc: global chunk counter -> TMEM buffer ring
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          for (int kb0 = 0; kb0 < KB; kb0 += F, ++gc) {
+            const uint32_t buf = gc & 1u, bph = (gc >> 1) & 1u;
+            mbar_wait(BAR(4, buf), bph ^ 1);        // epilogue has drained this TMEM buffer
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * TM_MAX;
+            const int kb1 = min(KB, kb0 + F);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(BAR(1, s), ph);             // TMA landed AND converters finished the split
+              tc_fence_after();
+              const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 8; ++k4) {
-            const uint64_t p_hi = make_smem_desc(sb + OFF_P_HI + k4 * 32);
-            const uint64_t p_lo = make_smem_desc(sb + OFF_P_LO + k4 * 32);
-            const uint64_t q_hi = make_smem_desc(sb + OFF_Q_HI + k4 * 32);
-            const uint64_t q_lo = make_smem_desc(sb + OFF_Q_LO + k4 * 32);
-            umma_tf32(d_tmem, p_hi, q_hi, idesc, (kb | k4) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, p_lo, q_hi, idesc, 1u);
-            umma_tf32(d_tmem, p_hi, q_lo, idesc, 1u);
+              for (int k4 = 0; k4 < BK / 8; ++k4) {
+                const uint64_t p_hi = make_smem_desc(sb + OFF_P_HI + k4 * 32);
+                const uint64_t p_lo = make_smem_desc(sb + OFF_P_LO + k4 * 32);
+                const uint64_t q_hi = make_smem_desc(sb + OFF_Q_HI + k4 * 32);
+                const uint64_t q_lo = make_smem_desc(sb + OFF_Q_LO + k4 * 32);
+                umma_tf32(d_tmem, p_hi, q_hi, idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
+                umma_tf32(d_tmem, p_lo, q_hi, idesc, 1u);
+                umma_tf32(d_tmem, p_hi, q_lo, idesc, 1u);
+              }
+              umma_commit(BAR(2, s));               // stage reusable once these MMAs retire
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(BAR(3, buf));               // partial accumulator complete -> epilogue warps
           }
-          umma_commit(BAR(2, s));                 // stage reusable once these MMAs retire
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(BAR(3, acc));                 // accumulator complete -> epilogue
       }
     }
   } else if (warp >= CONV_WARP0) {
     // ================================ converters ==================================
+    reg_dec<72>();
     const int ct = threadIdx.x - CONV_WARP0 * 32;     // 0..127
     const bool affine = g.a_scale != nullptr;
     int s = 0; uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int mt = tile % P.m_tiles;
-      const int m0 = mt * P.BA;
+      const int m0 = (tile % P.m_tiles) * P.BA;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(BAR(0, s), ph);
-        uint8_t* sb = smem + (uint32_t)s * STAGE_BYTES;
-        // weight tile: row ct
-        {
-          const uint32_t rbase = (uint32_t)ct * 128u;
+        const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
+        split_row<false>(sb + OFF_P_HI + (uint32_t)ct * 128u, P_BYTES, lane, 0, nullptr, nullptr);   // weight row ct
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t cp = (uint32_t)(j + lane) & 7u;     // rotate chunks across lanes: conflict-free
-            split_chunk(sb + OFF_P_HI, sb + OFF_P_LO, rbase + cp * 16u, false, nullptr, nullptr);
-          }
-        }
-        // activation tile: rows ct and ct+128
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 2; ++half) {                                                        // token rows
           const int r = ct + half * 128;
           if (r < P.BA) {
-            const uint32_t rbase = (uint32_t)r * 128u;
+            const uint32_t row = sb + OFF_Q_HI + (uint32_t)r * 128u;
             const int m = m0 + r;
-            const bool aff = affine && m < g.M;
-            const int64_t tbl = aff ? (int64_t)(m / g.a_rps) * g.K + (int64_t)kb * BK : 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t cp = (uint32_t)(j + lane) & 7u;
-              const uint32_t cl = cp ^ ((uint32_t)r & 7u);       // logical 16 B chunk held at physical chunk cp
-              split_chunk(sb + OFF_Q_HI, sb + OFF_Q_LO, rbase + cp * 16u, aff,
-                          aff ? g.a_scale + tbl + cl * 4 : nullptr, aff ? g.a_shift + tbl + cl * 4 : nullptr);
+            if (affine && m < g.M) {
+              const int64_t tbl = (int64_t)(m / g.a_rps) * g.K + (int64_t)kb * BK;
+              split_row<true>(row, Q_BYTES, lane, (uint32_t)r & 7u, g.a_scale + tbl, g.a_shift + tbl);
+            } else {
+              split_row<false>(row, Q_BYTES, lane, 0, nullptr, nullptr);
             }
           }
         }
@@ -289,49 +310,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else {
     // ================================ epilogue ====================================
-    const int ew = warp - EPI_WARP0;                  // 0..7
+    reg_inc<192>();
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may read
-    const int cpar = ew >> 2;                         // this warp takes the 32-column chunks of parity cpar
+    const int cpar = (warp - EPI_WARP0) >> 2;         // this warp owns the 32-column chunks 2*i + cpar
     const int nchunks = (P.BA + 31) / 32;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+    uint32_t gc = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
       const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
-      const int acc = lt & 1; const uint32_t aph = (lt >> 1) & 1;
-      const int n = nt * TN + quarter * 32 + lane;
-      const bool n_ok = n < g.N;
-      float* __restrict__ C = g.C + (int64_t)bz * g.sC;
-      const float* bias = g.bias ? g.bias + (int64_t)bz * g.sBias : nullptr;
-      const float bias_n = (bias && n_ok) ? bias[n] : 0.f;
-      mbar_wait(BAR(3, acc), aph);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t)acc * TM_MAX + ((uint32_t)(quarter * 32) << 16);
-      for (int ci = cpar; ci < nchunks; ci += 2) {
-        const int c0 = ci * 32;
-        uint32_t r[32];
-        tmem_ld32(t_row + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int cmax = min(32, P.BA - c0);
+      float acc[4][32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int m = mt * P.BA + c0 + j;
-          if (j < cmax && m < g.M && n_ok) {
-            float v = __uint_as_float(r[j]) + bias_n;
-            if (g.rowbias) v += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
-            v = act_apply(v, g.act);
-            if (g.c_scale) {
-              const int64_t o = (int64_t)(m / g.c_rps) * g.N + n;
-              v = fmaf(v, g.c_scale[o], g.c_shift[o]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[i][j] = 0.f;
+      for (int kb0 = 0; kb0 < KB; kb0 += F, ++gc) {
+        const uint32_t buf = gc & 1u, bph = (gc >> 1) & 1u;
+        mbar_wait(BAR(3, buf), bph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + buf * TM_MAX + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ci = 2 * i + cpar;
+          if (ci < nchunks) {
+            uint32_t r[32];
+            tmem_ld32(t_row + (uint32_t)(ci * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[i][j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(4, buf));
+      }
+      // ---- final epilogue from registers: lanes = 32 consecutive output channels -> coalesced lines
+      const int n = nt * TN + quarter * 32 + lane;
+      if (n < g.N) {
+        float* __restrict__ C = g.C + (int64_t)bz * g.sC;
+        const float bias_n = g.bias ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c0 = (2 * i + cpar) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = mt * P.BA + c0 + j;
+            if (c0 + j < P.BA && m < g.M) {
+              float v = acc[i][j] + bias_n;
+              if (g.rowbias) v += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
+              if (ACT_MODE == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+              else if (ACT_MODE == 2) v = act_apply(v, g.act);
+              if (g.c_scale) {
+                const int64_t o = (int64_t)(m / g.c_rps) * g.N + n;
+                v = fmaf(v, g.c_scale[o], g.c_shift[o]);
+              }
+              if (g.residual) v += g.residual[(int64_t)m * g.ldr + n];
+              C[gemm_c_offset(g, m) + n] = v;
             }
-            if (g.residual) v += g.residual[(int64_t)m * g.ldr + n];
-            C[gemm_c_offset(g, m) + n] = v;
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(BAR(4, acc));
     }
   }
 
@@ -384,6 +422,8 @@ bool device_ok() {
   return ok == 1;
 }
 
+int g_flush = 4;   // k-blocks (of 32) per in-TMEM accumulation chain; tunable for experiments
+
 }  // namespace
 
 bool gemm_tc_supports(const GemmDev& p, int batch) {
@@ -410,6 +450,7 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
   P.m_tiles = (int)ceil_div(p.M, P.BA);
   P.total_tiles = P.n_tiles * P.m_tiles * batch;
   P.kblocks = p.K / BK;
+  P.flush = g_flush < 1 ? 1 : g_flush;
 
   alignas(64) CUtensorMap mapW, mapA;
   const uint64_t sWb = batch > 1 ? (uint64_t)p.sW * 4 : (uint64_t)p.ldw * 4 * (uint64_t)p.N;
@@ -424,11 +465,18 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
     int dev = 0;
     DPOT_CUDA(cudaGetDevice(&dev));
     DPOT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set = true;
   }
   const int grid = P.total_tiles < sm_count ? P.total_tiles : sm_count;
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mapW, mapA, P);
+  if (p.act == DPOT_ACT_NONE)
+    gemm_tc_kernel<0><<<grid, NTHREADS, SMEM_BYTES, st>>>(mapW, mapA, P);
+  else if (p.act == DPOT_ACT_GELU)
+    gemm_tc_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(mapW, mapA, P);
+  else
+    gemm_tc_kernel<2><<<grid, NTHREADS, SMEM_BYTES, st>>>(mapW, mapA, P);
   DPOT_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -436,3 +484,9 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
 }  // namespace dpot
 
 extern "C" int dpot_tc_available(void) { return (dpot::device_ok() && dpot::get_encode() != nullptr) ? 1 : 0; }
+// experiment knob: k-blocks (32 fp32 each) accumulated in TMEM between register flushes (default 4)
+extern "C" int dpot_tc_set_flush(int kblocks) {
+  const int old = dpot::g_flush;
+  if (kblocks >= 1) dpot::g_flush = kblocks;
+  return old;
+}

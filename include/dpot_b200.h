@@ -58,6 +58,9 @@ DPOT_API int         dpot_device_supported(void);
 DPOT_API long long   dpot_launch_count(void);
 /* 1 if the tcgen05 3xTF32 GEMM engine is compiled in and the current device can run it */
 DPOT_API int         dpot_tc_available(void);
+/* tuning knob of the tcgen05 engine: k-blocks (32 fp32) accumulated in TMEM between round-to-nearest
+   flushes into the register accumulators (default 4); returns the previous value, <1 only queries */
+DPOT_API int         dpot_tc_set_flush(int kblocks);
 
 /* ------------------------------------------------------------------------------------------
  * The dense-contraction engine.  C = epilogue( A' * W^T ), fp32 in / fp32 out.

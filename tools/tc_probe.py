@@ -95,6 +95,24 @@ def main():
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             print(f"(e) M{M} N{N} K{K} engine={eng}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")
+    # (f) accumulation-chain length: accuracy and speed vs flush cadence
+    M, N, K = 8192, 1024, 1024
+    rngf = np.random.default_rng(9)
+    Af = rngf.standard_normal((M, K)).astype(np.float32); Wf = (rngf.standard_normal((N, K)) / 32).astype(np.float32)
+    reff = Af.astype(np.float64) @ Wf.T.astype(np.float64)
+    At, Wtt = t(Af), t(Wf); Ct = torch.empty((M, N), device="cuda")
+    for fl in (1, 2, 4, 8, 16, 32):
+        lib.dpot_tc_set_flush(fl)
+        ops.gemm(At, Wtt, out=Ct, engine=2); torch.cuda.synchronize()
+        err = rel(Ct.cpu().numpy(), reff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(10):
+            ops.gemm(At, Wtt, out=Ct, engine=2)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"(f) flush={fl:2d}: rel={err:.3e}  {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")
+    lib.dpot_tc_set_flush(4)
     # batched AFNO timing
     St = t(S); Wt = t(Wc); bt = t(bc)
     for eng in (1, 2):
