@@ -46,7 +46,9 @@ constexpr uint32_t Q_BYTES = TM_MAX * 128;      // 32 KB
 constexpr uint32_t OFF_P_HI = 0, OFF_P_LO = P_BYTES, OFF_Q_HI = 2 * P_BYTES, OFF_Q_LO = 2 * P_BYTES + Q_BYTES;
 constexpr uint32_t STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;   // 96 KB
 constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;        // + barriers + alignment slack
+constexpr uint32_t EPI_STAGE_OFF = BAR_OFF + 256;             // per-epilogue-warp 32x32 fp32 staging tiles
+constexpr uint32_t EPI_STAGE_BYTES = 32 * 32 * 4;
+constexpr uint32_t SMEM_BYTES = EPI_STAGE_OFF + EPI_WARPS * EPI_STAGE_BYTES + 1024;   // + alignment slack
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -158,7 +160,13 @@ struct TcParams {
   int BA;            // activation rows per tile (UMMA N), multiple of 16, <= 256
   int n_tiles, m_tiles, total_tiles, kblocks;
   int flush;         // k-blocks accumulated inside TMEM before the partial sum is flushed to registers
+  long long* trace;  // optional clock64() event log of CTA 0 (debug / profiling), NULL = off
 };
+
+constexpr int TRACE_SLOTS = 64;    // events per role
+__device__ __forceinline__ void trace_ev(const TcParams& P, int role, int& idx) {
+  if (P.trace != nullptr && blockIdx.x == 0 && idx < TRACE_SLOTS) P.trace[role * TRACE_SLOTS + idx++] = clock64();
+}
 
 // Split one 128 B operand row (8 swizzled 16 B chunks) into hi (in place) and lo (twin tile).
 // All 8 loads are issued before the first use; chunk order is rotated by lane so that a
@@ -231,12 +239,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     if (warp == 0) {
       // ================================ TMA producer ================================
       if (elect_one()) {
-        int s = 0; uint32_t ph = 0;
+        int s = 0; uint32_t ph = 0; int tr = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
           const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
           const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(BAR(2, s), ph ^ 1);
+            trace_ev(P, 0, tr);
             mbar_expect_tx(BAR(0, s), stage_tx);
             const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
             tma_load_3d(sb + OFF_P_HI, &mapW, BAR(0, s), kb * BK, nt * TN, bz);       // dims (k, n, batch)
@@ -250,6 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       if (elect_one()) {
         const uint32_t idesc = make_idesc((uint32_t)P.BA);
         int s = 0; uint32_t ph = 0; uint32_t gc = 0;       // gc: global chunk counter -> TMEM buffer ring
+        int tr = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
           for (int kb0 = 0; kb0 < KB; kb0 += F, ++gc) {
             const uint32_t buf = gc & 1u, bph = (gc >> 1) & 1u;
@@ -260,6 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             for (int kb = kb0; kb < kb1; ++kb) {
               mbar_wait(BAR(1, s), ph);             // TMA landed AND converters finished the split
               tc_fence_after();
+              trace_ev(P, 1, tr);
               const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
 #pragma unroll
               for (int k4 = 0; k4 < BK / 8; ++k4) {
@@ -284,11 +295,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     reg_dec<72>();
     const int ct = threadIdx.x - CONV_WARP0 * 32;     // 0..127
     const bool affine = g.a_scale != nullptr;
-    int s = 0; uint32_t ph = 0;
+    int s = 0; uint32_t ph = 0; int tr = 0, tr2 = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const int m0 = (tile % P.m_tiles) * P.BA;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(BAR(0, s), ph);
+        if (ct == 0) trace_ev(P, 2, tr);
         const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
         split_row<false>(sb + OFF_P_HI + (uint32_t)ct * 128u, P_BYTES, lane, 0, nullptr, nullptr);   // weight row ct
 #pragma unroll
@@ -307,6 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         }
         fence_proxy_async();                      // generic-proxy writes -> visible to the UMMA (async proxy)
         mbar_arrive(BAR(1, s));
+        if (ct == 0) trace_ev(P, 3, tr2);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -317,6 +330,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     const int cpar = (warp - EPI_WARP0) >> 2;         // this warp owns the 32-column chunks 2*i + cpar
     const int nchunks = (P.BA + 31) / 32;
     uint32_t gc = 0;
+    int tr = 0, tr2 = 0, tr3 = 0;
+    const bool tracer = (warp == EPI_WARP0 && lane == 0);
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
       const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
@@ -329,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const uint32_t buf = gc & 1u, bph = (gc >> 1) & 1u;
         mbar_wait(BAR(3, buf), bph);
         tc_fence_after();
+        if (tracer) trace_ev(P, 4, tr);
         const uint32_t t_row = tmem_base + buf * TM_MAX + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -344,19 +360,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         tc_fence_before();
         mbar_arrive(BAR(4, buf));
       }
-      // ---- final epilogue from registers: lanes = 32 consecutive output channels -> coalesced lines
+      if (tracer) trace_ev(P, 5, tr2);
+      // ---- final epilogue.  The accumulators are register arrays (static indices only), but a fully
+      // unrolled 128-element epilogue is ~100 KB of straight-line code and thrashes the instruction
+      // cache; so each 32x32 sub-tile is parked in a per-warp smem tile and consumed by a ROLLED loop.
+      // lanes = 32 consecutive output channels n -> every global access is one coalesced 128 B line.
       const int n = nt * TN + quarter * 32 + lane;
-      if (n < g.N) {
-        float* __restrict__ C = g.C + (int64_t)bz * g.sC;
-        const float bias_n = g.bias ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+      const bool n_ok = n < g.N;
+      float* __restrict__ C = g.C + (int64_t)bz * g.sC;
+      const float bias_n = (g.bias && n_ok) ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+      const uint32_t stg = smem0 + EPI_STAGE_OFF + (uint32_t)(warp - EPI_WARP0) * EPI_STAGE_BYTES + (uint32_t)lane * 4u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c0 = (2 * i + cpar) * 32;
+      for (int i = 0; i < 4; ++i) {
+        const int c0 = (2 * i + cpar) * 32;
+        if (c0 < P.BA) {
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int m = mt * P.BA + c0 + j;
-            if (c0 + j < P.BA && m < g.M) {
-              float v = acc[i][j] + bias_n;
+          for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + j * 128), "f"(acc[i][j]) : "memory");
+          __syncwarp();
+          const int mbase = mt * P.BA + c0;
+          const int jmax = min(32, min(P.BA - c0, g.M - mbase));
+          if (n_ok) {
+            for (int j = 0; j < jmax; ++j) {
+              const int m = mbase + j;
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg + j * 128));
+              v += bias_n;
               if (g.rowbias) v += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
               if (ACT_MODE == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
               else if (ACT_MODE == 2) v = act_apply(v, g.act);
@@ -370,6 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           }
         }
       }
+      if (tracer) trace_ev(P, 6, tr3);
     }
   }
 
@@ -422,7 +452,8 @@ bool device_ok() {
   return ok == 1;
 }
 
-int g_flush = 4;   // k-blocks (of 32) per in-TMEM accumulation chain; tunable for experiments
+int g_flush = 2;
+long long* g_trace = nullptr;   // k-blocks (of 32) per in-TMEM accumulation chain; tunable for experiments
 
 }  // namespace
 
@@ -451,6 +482,7 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
   P.total_tiles = P.n_tiles * P.m_tiles * batch;
   P.kblocks = p.K / BK;
   P.flush = g_flush < 1 ? 1 : g_flush;
+  P.trace = g_trace;
 
   alignas(64) CUtensorMap mapW, mapA;
   const uint64_t sWb = batch > 1 ? (uint64_t)p.sW * 4 : (uint64_t)p.ldw * 4 * (uint64_t)p.N;
@@ -485,6 +517,8 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
 
 extern "C" int dpot_tc_available(void) { return (dpot::device_ok() && dpot::get_encode() != nullptr) ? 1 : 0; }
 // experiment knob: k-blocks (32 fp32 each) accumulated in TMEM between register flushes (default 4)
+// debug: device buffer of 7*64 int64 receiving clock64() events of CTA 0 (NULL disables)
+extern "C" void dpot_tc_set_trace(long long* dev_buf) { dpot::g_trace = dev_buf; }
 extern "C" int dpot_tc_set_flush(int kblocks) {
   const int old = dpot::g_flush;
   if (kblocks >= 1) dpot::g_flush = kblocks;

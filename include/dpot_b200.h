@@ -59,8 +59,11 @@ DPOT_API long long   dpot_launch_count(void);
 /* 1 if the tcgen05 3xTF32 GEMM engine is compiled in and the current device can run it */
 DPOT_API int         dpot_tc_available(void);
 /* tuning knob of the tcgen05 engine: k-blocks (32 fp32) accumulated in TMEM between round-to-nearest
-   flushes into the register accumulators (default 4); returns the previous value, <1 only queries */
+   flushes into the register accumulators (default 2); returns the previous value, <1 only queries */
 DPOT_API int         dpot_tc_set_flush(int kblocks);
+/* profiling aid: device buffer of 7*64 int64 that receives clock64() pipeline events of CTA 0 of the
+   tcgen05 engine (rows: producer, mma, conv-start, conv-done, flush, tile-acc-done, tile-epilogue-done) */
+DPOT_API void        dpot_tc_set_trace(long long* dev_buf);
 
 /* ------------------------------------------------------------------------------------------
  * The dense-contraction engine.  C = epilogue( A' * W^T ), fp32 in / fp32 out.
