@@ -149,10 +149,9 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// round-to-nearest (ties away) to TF32 = cvt.rna.tf32.f32 for finite inputs, in two integer ops
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 struct TcParams {
@@ -381,20 +380,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           const int mbase = mt * P.BA + c0;
           const int jmax = min(32, min(P.BA - c0, g.M - mbase));
           if (n_ok) {
-            for (int j = 0; j < jmax; ++j) {
-              const int m = mbase + j;
-              float v;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg + j * 128));
-              v += bias_n;
-              if (g.rowbias) v += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
-              if (ACT_MODE == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-              else if (ACT_MODE == 2) v = act_apply(v, g.act);
-              if (g.c_scale) {
-                const int64_t o = (int64_t)(m / g.c_rps) * g.N + n;
-                v = fmaf(v, g.c_scale[o], g.c_shift[o]);
+            // 4 independent elements in flight per iteration (erff is a long dependent chain)
+            for (int j0 = 0; j0 < jmax; j0 += 4) {
+              float v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[u]) : "r"(stg + (j0 + u) * 128));
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int m = mbase + j0 + u;
+                if (j0 + u < jmax) {
+                  float x = v[u] + bias_n;
+                  if (g.rowbias) x += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
+                  if (ACT_MODE == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+                  else if (ACT_MODE == 2) x = act_apply(x, g.act);
+                  if (g.c_scale) {
+                    const int64_t o = (int64_t)(m / g.c_rps) * g.N + n;
+                    x = fmaf(x, g.c_scale[o], g.c_shift[o]);
+                  }
+                  if (g.residual) x += g.residual[(int64_t)m * g.ldr + n];
+                  C[gemm_c_offset(g, m) + n] = x;
+                }
               }
-              if (g.residual) v += g.residual[(int64_t)m * g.ldr + n];
-              C[gemm_c_offset(g, m) + n] = v;
             }
           }
         }
