@@ -95,14 +95,16 @@ extern "C" int dpot_adam_step_multi(float* const* p, const float* const* g, floa
   c.eps = (float)eps; c.wd = (float)weight_decay; c.decay_mul = (float)(1.0 - lr * weight_decay);
   c.grad_scale = (float)grad_scale; c.decoupled = decoupled;
   cudaStream_t st = as_stream(stream);
-  for (int t0 = 0; t0 < count; t0 += MT_MAX) {
+  int t = 0;
+  while (t < count) {
     MultiArgs a;
-    a.count = std::min(MT_MAX, count - t0);
+    a.count = 0;
     int blk = 0;
-    for (int k = 0; k < a.count; ++k) {
-      const int t = t0 + k;
-      DPOT_REQUIRE(p[t] && g[t] && m[t] && v[t] && n[t] >= 0 && steps[t] >= 1, DPOT_E_BADARG,
-                   "dpot_adam_step_multi: bad tensor %d", t);
+    for (; t < count && a.count < MT_MAX; ++t) {
+      DPOT_REQUIRE(n[t] >= 0 && steps[t] >= 1, DPOT_E_BADARG, "dpot_adam_step_multi: bad size/step of tensor %d", t);
+      if (n[t] == 0) continue;                      // empty tensors (NULL data pointers) are legal no-ops
+      DPOT_REQUIRE(p[t] && g[t] && m[t] && v[t], DPOT_E_BADARG, "dpot_adam_step_multi: null pointer in tensor %d", t);
+      const int k = a.count++;
       a.p[k] = p[t]; a.g[k] = g[t]; a.m[k] = m[t]; a.v[k] = v[t]; a.vmax[k] = vmax ? vmax[t] : nullptr;
       a.n[k] = n[t];
       a.blk_start[k] = blk;

@@ -46,9 +46,7 @@ constexpr uint32_t Q_BYTES = TM_MAX * 128;      // 32 KB
 constexpr uint32_t OFF_P_HI = 0, OFF_P_LO = P_BYTES, OFF_Q_HI = 2 * P_BYTES, OFF_Q_LO = 2 * P_BYTES + Q_BYTES;
 constexpr uint32_t STAGE_BYTES = 2 * P_BYTES + 2 * Q_BYTES;   // 96 KB
 constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
-constexpr uint32_t EPI_STAGE_OFF = BAR_OFF + 256;             // per-epilogue-warp 32x32 fp32 staging tiles
-constexpr uint32_t EPI_STAGE_BYTES = 32 * 32 * 4;
-constexpr uint32_t SMEM_BYTES = EPI_STAGE_OFF + EPI_WARPS * EPI_STAGE_BYTES + 1024;   // + alignment slack
+constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;        // + barriers + alignment slack
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -360,49 +358,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         mbar_arrive(BAR(4, buf));
       }
       if (tracer) trace_ev(P, 5, tr2);
-      // ---- final epilogue.  The accumulators are register arrays (static indices only), but a fully
-      // unrolled 128-element epilogue is ~100 KB of straight-line code and thrashes the instruction
-      // cache; so each 32x32 sub-tile is parked in a per-warp smem tile and consumed by a ROLLED loop.
-      // lanes = 32 consecutive output channels n -> every global access is one coalesced 128 B line.
+      // ---- final epilogue.  The accumulators are register arrays (static indices only).  A fully
+      // unrolled 128-element epilogue is ~100 KB of straight-line code (instruction-cache thrash) and
+      // parking the values in shared memory queues behind the converters' saturated LSU traffic, so the
+      // 16 groups of 8 registers are selected by a uniform switch and consumed by ONE shared body that
+      // keeps 8 independent elements in flight.  lanes = 32 consecutive output channels n -> every global
+      // access is one coalesced 128 B line.
       const int n = nt * TN + quarter * 32 + lane;
-      const bool n_ok = n < g.N;
-      float* __restrict__ C = g.C + (int64_t)bz * g.sC;
-      const float bias_n = (g.bias && n_ok) ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
-      const uint32_t stg = smem0 + EPI_STAGE_OFF + (uint32_t)(warp - EPI_WARP0) * EPI_STAGE_BYTES + (uint32_t)lane * 4u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c0 = (2 * i + cpar) * 32;
-        if (c0 < P.BA) {
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + j * 128), "f"(acc[i][j]) : "memory");
-          __syncwarp();
-          const int mbase = mt * P.BA + c0;
-          const int jmax = min(32, min(P.BA - c0, g.M - mbase));
-          if (n_ok) {
-            // 4 independent elements in flight per iteration (erff is a long dependent chain)
-            for (int j0 = 0; j0 < jmax; j0 += 4) {
-              float v[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[u]) : "r"(stg + (j0 + u) * 128));
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int m = mbase + j0 + u;
-                if (j0 + u < jmax) {
-                  float x = v[u] + bias_n;
-                  if (g.rowbias) x += g.rowbias[(int64_t)(m % g.rb_period) * g.ldrb + n];
-                  if (ACT_MODE == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-                  else if (ACT_MODE == 2) x = act_apply(x, g.act);
-                  if (g.c_scale) {
-                    const int64_t o = (int64_t)(m / g.c_rps) * g.N + n;
-                    x = fmaf(x, g.c_scale[o], g.c_shift[o]);
-                  }
-                  if (g.residual) x += g.residual[(int64_t)m * g.ldr + n];
-                  C[gemm_c_offset(g, m) + n] = x;
-                }
-              }
-            }
+      if (n < g.N) {
+        float* __restrict__ C = g.C + (int64_t)bz * g.sC;
+        const float bias_n = g.bias ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+#pragma unroll 1
+        for (int b = 0; b < 16; ++b) {
+          const int c0 = (2 * (b >> 2) + cpar) * 32 + (b & 3) * 8;     // first tile column of this group
+          const int m0 = mt * P.BA + c0;
+          const int cnt = min(8, min(P.BA - c0, g.M - m0));
+          if (cnt <= 0) continue;
+          float t[8];
+#define DPOT_GRP(B, I, J0) case B: _Pragma("unroll") for (int u = 0; u < 8; ++u) t[u] = acc[I][J0 + u]; break;
+          switch (b) {
+            DPOT_GRP(0, 0, 0) DPOT_GRP(1, 0, 8) DPOT_GRP(2, 0, 16) DPOT_GRP(3, 0, 24)
+            DPOT_GRP(4, 1, 0) DPOT_GRP(5, 1, 8) DPOT_GRP(6, 1, 16) DPOT_GRP(7, 1, 24)
+            DPOT_GRP(8, 2, 0) DPOT_GRP(9, 2, 8) DPOT_GRP(10, 2, 16) DPOT_GRP(11, 2, 24)
+            DPOT_GRP(12, 3, 0) DPOT_GRP(13, 3, 8) DPOT_GRP(14, 3, 16)
+            default: _Pragma("unroll") for (int u = 0; u < 8; ++u) t[u] = acc[3][24 + u]; break;
           }
+#undef DPOT_GRP
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] += bias_n;
+          if (g.rowbias) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u < cnt) t[u] += g.rowbias[(int64_t)((m0 + u) % g.rb_period) * g.ldrb + n];
+          }
+          if (ACT_MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = gelu_select(t[u]);
+          } else if (ACT_MODE == 2) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = act_apply(t[u], g.act);
+          }
+          if (g.c_scale) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u < cnt) {
+                const int64_t o = (int64_t)((m0 + u) / g.c_rps) * g.N + n;
+                t[u] = fmaf(t[u], g.c_scale[o], g.c_shift[o]);
+              }
+          }
+          if (g.residual) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u < cnt) t[u] += g.residual[(int64_t)(m0 + u) * g.ldr + n];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (u < cnt) C[gemm_c_offset(g, m0 + u) + n] = t[u];
         }
       }
       if (tracer) trace_ev(P, 6, tr3);
