@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("a_mode", C.c_int32), ("pX", C.c_int32), ("pY", C.c_int32), ("pT", C.c_int32), ("pC", C.c_int32),
         ("pP", C.c_int32),
         ("engine", C.c_int32),
+        ("out_stats", c_f32p), ("stats_groups", C.c_int32), ("stats_rows_per_sample", C.c_int32),
     ]
 
 

@@ -171,16 +171,17 @@ extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, cons
     dpot_gemm_args g = gemm_args(ws + WL.z1, d.Kp, packed + PL.WeffT, d.Kp, lat, d.E, Mt, d.E, d.Kp, nullptr, DPOT_ACT_NONE, engine);
     g.rowbias = packed + PL.bias_eff; g.rowbias_period = d.n; g.ldrb = d.E;
     if (cfg->normalize) { g.c_scale = ws + WL.ssg; g.c_shift = ws + WL.smu; g.c_rows_per_sample = d.n; }
+    g.out_stats = reinterpret_cast<double*>(ws + WL.st1); g.stats_groups = 8; g.stats_rows_per_sample = d.n;
     DPOT_CALL(dpot_gemm(&g, stream));
   }
 
-  // ---- blocks, models/dpot.py:165-180
+  // ---- blocks, models/dpot.py:165-180.  GroupNorm-1 statistics of the block input are produced by the
+  // epilogue of the GEMM that wrote it (time aggregation above, fc2 of the previous block below).
   double* st1 = reinterpret_cast<double*>(ws + WL.st1);
   double* st2 = reinterpret_cast<double*>(ws + WL.st2);
   for (int i = 0; i < d.depth; ++i) {
     const dpot_block_params& bp = prm->blocks[i];
     const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
-    DPOT_CALL(dpot_gn_stats(lat, B, d.n, d.E, groups, st1, stream));
     DPOT_CALL(dpot_gn_finalize(st1, bp.norm1_w, bp.norm1_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc1, ws + WL.sh1, stream));
     DPOT_CALL(dpot_afno_fft_fwd(lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.S, stream));
     {
@@ -199,6 +200,7 @@ extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, cons
       DPOT_CALL(dpot_gemm(&g, stream));
       g = gemm_args(ws + WL.hid, d.hid, bp.fc2_w, d.hid, lat_next, d.E, Mt, d.E, d.hid, bp.fc2_b, DPOT_ACT_NONE, engine);
       g.residual = lat; g.ldr = d.E;
+      if (i + 1 < d.depth) { g.out_stats = st1; g.stats_groups = groups; g.stats_rows_per_sample = d.n; }
       DPOT_CALL(dpot_gemm(&g, stream));
     }
     float* t = lat; lat = lat_next; lat_next = t;

@@ -29,6 +29,12 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   p.sA = a->strideA; p.sW = a->strideW; p.sC = a->strideC; p.sBias = a->strideBias;
   p.a_mode = a->a_mode; p.pX = a->pX; p.pY = a->pY; p.pT = a->pT; p.pC = a->pC; p.pP = a->pP;
   p.ph = p.pw = 0;
+  p.out_stats = nullptr; p.st_groups = a->stats_groups; p.st_rps = a->stats_rows_per_sample;
+  if (a->out_stats) {
+    DPOT_REQUIRE(a->batch == 1 && a->c_group == 0 && a->ldc == a->N, DPOT_E_BADARG, "dpot_gemm: out_stats needs a plain contiguous C");
+    DPOT_REQUIRE(a->stats_groups > 0 && a->N % a->stats_groups == 0 && a->stats_rows_per_sample > 0 &&
+                 a->M % a->stats_rows_per_sample == 0, DPOT_E_BADARG, "dpot_gemm: bad out_stats geometry");
+  }
   if (a->a_mode == DPOT_A_PATCH) {
     DPOT_REQUIRE(a->pP > 0 && a->pX % a->pP == 0 && a->pY % a->pP == 0, DPOT_E_BADARG, "dpot_gemm: patch geometry");
     p.ph = a->pX / a->pP; p.pw = a->pY / a->pP;
@@ -39,10 +45,20 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   int engine = a->engine;
   if (engine == DPOT_GEMM_AUTO) engine = gemm_tc_supports(p, a->batch) ? DPOT_GEMM_TC : DPOT_GEMM_SIMT;
+  const int B = a->out_stats ? a->M / a->stats_rows_per_sample : 0;
   if (engine == DPOT_GEMM_TC) {
     DPOT_REQUIRE(gemm_tc_supports(p, a->batch), DPOT_E_UNSUPPORTED,
                  "dpot_gemm: tcgen05 engine does not take this problem (M=%d N=%d K=%d)", a->M, a->N, a->K);
-    return gemm_tc_launch(p, a->batch, st);
+    if (a->out_stats && gemm_tc_fuses_stats(p)) {
+      DPOT_CUDA(cudaMemsetAsync(a->out_stats, 0, sizeof(double) * 2 * (size_t)B * a->stats_groups, st));
+      p.out_stats = a->out_stats;
+      return gemm_tc_launch(p, a->batch, st);
+    }
+    DPOT_CALL(gemm_tc_launch(p, a->batch, st));
+  } else {
+    DPOT_CALL(gemm_simt_launch(p, a->batch, st));
   }
-  return gemm_simt_launch(p, a->batch, st);
+  if (a->out_stats)   // engines without a fused reduction: one streaming pass over the (L2-hot) result
+    return dpot_gn_stats(a->C, B, a->stats_rows_per_sample, a->N, a->stats_groups, a->out_stats, stream);
+  return 0;
 }

@@ -18,6 +18,7 @@ struct GemmDev {
   int c_group; int64_t c_group_stride;
   int64_t sA, sW, sC, sBias;
   int a_mode, pX, pY, pT, pC, pP, ph, pw;
+  double* out_stats; int st_groups, st_rps;   // fused GroupNorm statistics (tcgen05 engine only)
 };
 
 // im2col address of PatchEmbed conv0 (models/dpot.py:199,375): row m = (b,p,q,t), k = (u,v,c)
@@ -66,5 +67,6 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, float* __r
 int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st);
 int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st);   // tcgen05 engine
 bool gemm_tc_supports(const GemmDev& p, int batch);
+bool gemm_tc_fuses_stats(const GemmDev& p);   // can the TC epilogue accumulate out_stats itself?
 
 }  // namespace dpot

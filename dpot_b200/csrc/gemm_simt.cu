@@ -140,6 +140,50 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
   }
 }
 
+
+// ---- skinny problems (M <= 64: classification head, AdaIN tables) --------------------------------
+// One warp per pair of output columns; lanes split K (coalesced 128 B rows of A and W), fp32 FMA,
+// shuffle reduction.  A (<= 64 x K) stays in L1/L2; the kernel is latency- not bandwidth-critical.
+constexpr int SK_MAXM = 64, SK_WARPS = 8;
+template <int MT>   // rows handled per pass (32): M is covered in ceil(M/32) passes
+__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDev p) {
+  const int lane = threadIdx.x & 31;
+  const int wglob = blockIdx.x * SK_WARPS + (threadIdx.x >> 5);
+  const int n0 = wglob * 2;
+  if (n0 >= p.N) return;
+  const bool two = (n0 + 1) < p.N;
+  const float* __restrict__ w0 = p.W + (int64_t)n0 * p.ldw;
+  const float* __restrict__ w1 = p.W + (int64_t)(two ? n0 + 1 : n0) * p.ldw;
+  for (int mb = 0; mb < p.M; mb += MT) {
+    float a0[MT], a1[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) a0[i] = a1[i] = 0.f;
+    for (int k = lane; k < p.K; k += 32) {
+      const float x0 = w0[k], x1 = w1[k];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int m = mb + i;
+        const float a = (m < p.M) ? gemm_load_a(p, p.A, m, k) : 0.f;
+        a0[i] = fmaf(a, x0, a0[i]);
+        a1[i] = fmaf(a, x1, a1[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      a0[i] = warp_sum(a0[i]);
+      a1[i] = warp_sum(a1[i]);
+    }
+    // lane i finalises row mb+i
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      if (lane == (i & 31) && mb + i < p.M) {
+        gemm_epilogue_store(p, p.C, p.bias, mb + i, n0, a0[i]);
+        if (two) gemm_epilogue_store(p, p.C, p.bias, mb + i, n0 + 1, a1[i]);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st) {
@@ -149,6 +193,12 @@ int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st) {
                        (p.lda % 4 == 0) && (p.ldw % 4 == 0) && (p.K % 4 == 0) && (p.sA % 4 == 0) && (p.sW % 4 == 0) &&
                        (!p.a_scale || (reinterpret_cast<uintptr_t>(p.a_scale) % 16 == 0 &&
                                        reinterpret_cast<uintptr_t>(p.a_shift) % 16 == 0));
+  if (p.M <= SK_MAXM && batch == 1 && p.a_mode == DPOT_A_PLAIN) {
+    const int warps = (p.N + 1) / 2;
+    gemm_skinny_kernel<32><<<(unsigned)ceil_div(warps, SK_WARPS), SK_WARPS * 32, 0, st>>>(p);
+    DPOT_LAUNCH_CHECK("gemm_skinny_kernel");
+    return 0;
+  }
   if (p.a_mode == DPOT_A_PLAIN && aligned)
     gemm_simt_kernel<true><<<grid, NT, 0, st>>>(p);
   else

@@ -368,6 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       if (n < g.N) {
         float* __restrict__ C = g.C + (int64_t)bz * g.sC;
         const float bias_n = g.bias ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+        float st1 = 0.f, st2 = 0.f;        // GroupNorm statistics of what this thread stores
 #pragma unroll 1
         for (int b = 0; b < 16; ++b) {
           const int c0 = (2 * (b >> 2) + cpar) * 32 + (b & 3) * 8;     // first tile column of this group
@@ -413,7 +414,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (u < cnt) C[gemm_c_offset(g, m0 + u) + n] = t[u];
+            if (u < cnt) {
+              C[gemm_c_offset(g, m0 + u) + n] = t[u];
+              st1 += t[u];
+              st2 = fmaf(t[u], t[u], st2);
+            }
+        }
+        if (g.out_stats) {   // host guarantees: the tile lies in one sample, the warp's 32 channels in one group
+          double d1 = (double)st1, d2 = (double)st2;
+          const unsigned msk = __activemask();
+          for (int o = 16; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(msk, d1, o);
+            d2 += __shfl_xor_sync(msk, d2, o);
+          }
+          if (lane == 0) {
+            const int smp = (mt * P.BA) / g.st_rps, grp = n / (g.N / g.st_groups);
+            double* dst = g.out_stats + ((int64_t)smp * g.st_groups + grp) * 2;
+            atomicAdd(dst, d1);
+            atomicAdd(dst + 1, d2);
+          }
         }
       }
       if (tracer) trace_ev(P, 6, tr3);
@@ -488,6 +507,11 @@ bool gemm_tc_supports(const GemmDev& p, int batch) {
     if (p.sW % p.ldw != 0 || p.sW < (int64_t)p.N * p.ldw) return false;   // (k, n, batch)
   }
   return true;
+}
+
+bool gemm_tc_fuses_stats(const GemmDev& p) {
+  const int BA = p.M >= TM_MAX ? TM_MAX : (int)round_up(p.M, 16);
+  return p.st_groups > 0 && p.st_rps > 0 && p.st_rps % BA == 0 && p.N % 32 == 0 && (p.N / p.st_groups) % 32 == 0;
 }
 
 int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {

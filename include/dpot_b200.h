@@ -100,6 +100,10 @@ typedef struct dpot_gemm_args {
      A[m,k] = x[b, p*P+u, q*P+v, t, c]   (PatchEmbed im2col, models/dpot.py:199,375) */
   int32_t a_mode, pX, pY, pT, pC, pP;
   int32_t engine;                        /* DPOT_GEMM_* */
+  /* optional GroupNorm statistics of the stored result: out_stats[s, g, 2] (double) receives
+     (sum, sum of squares) over the entries of sample s = m / stats_rows_per_sample and channel
+     group g = n / (N / stats_groups).  Zeroed by dpot_gemm itself.  Requires batch == 1. */
+  double* out_stats; int32_t stats_groups; int32_t stats_rows_per_sample;
 } dpot_gemm_args;
 
 DPOT_API int dpot_gemm(const dpot_gemm_args* args, void* stream);
