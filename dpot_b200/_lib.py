@@ -38,6 +38,19 @@ class GemmArgs(C.Structure):
         ("pP", C.c_int32),
         ("engine", C.c_int32),
         ("out_stats", c_f32p), ("stats_groups", C.c_int32), ("stats_rows_per_sample", C.c_int32),
+        ("C_pre", c_f32p), ("dact_src", c_f32p), ("dact", C.c_int32), ("c_mode", C.c_int32),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("X", c_f32p), ("ldx", C.c_int64), ("Y", c_f32p), ("ldy", C.c_int64), ("dW", c_f32p), ("ldw", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("y_scale", c_f32p), ("y_shift", c_f32p), ("y_rows_per_sample", C.c_int32),
+        ("batch", C.c_int32), ("strideX", C.c_int64), ("strideY", C.c_int64), ("strideW", C.c_int64),
+        ("y_mode", C.c_int32), ("pX", C.c_int32), ("pY", C.c_int32), ("pT", C.c_int32), ("pC", C.c_int32),
+        ("pP", C.c_int32),
+        ("accumulate", C.c_int32),
     ]
 
 
@@ -79,8 +92,16 @@ SIGNATURES = {
     "dpot_gemm": (C.c_int, [C.POINTER(GemmArgs), _p]),
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_gn_finalize": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p]),
-    "dpot_afno_fft_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
-    "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p]),
+    "dpot_afno_fft_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p]),
+    "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _p]),
+    "dpot_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),
+    "dpot_colsum": (C.c_int, [_p, _i64, _i32, _i32, _p, _i32, _p]),
+    "dpot_transpose": (C.c_int, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i64, _i64, _p]),
+    "dpot_gn_apply": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p]),
+    "dpot_gn_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p, _p, _p]),
+    "dpot_act_bwd": (C.c_int, [_p, _p, _i32, _i64, _p, _p]),
+    "dpot_pixel_shuffle": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dpot_unpack_afno_grad": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p]),
     "dpot_pack_afno": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p]),
     "dpot_pack_patch": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "dpot_fold_timeagg": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),

@@ -82,7 +82,7 @@ struct Cfg {
 template <int H>
 __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restrict__ a, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int E, int bs, int km1,
-                                                          int km2, float* __restrict__ S) {
+                                                          int km2, float* __restrict__ S, float wint) {
   constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, KH = Cfg<H>::KH, n = H * H;
   extern __shared__ __align__(16) float smem[];
   float* T_s = smem;                                        // [n][CH]
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
   const int tid = threadIdx.x, c = tid % CH, task0 = tid / CH;
   const int b = blockIdx.y, ch = blockIdx.x * CH + c;
   const bool live = ch < E;
-  const float sc = live ? scale[(int64_t)b * E + ch] : 0.f;
-  const float sh = live ? shift[(int64_t)b * E + ch] : 0.f;
+  const float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
+  const float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
 
   // phase 1: GroupNorm-1 applied on load
   const float* ap = a + (int64_t)b * n * E + ch;
@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
     for (int k1 = 0; k1 < H; ++k1) {
       if (k1 < km1) {
         float* dst = S + (((int64_t)b * km1 + k1) * km2 + k2) * (2 * E) + (int64_t)kap * 2 * bs + j;
-        dst[0] = zr[k1] * norm;
-        dst[bs] = zi[k1] * norm;
+        const float wk = (k2 > 0 && k2 < H / 2) ? norm * wint : norm;
+        dst[0] = zr[k1] * wk;
+        dst[bs] = zi[k1] * wk;
       }
     }
   }
@@ -149,7 +150,7 @@ template <int H>
 __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restrict__ O2, const float* __restrict__ a,
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                           int E, int bs, int km1, int km2, float* __restrict__ f,
-                                                          double* __restrict__ stats, int groups) {
+                                                          double* __restrict__ stats, int groups, float wint) {
   constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, KH = Cfg<H>::KH, n = H * H;
   extern __shared__ __align__(16) float smem[];
   float2* Z_s = reinterpret_cast<float2*>(smem);             // [H][KH][CH]
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
     float2 v = make_float2(0.f, 0.f);
     if (live && k1 < km1 && k2 < km2) {
       const float* src = O2 + (((int64_t)b * km1 + k1) * km2 + k2) * (2 * E) + (int64_t)kap * 2 * bs + j;
-      v = make_float2(src[0], src[bs]);
+      const float wk = (k2 > 0 && k2 < H / 2) ? wint : 1.f;
+      v = make_float2(src[0] * wk, src[bs] * wk);
     }
     Z_s[idx * CH + c] = v;
   }
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
 
   // phase 3: c2r along k2 -> q for two rows at once, + skip of the normalised input
   const float norm = 1.0f / (float)H;
-  const float sc = live ? scale[(int64_t)b * E + ch] : 0.f;
-  const float sh = live ? shift[(int64_t)b * E + ch] : 0.f;
+  const float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
+  const float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
   double s1 = 0.0, s2 = 0.0;
   for (int pr = task0; pr < H / 2; pr += NTASK) {
     float zr[H], zi[H];
@@ -213,8 +215,8 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
       const int64_t base1 = base0 + (int64_t)H * E;
 #pragma unroll
       for (int q = 0; q < H; ++q) {
-        const float v0 = fmaf(zr[q], norm, fmaf(a[base0 + (int64_t)q * E], sc, sh));
-        const float v1 = fmaf(zi[q], norm, fmaf(a[base1 + (int64_t)q * E], sc, sh));
+        const float v0 = fmaf(zr[q], norm, a ? fmaf(a[base0 + (int64_t)q * E], sc, sh) : 0.f);
+        const float v1 = fmaf(zi[q], norm, a ? fmaf(a[base1 + (int64_t)q * E], sc, sh) : 0.f);
         f[base0 + (int64_t)q * E] = v0;
         f[base1 + (int64_t)q * E] = v1;
         s1 += (double)v0 + (double)v1;
@@ -244,25 +246,25 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
 
 template <int H>
 int launch_fwd(const float* a, const float* scale, const float* shift, int B, int E, int nb, int km1, int km2,
-               float* S, cudaStream_t st) {
+               float* S, float wint, cudaStream_t st) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
   const size_t smem = (size_t)H * H * CH * 4 + (size_t)H * KH * CH * 8;
   DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_fwd_kernel<H><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S);
+  afno_fft_fwd_kernel<H><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S, wint);
   DPOT_LAUNCH_CHECK("afno_fft_fwd_kernel");
   return 0;
 }
 
 template <int H>
 int launch_inv(const float* O2, const float* a, const float* scale, const float* shift, int B, int E, int nb,
-               int km1, int km2, float* f, double* stats, int groups, cudaStream_t st) {
+               int km1, int km2, float* f, double* stats, int groups, float wint, cudaStream_t st) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
   size_t smem = (size_t)H * KH * CH * 8;
   if (smem < (size_t)2 * NT * 8) smem = (size_t)2 * NT * 8;
   DPOT_CUDA(cudaFuncSetAttribute(afno_fft_inv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_inv_kernel<H><<<grid, NT, smem, st>>>(O2, a, scale, shift, E, E / nb, km1, km2, f, stats, groups);
+  afno_fft_inv_kernel<H><<<grid, NT, smem, st>>>(O2, a, scale, shift, E, E / nb, km1, km2, f, stats, groups, wint);
   DPOT_LAUNCH_CHECK("afno_fft_inv_kernel");
   return 0;
 }
@@ -282,31 +284,32 @@ int check_common(int B, int h, int E, int nb, int km1, int km2) {
 using namespace dpot;
 
 extern "C" int dpot_afno_fft_fwd(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
-                                 int32_t E, int32_t nb, int32_t km1, int32_t km2, float* S, void* stream) {
-  DPOT_REQUIRE(a && scale && shift && S, DPOT_E_BADARG, "dpot_afno_fft_fwd: null pointer");
+                                 int32_t E, int32_t nb, int32_t km1, int32_t km2, float* S, float interior_weight,
+                                 void* stream) {
+  DPOT_REQUIRE(a && S && ((scale == nullptr) == (shift == nullptr)), DPOT_E_BADARG, "dpot_afno_fft_fwd: null pointer");
   DPOT_CALL(check_common(B, h, E, nb, km1, km2));
   cudaStream_t st = as_stream(stream);
   switch (h) {
-    case 2: return launch_fwd<2>(a, scale, shift, B, E, nb, km1, km2, S, st);
-    case 4: return launch_fwd<4>(a, scale, shift, B, E, nb, km1, km2, S, st);
-    case 8: return launch_fwd<8>(a, scale, shift, B, E, nb, km1, km2, S, st);
-    case 16: return launch_fwd<16>(a, scale, shift, B, E, nb, km1, km2, S, st);
-    default: return launch_fwd<32>(a, scale, shift, B, E, nb, km1, km2, S, st);
+    case 2: return launch_fwd<2>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
+    case 4: return launch_fwd<4>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
+    case 8: return launch_fwd<8>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
+    case 16: return launch_fwd<16>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
+    default: return launch_fwd<32>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
   }
 }
 
 extern "C" int dpot_afno_fft_inv(const float* O2, const float* a, const float* scale, const float* shift, int32_t B,
                                  int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, float* f,
-                                 double* stats_out, int32_t groups, void* stream) {
-  DPOT_REQUIRE(O2 && a && scale && shift && f, DPOT_E_BADARG, "dpot_afno_fft_inv: null pointer");
+                                 double* stats_out, int32_t groups, float interior_weight, void* stream) {
+  DPOT_REQUIRE(O2 && f && ((scale == nullptr) == (shift == nullptr)), DPOT_E_BADARG, "dpot_afno_fft_inv: null pointer");
   DPOT_CALL(check_common(B, h, E, nb, km1, km2));
   DPOT_REQUIRE(!stats_out || (groups > 0 && E % groups == 0), DPOT_E_BADARG, "dpot_afno_fft_inv: bad groups");
   cudaStream_t st = as_stream(stream);
   switch (h) {
-    case 2: return launch_inv<2>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, st);
-    case 4: return launch_inv<4>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, st);
-    case 8: return launch_inv<8>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, st);
-    case 16: return launch_inv<16>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, st);
-    default: return launch_inv<32>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, st);
+    case 2: return launch_inv<2>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
+    case 4: return launch_inv<4>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
+    case 8: return launch_inv<8>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
+    case 16: return launch_inv<16>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
+    default: return launch_inv<32>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
   }
 }

@@ -183,7 +183,7 @@ extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, cons
     const dpot_block_params& bp = prm->blocks[i];
     const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
     DPOT_CALL(dpot_gn_finalize(st1, bp.norm1_w, bp.norm1_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc1, ws + WL.sh1, stream));
-    DPOT_CALL(dpot_afno_fft_fwd(lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.S, stream));
+    DPOT_CALL(dpot_afno_fft_fwd(lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.S, 1.0f, stream));
     {
       dpot_gemm_args g = gemm_args(ws + WL.S, 2 * d.E, pk + PL.Wc1, 2 * d.bs, ws + WL.O1, 2 * d.E, Ms, 2 * d.bs, 2 * d.bs, pk + PL.bc1, act, engine);
       g.batch = d.nb; g.strideA = 2 * d.bs; g.strideW = (int64_t)4 * d.bs * d.bs; g.strideC = 2 * d.bs; g.strideBias = 2 * d.bs;
@@ -192,7 +192,7 @@ extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, cons
       DPOT_CALL(dpot_gemm(&g, stream));
     }
     DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
-    DPOT_CALL(dpot_afno_fft_inv(ws + WL.S, lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.f, st2, groups, stream));
+    DPOT_CALL(dpot_afno_fft_inv(ws + WL.S, lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.f, st2, groups, 1.0f, stream));
     DPOT_CALL(dpot_gn_finalize(st2, bp.norm2_w, bp.norm2_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc2, ws + WL.sh2, stream));
     {
       dpot_gemm_args g = gemm_args(ws + WL.f, d.E, bp.fc1_w, d.E, ws + WL.hid, d.hid, Mt, d.hid, d.E, bp.fc1_b, act, engine);

@@ -29,6 +29,15 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   p.sA = a->strideA; p.sW = a->strideW; p.sC = a->strideC; p.sBias = a->strideBias;
   p.a_mode = a->a_mode; p.pX = a->pX; p.pY = a->pY; p.pT = a->pT; p.pC = a->pC; p.pP = a->pP;
   p.ph = p.pw = 0;
+  if (a->a_mode == DPOT_A_PATCH) { p.ph = a->pX / (a->pP > 0 ? a->pP : 1); p.pw = a->pY / (a->pP > 0 ? a->pP : 1); }
+  p.C_pre = a->C_pre; p.dact_src = a->dact_src; p.dact = a->dact; p.c_mode = a->c_mode;
+  if (a->c_mode == DPOT_A_PATCH) {
+    DPOT_REQUIRE(a->a_mode == DPOT_A_PLAIN && a->pP > 0 && a->pX % a->pP == 0 && a->pY % a->pP == 0 &&
+                 a->N == a->pP * a->pP * a->pC && a->batch == 1 && !a->C_pre && !a->dact_src && !a->residual,
+                 DPOT_E_BADARG, "dpot_gemm: bad patch-scatter output geometry");
+    p.ph = a->pX / a->pP; p.pw = a->pY / a->pP;
+  }
+  DPOT_REQUIRE(!a->dact_src || (a->c_group == 0), DPOT_E_BADARG, "dpot_gemm: dact_src needs a plain C layout");
   p.out_stats = nullptr; p.st_groups = a->stats_groups; p.st_rps = a->stats_rows_per_sample;
   if (a->out_stats) {
     DPOT_REQUIRE(a->batch == 1 && a->c_group == 0 && a->ldc == a->N, DPOT_E_BADARG, "dpot_gemm: out_stats needs a plain contiguous C");

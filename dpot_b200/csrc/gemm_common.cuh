@@ -19,6 +19,7 @@ struct GemmDev {
   int64_t sA, sW, sC, sBias;
   int a_mode, pX, pY, pT, pC, pP, ph, pw;
   double* out_stats; int st_groups, st_rps;   // fused GroupNorm statistics (tcgen05 engine only)
+  float* C_pre; const float* dact_src; int dact; int c_mode;   // training extras
 };
 
 // im2col address of PatchEmbed conv0 (models/dpot.py:199,375): row m = (b,p,q,t), k = (u,v,c)
@@ -41,11 +42,18 @@ __device__ __forceinline__ float gemm_load_a(const GemmDev& p, const float* __re
   return v;
 }
 
+__device__ __forceinline__ int64_t gemm_c_offset(const GemmDev& p, int m) {
+  return p.c_group ? (int64_t)(m / p.c_group) * p.c_group_stride + (int64_t)(m % p.c_group) * p.ldc
+                   : (int64_t)m * p.ldc;
+}
+
 __device__ __forceinline__ float gemm_epilogue_value(const GemmDev& p, const float* __restrict__ bias, int m, int n,
                                                      float v) {
   if (bias) v += bias[n];
   if (p.rowbias) v += p.rowbias[(int64_t)(m % p.rb_period) * p.ldrb + n];
+  if (p.C_pre) p.C_pre[gemm_c_offset(p, m) + n] = v;
   v = act_apply(v, p.act);
+  if (p.dact_src) v *= act_grad(p.dact_src[(int64_t)m * p.ldc + n], p.dact);
   if (p.c_scale) {
     const int64_t o = (int64_t)(m / p.c_rps) * p.N + n;
     v = fmaf(v, p.c_scale[o], p.c_shift[o]);
@@ -54,14 +62,11 @@ __device__ __forceinline__ float gemm_epilogue_value(const GemmDev& p, const flo
   return v;
 }
 
-__device__ __forceinline__ int64_t gemm_c_offset(const GemmDev& p, int m) {
-  return p.c_group ? (int64_t)(m / p.c_group) * p.c_group_stride + (int64_t)(m % p.c_group) * p.ldc
-                   : (int64_t)m * p.ldc;
-}
-
 __device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, float* __restrict__ C,
                                                     const float* __restrict__ bias, int m, int n, float v) {
-  C[gemm_c_offset(p, m) + n] = gemm_epilogue_value(p, bias, m, n, v);
+  const float r = gemm_epilogue_value(p, bias, m, n, v);
+  if (p.c_mode == DPOT_A_PATCH) C[patch_offset(p, m, n)] = r;
+  else C[gemm_c_offset(p, m) + n] = r;
 }
 
 int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st);

@@ -392,12 +392,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             for (int u = 0; u < 8; ++u)
               if (u < cnt) t[u] += g.rowbias[(int64_t)((m0 + u) % g.rb_period) * g.ldrb + n];
           }
+          if (g.C_pre) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u < cnt) g.C_pre[gemm_c_offset(g, m0 + u) + n] = t[u];
+          }
           if (ACT_MODE == 1) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) t[u] = gelu_select(t[u]);
           } else if (ACT_MODE == 2) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) t[u] = act_apply(t[u], g.act);
+          }
+          if (g.dact_src) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u < cnt) t[u] *= act_grad(g.dact_src[(int64_t)(m0 + u) * g.ldc + n], g.dact);
           }
           if (g.c_scale) {
 #pragma unroll
@@ -495,7 +505,7 @@ long long* g_trace = nullptr;   // k-blocks (of 32) per in-TMEM accumulation cha
 
 bool gemm_tc_supports(const GemmDev& p, int batch) {
   if (!device_ok() || get_encode() == nullptr) return false;
-  if (p.a_mode != DPOT_A_PLAIN) return false;
+  if (p.a_mode != DPOT_A_PLAIN || p.c_mode != DPOT_A_PLAIN) return false;
   if (p.K < BK || p.K % BK != 0) return false;
   if (p.M < 64 || p.N < 32) return false;                       // tiny problems stay on the SIMT engine
   if (p.lda % 4 || p.ldw % 4) return false;

@@ -127,7 +127,7 @@ def afno_fft_fwd(a, scale, shift, B, h, nb, km1, km2):
     _need_cuda(a, scale, shift)
     E = a.shape[-1]
     S = torch.empty((B * km1 * km2, 2 * E), device=a.device, dtype=torch.float32)
-    check(_lib.load().dpot_afno_fft_fwd(ptr(a), ptr(scale), ptr(shift), B, h, E, nb, km1, km2, ptr(S), _stream()),
+    check(_lib.load().dpot_afno_fft_fwd(ptr(a), ptr(scale), ptr(shift), B, h, E, nb, km1, km2, ptr(S), 1.0, _stream()),
           "dpot_afno_fft_fwd")
     return S
 
@@ -138,7 +138,7 @@ def afno_fft_inv(O2, a, scale, shift, B, h, nb, km1, km2, want_stats=True, group
     f = torch.empty_like(a)
     stats = torch.zeros((B, groups, 2), device=a.device, dtype=torch.float64) if want_stats else None
     check(_lib.load().dpot_afno_fft_inv(ptr(O2), ptr(a), ptr(scale), ptr(shift), B, h, E, nb, km1, km2, ptr(f),
-                                        ptr(stats), groups, _stream()), "dpot_afno_fft_inv")
+                                        ptr(stats), groups, 1.0, _stream()), "dpot_afno_fft_inv")
     return f, stats
 
 

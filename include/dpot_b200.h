@@ -104,6 +104,14 @@ typedef struct dpot_gemm_args {
      (sum, sum of squares) over the entries of sample s = m / stats_rows_per_sample and channel
      group g = n / (N / stats_groups).  Zeroed by dpot_gemm itself.  Requires batch == 1. */
   double* out_stats; int32_t stats_groups; int32_t stats_rows_per_sample;
+  /* training extras.  C_pre: also store the pre-activation value (after bias/rowbias), same layout as C.
+     dact_src/dact: multiply by act'(dact_src[m,n]) of activation `dact` before c_scale/residual (chain rule
+     through the activation of the previous layer).  c_mode = DPOT_A_PATCH scatters row m = (b,p,q,t),
+     column n = (u,v,c) to the field layout x[b, p*P+u, q*P+v, t, c] (p* geometry; gradient w.r.t. the
+     input field, the transpose of the im2col load). */
+  float* C_pre;
+  const float* dact_src; int32_t dact;
+  int32_t c_mode;
 } dpot_gemm_args;
 
 DPOT_API int dpot_gemm(const dpot_gemm_args* args, void* stream);
@@ -129,10 +137,14 @@ DPOT_API int dpot_gn_finalize(const double* stats, const float* gamma, const flo
  * h must be a power of two in [2, 32].
  * ---------------------------------------------------------------------------------------- */
 DPOT_API int dpot_afno_fft_fwd(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
-                      int32_t E, int32_t nb, int32_t km1, int32_t km2, float* S, void* stream);
+                      int32_t E, int32_t nb, int32_t km1, int32_t km2, float* S, float interior_weight, void* stream);
 DPOT_API int dpot_afno_fft_inv(const float* O2, const float* a, const float* scale, const float* shift, int32_t B,
                       int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, float* f,
-                      double* stats_out, int32_t groups, void* stream);
+                      double* stats_out, int32_t groups, float interior_weight, void* stream);
+/* interior_weight multiplies the spectrum columns 0 < k2 < h/2 (on output of fwd / on input of inv); 1 for the
+   forward pass.  The two transforms are each other's adjoint up to that weight (Hermitian packing):
+   adjoint(inv) = fwd with weight 2, adjoint(fwd) = inv with weight 1/2 -- this is the whole FFT backward.
+   scale/shift may be NULL (identity); inv: `a` may be NULL (no skip term). */
 
 /* ------------------------------------------------------------------------------------------
  * Weight packing (run when weights change, not per step).
@@ -157,6 +169,43 @@ DPOT_API int dpot_fold_timeagg(const float* W2, const float* b2, const float* po
    WtT[(u,v,o), E], bias_t[(u,v,o)]. */
 DPOT_API int dpot_pack_out(const float* wt, const float* bt, int32_t E, int32_t old, int32_t P,
                   float* WtT, float* bias_t, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward-pass building blocks (autograd of models/dpot.py:364-403; train_temporal.py:227).
+ * ---------------------------------------------------------------------------------------- */
+/* weight gradient: dW[n,k] (+)= sum_m X[m,n] * Y'[m,k], Y' = Y*y_scale+y_shift (optional) or the im2col view */
+typedef struct dpot_wgrad_args {
+  const float* X; int64_t ldx;           /* [M,N] upstream gradient */
+  const float* Y; int64_t ldy;           /* [M,K] forward input (y_mode = DPOT_A_PATCH: the field) */
+  float* dW; int64_t ldw;                /* [N,K] */
+  int32_t M, N, K;
+  const float* y_scale; const float* y_shift; int32_t y_rows_per_sample;
+  int32_t batch; int64_t strideX, strideY, strideW;
+  int32_t y_mode, pX, pY, pT, pC, pP;
+  int32_t accumulate;                    /* 0: overwrite dW, 1: add */
+} dpot_wgrad_args;
+DPOT_API int dpot_wgrad(const dpot_wgrad_args* args, void* stream);
+/* out[n] (+)= sum_m X[m,n]   (bias gradients) */
+DPOT_API int dpot_colsum(const float* X, int64_t ldx, int32_t M, int32_t N, float* out, int32_t accumulate, void* stream);
+/* dst[c,r] = src[r,c] for `batch` matrices (weight transposes for the data-gradient GEMMs) */
+DPOT_API int dpot_transpose(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t R, int32_t C, int32_t batch,
+                   int64_t stride_src, int64_t stride_dst, void* stream);
+/* out = x*scale[b,:]+shift[b,:]  (GroupNorm materialised; training path) */
+DPOT_API int dpot_gn_apply(const float* x, const float* scale, const float* shift, int32_t B, int32_t n, int32_t E,
+                  float* out, void* stream);
+/* GroupNorm backward: dx = rstd*(gamma*dy - mean_g(gamma*dy) - xhat*mean_g(gamma*dy*xhat)) (+ add), dgamma += ,
+   dbeta += ; stats = the forward (sum, sumsq) doubles; scratch: 2*B*E + 2*B*groups floats. */
+DPOT_API int dpot_gn_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* add,
+                int32_t B, int32_t n, int32_t E, int32_t groups, float eps, float* scratch, float* dx,
+                float* dgamma, float* dbeta, void* stream);
+/* out = dy * act'(pre)  (activation backward from the stored pre-activation) */
+DPOT_API int dpot_act_bwd(const float* dy, const float* pre, int32_t act, int64_t total, float* out, void* stream);
+/* rows (b,p,q,u,v) x C  <->  field [b, p*P+u, q*P+v, C]  (to_field = 1 / 0) */
+DPOT_API int dpot_pixel_shuffle(const float* src, float* dst, int32_t B, int32_t h, int32_t w, int32_t P, int32_t C,
+                       int32_t to_field, void* stream);
+/* transpose of dpot_pack_afno for gradients: dw += unpack(dWc), db += unpack(dbc) */
+DPOT_API int dpot_unpack_afno_grad(const float* dWc, const float* dbc, int32_t nb, int32_t bs, float* dw, float* db,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Output head tail (models/dpot.py:317-321, 397-401): per pixel

@@ -215,3 +215,66 @@ def test_window_advance_and_rollout_buffers():
     want = torch.cat((xx[..., 2:, :], im), dim=-2)
     assert torch.equal(nxt, want)
     assert torch.equal(pred[..., 2:4, :], im) and pred[..., :2, :].abs().sum() == 0
+
+
+def _simple_lp_loss(x, y, mask):
+    """SimpleLpLoss(size_average=False) of utils/criterion.py:38-59 restated with torch ops (test side)."""
+    n = x.shape[0]
+    x = x * mask
+    y = y * mask
+    msk_ch = mask.sum(dim=list(range(1, mask.ndim - 1))).count_nonzero(dim=-1)
+    Cc = x.shape[-1]
+    d = torch.norm(x.reshape(n, -1, Cc) - y.reshape(n, -1, Cc), 2, dim=1)
+    yn = torch.norm(y.reshape(n, -1, Cc), 2, dim=1) + 1e-8
+    return torch.sum(torch.sum(d / yn, dim=-1) / msk_ch)
+
+
+def test_training_gradients_match_reference_autograd():
+    """2-step autoregressive training loss (train_temporal.py:201-227, noise_scale=0): loss, dL/dx and every
+    parameter gradient against the reference's autograd (golden fixture)."""
+    z = np.load(os.path.join(G, "train_grads_tiny.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    params = O.make_params(cfg, seed=0)
+    x = O.make_input(cfg, int(z["B"]), seed=0)
+    m = build_model(cfg, params).train()
+    xx = torch.from_numpy(x).cuda().requires_grad_(True)
+    x_in = xx
+    yy = torch.from_numpy(z["yy"]).cuda()
+    msk = torch.from_numpy(z["msk"]).cuda()
+    Tb = cfg["out_timesteps"]
+    loss = 0.0
+    for t in range(0, yy.shape[-2], Tb):
+        im, cls_pred = m(xx)
+        loss = loss + _simple_lp_loss(im, yy[..., t:t + Tb, :], msk)
+        xx = torch.cat((xx[..., Tb:, :], im), dim=-2)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(z["loss"]), rel=2e-5)
+    assert O.rel_l2(x_in.grad.cpu().numpy(), z["dx"]) < 5e-5
+    worst = 0.0
+    for k, p in m.named_parameters():
+        has = bool(z["hasgrad." + k])
+        if not has:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        e = O.rel_l2(p.grad.cpu().numpy(), z["grad." + k])
+        worst = max(worst, e)
+        assert e < 1e-4, (k, e)
+    print("worst parameter-gradient rel-L2:", worst)
+
+
+def test_train_step_matches_eval_forward():
+    """The differentiable forward and the inference engine are two paths to the same numbers."""
+    z = np.load(os.path.join(G, "fwd_tiny_bundle.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    params = O.make_params(cfg, seed=0)
+    x = torch.from_numpy(O.make_input(cfg, int(z["B"]), seed=0)).cuda()
+    m = build_model(cfg, params)
+    with torch.no_grad():
+        y0, c0 = m(x)
+    m.train()
+    y1, c1 = m(x)        # parameters require grad -> training path
+    assert y1.requires_grad
+    assert O.rel_l2(y1.detach().cpu().numpy(), z["y"]) < TOL
+    assert O.rel_l2(c1.detach().cpu().numpy(), z["cls"]) < TOL
+    assert O.rel_l2(y1.detach().cpu().numpy(), y0.cpu().numpy()) < 2e-6
