@@ -47,13 +47,14 @@ __device__ __forceinline__ int64_t gemm_c_offset(const GemmDev& p, int m) {
                    : (int64_t)m * p.ldc;
 }
 
+// boff = batch offset (elements) of this problem inside C-shaped side tensors (C_pre, dact_src)
 __device__ __forceinline__ float gemm_epilogue_value(const GemmDev& p, const float* __restrict__ bias, int m, int n,
-                                                     float v) {
+                                                     float v, int64_t boff = 0) {
   if (bias) v += bias[n];
   if (p.rowbias) v += p.rowbias[(int64_t)(m % p.rb_period) * p.ldrb + n];
-  if (p.C_pre) p.C_pre[gemm_c_offset(p, m) + n] = v;
+  if (p.C_pre) p.C_pre[boff + gemm_c_offset(p, m) + n] = v;
   v = act_apply(v, p.act);
-  if (p.dact_src) v *= act_grad(p.dact_src[(int64_t)m * p.ldc + n], p.dact);
+  if (p.dact_src) v *= act_grad(p.dact_src[boff + (int64_t)m * p.ldc + n], p.dact);
   if (p.c_scale) {
     const int64_t o = (int64_t)(m / p.c_rps) * p.N + n;
     v = fmaf(v, p.c_scale[o], p.c_shift[o]);
@@ -63,8 +64,9 @@ __device__ __forceinline__ float gemm_epilogue_value(const GemmDev& p, const flo
 }
 
 __device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, float* __restrict__ C,
-                                                    const float* __restrict__ bias, int m, int n, float v) {
-  const float r = gemm_epilogue_value(p, bias, m, n, v);
+                                                    const float* __restrict__ bias, int m, int n, float v,
+                                                    int64_t boff = 0) {
+  const float r = gemm_epilogue_value(p, bias, m, n, v, boff);
   if (p.c_mode == DPOT_A_PATCH) C[patch_offset(p, m, n)] = r;
   else C[gemm_c_offset(p, m) + n] = r;
 }

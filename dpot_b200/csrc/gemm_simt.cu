@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
       if (n >= p.N) continue;
-      gemm_epilogue_store(p, C, bias, m, n, acc[i][j]);
+      gemm_epilogue_store(p, C, bias, m, n, acc[i][j], bz * p.sC);
     }
   }
 }

@@ -395,7 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           if (g.C_pre) {
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-              if (u < cnt) g.C_pre[gemm_c_offset(g, m0 + u) + n] = t[u];
+              if (u < cnt) g.C_pre[(int64_t)bz * g.sC + gemm_c_offset(g, m0 + u) + n] = t[u];
           }
           if (ACT_MODE == 1) {
 #pragma unroll
@@ -407,7 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           if (g.dact_src) {
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-              if (u < cnt) t[u] *= act_grad(g.dact_src[(int64_t)(m0 + u) * g.ldc + n], g.dact);
+              if (u < cnt) t[u] *= act_grad(g.dact_src[(int64_t)bz * g.sC + (int64_t)(m0 + u) * g.ldc + n], g.dact);
           }
           if (g.c_scale) {
 #pragma unroll
