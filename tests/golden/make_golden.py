@@ -178,9 +178,49 @@ def gen_loss_and_grads():
     print("grads ok, loss", loss.item())
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--traj" not in sys.argv:
     for name in CASES:
         gen_forward(name)
     gen_afno()
     gen_adam()
     gen_loss_and_grads()
+
+
+def gen_train_trajectory():
+    """3 optimizer steps of the loop of train_temporal.py:189-230 (noise_scale=0, Adam(betas=(0.9,0.9), wd=1e-6),
+    clip_grad_norm_(1e4), OneCycle-like lr changes) on the tiny_trunc config: losses and final weights."""
+    cfg, B, kind, nsteps = CASES["tiny_trunc"]
+    params = O.make_params(cfg, seed=0)
+    m = ref_model(cfg, params).train()
+    opt = Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.9), weight_decay=1e-6)
+    myloss = SimpleLpLoss(size_average=False)
+    rng = np.random.default_rng(11)
+    Tb = cfg["out_timesteps"]
+    losses, lrs = [], [1e-3, 2e-3, 5e-4]
+    xs, ys = [], []
+    msk = torch.ones((B, cfg["img_size"], cfg["img_size"], 1, cfg["out_channels"]))
+    for it in range(3):
+        x = rng.standard_normal((B, cfg["img_size"], cfg["img_size"], cfg["in_timesteps"], cfg["in_channels"])).astype(np.float32)
+        yy = rng.standard_normal((B, cfg["img_size"], cfg["img_size"], nsteps, cfg["out_channels"])).astype(np.float32)
+        xs.append(x); ys.append(yy)
+        xx, yt = torch.from_numpy(x), torch.from_numpy(yy)
+        loss = 0.0
+        for t in range(0, nsteps, Tb):
+            im, _ = m(xx)
+            loss = loss + myloss(im, yt[..., t:t + Tb, :], mask=msk)
+            xx = torch.cat((xx[..., Tb:, :], im), dim=-2)
+        opt.param_groups[0]["lr"] = lrs[it]
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 10000.0)
+        opt.step()
+        losses.append(loss.item())
+    out = dict(cfg=json.dumps(cfg), B=B, losses=np.array(losses, np.float32), lrs=np.array(lrs), xs=np.stack(xs), ys=np.stack(ys))
+    for k, v in m.state_dict().items():
+        out["final." + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "train_traj_tiny.npz"), **out)
+    print("trajectory ok", losses)
+
+
+if __name__ == "__main__" and "--traj" in sys.argv:
+    gen_train_trajectory()
