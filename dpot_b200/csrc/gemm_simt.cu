@@ -33,6 +33,14 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
 
   // register staging for the next slab
   float ra[8], rw[4];
+  int64_t prow[8];     // im2col: field offset of (row, k=0) for the 8 rows this thread stages; -1 = out of range
+  if (!VEC && p.a_mode == DPOT_A_PATCH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = m0 + tid / BK + j * (NT / BK);
+      prow[j] = (m < p.M) ? patch_offset(p, m, 0) : -1;
+    }
+  }
 
   auto load_slab = [&](int k0) {
     if (VEC) {
@@ -60,6 +68,28 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n < p.N && k < p.K) v = *reinterpret_cast<const float4*>(W + (int64_t)n * p.ldw + k);
         rw[0] = v.x; rw[1] = v.y; rw[2] = v.z; rw[3] = v.w;
+      }
+    } else if (p.a_mode == DPOT_A_PATCH) {
+      // im2col: the 8 rows of this thread are fixed (row bases precomputed), only k moves with the slab
+      const int k = k0 + (tid % BK);
+      if (k < p.K) {
+        const int c = k % p.pC, uv = k / p.pC;
+        const int64_t koff = (((int64_t)(uv / p.pP) * p.pY + (uv % p.pP)) * p.pT) * p.pC + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = 0.f;
+          if (prow[j] >= 0) {
+            v = A[prow[j] + koff];
+            if (p.a_scale) {
+              const int64_t o = (int64_t)((m0 + tid / BK + j * (NT / BK)) / p.a_rps) * p.K + k;
+              v = fmaf(v, p.a_scale[o], p.a_shift[o]);
+            }
+          }
+          ra[j] = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ra[j] = 0.f;
       }
     } else {
 #pragma unroll
