@@ -88,6 +88,7 @@ SIGNATURES = {
     "dpot_launch_count": (C.c_longlong, []),
     "dpot_tc_available": (C.c_int, []),
     "dpot_tc_set_flush": (C.c_int, [C.c_int]),
+    "dpot_tc_set_trunc": (C.c_int, [C.c_int]),
     "dpot_tc_set_trace": (None, [C.c_void_p]),
     "dpot_gemm": (C.c_int, [C.POINTER(GemmArgs), _p]),
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),

@@ -69,16 +69,17 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
         if (n < p.N && k < p.K) v = *reinterpret_cast<const float4*>(W + (int64_t)n * p.ldw + k);
         rw[0] = v.x; rw[1] = v.y; rw[2] = v.z; rw[3] = v.w;
       }
-    } else if (p.a_mode == DPOT_A_PATCH) {
-      // im2col: the 8 rows of this thread are fixed (row bases precomputed), only k moves with the slab
-      const int k = k0 + (tid % BK);
-      if (k < p.K) {
+    } else {
+      if (p.a_mode == DPOT_A_PATCH) {
+        // im2col: the 8 rows of this thread are fixed (row bases precomputed), only k moves with the slab
+        const int k = k0 + (tid % BK);
+        const bool kin = k < p.K;
         const int c = k % p.pC, uv = k / p.pC;
         const int64_t koff = (((int64_t)(uv / p.pP) * p.pY + (uv % p.pP)) * p.pT) * p.pC + c;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = 0.f;
-          if (prow[j] >= 0) {
+          if (kin && prow[j] >= 0) {
             v = A[prow[j] + koff];
             if (p.a_scale) {
               const int64_t o = (int64_t)((m0 + tid / BK + j * (NT / BK)) / p.a_rps) * p.K + k;
@@ -89,14 +90,11 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ra[j] = 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = tid + j * NT;
-        const int row = idx / BK, kk = idx % BK;
-        ra[j] = gemm_load_a(p, A, m0 + row, k0 + kk);
+        for (int j = 0; j < 8; ++j) {
+          const int idx = tid + j * NT;
+          const int row = idx / BK, kk = idx % BK;
+          ra[j] = gemm_load_a(p, A, m0 + row, k0 + kk);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

@@ -152,12 +152,15 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 struct TcParams {
   GemmDev g;
   int BA;            // activation rows per tile (UMMA N), multiple of 16, <= 256
   int n_tiles, m_tiles, total_tiles, kblocks;
   int flush;         // k-blocks accumulated inside TMEM before the partial sum is flushed to registers
   long long* trace;  // optional clock64() event log of CTA 0 (debug / profiling), NULL = off
+  int trunc;         // 1: hi = hardware truncation of the raw tile (no hi store), 0: explicit round-to-nearest hi
 };
 
 constexpr int TRACE_SLOTS = 64;    // events per role
@@ -168,7 +171,9 @@ __device__ __forceinline__ void trace_ev(const TcParams& P, int role, int& idx) 
 // Split one 128 B operand row (8 swizzled 16 B chunks) into hi (in place) and lo (twin tile).
 // All 8 loads are issued before the first use; chunk order is rotated by lane so that a
 // quarter-warp touches 8 distinct 16 B bank groups (row pitch is 128 B).
-template <bool AFFINE>
+// TRUNC: the UMMA ignores the low 13 mantissa bits of an fp32 container read as TF32, so the raw tile already
+// IS the hi operand (hi = trunc(x)); only lo = x - trunc(x) is written (halves the converter's smem stores).
+template <bool AFFINE, bool TRUNC>
 __device__ __forceinline__ void split_row(uint32_t row_hi, uint32_t lo_delta, int lane, uint32_t rsw,
                                           const float* __restrict__ sc, const float* __restrict__ sh) {
   float4 v[8];
@@ -185,9 +190,14 @@ __device__ __forceinline__ void split_row(uint32_t row_hi, uint32_t lo_delta, in
       x.x = fmaf(x.x, s.x, h.x); x.y = fmaf(x.y, s.y, h.y); x.z = fmaf(x.z, s.z, h.z); x.w = fmaf(x.w, s.w, h.w);
     }
     float4 hi, lo;
-    hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+    if (TRUNC) {
+      hi.x = tf32_trunc(x.x); hi.y = tf32_trunc(x.y); hi.z = tf32_trunc(x.z); hi.w = tf32_trunc(x.w);
+    } else {
+      hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+    }
     lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
-    sts128(row_hi + (cp << 4), hi);
+    if (!TRUNC) sts128(row_hi + (cp << 4), hi);
+    else if (AFFINE) sts128(row_hi + (cp << 4), x);      // the transformed value must replace the raw one
     sts128(row_hi + lo_delta + (cp << 4), lo);
   }
 }
@@ -299,7 +309,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         mbar_wait(BAR(0, s), ph);
         if (ct == 0) trace_ev(P, 2, tr);
         const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
-        split_row<false>(sb + OFF_P_HI + (uint32_t)ct * 128u, P_BYTES, lane, 0, nullptr, nullptr);   // weight row ct
+        if (P.trunc) split_row<false, true>(sb + OFF_P_HI + (uint32_t)ct * 128u, P_BYTES, lane, 0, nullptr, nullptr);
+        else split_row<false, false>(sb + OFF_P_HI + (uint32_t)ct * 128u, P_BYTES, lane, 0, nullptr, nullptr);   // weight row ct
 #pragma unroll
         for (int half = 0; half < 2; ++half) {                                                        // token rows
           const int r = ct + half * 128;
@@ -308,9 +319,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             const int m = m0 + r;
             if (affine && m < g.M) {
               const int64_t tbl = (int64_t)(m / g.a_rps) * g.K + (int64_t)kb * BK;
-              split_row<true>(row, Q_BYTES, lane, (uint32_t)r & 7u, g.a_scale + tbl, g.a_shift + tbl);
+              if (P.trunc) split_row<true, true>(row, Q_BYTES, lane, (uint32_t)r & 7u, g.a_scale + tbl, g.a_shift + tbl);
+              else split_row<true, false>(row, Q_BYTES, lane, (uint32_t)r & 7u, g.a_scale + tbl, g.a_shift + tbl);
             } else {
-              split_row<false>(row, Q_BYTES, lane, 0, nullptr, nullptr);
+              if (P.trunc) split_row<false, true>(row, Q_BYTES, lane, 0, nullptr, nullptr);
+              else split_row<false, false>(row, Q_BYTES, lane, 0, nullptr, nullptr);
             }
           }
         }
@@ -499,6 +512,7 @@ bool device_ok() {
 }
 
 int g_flush = 2;
+int g_trunc = 0;
 long long* g_trace = nullptr;   // k-blocks (of 32) per in-TMEM accumulation chain; tunable for experiments
 
 }  // namespace
@@ -534,6 +548,7 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
   P.kblocks = p.K / BK;
   P.flush = g_flush < 1 ? 1 : g_flush;
   P.trace = g_trace;
+  P.trunc = g_trunc;
 
   alignas(64) CUtensorMap mapW, mapA;
   const uint64_t sWb = batch > 1 ? (uint64_t)p.sW * 4 : (uint64_t)p.ldw * 4 * (uint64_t)p.N;
@@ -570,6 +585,12 @@ extern "C" int dpot_tc_available(void) { return (dpot::device_ok() && dpot::get_
 // experiment knob: k-blocks (32 fp32 each) accumulated in TMEM between register flushes (default 4)
 // debug: device buffer of 7*64 int64 receiving clock64() events of CTA 0 (NULL disables)
 extern "C" void dpot_tc_set_trace(long long* dev_buf) { dpot::g_trace = dev_buf; }
+// experiment knob: 1 = rely on the hardware's TF32 truncation for the hi operand (see split_row)
+extern "C" int dpot_tc_set_trunc(int on) {
+  const int old = dpot::g_trunc;
+  if (on >= 0) dpot::g_trunc = on ? 1 : 0;
+  return old;
+}
 extern "C" int dpot_tc_set_flush(int kblocks) {
   const int old = dpot::g_flush;
   if (kblocks >= 1) dpot::g_flush = kblocks;

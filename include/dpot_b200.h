@@ -61,6 +61,9 @@ DPOT_API int         dpot_tc_available(void);
 /* tuning knob of the tcgen05 engine: k-blocks (32 fp32) accumulated in TMEM between round-to-nearest
    flushes into the register accumulators (default 2); returns the previous value, <1 only queries */
 DPOT_API int         dpot_tc_set_flush(int kblocks);
+/* tuning knob: 1 = the hi operand is the hardware truncation of the raw fp32 tile (converter writes only lo),
+   0 = explicit round-to-nearest hi; returns the previous value, <0 only queries */
+DPOT_API int         dpot_tc_set_trunc(int on);
 /* profiling aid: device buffer of 7*64 int64 that receives clock64() pipeline events of CTA 0 of the
    tcgen05 engine (rows: producer, mma, conv-start, conv-done, flush, tile-acc-done, tile-epilogue-done) */
 DPOT_API void        dpot_tc_set_trace(long long* dev_buf);

@@ -112,7 +112,19 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"(f) flush={fl:2d}: rel={err:.3e}  {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")
-    lib.dpot_tc_set_flush(4)
+    lib.dpot_tc_set_flush(2)
+    for tr in (0, 1):
+        lib.dpot_tc_set_trunc(tr)
+        ops.gemm(At, Wtt, out=Ct, engine=2); torch.cuda.synchronize()
+        err = rel(Ct.cpu().numpy(), reff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(10):
+            ops.gemm(At, Wtt, out=Ct, engine=2)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"(g) trunc={tr}: rel={err:.3e}  {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")
+    lib.dpot_tc_set_trunc(0)
     # batched AFNO timing
     St = t(S); Wt = t(Wc); bt = t(bc)
     for eng in (1, 2):
