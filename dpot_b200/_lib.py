@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdpot_b200.so")
 
 ACT_IDS = {"gelu": 0, "tanh": 1, "sigmoid": 2, "relu": 3, "leaky_relu": 4, "softplus": 5, "ELU": 6, "silu": 7}
 ACT_NONE = -1
-GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TC16 = 0, 1, 2, 3
+FMT_F32, FMT_HL16 = 0, 1
 A_PLAIN, A_PATCH = 0, 1
 
 c_f32p = C.c_void_p  # device pointers travel as integers
@@ -39,6 +40,8 @@ class GemmArgs(C.Structure):
         ("engine", C.c_int32),
         ("out_stats", c_f32p), ("stats_groups", C.c_int32), ("stats_rows_per_sample", C.c_int32),
         ("C_pre", c_f32p), ("dact_src", c_f32p), ("dact", C.c_int32), ("c_mode", C.c_int32),
+        ("a_fmt", C.c_int32), ("w_fmt", C.c_int32), ("c_fmt", C.c_int32),
+        ("a_lo_off", C.c_int64), ("w_lo_off", C.c_int64), ("c_lo_off", C.c_int64),
     ]
 
 
@@ -91,6 +94,8 @@ SIGNATURES = {
     "dpot_tc_set_trunc": (C.c_int, [C.c_int]),
     "dpot_tc_set_trace": (None, [C.c_void_p]),
     "dpot_gemm": (C.c_int, [C.POINTER(GemmArgs), _p]),
+    "dpot_split_f16": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _i64, _i64, _p]),
+    "dpot_tc16_available": (C.c_int, []),
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_gn_finalize": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p]),
     "dpot_afno_fft_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p]),

@@ -31,6 +31,13 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   p.ph = p.pw = 0;
   if (a->a_mode == DPOT_A_PATCH) { p.ph = a->pX / (a->pP > 0 ? a->pP : 1); p.pw = a->pY / (a->pP > 0 ? a->pP : 1); }
   p.C_pre = a->C_pre; p.dact_src = a->dact_src; p.dact = a->dact; p.c_mode = a->c_mode;
+  p.a_fmt = a->a_fmt; p.w_fmt = a->w_fmt; p.c_fmt = a->c_fmt; p.a_lo = a->a_lo_off; p.w_lo = a->w_lo_off; p.c_lo = a->c_lo_off;
+  DPOT_REQUIRE((a->a_fmt == DPOT_FMT_F32 || a->a_fmt == DPOT_FMT_HL16) && a->a_fmt == a->w_fmt, DPOT_E_BADARG,
+               "dpot_gemm: a_fmt and w_fmt must both be F32 or both HL16");
+  DPOT_REQUIRE(a->c_fmt == DPOT_FMT_F32 || a->c_fmt == DPOT_FMT_HL16, DPOT_E_BADARG, "dpot_gemm: bad c_fmt");
+  if (a->c_fmt == DPOT_FMT_HL16)
+    DPOT_REQUIRE(!a->C_pre && !a->dact_src && a->c_mode == DPOT_A_PLAIN && !a->out_stats && a->c_lo_off > 0, DPOT_E_BADARG,
+                 "dpot_gemm: split-fp16 output excludes C_pre/dact_src/patch scatter/out_stats");
   if (a->c_mode == DPOT_A_PATCH) {
     DPOT_REQUIRE(a->a_mode == DPOT_A_PLAIN && a->pP > 0 && a->pX % a->pP == 0 && a->pY % a->pP == 0 &&
                  a->N == a->pP * a->pP * a->pC && a->batch == 1 && !a->C_pre && !a->dact_src && !a->residual,
@@ -53,8 +60,29 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   }
   cudaStream_t st = as_stream(stream);
   int engine = a->engine;
-  if (engine == DPOT_GEMM_AUTO) engine = gemm_tc_supports(p, a->batch) ? DPOT_GEMM_TC : DPOT_GEMM_SIMT;
   const int B = a->out_stats ? a->M / a->stats_rows_per_sample : 0;
+  if (a->a_fmt == DPOT_FMT_HL16) {   // split-fp16 operands: only the f16 tensor-core engine reads them
+    DPOT_REQUIRE(engine == DPOT_GEMM_AUTO || engine == DPOT_GEMM_TC16, DPOT_E_BADARG,
+                 "dpot_gemm: split-fp16 operands need the TC16 engine");
+    DPOT_REQUIRE(gemm_tc16_supports(p, a->batch), DPOT_E_UNSUPPORTED,
+                 "dpot_gemm: f16-split tcgen05 engine does not take this problem (M=%d N=%d K=%d)", a->M, a->N, a->K);
+    if (a->out_stats && gemm_tc16_fuses_stats(p)) {
+      DPOT_CUDA(cudaMemsetAsync(a->out_stats, 0, sizeof(double) * 2 * (size_t)B * a->stats_groups, st));
+      p.out_stats = a->out_stats;
+      return gemm_tc16_launch(p, a->batch, st);
+    }
+    DPOT_CALL(gemm_tc16_launch(p, a->batch, st));
+    if (a->out_stats)
+      return dpot_gn_stats(a->C, B, a->stats_rows_per_sample, a->N, a->stats_groups, a->out_stats, stream);
+    return 0;
+  }
+  DPOT_REQUIRE(engine != DPOT_GEMM_TC16, DPOT_E_BADARG, "dpot_gemm: the TC16 engine needs split-fp16 operands");
+  if (a->c_fmt == DPOT_FMT_HL16) {
+    DPOT_REQUIRE(engine != DPOT_GEMM_TC && a->batch == 1, DPOT_E_UNSUPPORTED,
+                 "dpot_gemm: split-fp16 output from fp32 operands is served by the SIMT engine, batch 1");
+    engine = DPOT_GEMM_SIMT;
+  }
+  if (engine == DPOT_GEMM_AUTO) engine = gemm_tc_supports(p, a->batch) ? DPOT_GEMM_TC : DPOT_GEMM_SIMT;
   if (engine == DPOT_GEMM_TC) {
     DPOT_REQUIRE(gemm_tc_supports(p, a->batch), DPOT_E_UNSUPPORTED,
                  "dpot_gemm: tcgen05 engine does not take this problem (M=%d N=%d K=%d)", a->M, a->N, a->K);

@@ -1,6 +1,7 @@
 // Device-side view of dpot_gemm_args and the A-prologue / C-epilogue shared by both engines.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace dpot {
 
@@ -20,7 +21,15 @@ struct GemmDev {
   int a_mode, pX, pY, pT, pC, pP, ph, pw;
   double* out_stats; int st_groups, st_rps;   // fused GroupNorm statistics (tcgen05 engine only)
   float* C_pre; const float* dact_src; int dact; int c_mode;   // training extras
+  int a_fmt, w_fmt, c_fmt; int64_t a_lo, w_lo, c_lo;           // DPOT_FMT_* storage (strides in halves when HL16)
 };
+
+// split fp16 storage (include/dpot_b200.h, DPOT_FMT_HL16): x ~= hi + lo / 2048
+constexpr float HL_SCALE = 2048.0f, HL_INV = 1.0f / 2048.0f;
+__device__ __forceinline__ void hl_split(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * HL_SCALE);
+}
 
 // im2col address of PatchEmbed conv0 (models/dpot.py:199,375): row m = (b,p,q,t), k = (u,v,c)
 __device__ __forceinline__ int64_t patch_offset(const GemmDev& p, int m, int k) {
@@ -67,7 +76,13 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmDev& p, float* __r
                                                     const float* __restrict__ bias, int m, int n, float v,
                                                     int64_t boff = 0) {
   const float r = gemm_epilogue_value(p, bias, m, n, v, boff);
-  if (p.c_mode == DPOT_A_PATCH) C[patch_offset(p, m, n)] = r;
+  if (p.c_fmt == DPOT_FMT_HL16) {
+    __half* Ch = reinterpret_cast<__half*>(C) + gemm_c_offset(p, m) + n;
+    __half hi, lo;
+    hl_split(r, hi, lo);
+    Ch[0] = hi;
+    Ch[p.c_lo] = lo;
+  } else if (p.c_mode == DPOT_A_PATCH) C[patch_offset(p, m, n)] = r;
   else C[gemm_c_offset(p, m) + n] = r;
 }
 
@@ -75,5 +90,12 @@ int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st);
 int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st);   // tcgen05 engine
 bool gemm_tc_supports(const GemmDev& p, int batch);
 bool gemm_tc_fuses_stats(const GemmDev& p);   // can the TC epilogue accumulate out_stats itself?
+// f16-split tcgen05 engine (gemm_tc16.cu)
+int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st);
+bool gemm_tc16_supports(const GemmDev& p, int batch);
+bool gemm_tc16_fuses_stats(const GemmDev& p);
+bool tc_device_ok();
+int tc_encode_map_f16(void* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                      uint32_t b0, uint32_t b1, uint32_t b2);
 
 }  // namespace dpot

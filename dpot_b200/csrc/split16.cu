@@ -1,0 +1,60 @@
+// fp32 -> split fp16 (DPOT_FMT_HL16, include/dpot_b200.h) with an optional per-(sample, column) affine:
+// weight packing for the f16-split tensor-core engine, and GroupNorm-apply fused with the split of
+// the channel-MLP input (models/dpot.py:175-176).
+#include "common.cuh"
+#include "gemm_common.cuh"
+
+namespace dpot {
+namespace {
+
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols8,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        int rps, __half* __restrict__ dst, int64_t ldd, int64_t lo_off) {
+  const int64_t total = rows * cols8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols8;
+    const int c = (int)(i % cols8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src + r * lds + c);
+    const float4 b = *reinterpret_cast<const float4*>(src + r * lds + c + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (scale) {
+      const int64_t o = (r / rps) * (int64_t)(cols8 * 8) + c;
+      const float4 s0 = *reinterpret_cast<const float4*>(scale + o), s1 = *reinterpret_cast<const float4*>(scale + o + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(shift + o), h1 = *reinterpret_cast<const float4*>(shift + o + 4);
+      const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = fmaf(v[u], s[u], h[u]);
+    }
+    alignas(16) __half hi[8];
+    alignas(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) hl_split(v[u], hi[u], lo[u]);
+    *reinterpret_cast<uint4*>(dst + r * ldd + c) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + r * ldd + c + lo_off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+}  // namespace
+}  // namespace dpot
+
+using namespace dpot;
+
+extern "C" int dpot_split_f16(const float* src, int64_t lds, int64_t rows, int32_t cols, const float* scale,
+                              const float* shift, int32_t rows_per_sample, void* dst, int64_t ldd, int64_t lo_off,
+                              void* stream) {
+  DPOT_REQUIRE(src && dst && rows >= 0 && cols > 0, DPOT_E_BADARG, "dpot_split_f16: null pointer / bad shape");
+  DPOT_REQUIRE(cols % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0 && lo_off % 8 == 0, DPOT_E_ALIGN,
+               "dpot_split_f16: cols, ldd, lo_off must be multiples of 8 (lds of 4)");
+  DPOT_REQUIRE((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0, DPOT_E_ALIGN,
+               "dpot_split_f16: pointers must be 16-byte aligned");
+  DPOT_REQUIRE((scale == nullptr) == (shift == nullptr) && (!scale || rows_per_sample > 0), DPOT_E_BADARG,
+               "dpot_split_f16: scale/shift come together with rows_per_sample");
+  if (rows == 0) return 0;
+  const int64_t total = rows * (cols / 8);
+  const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
+  split_f16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, lds, rows, cols / 8, scale, shift, rows_per_sample,
+                                                        reinterpret_cast<__half*>(dst), ldd, lo_off);
+  DPOT_LAUNCH_CHECK("split_f16_kernel");
+  return 0;
+}

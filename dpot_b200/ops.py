@@ -63,6 +63,58 @@ def gemm(A: torch.Tensor, W: torch.Tensor, *, bias=None, act=None, residual=None
     return out
 
 
+def split_f16(x: torch.Tensor, scale=None, shift=None, rows_per_sample: int = 0) -> torch.Tensor:
+    """fp32 [M,K] -> split fp16 [M, 2K] (DPOT_FMT_HL16: columns [0,K) = hi, [K,2K) = lo * 2048)."""
+    _need_cuda(x, scale, shift)
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, K = x.shape
+    out = torch.empty((M, 2 * K), device=x.device, dtype=torch.float16)
+    check(_lib.load().dpot_split_f16(ptr(x), x.stride(0), M, K, ptr(scale), ptr(shift), rows_per_sample, ptr(out),
+                                     2 * K, K, _stream()), "dpot_split_f16")
+    return out
+
+
+def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residual=None, rowbias=None, c_scale=None,
+           c_shift=None, c_rows_per_sample=0, out16: bool = False, nb: int = 1) -> torch.Tensor:
+    """The f16-split tcgen05 engine on pre-split operands A16[M, 2*Kt], W16[nb*N, 2*K] (see split_f16).
+    nb > 1: block-diagonal form, A16 hi plane [M, nb*K], W16 [nb, N, 2K], bias [nb, N] -> C[M, nb*N]."""
+    _need_cuda(bias, residual, rowbias, c_scale, c_shift)
+    assert A16.dtype == torch.float16 and W16.dtype == torch.float16 and A16.is_cuda and W16.is_cuda
+    M, Kt = A16.shape[0], A16.shape[1] // 2
+    K = W16.shape[-1] // 2
+    N = W16.shape[-2] if nb > 1 else W16.shape[0]
+    assert Kt == nb * K
+    Nt = nb * N
+    g = GemmArgs()
+    if out16:
+        out = torch.empty((M, 2 * Nt), device=A16.device, dtype=torch.float16)
+        g.C, g.ldc, g.c_fmt, g.c_lo_off = ptr(out), 2 * Nt, _lib.FMT_HL16, Nt
+    else:
+        out = torch.empty((M, Nt), device=A16.device, dtype=torch.float32)
+        g.C, g.ldc = ptr(out), Nt
+    g.A, g.lda, g.a_fmt, g.a_lo_off = ptr(A16), 2 * Kt, _lib.FMT_HL16, Kt
+    g.W, g.ldw, g.w_fmt, g.w_lo_off = ptr(W16), 2 * K, _lib.FMT_HL16, K
+    g.M, g.N, g.K = M, N, K
+    g.bias, g.act = ptr(bias), act_id(act)
+    if rowbias is not None:
+        g.rowbias, g.rowbias_period, g.ldrb = ptr(rowbias), rowbias.shape[0], rowbias.stride(0)
+    if residual is not None:
+        g.residual, g.ldr = ptr(residual), residual.stride(0)
+    if c_scale is not None:
+        g.c_scale, g.c_shift, g.c_rows_per_sample = ptr(c_scale), ptr(c_shift), c_rows_per_sample
+    g.batch, g.engine, g.a_mode = nb, _lib.GEMM_TC16, _lib.A_PLAIN
+    if nb > 1:
+        g.strideA, g.strideW, g.strideC, g.strideBias = K, N * 2 * K, N, N
+    check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(tc16)")
+    return out
+
+
+def unsplit_f16(x16: torch.Tensor) -> torch.Tensor:
+    """Inverse of split_f16 (test helper: plain torch arithmetic on the stored halves)."""
+    K = x16.shape[1] // 2
+    return x16[:, :K].float() + x16[:, K:].float() / 2048.0
+
+
 def gemm_batched_cols(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, nb: int, *, act=None,
                       out: Optional[torch.Tensor] = None, engine: int = GEMM_AUTO) -> torch.Tensor:
     """Block-diagonal GEMM of the AFNO spectral MLP: A[M, nb*k], W[nb, n, k], bias[nb, n] -> C[M, nb*n]."""

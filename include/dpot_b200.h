@@ -48,7 +48,17 @@ enum {
 };
 
 /* GEMM engines */
-enum { DPOT_GEMM_AUTO = 0, DPOT_GEMM_SIMT = 1, DPOT_GEMM_TC = 2 };
+enum { DPOT_GEMM_AUTO = 0, DPOT_GEMM_SIMT = 1, DPOT_GEMM_TC = 2, DPOT_GEMM_TC16 = 3 };
+
+/* Operand storage formats.  DPOT_FMT_HL16 ("split fp16") stores an fp32 value x as two halves
+ *   hi = fp16_rn(x),  lo = fp16_rn((x - hi) * 2048)        (x ~= hi + lo / 2048 to ~2^-22 relative)
+ * in the SAME 4 bytes per element as fp32: element (r, k) of a matrix has hi at half-index
+ * r*ld + k and lo at r*ld + k + lo_off (ld, lo_off and batch strides counted in halves).  It is
+ * the native operand format of the DPOT_GEMM_TC16 engine (tcgen05 kind::f16, 3 MMAs per product:
+ * hi*hi into one TMEM accumulator, hi*lo + lo*hi into a second one scaled by 2^-11), written
+ * directly by the kernels that produce activations, so the GEMM needs no conversion pass.
+ * Range: |x| <= 65504 (fp16); larger magnitudes become inf/NaN (loud, never silent). */
+enum { DPOT_FMT_F32 = 0, DPOT_FMT_HL16 = 1 };
 
 DPOT_API int         dpot_abi_version(void);
 DPOT_API const char* dpot_last_error_string(void);
@@ -115,9 +125,25 @@ typedef struct dpot_gemm_args {
   float* C_pre;
   const float* dact_src; int32_t dact;
   int32_t c_mode;
+  /* storage formats (DPOT_FMT_*).  a_fmt/w_fmt = HL16 select the DPOT_GEMM_TC16 engine (both must be
+     HL16; then A/W point to halves and lda/ldw/strideA/strideW/*_lo_off are in halves).  c_fmt = HL16
+     makes the epilogue store the result in split form (ldc/strideC/c_group_stride/c_lo_off in halves);
+     supported by the SIMT and TC16 engines.  out_stats, C_pre, dact_src, c_mode=PATCH need c_fmt = F32
+     except out_stats on TC16. */
+  int32_t a_fmt, w_fmt, c_fmt;
+  int64_t a_lo_off, w_lo_off, c_lo_off;
 } dpot_gemm_args;
 
 DPOT_API int dpot_gemm(const dpot_gemm_args* args, void* stream);
+
+/* fp32 [rows, cols] (leading dimension lds floats) -> split fp16 (DPOT_FMT_HL16): dst half-index
+   r*ldd + c (hi) and r*ldd + c + lo_off (lo).  Optional per-(sample, column) affine applied first:
+   x' = x*scale[s, c] + shift[s, c], s = r / rows_per_sample (GroupNorm-apply fused into the split;
+   models/dpot.py:175).  cols must be a multiple of 8, pointers 16-byte aligned. */
+DPOT_API int dpot_split_f16(const float* src, int64_t lds, int64_t rows, int32_t cols, const float* scale,
+                   const float* shift, int32_t rows_per_sample, void* dst, int64_t ldd, int64_t lo_off, void* stream);
+/* 1 if the f16-split tcgen05 engine can serve this device */
+DPOT_API int dpot_tc16_available(void);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm pieces (torch.nn.GroupNorm(8,E), models/dpot.py:142,152,167,175).

@@ -310,3 +310,51 @@ def test_training_trajectory_matches_reference():
         err = np.abs(v.cpu().numpy() - ref).max()
         # Adam moves every weight by ~lr per step; agreement is limited by sign-level noise on tiny gradients
         assert err < 2e-4 * max(1.0, np.abs(ref).max()), (k, err)
+
+
+@pytest.mark.parametrize("shape", [(256, 128, 64), (300, 200, 96), (144, 256, 256), (1024, 512, 1024), (8192, 1024, 352),
+                                   (40, 24, 8), (4608, 256, 256)])
+@pytest.mark.parametrize("out16", [False, True])
+def test_tc16_engine_matches_fp64(shape, out16):
+    """f16-split tcgen05 engine (3 fp16 MMAs per product, two TMEM accumulators) sits at fp32-level error."""
+    from dpot_b200 import _lib, ops
+    if not _lib.load().dpot_tc16_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).cuda()
+    A16, W16 = ops.split_f16(t(A)), ops.split_f16(t(W))
+    assert O.rel_l2(ops.unsplit_f16(A16).cpu().numpy(), A) < 2e-7
+    out = ops.gemm16(A16, W16, bias=t(b), act="gelu", residual=t(R), out16=out16)
+    if out16:
+        out = ops.unsplit_f16(out)
+    ref = O.activation(A.astype(np.float64) @ W.T.astype(np.float64) + b, "gelu") + R
+    assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
+
+
+def test_tc16_engine_small_magnitudes_and_batched():
+    """Scale robustness (lo halves are pre-scaled by 2^11: no fp16-subnormal loss) and the block-diagonal form."""
+    from dpot_b200 import _lib, ops
+    if not _lib.load().dpot_tc16_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    rng = np.random.default_rng(5)
+    t = lambda x: torch.from_numpy(x).cuda()
+    for sa, sw in [(1e-3, 3e-5), (30.0, 1.0), (1.0, 1.0)]:
+        A = (sa * rng.standard_normal((512, 256))).astype(np.float32)
+        W = (sw * rng.standard_normal((128, 256))).astype(np.float32)
+        out = ops.gemm16(ops.split_f16(t(A)), ops.split_f16(t(W)))
+        ref = A.astype(np.float64) @ W.T.astype(np.float64)
+        assert O.rel_l2(out.cpu().numpy(), ref) < 1e-6, (sa, sw)
+    nb, M, N, K = 4, 288, 64, 64
+    A = rng.standard_normal((M, nb * K)).astype(np.float32)
+    W = (rng.standard_normal((nb, N, K)) / 8).astype(np.float32)
+    b = rng.standard_normal((nb, N)).astype(np.float32)
+    W16 = ops.split_f16(t(W.reshape(nb * N, K))).reshape(nb, N, 2 * K)
+    out = ops.gemm16(ops.split_f16(t(A)), W16, bias=t(b), act="gelu", nb=nb)
+    ref = np.concatenate([O.activation(A[:, i * K:(i + 1) * K].astype(np.float64) @ W[i].T.astype(np.float64) + b[i], "gelu")
+                          for i in range(nb)], axis=1)
+    assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
