@@ -99,6 +99,7 @@ SIGNATURES = {
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_gn_finalize": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p]),
     "dpot_afno_fft_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p]),
+    "dpot_afno_fft_fwd16": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _p]),
     "dpot_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),
     "dpot_colsum": (C.c_int, [_p, _i64, _i32, _i32, _p, _i32, _p]),
@@ -116,12 +117,15 @@ SIGNATURES = {
     "dpot_spatial_mean": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "dpot_input_stats": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p]),
     "dpot_window_advance": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dpot_ring_insert": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dpot_patch_embed": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
     "dpot_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _d, _i32, _i32, _d, _p]),
     "dpot_adam_step_multi": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _p, _i32, _d, _p]),
     "dpot_packed_floats": (C.c_int64, [C.POINTER(Config)]),
     "dpot_workspace_floats": (C.c_int64, [C.POINTER(Config), _i32]),
     "dpot_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p]),
     "dpot_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _p, _p, _p, _i32, _p]),
+    "dpot_forward_ring": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _i32, _p, _p, _p, _i32, _p]),
 }
 
 _lib = None

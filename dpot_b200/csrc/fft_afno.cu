@@ -9,6 +9,7 @@
 // batch dimension (channels) is the SIMD dimension.  Two real rows are packed into one complex
 // transform (z = row_a + i row_b), halving the row-FFT work in both directions.
 #include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace dpot {
 namespace {
@@ -79,14 +80,22 @@ struct Cfg {
 };
 
 // ------------------------------------------------------------------------------------------
-template <int H>
+// Both kernels pack the DC and Nyquist columns (k2 = 0 and H/2) into ONE complex transform along k1: after
+// the real row transform those two columns are real, and before the c2r only the real part of their
+// k1-inverse is used (torch.fft.irfft2 ignores Im there), i.e. only the Hermitian part of the column.
+// That makes H/2 column transforms and H/2 row-pair transforms per channel: with NT / CH = H/2 concurrent
+// tasks (H = 16, 32) every thread owns exactly one transform per phase, and every global access is issued
+// as a batch of independent coalesced 128 B lines (lanes = channels) straight from / to registers.
+//
+// OUT16: the spectrum is stored as split fp16 (DPOT_FMT_HL16; row = [hi 2E | lo 2E] halves), the operand format
+// of the f16-split tensor-core engine that consumes it.
+template <int H, bool OUT16>
 __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restrict__ a, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int E, int bs, int km1,
                                                           int km2, float* __restrict__ S, float wint) {
-  constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, KH = Cfg<H>::KH, n = H * H;
+  constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, HC = (H >= 2) ? H / 2 : 1, n = H * H;
   extern __shared__ __align__(16) float smem[];
-  float* T_s = smem;                                        // [n][CH]
-  float2* R_s = reinterpret_cast<float2*>(smem + n * CH);    // [H][KH][CH]
+  float2* R_s = reinterpret_cast<float2*>(smem);             // [H][HC][CH]; column 0 = (DC, Nyquist) real pair
 
   const int tid = threadIdx.x, c = tid % CH, task0 = tid / CH;
   const int b = blockIdx.y, ch = blockIdx.x * CH + c;
@@ -94,52 +103,76 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
   const float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
   const float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
 
-  // phase 1: GroupNorm-1 applied on load
-  const float* ap = a + (int64_t)b * n * E + ch;
-  for (int pos = task0; pos < n; pos += NTASK) T_s[pos * CH + c] = live ? fmaf(ap[(int64_t)pos * E], sc, sh) : 0.f;
-  __syncthreads();
-
-  // phase 2: real row transforms, two rows per complex FFT
+  // phase A: GroupNorm-1 applied on load; real row transforms, two rows per complex FFT
   for (int pr = task0; pr < H / 2; pr += NTASK) {
     float zr[H], zi[H];
+    const float* ap = a + ((int64_t)b * n + (2 * pr) * H) * E + ch;
 #pragma unroll
     for (int q = 0; q < H; ++q) {
-      zr[q] = T_s[((2 * pr) * H + q) * CH + c];
-      zi[q] = T_s[((2 * pr + 1) * H + q) * CH + c];
+      zr[q] = live ? __ldg(ap + (int64_t)q * E) : 0.f;
+      zi[q] = live ? __ldg(ap + (int64_t)(H + q) * E) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < H; ++q) {
+      zr[q] = fmaf(zr[q], sc, sh);
+      zi[q] = fmaf(zi[q], sc, sh);
     }
     fft_reg<H, -1>(zr, zi);
+    R_s[((2 * pr) * HC + 0) * CH + c] = make_float2(zr[0], zr[H / 2]);
+    R_s[((2 * pr + 1) * HC + 0) * CH + c] = make_float2(zi[0], zi[H / 2]);
 #pragma unroll
-    for (int k = 0; k < KH; ++k) {
-      if (k < km2) {
-        const int kn = (H - k) % H;
-        const float ar = 0.5f * (zr[k] + zr[kn]), ai = 0.5f * (zi[k] - zi[kn]);
-        const float br = 0.5f * (zi[k] + zi[kn]), bi = -0.5f * (zr[k] - zr[kn]);
-        R_s[((2 * pr) * KH + k) * CH + c] = make_float2(ar, ai);
-        R_s[((2 * pr + 1) * KH + k) * CH + c] = make_float2(br, bi);
-      }
+    for (int k = 1; k < H / 2; ++k) {
+      const int kn = H - k;
+      const float ar = 0.5f * (zr[k] + zr[kn]), ai = 0.5f * (zi[k] - zi[kn]);
+      const float br = 0.5f * (zi[k] + zi[kn]), bi = -0.5f * (zr[k] - zr[kn]);
+      R_s[((2 * pr) * HC + k) * CH + c] = make_float2(ar, ai);
+      R_s[((2 * pr + 1) * HC + k) * CH + c] = make_float2(br, bi);
     }
   }
   __syncthreads();
 
-  // phase 3: complex column transforms, write the kept modes
+  // phase B: complex column transforms, write the kept modes
   if (!live) return;
   const float norm = 1.0f / (float)H;  // ortho: 1/sqrt(H*W), H == W
   const int kap = ch / bs, j = ch % bs;
-  for (int k2 = task0; k2 < km2; k2 += NTASK) {
+  auto store = [&](int k1, int k2, float re, float im) {
+    if (OUT16) {
+      __half* dst = reinterpret_cast<__half*>(S) + (((int64_t)b * km1 + k1) * km2 + k2) * (4 * E) + (int64_t)kap * 2 * bs + j;
+      __half hi, lo;
+      hl_split(re, hi, lo);
+      dst[0] = hi; dst[2 * E] = lo;
+      hl_split(im, hi, lo);
+      dst[bs] = hi; dst[2 * E + bs] = lo;
+    } else {
+      float* dst = S + (((int64_t)b * km1 + k1) * km2 + k2) * (2 * E) + (int64_t)kap * 2 * bs + j;
+      dst[0] = re;
+      dst[bs] = im;
+    }
+  };
+  for (int kc = task0; kc < HC; kc += NTASK) {
+    if (kc > 0 && kc >= km2) continue;
     float zr[H], zi[H];
 #pragma unroll
     for (int p = 0; p < H; ++p) {
-      const float2 v = R_s[(p * KH + k2) * CH + c];
+      const float2 v = R_s[(p * HC + kc) * CH + c];
       zr[p] = v.x; zi[p] = v.y;
     }
     fft_reg<H, -1>(zr, zi);
+    if (kc > 0) {
+      const float wk = norm * wint;
 #pragma unroll
-    for (int k1 = 0; k1 < H; ++k1) {
-      if (k1 < km1) {
-        float* dst = S + (((int64_t)b * km1 + k1) * km2 + k2) * (2 * E) + (int64_t)kap * 2 * bs + j;
-        const float wk = (k2 > 0 && k2 < H / 2) ? norm * wint : norm;
-        dst[0] = zr[k1] * wk;
-        dst[bs] = zi[k1] * wk;
+      for (int k1 = 0; k1 < H; ++k1)
+        if (k1 < km1) store(k1, kc, zr[k1] * wk, zi[k1] * wk);
+    } else {
+      // F = FFT(col_0 + i col_{H/2}) -> X0[k1] = (F[k1] + conj F[-k1]) / 2, X_{H/2}[k1] = (F[k1] - conj F[-k1]) / 2i
+      const bool nyq = (H / 2) < km2;
+#pragma unroll
+      for (int k1 = 0; k1 < H; ++k1) {
+        if (k1 < km1) {
+          const int kn = (H - k1) % H;
+          store(k1, 0, 0.5f * (zr[k1] + zr[kn]) * norm, 0.5f * (zi[k1] - zi[kn]) * norm);
+          if (nyq) store(k1, H / 2, 0.5f * (zi[k1] + zi[kn]) * norm, -0.5f * (zr[k1] - zr[kn]) * norm);
+        }
       }
     }
   }
@@ -151,9 +184,9 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                           int E, int bs, int km1, int km2, float* __restrict__ f,
                                                           double* __restrict__ stats, int groups, float wint) {
-  constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, KH = Cfg<H>::KH, n = H * H;
+  constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, HC = (H >= 2) ? H / 2 : 1, n = H * H;
   extern __shared__ __align__(16) float smem[];
-  float2* Z_s = reinterpret_cast<float2*>(smem);             // [H][KH][CH]
+  float2* Z_s = reinterpret_cast<float2*>(smem);             // [H][HC][CH]; column 0 = (x_0[p], x_{H/2}[p]) real pair
   double* red = reinterpret_cast<double*>(smem);             // reused for the statistics (after a sync)
 
   const int tid = threadIdx.x, c = tid % CH, task0 = tid / CH;
@@ -161,64 +194,88 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
   const bool live = ch < E;
   const int kap = live ? ch / bs : 0, j = live ? ch % bs : 0;
 
-  // phase 1: gather the kept modes of this channel chunk (zero elsewhere)
-  for (int idx = task0; idx < H * KH; idx += NTASK) {
-    const int k1 = idx / KH, k2 = idx % KH;
-    float2 v = make_float2(0.f, 0.f);
-    if (live && k1 < km1 && k2 < km2) {
-      const float* src = O2 + (((int64_t)b * km1 + k1) * km2 + k2) * (2 * E) + (int64_t)kap * 2 * bs + j;
-      const float wk = (k2 > 0 && k2 < H / 2) ? wint : 1.f;
-      v = make_float2(src[0] * wk, src[bs] * wk);
-    }
-    Z_s[idx * CH + c] = v;
-  }
-  __syncthreads();
-
-  // phase 2: inverse complex transform along k1 -> p, in place per column
-  for (int k2 = task0; k2 < km2; k2 += NTASK) {
+  // phase A: kept modes (zero elsewhere) -> inverse complex transform along k1, one column per thread
+  for (int kc = task0; kc < HC; kc += NTASK) {
     float zr[H], zi[H];
+    const float* src = O2 + ((int64_t)b * km1 * km2 + kc) * (2 * E) + (int64_t)kap * 2 * bs + j;   // (k1 = 0, k2 = kc)
+    const bool kin = live && kc < km2;
 #pragma unroll
     for (int k1 = 0; k1 < H; ++k1) {
-      const float2 v = Z_s[(k1 * KH + k2) * CH + c];
-      zr[k1] = v.x; zi[k1] = v.y;
+      const bool ok = kin && k1 < km1;
+      zr[k1] = ok ? __ldg(src + (int64_t)k1 * km2 * (2 * E)) : 0.f;
+      zi[k1] = ok ? __ldg(src + (int64_t)k1 * km2 * (2 * E) + bs) : 0.f;
+    }
+    if (kc > 0) {
+#pragma unroll
+      for (int k1 = 0; k1 < H; ++k1) { zr[k1] *= wint; zi[k1] *= wint; }
+    } else {
+      // Nyquist column (k2 = H/2), then pack the Hermitian parts: W = Herm(col_0) + i Herm(col_{H/2})
+      float yr[H], yi[H];
+      const bool nin = live && (H / 2) < km2;
+      const float* srcn = src + (int64_t)(H / 2) * (2 * E);
+#pragma unroll
+      for (int k1 = 0; k1 < H; ++k1) {
+        const bool ok = nin && k1 < km1;
+        yr[k1] = ok ? __ldg(srcn + (int64_t)k1 * km2 * (2 * E)) : 0.f;
+        yi[k1] = ok ? __ldg(srcn + (int64_t)k1 * km2 * (2 * E) + bs) : 0.f;
+      }
+      float wr[H], wi[H];
+#pragma unroll
+      for (int k1 = 0; k1 < H; ++k1) {
+        const int kn = (H - k1) % H;
+        const float s0r = 0.5f * (zr[k1] + zr[kn]), s0i = 0.5f * (zi[k1] - zi[kn]);
+        const float s8r = 0.5f * (yr[k1] + yr[kn]), s8i = 0.5f * (yi[k1] - yi[kn]);
+        wr[k1] = s0r - s8i;
+        wi[k1] = s0i + s8r;
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < H; ++k1) { zr[k1] = wr[k1]; zi[k1] = wi[k1]; }
     }
     fft_reg<H, +1>(zr, zi);
 #pragma unroll
-    for (int p = 0; p < H; ++p) Z_s[(p * KH + k2) * CH + c] = make_float2(zr[p], zi[p]);
+    for (int p = 0; p < H; ++p) Z_s[(p * HC + kc) * CH + c] = make_float2(zr[p], zi[p]);
   }
-  __syncthreads();
 
-  // phase 3: c2r along k2 -> q for two rows at once, + skip of the normalised input
+  // skip term: the normalised block input, fetched before the barrier so that its latency overlaps phase A/C
   const float norm = 1.0f / (float)H;
   const float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
   const float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
   double s1 = 0.0, s2 = 0.0;
-  for (int pr = task0; pr < H / 2; pr += NTASK) {
-    float zr[H], zi[H];
+  float k0[H], k1v[H];
+  auto load_skip = [&](int pr) {
+    const float* ap = a + ((int64_t)b * n + (2 * pr) * H) * E + ch;
 #pragma unroll
-    for (int k = 0; k < KH; ++k) {
-      float2 A = make_float2(0.f, 0.f), Bv = make_float2(0.f, 0.f);
-      if (k < km2) {
-        A = Z_s[((2 * pr) * KH + k) * CH + c];
-        Bv = Z_s[((2 * pr + 1) * KH + k) * CH + c];
-      }
-      if (k == 0 || k == H / 2) {  // c2r ignores Im of the DC and Nyquist columns
-        zr[k] = A.x; zi[k] = Bv.x;
-      } else {
-        zr[k] = A.x - Bv.y; zi[k] = A.y + Bv.x;
-        zr[H - k] = A.x + Bv.y; zi[H - k] = -A.y + Bv.x;
-      }
+    for (int q = 0; q < H; ++q) {
+      k0[q] = (a && live) ? __ldg(ap + (int64_t)q * E) : 0.f;
+      k1v[q] = (a && live) ? __ldg(ap + (int64_t)(H + q) * E) : 0.f;
+    }
+  };
+  if (task0 < H / 2) load_skip(task0);
+  __syncthreads();                         // Z_s complete
+  for (int pr = task0; pr < H / 2; pr += NTASK) {
+    const int64_t base0 = ((int64_t)b * n + (2 * pr) * H) * E + ch;
+    if (pr != task0) load_skip(pr);
+    // phase C: c2r along k2 -> q for two rows at once
+    float zr[H], zi[H];
+    {
+      const float2 A = Z_s[((2 * pr) * HC + 0) * CH + c], Bv = Z_s[((2 * pr + 1) * HC + 0) * CH + c];
+      zr[0] = A.x; zi[0] = Bv.x;                 // c2r ignores Im of the DC and Nyquist columns
+      zr[H / 2] = A.y; zi[H / 2] = Bv.y;
+    }
+#pragma unroll
+    for (int k = 1; k < H / 2; ++k) {
+      const float2 A = Z_s[((2 * pr) * HC + k) * CH + c], Bv = Z_s[((2 * pr + 1) * HC + k) * CH + c];
+      zr[k] = A.x - Bv.y; zi[k] = A.y + Bv.x;
+      zr[H - k] = A.x + Bv.y; zi[H - k] = -A.y + Bv.x;
     }
     fft_reg<H, +1>(zr, zi);
     if (live) {
-      const int64_t base0 = ((int64_t)b * n + (2 * pr) * H) * E + ch;
-      const int64_t base1 = base0 + (int64_t)H * E;
 #pragma unroll
       for (int q = 0; q < H; ++q) {
-        const float v0 = fmaf(zr[q], norm, a ? fmaf(a[base0 + (int64_t)q * E], sc, sh) : 0.f);
-        const float v1 = fmaf(zi[q], norm, a ? fmaf(a[base1 + (int64_t)q * E], sc, sh) : 0.f);
+        const float v0 = fmaf(zr[q], norm, a ? fmaf(k0[q], sc, sh) : 0.f);
+        const float v1 = fmaf(zi[q], norm, a ? fmaf(k1v[q], sc, sh) : 0.f);
         f[base0 + (int64_t)q * E] = v0;
-        f[base1 + (int64_t)q * E] = v1;
+        f[base0 + (int64_t)(H + q) * E] = v1;
         s1 += (double)v0 + (double)v1;
         s2 += (double)v0 * v0 + (double)v1 * v1;
       }
@@ -244,14 +301,15 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
   }
 }
 
-template <int H>
+template <int H, bool OUT16 = false>
 int launch_fwd(const float* a, const float* scale, const float* shift, int B, int E, int nb, int km1, int km2,
                float* S, float wint, cudaStream_t st) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
-  const size_t smem = (size_t)H * H * CH * 4 + (size_t)H * KH * CH * 8;
-  DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)H * (H >= 2 ? H / 2 : 1) * CH * 8;
+  (void)KH;
+  DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_fwd_kernel<H><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S, wint);
+  afno_fft_fwd_kernel<H, OUT16><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S, wint);
   DPOT_LAUNCH_CHECK("afno_fft_fwd_kernel");
   return 0;
 }
@@ -260,7 +318,8 @@ template <int H>
 int launch_inv(const float* O2, const float* a, const float* scale, const float* shift, int B, int E, int nb,
                int km1, int km2, float* f, double* stats, int groups, float wint, cudaStream_t st) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
-  size_t smem = (size_t)H * KH * CH * 8;
+  size_t smem = (size_t)H * (H >= 2 ? H / 2 : 1) * CH * 8;
+  (void)KH;
   if (smem < (size_t)2 * NT * 8) smem = (size_t)2 * NT * 8;
   DPOT_CUDA(cudaFuncSetAttribute(afno_fft_inv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
@@ -295,6 +354,21 @@ extern "C" int dpot_afno_fft_fwd(const float* a, const float* scale, const float
     case 8: return launch_fwd<8>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
     case 16: return launch_fwd<16>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
     default: return launch_fwd<32>(a, scale, shift, B, E, nb, km1, km2, S, interior_weight, st);
+  }
+}
+
+extern "C" int dpot_afno_fft_fwd16(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
+                                   int32_t E, int32_t nb, int32_t km1, int32_t km2, void* S16, void* stream) {
+  DPOT_REQUIRE(a && S16 && ((scale == nullptr) == (shift == nullptr)), DPOT_E_BADARG, "dpot_afno_fft_fwd16: null pointer");
+  DPOT_CALL(check_common(B, h, E, nb, km1, km2));
+  cudaStream_t st = as_stream(stream);
+  float* S = reinterpret_cast<float*>(S16);
+  switch (h) {
+    case 2: return launch_fwd<2, true>(a, scale, shift, B, E, nb, km1, km2, S, 1.0f, st);
+    case 4: return launch_fwd<4, true>(a, scale, shift, B, E, nb, km1, km2, S, 1.0f, st);
+    case 8: return launch_fwd<8, true>(a, scale, shift, B, E, nb, km1, km2, S, 1.0f, st);
+    case 16: return launch_fwd<16, true>(a, scale, shift, B, E, nb, km1, km2, S, 1.0f, st);
+    default: return launch_fwd<32, true>(a, scale, shift, B, E, nb, km1, km2, S, 1.0f, st);
   }
 }
 

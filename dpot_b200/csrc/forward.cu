@@ -36,6 +36,8 @@ static inline int64_t slot(int64_t n) { return round_up(n, 64); }  // 256 B gran
 
 struct Packed {
   int64_t W0p, rowbias0, WeffT, bias_eff, blocks, blk_stride, Wc1, bc1, Wc2, bc2, WtT, bias_t, total;
+  // split-fp16 (DPOT_FMT_HL16) copies for the f16-split tensor-core engine; same float counts as the fp32 originals
+  int64_t WeffT16, WtT16, Wc1_16, Wc2_16, fc1_16, fc2_16;   // the last four are offsets inside a block slab
 };
 static Packed packed_layout(const Dims& d) {
   Packed L; int64_t o = 0;
@@ -49,15 +51,21 @@ static Packed packed_layout(const Dims& d) {
   L.bc1 = b; b += slot(2 * d.E);
   L.Wc2 = b; b += slot((int64_t)d.nb * 4 * d.bs * d.bs);
   L.bc2 = b; b += slot(2 * d.E);
+  L.Wc1_16 = b; b += slot((int64_t)d.nb * 4 * d.bs * d.bs);
+  L.Wc2_16 = b; b += slot((int64_t)d.nb * 4 * d.bs * d.bs);
+  L.fc1_16 = b; b += slot((int64_t)d.hid * d.E);
+  L.fc2_16 = b; b += slot((int64_t)d.hid * d.E);
   L.blk_stride = b; o += b * d.depth;
   L.WtT = o; o += slot((int64_t)d.NP * d.E);
   L.bias_t = o; o += slot(d.NP);
+  L.WeffT16 = o; o += slot((int64_t)d.E * d.Kp);
+  L.WtT16 = o; o += slot((int64_t)d.NP * d.E);
   L.total = o;
   return L;
 }
 
 struct Work {
-  int64_t z1, lat0, lat1, f, hid, S, O1, sc1, sh1, sc2, sh2, st1, st2, Y1, Y2, tok, c1, c2, musig, asc, ash, smu, ssg, total;
+  int64_t z1, lat0, lat1, f, n2, hid, S, O1, sc1, sh1, sc2, sh2, st1, st2, Y1, Y2, tok, c1, c2, musig, asc, ash, smu, ssg, total;
 };
 static Work work_layout(const Dims& d, const dpot_config* c, int B) {
   Work L; int64_t o = 0;
@@ -66,6 +74,7 @@ static Work work_layout(const Dims& d, const dpot_config* c, int B) {
   L.lat0 = o; o += slot(Mt * d.E);
   L.lat1 = o; o += slot(Mt * d.E);
   L.f = o; o += slot(Mt * d.E);
+  L.n2 = o; o += slot(Mt * d.E);      // split-fp16 GroupNorm-2 output / last latent (TC16 pipeline)
   L.hid = o; o += slot(Mt * d.hid);
   L.S = o; o += slot(Ms * 2 * d.E);
   L.O1 = o; o += slot(Ms * 2 * d.E);
@@ -97,6 +106,126 @@ static dpot_gemm_args gemm_args(const float* A, int64_t lda, const float* W, int
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.act = act; g.batch = 1; g.engine = engine; g.a_mode = DPOT_A_PLAIN;
   return g;
+}
+
+// split-fp16 operands: A16 rows of `lda_f` floats' worth of bytes ([hi lda_f halves | lo lda_f halves]), likewise W16
+static dpot_gemm_args gemm16_args(const float* A16, int64_t a_row_f, const float* W16, int64_t w_row_f, float* C,
+                                  int64_t ldc, int M, int N, int K, const float* bias, int act) {
+  dpot_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = A16; g.lda = 2 * a_row_f; g.a_lo_off = a_row_f; g.a_fmt = DPOT_FMT_HL16;
+  g.W = W16; g.ldw = 2 * w_row_f; g.w_lo_off = w_row_f; g.w_fmt = DPOT_FMT_HL16;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.act = act; g.batch = 1; g.engine = DPOT_GEMM_TC16; g.a_mode = DPOT_A_PLAIN;
+  return g;
+}
+static void out16(dpot_gemm_args& g, int64_t c_row_f) {   // store the result split: rows of c_row_f floats' worth
+  g.c_fmt = DPOT_FMT_HL16; g.ldc = 2 * c_row_f; g.c_lo_off = c_row_f;
+}
+
+// The f16-split pipeline serves every dense contraction when the device has tcgen05 and the row
+// lengths keep the 16-byte alignment TMA needs.
+static bool use_tc16(const Dims& d, int engine) {
+  if (engine != DPOT_GEMM_AUTO && engine != DPOT_GEMM_TC16) return false;
+  if (!dpot_tc16_available()) return false;
+  return d.E % 8 == 0 && d.Kp % 8 == 0 && (2 * d.bs) % 8 == 0 && d.hid % 8 == 0 && d.NP % 8 == 0 && d.mid > 0;
+}
+
+// ---- the f16-split tensor-core pipeline (DPOT_GEMM_TC16) ---------------------------------------
+// Every activation that feeds a dense contraction is written by its producer as split fp16
+// (DPOT_FMT_HL16, 4 bytes per element like fp32): conv0 epilogue -> z1, forward FFT -> S, GEMM
+// epilogues -> O1 / hidden, GroupNorm-2 apply -> n2.  The residual stream, the inverse-FFT input
+// and the head stay fp32.
+static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int t0, int B,
+                        float* y, float* cls, float* ws, const Dims& d, const Packed& PL, const Work& WL, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const int Mt = B * d.n, Ms = B * d.km1 * d.km2, act = cfg->act, R = cfg->img_size;
+  const int groups = 8;
+  // PatchEmbed conv0 + act on the CUDA cores (N = 4P+3 is tiny), result stored split
+  if (d.Kp != d.T * d.mid) DPOT_CUDA(cudaMemsetAsync(ws + WL.z1, 0, sizeof(float) * (size_t)Mt * d.Kp, st));
+  DPOT_CALL(dpot_patch_embed(x, t0, packed + PL.W0p, packed + PL.rowbias0, cfg->normalize ? ws + WL.asc : nullptr,
+                             cfg->normalize ? ws + WL.ash : nullptr, B, R, R, d.T, d.C, d.P, d.mid, act, ws + WL.z1, d.Kp,
+                             DPOT_FMT_HL16, stream));
+  // folded (conv 1x1 + pos_embed + TimeAggregator) GEMM (+ AdaIN) with GroupNorm-1 statistics
+  float* lat = ws + WL.lat0;
+  float* lat_next = ws + WL.lat1;
+  double* st1 = reinterpret_cast<double*>(ws + WL.st1);
+  double* st2 = reinterpret_cast<double*>(ws + WL.st2);
+  {
+    dpot_gemm_args g = gemm16_args(ws + WL.z1, d.Kp, packed + PL.WeffT16, d.Kp, lat, d.E, Mt, d.E, d.Kp, nullptr, DPOT_ACT_NONE);
+    g.rowbias = packed + PL.bias_eff; g.rowbias_period = d.n; g.ldrb = d.E;
+    if (cfg->normalize) { g.c_scale = ws + WL.ssg; g.c_shift = ws + WL.smu; g.c_rows_per_sample = d.n; }
+    g.out_stats = st1; g.stats_groups = groups; g.stats_rows_per_sample = d.n;
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+  const int64_t kb = 2 * d.bs;
+  for (int i = 0; i < d.depth; ++i) {
+    const dpot_block_params& bp = prm->blocks[i];
+    const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
+    DPOT_CALL(dpot_gn_finalize(st1, bp.norm1_w, bp.norm1_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc1, ws + WL.sh1, stream));
+    DPOT_CALL(dpot_afno_fft_fwd16(lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.S, stream));
+    {
+      // block-diagonal complex MLP as nb real GEMMs of size [Ms, 2bs] x [2bs, 2bs]
+      dpot_gemm_args g = gemm16_args(ws + WL.S, 2 * d.E, pk + PL.Wc1_16, kb, ws + WL.O1, 0, Ms, (int)kb, (int)kb, pk + PL.bc1, act);
+      g.batch = d.nb; g.strideA = kb; g.strideW = 2 * kb * kb; g.strideC = kb; g.strideBias = kb;
+      out16(g, 2 * d.E);
+      DPOT_CALL(dpot_gemm(&g, stream));
+      g = gemm16_args(ws + WL.O1, 2 * d.E, pk + PL.Wc2_16, kb, ws + WL.S, 2 * d.E, Ms, (int)kb, (int)kb, pk + PL.bc2, DPOT_ACT_NONE);
+      g.batch = d.nb; g.strideA = kb; g.strideW = 2 * kb * kb; g.strideC = kb; g.strideBias = kb;
+      DPOT_CALL(dpot_gemm(&g, stream));     // O2 overwrites S as fp32 (the inverse FFT reads fp32)
+    }
+    DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
+    DPOT_CALL(dpot_afno_fft_inv(ws + WL.S, lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.f, st2, groups, 1.0f, stream));
+    DPOT_CALL(dpot_gn_finalize(st2, bp.norm2_w, bp.norm2_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc2, ws + WL.sh2, stream));
+    // GroupNorm-2 apply fused with the fp16 split of the channel-MLP input
+    DPOT_CALL(dpot_split_f16(ws + WL.f, d.E, Mt, d.E, ws + WL.sc2, ws + WL.sh2, d.n, ws + WL.n2, 2 * d.E, d.E, stream));
+    {
+      dpot_gemm_args g = gemm16_args(ws + WL.n2, d.E, pk + PL.fc1_16, d.E, ws + WL.hid, 0, Mt, d.hid, d.E, bp.fc1_b, act);
+      out16(g, d.hid);
+      DPOT_CALL(dpot_gemm(&g, stream));
+      g = gemm16_args(ws + WL.hid, d.hid, pk + PL.fc2_16, d.hid, lat_next, d.E, Mt, d.E, d.hid, bp.fc2_b, DPOT_ACT_NONE);
+      g.residual = lat; g.ldr = d.E;
+      if (i + 1 < d.depth) { g.out_stats = st1; g.stats_groups = groups; g.stats_rows_per_sample = d.n; }
+      DPOT_CALL(dpot_gemm(&g, stream));
+    }
+    float* tmp = lat; lat = lat_next; lat_next = tmp;
+  }
+
+  if (cls) {   // classification head (M = B rows: skinny CUDA-core GEMMs)
+    DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, stream));
+    dpot_gemm_args g = gemm_args(ws + WL.tok, d.E, prm->cls0_w, d.E, ws + WL.c1, d.E, B, d.E, d.E, prm->cls0_b, act, DPOT_GEMM_AUTO);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(ws + WL.c1, d.E, prm->cls2_w, d.E, ws + WL.c2, d.E, B, d.E, d.E, prm->cls2_b, act, DPOT_GEMM_AUTO);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(ws + WL.c2, d.E, prm->cls4_w, d.E, cls, d.ncls, B, d.ncls, d.E, prm->cls4_b, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+
+  // output head: ConvTranspose as a GEMM on the split latent, then the fused per-pixel tail
+  DPOT_CALL(dpot_split_f16(lat, d.E, Mt, d.E, nullptr, nullptr, 0, ws + WL.n2, 2 * d.E, d.E, stream));
+  {
+    dpot_gemm_args g = gemm16_args(ws + WL.n2, d.E, packed + PL.WtT16, d.E, ws + WL.Y1, d.NP, Mt, d.NP, d.E, packed + PL.bias_t, act);
+    DPOT_CALL(dpot_gemm(&g, stream));
+    const int nout = d.Co * d.To;
+    const bool fused_tail = (d.old == 4 || d.old == 8 || d.old == 16 || d.old == 32);
+    if (cfg->normalize) DPOT_REQUIRE(d.C == d.Co, DPOT_E_UNSUPPORTED, "normalize=True needs in_channels == out_channels");
+    const float* mu_c = nullptr; const float* sg_c = nullptr;
+    if (cfg->normalize) {
+      const float* mu = ws + WL.musig;
+      float* mc = ws + WL.smu; float* sc = ws + WL.ssg;
+      DPOT_CUDA(cudaMemcpy2DAsync(mc, sizeof(float) * d.C, mu, sizeof(float) * 2 * d.C, sizeof(float) * d.C, B, cudaMemcpyDeviceToDevice, st));
+      DPOT_CUDA(cudaMemcpy2DAsync(sc, sizeof(float) * d.C, mu + d.C, sizeof(float) * 2 * d.C, sizeof(float) * d.C, B, cudaMemcpyDeviceToDevice, st));
+      mu_c = mc; sg_c = sc;
+    }
+    if (fused_tail) {
+      DPOT_CALL(dpot_out_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+    } else {
+      g = gemm_args(ws + WL.Y1, d.old, prm->out2_w, d.old, ws + WL.Y2, d.old, Mt * d.P * d.P, d.old, d.old, prm->out2_b, act, DPOT_GEMM_AUTO);
+      DPOT_CALL(dpot_gemm(&g, stream));
+      DPOT_CALL(dpot_out_tail(ws + WL.Y2, nullptr, nullptr, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+    }
+  }
+  return 0;
 }
 
 }  // namespace dpot
@@ -131,19 +260,47 @@ extern "C" int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm,
     DPOT_CALL(dpot_pack_afno(b.w2, b.b2, d.nb, d.bs, base + L.Wc2, base + L.bc2, stream));
   }
   DPOT_CALL(dpot_pack_out(prm->out0_w, prm->out0_b, d.E, d.old, d.P, packed + L.WtT, packed + L.bias_t, stream));
+  if (use_tc16(d, DPOT_GEMM_AUTO)) {   // split-fp16 copies of every GEMM weight
+    DPOT_CALL(dpot_split_f16(packed + L.WeffT, d.Kp, d.E, d.Kp, nullptr, nullptr, 0, packed + L.WeffT16, 2 * d.Kp, d.Kp, stream));
+    DPOT_CALL(dpot_split_f16(packed + L.WtT, d.E, d.NP, d.E, nullptr, nullptr, 0, packed + L.WtT16, 2 * d.E, d.E, stream));
+    for (int i = 0; i < d.depth; ++i) {
+      float* base = packed + L.blocks + (int64_t)i * L.blk_stride;
+      const dpot_block_params& b = prm->blocks[i];
+      const int64_t kb = 2 * d.bs;
+      DPOT_CALL(dpot_split_f16(base + L.Wc1, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc1_16, 2 * kb, kb, stream));
+      DPOT_CALL(dpot_split_f16(base + L.Wc2, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc2_16, 2 * kb, kb, stream));
+      DPOT_CALL(dpot_split_f16(b.fc1_w, d.E, d.hid, d.E, nullptr, nullptr, 0, base + L.fc1_16, 2 * d.E, d.E, stream));
+      DPOT_CALL(dpot_split_f16(b.fc2_w, d.hid, d.E, d.hid, nullptr, nullptr, 0, base + L.fc2_16, 2 * d.hid, d.hid, stream));
+    }
+  }
   return 0;
 }
 
 extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                             int32_t B, float* y, float* cls, float* ws, int32_t engine, void* stream) {
+  return dpot_forward_ring(cfg, prm, packed, x, 0, B, y, cls, ws, engine, stream);
+}
+
+extern "C" int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
+                                 int32_t t0, int32_t B, float* y, float* cls, float* ws, int32_t engine, void* stream) {
   Dims d;
   DPOT_CALL(make_dims(cfg, d));
   DPOT_REQUIRE(prm && packed && x && y && ws && prm->blocks && B > 0, DPOT_E_BADARG, "dpot_forward: null pointer / bad B");
+  DPOT_REQUIRE(t0 >= 0 && t0 < d.T, DPOT_E_BADARG, "dpot_forward_ring: t0=%d outside [0,%d)", t0, d.T);
   const Packed PL = packed_layout(d);
   const Work WL = work_layout(d, cfg, B);
   cudaStream_t st = as_stream(stream);
   const int Mt = B * d.n, Ms = B * d.km1 * d.km2, act = cfg->act, R = cfg->img_size;
   const int groups = 8;
+
+  // engine: AUTO / TC16 = the f16-split tensor-core pipeline when available; TC = fp32 operands with 3xTF32
+  // tensor cores wherever a problem fits (CUDA cores elsewhere); SIMT = CUDA cores only.
+  const bool tc16 = use_tc16(d, engine);
+  if (engine == DPOT_GEMM_TC16 && !tc16) {
+    set_error("dpot_forward: the f16-split engine is not available for this device / configuration");
+    return DPOT_E_UNSUPPORTED;
+  }
+  if (engine == DPOT_GEMM_TC || engine == DPOT_GEMM_TC16) engine = DPOT_GEMM_AUTO;
 
   // ---- input normalisation (normalize=True only), models/dpot.py:366-370
   if (cfg->normalize) {
@@ -154,16 +311,13 @@ extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, cons
     DPOT_CALL(dpot_gemm(&g, stream));
   }
 
-  // ---- PatchEmbed conv0 + act as an im2col GEMM, coordinate channels folded into rowbias0
+  if (tc16) return forward_tc16(cfg, prm, packed, x, t0, B, y, cls, ws, d, PL, WL, stream);
+
+  // ---- PatchEmbed conv0 + act, coordinate channels folded into rowbias0
   if (d.Kp != d.T * d.mid) DPOT_CUDA(cudaMemsetAsync(ws + WL.z1, 0, sizeof(float) * (size_t)Mt * d.Kp, st));
-  {
-    dpot_gemm_args g = gemm_args(x, 0, packed + PL.W0p, d.K0, ws + WL.z1, d.mid, Mt * d.T, d.mid, d.K0, nullptr, act, engine);
-    g.a_mode = DPOT_A_PATCH; g.pX = R; g.pY = R; g.pT = d.T; g.pC = d.C; g.pP = d.P;
-    g.rowbias = packed + PL.rowbias0; g.rowbias_period = d.n * d.T; g.ldrb = d.mid;
-    g.c_group = d.T; g.c_group_stride = d.Kp;
-    if (cfg->normalize) { g.a_scale = ws + WL.asc; g.a_shift = ws + WL.ash; g.a_rows_per_sample = d.n * d.T; }
-    DPOT_CALL(dpot_gemm(&g, stream));
-  }
+  DPOT_CALL(dpot_patch_embed(x, t0, packed + PL.W0p, packed + PL.rowbias0, cfg->normalize ? ws + WL.asc : nullptr,
+                             cfg->normalize ? ws + WL.ash : nullptr, B, R, R, d.T, d.C, d.P, d.mid, act, ws + WL.z1, d.Kp,
+                             DPOT_FMT_F32, stream));
   // ---- folded (conv 1x1 + pos_embed + TimeAggregator) GEMM (+ AdaIN), models/dpot.py:201,378-387
   float* lat = ws + WL.lat0;
   float* lat_next = ws + WL.lat1;

@@ -59,7 +59,9 @@ struct Tc16Params {
 };
 
 // ACT_MODE: 0 = none, 1 = GELU (erf), 2 = runtime switch.  OUT16: store the result as DPOT_FMT_HL16.
-template <int ACT_MODE, bool OUT16>
+// SIDE: the epilogue has side inputs (row-periodic bias, residual, per-sample affine); without them that code
+// (and its registers) is compiled out -- the AFNO GEMMs (K = 2*bs) are epilogue-bound.
+template <int ACT_MODE, bool OUT16, bool SIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                  const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
@@ -160,6 +162,20 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       const bool nok = n < g.N;
       const float bias_n = (g.bias && nok) ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
       float st1 = 0.f, st2 = 0.f;
+      // side inputs (row-periodic bias, residual) of a group are fetched one group ahead: their global-load
+      // latency hides behind the arithmetic of the previous group instead of serialising the epilogue
+      float nrb[8], nrs[8];
+      auto load_side = [&](int gi) {
+        if (!SIDE) return;
+        const int m0 = mt * BA + gi * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool ok = nok && (m0 + u) < g.M;
+          nrb[u] = (g.rowbias && ok) ? __ldg(g.rowbias + (int64_t)((m0 + u) % g.rb_period) * g.ldrb + n) : 0.f;
+          nrs[u] = (g.residual && ok) ? __ldg(g.residual + (int64_t)(m0 + u) * g.ldr + n) : 0.f;
+        }
+      };
+      if (half < ngroups) load_side(half);
       mbar_wait(TFULL(buf), bph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
@@ -169,18 +185,17 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         uint32_t r1[8], r2[8];
         tmem_ld8(t_row + (uint32_t)c0, r1);
         tmem_ld8(t_row + (uint32_t)(BA + c0), r2);
+        float rb[8], rs[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { rb[u] = SIDE ? nrb[u] : 0.f; rs[u] = SIDE ? nrs[u] : 0.f; }
+        if (gi + 2 < ngroups) load_side(gi + 2);
         tmem_ld_wait();
         const int m0 = mt * BA + c0;
         const int cnt = min(8, g.M - m0);
         if (cnt <= 0 || !nok) continue;
         float t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = fmaf(__uint_as_float(r2[u]), HL_INV, __uint_as_float(r1[u])) + bias_n;
-        if (g.rowbias) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (u < cnt) t[u] += g.rowbias[(int64_t)((m0 + u) % g.rb_period) * g.ldrb + n];
-        }
+        for (int u = 0; u < 8; ++u) t[u] = fmaf(__uint_as_float(r2[u]), HL_INV, __uint_as_float(r1[u])) + bias_n + rb[u];
         if (ACT_MODE == 1) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] = gelu_select(t[u]);
@@ -188,7 +203,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] = act_apply(t[u], g.act);
         }
-        if (g.c_scale) {
+        if (SIDE && g.c_scale) {
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (u < cnt) {
@@ -196,11 +211,9 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
               t[u] = fmaf(t[u], g.c_scale[o], g.c_shift[o]);
             }
         }
-        if (g.residual) {
-          const float* __restrict__ rp = g.residual + (int64_t)m0 * g.ldr + n;
+        if (SIDE) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (u < cnt) t[u] += rp[(int64_t)u * g.ldr];
+          for (int u = 0; u < 8; ++u) t[u] += rs[u];
         }
         if (OUT16) {
           __half* __restrict__ cp = Ch_base + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + n;
@@ -250,7 +263,21 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   }
 }
 
-int pick_ba(int M) { return M >= TA ? TA : (int)round_up(M, 16); }
+int g_sm_count = 0;
+// Tokens per tile.  The persistent grid runs ceil(tiles / #SM) rounds of one tile per SM; a slightly smaller
+// tile (e.g. 112 instead of 128 rows: 592 = 4 x 148 tiles for M = 8192, N = 1024) can fill the last round.
+int pick_ba(int M, int other_tiles, int divides = 0) {   // divides > 0: BA must divide it (fused GroupNorm statistics)
+  if (M <= TA) return (int)round_up(M, 16);
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  int best = TA; int64_t best_cost = -1;
+  for (int ba = TA; ba >= 64; ba -= 16) {
+    if (divides > 0 && divides % ba != 0) continue;
+    const int64_t tiles = ceil_div(M, ba) * other_tiles;
+    const int64_t cost = ceil_div(tiles, sms) * (ba + 12);      // + fixed per-tile overhead (pipeline fill, epilogue tail)
+    if (best_cost < 0 || cost < best_cost) { best = ba; best_cost = cost; }
+  }
+  return best;
+}
 
 }  // namespace
 
@@ -269,7 +296,7 @@ bool gemm_tc16_supports(const GemmDev& p, int batch) {
 }
 
 bool gemm_tc16_fuses_stats(const GemmDev& p) {
-  const int BA = pick_ba(p.M);
+  const int BA = pick_ba(p.M, (int)ceil_div(p.N, TN), p.st_rps);
   return p.c_fmt == DPOT_FMT_F32 && p.st_groups > 0 && p.st_rps > 0 && p.st_rps % BA == 0 && p.N % 32 == 0 &&
          (p.N / p.st_groups) % 32 == 0;
 }
@@ -277,8 +304,13 @@ bool gemm_tc16_fuses_stats(const GemmDev& p) {
 int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
-  P.BA = pick_ba(p.M);
+  if (g_sm_count == 0) {
+    int dev = 0;
+    DPOT_CUDA(cudaGetDevice(&dev));
+    DPOT_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
   P.n_tiles = (int)ceil_div(p.N, TN);
+  P.BA = pick_ba(p.M, P.n_tiles * batch, p.out_stats ? p.st_rps : 0);
   P.m_tiles = (int)ceil_div(p.M, P.BA);
   P.total_tiles = P.n_tiles * P.m_tiles * batch;
   P.kblocks = (int)ceil_div(p.K, BKH);
@@ -293,27 +325,28 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, (uint32_t)P.BA));
   DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, (uint32_t)P.BA));
 
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    DPOT_CUDA(cudaGetDevice(&dev));
-    DPOT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  const int sm_count = g_sm_count;
   const int grid = P.total_tiles < sm_count ? P.total_tiles : sm_count;
   const int am = p.act == DPOT_ACT_NONE ? 0 : (p.act == DPOT_ACT_GELU ? 1 : 2);
   const bool o16 = p.c_fmt == DPOT_FMT_HL16;
-#define DPOT_TC16_LAUNCH(AM, O16) gemm_tc16_kernel<AM, O16><<<grid, NTHREADS, SMEM_BYTES, st>>>(mWh, mWl, mAh, mAl, P)
-  if (am == 0) { if (o16) DPOT_TC16_LAUNCH(0, true); else DPOT_TC16_LAUNCH(0, false); }
-  else if (am == 1) { if (o16) DPOT_TC16_LAUNCH(1, true); else DPOT_TC16_LAUNCH(1, false); }
-  else { if (o16) DPOT_TC16_LAUNCH(2, true); else DPOT_TC16_LAUNCH(2, false); }
+  const bool side = p.rowbias || p.residual || p.c_scale;
+#define DPOT_TC16_LAUNCH(AM, O16, SD)                                                                                  \
+  do {                                                                                                                 \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<AM, O16, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)SMEM_BYTES));                                                                \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    gemm_tc16_kernel<AM, O16, SD><<<grid, NTHREADS, SMEM_BYTES, st>>>(mWh, mWl, mAh, mAl, P);                          \
+  } while (0)
+#define DPOT_TC16_SD(AM, O16) do { if (side) DPOT_TC16_LAUNCH(AM, O16, true); else DPOT_TC16_LAUNCH(AM, O16, false); } while (0)
+#define DPOT_TC16_O(AM) do { if (o16) DPOT_TC16_SD(AM, true); else DPOT_TC16_SD(AM, false); } while (0)
+  if (am == 0) DPOT_TC16_O(0);
+  else if (am == 1) DPOT_TC16_O(1);
+  else DPOT_TC16_O(2);
+#undef DPOT_TC16_O
+#undef DPOT_TC16_SD
 #undef DPOT_TC16_LAUNCH
   DPOT_LAUNCH_CHECK("gemm_tc16_kernel");
   return 0;

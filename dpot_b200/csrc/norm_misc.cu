@@ -332,10 +332,37 @@ __global__ void window_advance_kernel(const float* __restrict__ xx, const float*
   }
 }
 
+// ring form of the window advance: the new frames overwrite the oldest slots, nothing else moves
+__global__ void ring_insert_kernel(const float* __restrict__ im, float* __restrict__ ring, float* __restrict__ pred,
+                                   int64_t npix, int T, int Tb, int C, int Ttot, int slot0, int step) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = npix * Tb * C;
+  if (i < total) {
+    const int c = (int)(i % C);
+    const int j = (int)((i / C) % Tb);
+    const int64_t pix = i / ((int64_t)C * Tb);
+    const float v = im[i];
+    int slot = slot0 + j; if (slot >= T) slot -= T;
+    ring[(pix * T + slot) * C + c] = v;
+    if (pred) pred[(pix * Ttot + (int64_t)step * Tb + j) * C + c] = v;
+  }
+}
+
 }  // namespace
 }  // namespace dpot
 
 using namespace dpot;
+
+extern "C" int dpot_ring_insert(const float* im, float* ring, float* pred, int64_t npix, int32_t T, int32_t Tb,
+                                int32_t C, int32_t Ttot, int32_t slot0, int32_t step, void* stream) {
+  DPOT_REQUIRE(im && ring, DPOT_E_BADARG, "dpot_ring_insert: null pointer");
+  DPOT_REQUIRE(Tb >= 1 && Tb <= T && slot0 >= 0 && slot0 < T, DPOT_E_BADARG, "dpot_ring_insert: bad T_bundle / slot");
+  const int64_t total = npix * Tb * C;
+  ring_insert_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(im, ring, pred, npix, T, Tb, C, Ttot,
+                                                                                    slot0, step);
+  DPOT_LAUNCH_CHECK("ring_insert_kernel");
+  return 0;
+}
 
 extern "C" int dpot_gn_stats(const float* x, int32_t B, int32_t n, int32_t E, int32_t groups, double* stats, void* stream) {
   DPOT_REQUIRE(x && stats, DPOT_E_BADARG, "dpot_gn_stats: null pointer");

@@ -477,7 +477,8 @@ class _InferenceEngine:
         return ws
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, want_cls: bool = True):
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, want_cls: bool = True, t0: int = 0):
+        """t0: x is a ring in time whose logical frame t is slot (t + t0) % T (0 = the plain layout)."""
         net = self.net
         if x.dtype != torch.float32:
             x = x.float()
@@ -491,9 +492,9 @@ class _InferenceEngine:
                 out = torch.empty((B, net.img_size, net.img_size, net.out_timesteps, net.out_channels), device=dev,
                                   dtype=torch.float32)
             cls = torch.empty((B, net.n_cls), device=dev, dtype=torch.float32) if want_cls else None
-            check(self.lib.dpot_forward(C.byref(self.cfg), C.byref(self.prm), ptr(self.packed), ptr(x), B, ptr(out),
-                                        ptr(cls), ptr(ws), net.gemm_engine, torch.cuda.current_stream().cuda_stream),
-                  "dpot_forward")
+            check(self.lib.dpot_forward_ring(C.byref(self.cfg), C.byref(self.prm), ptr(self.packed), ptr(x), t0, B,
+                                             ptr(out), ptr(cls), ptr(ws), net.gemm_engine,
+                                             torch.cuda.current_stream().cuda_stream), "dpot_forward_ring")
         return out, cls
 
 

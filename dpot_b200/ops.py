@@ -214,6 +214,17 @@ def window_advance(xx, im, xx_next, pred=None, step=0):
     return xx_next
 
 
+def ring_insert(im, ring, pred=None, slot0=0, step=0):
+    """ring[..., (slot0+j) % T, :] = im[..., j, :]; pred[..., step*Tb+j, :] = im[..., j, :]."""
+    _need_cuda(im, ring, pred)
+    B, X, Y, T, Cc = ring.shape
+    Tb = im.shape[-2]
+    Ttot = pred.shape[-2] if pred is not None else 0
+    check(_lib.load().dpot_ring_insert(ptr(im), ptr(ring), ptr(pred), B * X * Y, T, Tb, Cc, Ttot, slot0, step, _stream()),
+          "dpot_ring_insert")
+    return ring
+
+
 def adam_step_multi(params, grads, ms, vs, vmaxs, steps, *, lr, beta1, beta2, eps, weight_decay, decoupled,
                     grad_scale=1.0):
     n = len(params)

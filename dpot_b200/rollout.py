@@ -1,9 +1,11 @@
 """Pipelined autoregressive rollout (the loop of evaluate.py:192-208 / train_temporal.py:262-272
 under no_grad): im = model(xx); pred[..., t] = im; xx = cat(xx[..., T_bundle:, :], im).
 
-Everything is enqueued on one CUDA stream without host synchronisation: the window is advanced by
-a kernel into a ping-pong buffer (no torch.cat allocation per step) which also scatters the new
-frame into the preallocated prediction tensor."""
+Everything is enqueued on one CUDA stream without host synchronisation.  The window is a RING in
+time: logical frame t lives in slot (t + t0) % T, the model reads it through that offset
+(dpot_forward_ring) and each step only overwrites the oldest T_bundle slots with the new frames
+(dpot_ring_insert, which also scatters them into the preallocated prediction tensor) -- no
+torch.cat, no copy of the surviving T - T_bundle frames."""
 from __future__ import annotations
 
 from typing import Optional
@@ -22,7 +24,7 @@ class RolloutEngine:
         Tb, Co = model.out_timesteps, model.out_channels
         if Co != Cc:
             raise ValueError("autoregressive rollout needs out_channels == in_channels")
-        self.win = [torch.empty((batch, R, R, T, Cc), device=dev), torch.empty((batch, R, R, T, Cc), device=dev)]
+        self.win = torch.empty((batch, R, R, T, Cc), device=dev)
         self.im = torch.empty((batch, R, R, Tb, Co), device=dev)
         self.pred = torch.empty((batch, R, R, n_steps * Tb, Co), device=dev)
 
@@ -30,12 +32,13 @@ class RolloutEngine:
     def run(self, xx: torch.Tensor, non_blocking: bool = True) -> torch.Tensor:
         """xx[B,X,Y,T,C] (host-pinned or device) -> pred[B,X,Y,n_steps*T_bundle,C] on the device."""
         eng = self.model.engine()
-        self.win[0].copy_(xx, non_blocking=non_blocking)
-        cur = 0
+        self.win.copy_(xx, non_blocking=non_blocking)
+        T, Tb = self.model.in_timesteps, self.model.out_timesteps
+        t0 = 0
         for s in range(self.n_steps):
-            eng.forward(self.win[cur], out=self.im, want_cls=False)
-            ops.window_advance(self.win[cur], self.im, self.win[1 - cur], self.pred, step=s)
-            cur = 1 - cur
+            eng.forward(self.win, out=self.im, want_cls=False, t0=t0)
+            ops.ring_insert(self.im, self.win, self.pred, slot0=t0, step=s)
+            t0 = (t0 + Tb) % T
         return self.pred
 
 

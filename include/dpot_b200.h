@@ -170,6 +170,9 @@ DPOT_API int dpot_afno_fft_fwd(const float* a, const float* scale, const float* 
 DPOT_API int dpot_afno_fft_inv(const float* O2, const float* a, const float* scale, const float* shift, int32_t B,
                       int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, float* f,
                       double* stats_out, int32_t groups, float interior_weight, void* stream);
+/* fwd with the spectrum stored as split fp16 (DPOT_FMT_HL16): S16 row (b,k1,k2) = [hi: 2E halves | lo: 2E halves] */
+DPOT_API int dpot_afno_fft_fwd16(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
+                        int32_t E, int32_t nb, int32_t km1, int32_t km2, void* S16, void* stream);
 /* interior_weight multiplies the spectrum columns 0 < k2 < h/2 (on output of fwd / on input of inv); 1 for the
    forward pass.  The two transforms are each other's adjoint up to that weight (Hermitian packing):
    adjoint(inv) = fwd with weight 2, adjoint(fwd) = inv with weight 1/2 -- this is the whole FFT backward.
@@ -259,6 +262,22 @@ DPOT_API int dpot_input_stats(const float* x, int32_t B, int64_t per_sample, int
 DPOT_API int dpot_window_advance(const float* xx, const float* im, float* xx_next, float* pred, int64_t npix,
                         int32_t T, int32_t Tb, int32_t C, int32_t Ttot, int32_t step, void* stream);
 
+/* Ring form of the same advance: the window lives in a ring buffer ring[B,X,Y,T,C] whose logical frame t
+ * is slot (t + t0) % T.  The Tb new frames overwrite the oldest slots slot0 = t0 .. t0+Tb-1 (mod T) and the
+ * caller advances t0 <- (t0 + Tb) % T; `pred` as above.  Moves Tb/T of the bytes of dpot_window_advance. */
+DPOT_API int dpot_ring_insert(const float* im, float* ring, float* pred, int64_t npix, int32_t T, int32_t Tb,
+                     int32_t C, int32_t Ttot, int32_t slot0, int32_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PatchEmbed conv0 + activation from the field layout (models/dpot.py:199-200,375), coordinate channels
+ * folded into rowbias0 (dpot_pack_patch):  z1[(b,p,q), t*mid + m], row pitch Kp (fp32) or 2*Kp halves with the
+ * lo plane at +Kp (out_fmt = DPOT_FMT_HL16).  x[B,X,Y,T,C] is read as a ring in time: logical frame t = slot
+ * (t + t0) % T (t0 = 0: the plain layout).  a_scale/a_shift[B, P*P*C]: optional input normalisation tables.
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, const float* rowbias0, const float* a_scale,
+                     const float* a_shift, int32_t B, int32_t X, int32_t Y, int32_t T, int32_t C, int32_t P,
+                     int32_t mid, int32_t act, void* z1, int32_t Kp, int32_t out_fmt, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer: adam()/adamw() of utils/optimizer.py:9-52 / :170-212 on one flat tensor.
  * step = 1-based count after the increment; decoupled = 0 (Adam, L2-coupled decay) or 1 (AdamW);
@@ -308,6 +327,10 @@ DPOT_API int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm, f
 /* x[B,X,Y,T,C] -> y[B,X,Y,To,Co], cls[B,n_cls] (cls may be NULL) */
 DPOT_API int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                  int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
+
+/* dpot_forward on a time-ring input window (see dpot_ring_insert): logical frame t of x is slot (t + t0) % T */
+DPOT_API int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
+                      int32_t t0, int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
 
 #ifdef __cplusplus
 }

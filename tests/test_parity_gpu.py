@@ -23,7 +23,7 @@ def build_model(cfg, params):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("engine", [1, 0], ids=["simt", "auto"])
+@pytest.mark.parametrize("engine", [1, 2, 0], ids=["simt", "tf32x3", "auto_f16split"])
 @pytest.mark.parametrize("name", FWD)
 def test_forward_and_rollout_match_reference_golden(name, engine):
     from dpot_b200.rollout import rollout
