@@ -33,39 +33,50 @@
 namespace dpot {
 namespace {
 
-constexpr int TN = 128;            // weight rows (output channels) per tile = UMMA M
+constexpr int TN = 128;            // weight rows (output channels) per CTA tile = TMEM lanes
 constexpr int TA = 128;            // max activation rows (tokens) per tile
 constexpr int BKH = 64;            // halves per k-block = one 128 B swizzle row
-constexpr int STAGES = 3;
 constexpr int NTHREADS = 384;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;
 
 constexpr uint32_t W_BYTES = TN * 128;          // 16 KB per plane
-constexpr uint32_t A_BYTES = TA * 128;          // 16 KB per plane (max)
-constexpr uint32_t OFF_W_HI = 0, OFF_W_LO = W_BYTES, OFF_A = 2 * W_BYTES;   // A_hi at OFF_A, A_lo at OFF_A + BA*128
-constexpr uint32_t STAGE_BYTES = 2 * W_BYTES + 2 * A_BYTES;   // 64 KB
-constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;
+constexpr uint32_t OFF_W_HI = 0, OFF_W_LO = W_BYTES, OFF_A = 2 * W_BYTES;   // A_hi at OFF_A, A_lo one plane later
 
-// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc16(uint32_t n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// CG = 1: one CTA per tile (128 channels x BA tokens).  CG = 2: a CTA PAIR (tcgen05 cta_group::2) owns a
+// 256-channel x BA-token tile: each CTA stages its own 128 weight rows and HALF of the tokens, the pair's MMA
+// (UMMA M = 256) reads the token operand from both shared memories -- 48 KB instead of 64 KB of L2->SM traffic
+// per k-block and CTA.  The L2->SM fabric (~6300 B/clk chip-wide, measured) is what bounds this engine.
+template <int CG>
+struct Geo {
+  static constexpr int STAGES = CG == 2 ? 4 : 3;
+  static constexpr uint32_t A_BYTES = (TA / CG) * 128;                // per plane (max)
+  static constexpr uint32_t STAGE_BYTES = 2 * W_BYTES + 2 * A_BYTES;  // 64 KB / 48 KB
+  static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;
+};
+
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=m, N=n
+__host__ __device__ constexpr uint32_t make_idesc16(uint32_t n, uint32_t m = 128u) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 struct Tc16Params {
   GemmDev g;
   int BA;            // activation rows per tile, multiple of 16, <= 128
   int n_tiles, m_tiles, total_tiles, kblocks;
+  int dbg;           // experiment mask (dpot_tc16_set_debug): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
 };
 
 // ACT_MODE: 0 = none, 1 = GELU (erf), 2 = runtime switch.  OUT16: store the result as DPOT_FMT_HL16.
 // SIDE: the epilogue has side inputs (row-periodic bias, residual, per-sample affine); without them that code
 // (and its registers) is compiled out -- the AFNO GEMMs (K = 2*bs) are epilogue-bound.
-template <int ACT_MODE, bool OUT16, bool SIDE>
+template <int CG, int ACT_MODE, bool OUT16, bool SIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                  const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                  const Tc16Params P) {
+  constexpr int STAGES = Geo<CG>::STAGES;
+  constexpr uint32_t STAGE_BYTES = Geo<CG>::STAGE_BYTES, BAR_OFF = Geo<CG>::BAR_OFF;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // barriers: [0,S) full  [S,2S) empty  [2S,2S+2) tmem_full  [2S+2,2S+4) tmem_empty ; then the TMEM base slot
@@ -78,54 +89,73 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmDev& g = P.g;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;     // 0 = leader of the pair (issues the MMAs)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&mapWh); tma_prefetch_desc(&mapWl); tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapAl);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), EPI_WARPS * 32); }
+    // tmem_empty lives in the leader and counts one arrival per epilogue warp of every CTA of the group
+    for (int b = 0; b < 2; ++b) { mbar_init(TFULL(b), 1); mbar_init(TEMPTY(b), CG * EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_2cta(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int KB = P.kblocks, BA = P.BA;
-  const uint32_t a_plane = (uint32_t)BA * 128u;
-  const uint32_t stage_tx = 2u * W_BYTES + 2u * a_plane;
+  const int rows_a = BA / CG;                                  // token rows this CTA stages
+  const uint32_t a_plane = (uint32_t)rows_a * 128u;
+  const uint32_t stage_tx = 2u * W_BYTES + 2u * a_plane;       // bytes this CTA loads per stage
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
+      const uint32_t full_leader = CG == 2 ? mapa_rank(FULL(0), 0) : FULL(0);   // completion barrier of the group
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
         const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
         const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
+        const int n0 = (nt * CG + (int)rank) * TN, m0 = mt * BA + (int)rank * rows_a;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(EMPTY(s), ph ^ 1);
-          mbar_expect_tx(FULL(s), stage_tx);
           const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
-          tma_load_3d(sb + OFF_W_HI, &mapWh, FULL(s), kb * BKH, nt * TN, bz);        // dims (k, n, batch)
-          tma_load_3d(sb + OFF_W_LO, &mapWl, FULL(s), kb * BKH, nt * TN, bz);
-          tma_load_3d(sb + OFF_A, &mapAh, FULL(s), kb * BKH, bz, mt * BA);           // dims (k, batch, m)
-          tma_load_3d(sb + OFF_A + a_plane, &mapAl, FULL(s), kb * BKH, bz, mt * BA);
+          if (P.dbg & 1) {                      // experiment: the MMA pipeline alone (operands = whatever is in smem)
+            if (rank == 0) mbar_arrive(FULL(s));
+          } else if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(FULL(s), 2u * stage_tx);   // the leader's barrier collects both CTAs' bytes
+            const uint32_t fb = full_leader + 8u * s;
+            tma_load_3d_2cta(sb + OFF_W_HI, &mapWh, fb, kb * BKH, n0, bz);         // dims (k, n, batch)
+            tma_load_3d_2cta(sb + OFF_W_LO, &mapWl, fb, kb * BKH, n0, bz);
+            tma_load_3d_2cta(sb + OFF_A, &mapAh, fb, kb * BKH, bz, m0);            // dims (k, batch, m)
+            tma_load_3d_2cta(sb + OFF_A + a_plane, &mapAl, fb, kb * BKH, bz, m0);
+          } else {
+            mbar_expect_tx(FULL(s), stage_tx);
+            tma_load_3d(sb + OFF_W_HI, &mapWh, FULL(s), kb * BKH, n0, bz);
+            tma_load_3d(sb + OFF_W_LO, &mapWl, FULL(s), kb * BKH, n0, bz);
+            tma_load_3d(sb + OFF_A, &mapAh, FULL(s), kb * BKH, bz, m0);
+            tma_load_3d(sb + OFF_A + a_plane, &mapAl, FULL(s), kb * BKH, bz, m0);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (elect_one()) {
-      const uint32_t idesc_a = make_idesc16((uint32_t)(2 * BA));
-      const uint32_t idesc_b = make_idesc16((uint32_t)BA);
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc_2ba = make_idesc16((uint32_t)(2 * BA));         // CG 1: [hi ; lo] token rows in one MMA
+      const uint32_t idesc_ba = make_idesc16((uint32_t)BA, 128u * CG);
       int s = 0; uint32_t ph = 0; uint32_t tc = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
+      for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++tc) {
         const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
-        mbar_wait(TEMPTY(buf), bph ^ 1);          // epilogue has drained this TMEM buffer
+        mbar_wait(TEMPTY(buf), bph ^ 1);          // every epilogue warp (of both CTAs) has drained this TMEM buffer
         tc_fence_after();
         const uint32_t d1 = tmem_base + buf * 256u;
         const uint32_t d2 = d1 + (uint32_t)BA;
@@ -137,14 +167,24 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
           for (int k4 = 0; k4 < BKH / 16; ++k4) {
             const uint64_t w_hi = make_smem_desc(sb + OFF_W_HI + k4 * 32);
             const uint64_t w_lo = make_smem_desc(sb + OFF_W_LO + k4 * 32);
-            const uint64_t a_hl = make_smem_desc(sb + OFF_A + k4 * 32);      // rows [0,BA) = hi, [BA,2BA) = lo
-            umma_f16(d1, w_hi, a_hl, idesc_a, (kb > 0 || k4 > 0) ? 1u : 0u);
-            umma_f16(d2, w_lo, a_hl, idesc_b, 1u);
+            const uint64_t a_hi = make_smem_desc(sb + OFF_A + k4 * 32);      // CG 1: rows [0,BA) = hi, [BA,2BA) = lo
+            const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
+            if (P.dbg & 2) {                    // experiment: the load pipeline alone
+            } else if (CG == 2) {
+              // the pair's token operand: first BA/2 rows from the leader's shared memory, the rest from the peer's
+              const uint64_t a_lo = make_smem_desc(sb + OFF_A + a_plane + k4 * 32);
+              umma_f16_2cta(d1, w_hi, a_hi, idesc_ba, acc);
+              umma_f16_2cta(d2, w_hi, a_lo, idesc_ba, acc);
+              umma_f16_2cta(d2, w_lo, a_hi, idesc_ba, 1u);
+            } else {
+              umma_f16(d1, w_hi, a_hi, idesc_2ba, acc);
+              umma_f16(d2, w_lo, a_hi, idesc_ba, 1u);
+            }
           }
-          umma_commit(EMPTY(s));
+          if (CG == 2) umma_commit_2cta(EMPTY(s)); else umma_commit(EMPTY(s));
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(TFULL(buf));
+        if (CG == 2) umma_commit_2cta(TFULL(buf)); else umma_commit(TFULL(buf));
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -153,15 +193,19 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
     const int half = (warp - EPI_WARP0) >> 2;         // interleaved 8-column groups: g = half, half+2, ...
     const int ngroups = BA / 8;
     __half* const Ch_base = reinterpret_cast<__half*>(g.C);
+    const uint32_t tempty_leader = CG == 2 ? mapa_rank(TEMPTY(0), 0) : TEMPTY(0);
     uint32_t tc = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++tc) {
+    for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++tc) {
       const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
       const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
       const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
-      const int n = nt * TN + quarter * 32 + lane;
+      const int n = (nt * CG + (int)rank) * TN + quarter * 32 + lane;
       const bool nok = n < g.N;
       const float bias_n = (g.bias && nok) ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
-      float st1 = 0.f, st2 = 0.f;
+      // fused GroupNorm statistics: a tile of <= 128 tokens touches at most two samples (slot 0 / slot 1)
+      float st1a = 0.f, st2a = 0.f, st1b = 0.f, st2b = 0.f;
+      const int smp0 = g.out_stats ? (mt * BA) / g.st_rps : 0;
+      const int m_next = (smp0 + 1) * g.st_rps;       // first token of the next sample
       // side inputs (row-periodic bias, residual) of a group are fetched one group ahead: their global-load
       // latency hides behind the arithmetic of the previous group instead of serialising the epilogue
       float nrb[8], nrs[8];
@@ -181,6 +225,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       const uint32_t t_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
       for (int gi = half; gi < ngroups; gi += 2) {
+        if (P.dbg & 4) break;                   // experiment: no epilogue work
         const int c0 = gi * 8;
         uint32_t r1[8], r2[8];
         tmem_ld8(t_row + (uint32_t)c0, r1);
@@ -227,56 +272,98 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
             }
         } else {
           float* __restrict__ cp = g.C + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + n;
+          float a1 = 0.f, a2 = 0.f;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (u < cnt) {
               cp[(int64_t)u * g.ldc] = t[u];
-              st1 += t[u];
-              st2 = fmaf(t[u], t[u], st2);
+              a1 += t[u];
+              a2 = fmaf(t[u], t[u], a2);
             }
+          const bool nxt = m0 >= m_next;             // st_rps % 8 == 0: a group of 8 tokens never straddles samples
+          st1a += nxt ? 0.f : a1; st2a += nxt ? 0.f : a2;
+          st1b += nxt ? a1 : 0.f; st2b += nxt ? a2 : 0.f;
         }
       }
       tc_fence_before();
-      mbar_arrive(TEMPTY(buf));
-      if (!OUT16 && g.out_stats && nok) {   // host guarantees: tile within one sample, the warp's 32 channels in one group
-        double d1 = (double)st1, d2 = (double)st2;
-        const unsigned msk = __activemask();
-        for (int o = 16; o > 0; o >>= 1) {
-          d1 += __shfl_xor_sync(msk, d1, o);
-          d2 += __shfl_xor_sync(msk, d2, o);
-        }
-        if (lane == 0) {
-          const int smp = (mt * BA) / g.st_rps, grp = n / (g.N / g.st_groups);
-          double* dst = g.out_stats + ((int64_t)smp * g.st_groups + grp) * 2;
-          atomicAdd(dst, d1);
-          atomicAdd(dst + 1, d2);
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * buf); else mbar_arrive(TEMPTY(buf));
+      }
+      if (!OUT16 && g.out_stats) {   // host guarantees: the warp's 32 channels lie in one group
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          const int smp = smp0 + slot;
+          if (slot == 1 && (mt * BA + BA <= m_next || m_next >= g.M)) break;   // uniform: the tile ends inside sample smp0
+          double d1 = nok ? (double)(slot ? st1b : st1a) : 0.0, d2 = nok ? (double)(slot ? st2b : st2a) : 0.0;
+          for (int o = 16; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+          }
+          if (lane == 0 && nok) {
+            const int grp = n / (g.N / g.st_groups);
+            double* dst = g.out_stats + ((int64_t)smp * g.st_groups + grp) * 2;
+            atomicAdd(dst, d1);
+            atomicAdd(dst + 1, d2);
+          }
         }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: no CTA may exit while its peer can still reach its smem / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
 int g_sm_count = 0;
-// Tokens per tile.  The persistent grid runs ceil(tiles / #SM) rounds of one tile per SM; a slightly smaller
-// tile (e.g. 112 instead of 128 rows: 592 = 4 x 148 tiles for M = 8192, N = 1024) can fill the last round.
-int pick_ba(int M, int other_tiles, int divides = 0) {   // divides > 0: BA must divide it (fused GroupNorm statistics)
-  if (M <= TA) return (int)round_up(M, 16);
-  const int sms = g_sm_count > 0 ? g_sm_count : 148;
-  int best = TA; int64_t best_cost = -1;
-  for (int ba = TA; ba >= 64; ba -= 16) {
-    if (divides > 0 && divides % ba != 0) continue;
-    const int64_t tiles = ceil_div(M, ba) * other_tiles;
-    const int64_t cost = ceil_div(tiles, sms) * (ba + 12);      // + fixed per-tile overhead (pipeline fill, epilogue tail)
-    if (best_cost < 0 || cost < best_cost) { best = ba; best_cost = cost; }
+int g_dbg = 0;
+int g_pair_mode = -1;    // -1: auto (cost model below), 0: never, 1: pairs whenever legal (dpot_tc16_set_pair)
+
+bool stats_any_ba(const GemmDev& p) { return p.st_rps % 8 == 0 && p.st_rps >= TA; }
+
+// Tile plan.  The persistent grid runs ceil(tiles / #units) rounds of one tile per unit (unit = SM, or SM pair); a
+// slightly smaller tile (e.g. 112 instead of 128 tokens: 592 = 4 x 148 tiles for M = 8192, N = 1024) can fill the
+// last round.  Cost of a plan = rounds x (BA x k-blocks + fixed per-tile overhead), in token-k-block units; a CTA
+// pair moves 25 % fewer operand bytes per MMA (measured: ~7 % faster per tile at K = 1024) but pays a larger
+// per-tile overhead (cluster-wide handshakes), so short-K problems stay on single-CTA tiles.
+// divides > 0: BA must divide it (fused GroupNorm statistics when a tile may not straddle samples).
+struct Plan { int cg, BA, n_tiles, m_tiles; int64_t cost; };
+Plan plan_for(const GemmDev& p, int batch, int cg, int sms, int divides) {
+  Plan pl;
+  pl.cg = cg;
+  pl.n_tiles = (int)ceil_div(p.N, TN * cg);
+  const int other = pl.n_tiles * batch, units = sms / cg, step = 16 * cg;
+  const int64_t kblocks = ceil_div(p.K, BKH), ovh = cg == 2 ? 320 : 192;
+  pl.BA = 0; pl.cost = -1;
+  if (p.M <= TA) {
+    pl.BA = (int)round_up(p.M, step);
+    pl.cost = ceil_div(other, units) * (pl.BA * kblocks + ovh);
+  } else {
+    for (int ba = TA; ba >= (cg == 2 ? 96 : 64); ba -= step) {
+      if (divides > 0 && divides % ba != 0) continue;
+      const int64_t tiles = ceil_div(p.M, ba) * other;
+      const int64_t cost = ceil_div(tiles, units) * (ba * kblocks + ovh);
+      if (pl.cost < 0 || cost < pl.cost) { pl.BA = ba; pl.cost = cost; }
+    }
   }
-  return best;
+  if (cg == 2 && pl.cost >= 0) pl.cost = pl.cost * 93 / 100;
+  pl.m_tiles = pl.BA > 0 ? (int)ceil_div(p.M, pl.BA) : 0;
+  return pl;
+}
+Plan make_plan(const GemmDev& p, int batch) {
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  const int divides = (p.st_groups > 0 && p.st_rps > 0 && !stats_any_ba(p)) ? p.st_rps : 0;
+  Plan one = plan_for(p, batch, 1, sms, divides);
+  // pairs need >= 256 output channels to fill both CTAs and enough tokens to split
+  if (g_pair_mode == 0 || p.N <= TN || p.M < 32 || sms % 2 != 0) return one;
+  Plan two = plan_for(p, batch, 2, sms, divides);
+  if (two.cost < 0) return one;
+  if (one.cost < 0 || g_pair_mode == 1) return two;
+  return two.cost < one.cost ? two : one;
 }
 
 }  // namespace
@@ -296,9 +383,11 @@ bool gemm_tc16_supports(const GemmDev& p, int batch) {
 }
 
 bool gemm_tc16_fuses_stats(const GemmDev& p) {
-  const int BA = pick_ba(p.M, (int)ceil_div(p.N, TN), p.st_rps);
-  return p.c_fmt == DPOT_FMT_F32 && p.st_groups > 0 && p.st_rps > 0 && p.st_rps % BA == 0 && p.N % 32 == 0 &&
-         (p.N / p.st_groups) % 32 == 0;
+  if (!(p.c_fmt == DPOT_FMT_F32 && p.st_groups > 0 && p.st_rps > 0 && p.N % 32 == 0 && (p.N / p.st_groups) % 32 == 0))
+    return false;
+  if (stats_any_ba(p)) return true;
+  const Plan pl = make_plan(p, 1);
+  return p.st_rps % pl.BA == 0;
 }
 
 int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
@@ -309,11 +398,16 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
     DPOT_CUDA(cudaGetDevice(&dev));
     DPOT_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  P.n_tiles = (int)ceil_div(p.N, TN);
-  P.BA = pick_ba(p.M, P.n_tiles * batch, p.out_stats ? p.st_rps : 0);
-  P.m_tiles = (int)ceil_div(p.M, P.BA);
+  GemmDev q = p;
+  if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
+  const Plan pl = make_plan(q, batch);
+  const int CGn = pl.cg;
+  P.n_tiles = pl.n_tiles;
+  P.BA = pl.BA;
+  P.m_tiles = pl.m_tiles;
   P.total_tiles = P.n_tiles * P.m_tiles * batch;
   P.kblocks = (int)ceil_div(p.K, BKH);
+  P.dbg = g_dbg;
 
   const __half* Ah = reinterpret_cast<const __half*>(p.A);
   const __half* Wh = reinterpret_cast<const __half*>(p.W);
@@ -322,29 +416,37 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
   DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
   const uint64_t sAb = batch > 1 ? (uint64_t)p.sA * 2 : (uint64_t)p.lda * 2;
-  DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, (uint32_t)P.BA));
-  DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, (uint32_t)P.BA));
+  const uint32_t box_m = (uint32_t)(P.BA / CGn);
+  DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
+  DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
 
-  const int sm_count = g_sm_count;
-  const int grid = P.total_tiles < sm_count ? P.total_tiles : sm_count;
+  const int units = g_sm_count / CGn;
+  const int grid = CGn * (P.total_tiles < units ? P.total_tiles : units);
   const int am = p.act == DPOT_ACT_NONE ? 0 : (p.act == DPOT_ACT_GELU ? 1 : 2);
   const bool o16 = p.c_fmt == DPOT_FMT_HL16;
   const bool side = p.rowbias || p.residual || p.c_scale;
-#define DPOT_TC16_LAUNCH(AM, O16, SD)                                                                                  \
+#define DPOT_TC16_LAUNCH(CGV, AM, O16, SD)                                                                             \
   do {                                                                                                                 \
     static bool attr = false;                                                                                          \
     if (!attr) {                                                                                                       \
-      DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<AM, O16, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                     (int)SMEM_BYTES));                                                                \
+      DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<CGV, AM, O16, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)Geo<CGV>::SMEM_BYTES));                                                      \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    gemm_tc16_kernel<AM, O16, SD><<<grid, NTHREADS, SMEM_BYTES, st>>>(mWh, mWl, mAh, mAl, P);                          \
+    cudaLaunchConfig_t lc = {};                                                                                        \
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = Geo<CGV>::SMEM_BYTES;       \
+    lc.stream = st;                                                                                                    \
+    cudaLaunchAttribute at[1];                                                                                         \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
+    at[0].val.clusterDim.x = CGV; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                              \
+    lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+    DPOT_CUDA(cudaLaunchKernelEx(&lc, gemm_tc16_kernel<CGV, AM, O16, SD>, mWh, mWl, mAh, mAl, P));                     \
   } while (0)
-#define DPOT_TC16_SD(AM, O16) do { if (side) DPOT_TC16_LAUNCH(AM, O16, true); else DPOT_TC16_LAUNCH(AM, O16, false); } while (0)
-#define DPOT_TC16_O(AM) do { if (o16) DPOT_TC16_SD(AM, true); else DPOT_TC16_SD(AM, false); } while (0)
-  if (am == 0) DPOT_TC16_O(0);
-  else if (am == 1) DPOT_TC16_O(1);
-  else DPOT_TC16_O(2);
+#define DPOT_TC16_SD(CGV, AM, O16) do { if (side) DPOT_TC16_LAUNCH(CGV, AM, O16, true); else DPOT_TC16_LAUNCH(CGV, AM, O16, false); } while (0)
+#define DPOT_TC16_O(CGV, AM) do { if (o16) DPOT_TC16_SD(CGV, AM, true); else DPOT_TC16_SD(CGV, AM, false); } while (0)
+#define DPOT_TC16_A(CGV) do { if (am == 0) DPOT_TC16_O(CGV, 0); else if (am == 1) DPOT_TC16_O(CGV, 1); else DPOT_TC16_O(CGV, 2); } while (0)
+  if (CGn == 2) DPOT_TC16_A(2); else DPOT_TC16_A(1);
+#undef DPOT_TC16_A
 #undef DPOT_TC16_O
 #undef DPOT_TC16_SD
 #undef DPOT_TC16_LAUNCH
@@ -355,3 +457,6 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
 }  // namespace dpot
 
 extern "C" int dpot_tc16_available(void) { return dpot::tc_device_ok() ? 1 : 0; }
+// experiment / test knob: -1 auto, 0 single-CTA tiles only, 1 CTA pairs whenever legal
+extern "C" void dpot_tc16_set_pair(int32_t mode) { dpot::g_pair_mode = mode; }
+extern "C" void dpot_tc16_set_debug(int32_t mask) { dpot::g_dbg = mask; }

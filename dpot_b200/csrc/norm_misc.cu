@@ -432,6 +432,14 @@ extern "C" int dpot_pack_out(const float* wt, const float* bt, int32_t E, int32_
   return 0;
 }
 
+namespace dpot {
+int g_tail_engine = 0;   // 0 auto, 1 CUDA cores only (dpot_out_tail_set_engine; tests)
+int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4, int B, int h,
+                        int w, int P, int old, int nout, int act, const float* mu, const float* sigma, int Co, float* out,
+                        cudaStream_t st, bool* served);
+}
+extern "C" void dpot_out_tail_set_engine(int32_t engine) { dpot::g_tail_engine = engine; }
+
 extern "C" int dpot_out_tail(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4,
                              int32_t B, int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act,
                              const float* mu, const float* sigma, int32_t Co, float* out, void* stream) {
@@ -442,6 +450,12 @@ extern "C" int dpot_out_tail(const float* Y1, const float* w2, const float* b2, 
   const unsigned grid = (unsigned)ceil_div(npix, 128);
   cudaStream_t st = as_stream(stream);
   const bool l2 = (w2 != nullptr);
+  if (l2 && g_tail_engine != 1) {   // warp-MMA kernel (out_tail_mma.cu) when the geometry allows
+    DPOT_REQUIRE(b2 != nullptr, DPOT_E_BADARG, "dpot_out_tail: b2 missing");
+    bool served = false;
+    DPOT_CALL(out_tail_mma_launch(Y1, w2, b2, w4, b4, B, h, w, P, old, nout, act, mu, sigma, Co, out, st, &served));
+    if (served) return 0;
+  }
   const size_t smem = sizeof(float) * ((l2 ? (size_t)old * old + old : 0) + (size_t)nout * old + nout);
 #define TAIL_CASE(O)                                                                                              \
   case O:                                                                                                         \

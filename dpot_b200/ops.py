@@ -75,9 +75,10 @@ def split_f16(x: torch.Tensor, scale=None, shift=None, rows_per_sample: int = 0)
 
 
 def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residual=None, rowbias=None, c_scale=None,
-           c_shift=None, c_rows_per_sample=0, out16: bool = False, nb: int = 1) -> torch.Tensor:
+           c_shift=None, c_rows_per_sample=0, out16: bool = False, nb: int = 1, stats=None):
     """The f16-split tcgen05 engine on pre-split operands A16[M, 2*Kt], W16[nb*N, 2*K] (see split_f16).
-    nb > 1: block-diagonal form, A16 hi plane [M, nb*K], W16 [nb, N, 2K], bias [nb, N] -> C[M, nb*N]."""
+    nb > 1: block-diagonal form, A16 hi plane [M, nb*K], W16 [nb, N, 2K], bias [nb, N] -> C[M, nb*N].
+    stats=(groups, rows_per_sample): also return the GroupNorm statistics [M/rps, groups, 2] (double) of the result."""
     _need_cuda(bias, residual, rowbias, c_scale, c_shift)
     assert A16.dtype == torch.float16 and W16.dtype == torch.float16 and A16.is_cuda and W16.is_cuda
     M, Kt = A16.shape[0], A16.shape[1] // 2
@@ -105,8 +106,13 @@ def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residua
     g.batch, g.engine, g.a_mode = nb, _lib.GEMM_TC16, _lib.A_PLAIN
     if nb > 1:
         g.strideA, g.strideW, g.strideC, g.strideBias = K, N * 2 * K, N, N
+    st = None
+    if stats is not None:
+        groups, rps = stats
+        st = torch.empty((M // rps, groups, 2), device=A16.device, dtype=torch.float64)
+        g.out_stats, g.stats_groups, g.stats_rows_per_sample = ptr(st), groups, rps
     check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(tc16)")
-    return out
+    return out if st is None else (out, st)
 
 
 def unsplit_f16(x16: torch.Tensor) -> torch.Tensor:
@@ -155,6 +161,36 @@ def patch_gemm(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: in
     g.a_mode, g.pX, g.pY, g.pT, g.pC, g.pP = _lib.A_PATCH, X, Y, T, Cc, P
     check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(patch)")
     return z1
+
+
+def patch_embed(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: int, act, Kp: int, *, t0: int = 0,
+                a_scale=None, a_shift=None, out16: bool = False) -> torch.Tensor:
+    """dpot_patch_embed: x[B,X,Y,T,C] (a ring in time, logical frame t = slot (t+t0)%T) -> z1[B*n, Kp] fp32, or the
+    split-fp16 form [B*n, 2*Kp] halves (out16)."""
+    _need_cuda(x, W0p, rowbias0, a_scale, a_shift)
+    B, X, Y, T, Cc = x.shape
+    assert x.is_contiguous()
+    mid = W0p.shape[0]
+    n = (X // P) * (Y // P)
+    if out16:
+        z1 = torch.zeros((B * n, 2 * Kp), device=x.device, dtype=torch.float16)
+    else:
+        z1 = torch.zeros((B * n, Kp), device=x.device, dtype=torch.float32)
+    check(_lib.load().dpot_patch_embed(ptr(x), t0, ptr(W0p), ptr(rowbias0), ptr(a_scale), ptr(a_shift), B, X, Y, T, Cc, P,
+                                       mid, act_id(act), ptr(z1), Kp, _lib.FMT_HL16 if out16 else _lib.FMT_F32, _stream()),
+          "dpot_patch_embed")
+    return z1
+
+
+def out_tail(Y1: torch.Tensor, w2, b2, w4, b4, B: int, h: int, w: int, P: int, act, *, mu=None, sigma=None,
+             Co: int = 0) -> torch.Tensor:
+    """dpot_out_tail: Y1[(b,p,q), (u,v,o)] -> per-pixel act(W2 y + b2) -> W4 . + b4 -> out[B, h*P, w*P, nout]."""
+    _need_cuda(Y1, w2, b2, w4, b4, mu, sigma)
+    nout, old = w4.shape[0], w4.shape[1]
+    out = torch.empty((B, h * P, w * P, nout), device=Y1.device, dtype=torch.float32)
+    check(_lib.load().dpot_out_tail(ptr(Y1), ptr(w2), ptr(b2), ptr(w4), ptr(b4), B, h, w, P, old, nout, act_id(act),
+                                    ptr(mu), ptr(sigma), Co or nout, ptr(out), _stream()), "dpot_out_tail")
+    return out
 
 
 def gn_stats(x: torch.Tensor, B: int, n: int, groups: int = GROUPS) -> torch.Tensor:

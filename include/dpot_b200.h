@@ -144,6 +144,11 @@ DPOT_API int dpot_split_f16(const float* src, int64_t lds, int64_t rows, int32_t
                    const float* shift, int32_t rows_per_sample, void* dst, int64_t ldd, int64_t lo_off, void* stream);
 /* 1 if the f16-split tcgen05 engine can serve this device */
 DPOT_API int dpot_tc16_available(void);
+/* tile-plan knob of the f16-split engine (tests / experiments): -1 = auto (cost model), 0 = single-CTA tiles only,
+   1 = CTA pairs (tcgen05 cta_group::2, UMMA M = 256) whenever N > 128 */
+DPOT_API void dpot_tc16_set_pair(int32_t mode);
+/* pipeline-isolation experiments (results are garbage when non-zero): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue */
+DPOT_API void dpot_tc16_set_debug(int32_t mask);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm pieces (torch.nn.GroupNorm(8,E), models/dpot.py:142,152,167,175).
@@ -247,6 +252,8 @@ DPOT_API int dpot_unpack_afno_grad(const float* dWc, const float* dbc, int32_t n
 DPOT_API int dpot_out_tail(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4,
                   int32_t B, int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act,
                   const float* mu, const float* sigma, int32_t Co, float* out, void* stream);
+/* engine knob (tests): 0 = auto (warp-MMA kernel for out_layer_dim in {16,32}, nout <= 8), 1 = CUDA cores only */
+DPOT_API void dpot_out_tail_set_engine(int32_t engine);
 /* spatial mean a[B*n,E] -> tok[B,E]  (models/dpot.py:394) */
 DPOT_API int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E, float* tok, void* stream);
 /* per (sample, channel) mean and unbiased std + 1e-6 over (X,Y,T)  (models/dpot.py:367);
@@ -277,6 +284,8 @@ DPOT_API int dpot_ring_insert(const float* im, float* ring, float* pred, int64_t
 DPOT_API int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, const float* rowbias0, const float* a_scale,
                      const float* a_shift, int32_t B, int32_t X, int32_t Y, int32_t T, int32_t C, int32_t P,
                      int32_t mid, int32_t act, void* z1, int32_t Kp, int32_t out_fmt, void* stream);
+/* engine knob (tests): 0 = auto (warp-MMA on split fp16 when the geometry allows), 1 = fp32 CUDA cores, 2 = warp-MMA only */
+DPOT_API void dpot_patch_embed_set_engine(int32_t engine);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer: adam()/adamw() of utils/optimizer.py:9-52 / :170-212 on one flat tensor.

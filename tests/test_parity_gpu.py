@@ -358,3 +358,124 @@ def test_tc16_engine_small_magnitudes_and_batched():
     ref = np.concatenate([O.activation(A[:, i * K:(i + 1) * K].astype(np.float64) @ W[i].T.astype(np.float64) + b[i], "gelu")
                           for i in range(nb)], axis=1)
     assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("shape", [(8192, 1024, 1024), (300, 200, 96), (1000, 384, 128), (4608, 256, 256), (96, 512, 64)])
+def test_tc16_pair_and_single_tile_plans(shape, pair):
+    """CTA-pair tiles (tcgen05 cta_group::2, UMMA M=256) and single-CTA tiles give the same fp32-level result."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    if not lib.dpot_tc16_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).cuda()
+    ref = O.activation(A.astype(np.float64) @ W.T.astype(np.float64) + b, "gelu") + R
+    lib.dpot_tc16_set_pair(pair)
+    try:
+        for out16 in (False, True):
+            out = ops.gemm16(ops.split_f16(t(A)), ops.split_f16(t(W)), bias=t(b), act="gelu", residual=t(R), out16=out16)
+            if out16:
+                out = ops.unsplit_f16(out)
+            assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6, (shape, pair, out16)
+    finally:
+        lib.dpot_tc16_set_pair(-1)
+
+
+@pytest.mark.parametrize("pair", [0, 1, -1])
+@pytest.mark.parametrize("M,N,K,rps", [(8192, 1024, 1024, 256), (2048, 256, 128, 256), (1024, 512, 64, 64)])
+def test_tc16_fused_groupnorm_statistics(M, N, K, rps, pair):
+    """GroupNorm statistics fused into the TC16 epilogue, including tiles that straddle two samples."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    if not lib.dpot_tc16_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    rng = np.random.default_rng(M + N + K + rps)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).cuda()
+    lib.dpot_tc16_set_pair(pair)
+    try:
+        out, st = ops.gemm16(ops.split_f16(t(A)), ops.split_f16(t(W)), residual=t(R), stats=(8, rps))
+    finally:
+        lib.dpot_tc16_set_pair(-1)
+    ref = A.astype(np.float64) @ W.T.astype(np.float64) + R
+    assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
+    g = ref.reshape(M // rps, rps, 8, N // 8)
+    s1, s2 = g.sum(axis=(1, 3)), (g * g).sum(axis=(1, 3))
+    st = st.cpu().numpy()
+    assert np.abs(st[..., 0] - s1).max() < 1e-3 * np.sqrt(rps * N / 8)
+    assert np.abs(st[..., 1] / s2 - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("geo", [(2, 64, 8, 10, 4, 35, 3), (3, 32, 4, 6, 4, 19, 0), (1, 128, 8, 10, 4, 35, 7), (2, 32, 8, 5, 4, 11, 2)])
+def test_patch_embed_engines(geo, engine):
+    """PatchEmbed conv0 + GELU from the ring-in-time field layout: fp32 CUDA-core kernel and the warp-MMA kernel on
+    split fp16 against float64 (models/dpot.py:199-200,375), incl. ring offset and input-normalisation tables."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    B, R, P, T, Cc, mid, t0 = geo
+    h = R // P
+    rng = np.random.default_rng(sum(geo))
+    x = rng.standard_normal((B, R, R, T, Cc)).astype(np.float32)
+    W = (rng.standard_normal((mid, P * P * Cc)) / np.sqrt(P * P * Cc)).astype(np.float32)
+    rb = rng.standard_normal((h * h * T, mid)).astype(np.float32)
+    sc = (1 + 0.1 * rng.standard_normal((B, P * P * Cc))).astype(np.float32)
+    sh = (0.1 * rng.standard_normal((B, P * P * Cc))).astype(np.float32)
+    Kp = -(-T * mid // 32) * 32
+    t = lambda a: torch.from_numpy(a).cuda()
+    # float64 reference: logical frame tt lives in slot (tt + t0) % T
+    xl = np.stack([x[:, :, :, (tt + t0) % T, :] for tt in range(T)], axis=3).astype(np.float64)
+    pat = xl.reshape(B, h, P, h, P, T, Cc).transpose(0, 1, 3, 5, 2, 4, 6).reshape(B, h, h, T, P * P * Cc)
+    for affine in (False, True):
+        pin = pat * sc[:, None, None, None, :] + sh[:, None, None, None, :] if affine else pat
+        z = pin @ W.T.astype(np.float64) + rb.reshape(1, h, h, T, mid)
+        want = O.activation(z, "gelu").reshape(B * h * h, T * mid)
+        lib.dpot_patch_embed_set_engine(engine)
+        try:
+            for out16 in (False, True):
+                got = ops.patch_embed(t(x), t(W), t(rb), P, "gelu", Kp, t0=t0, a_scale=t(sc) if affine else None,
+                                      a_shift=t(sh) if affine else None, out16=out16)
+                if out16:
+                    got = ops.unsplit_f16(got)
+                got = got.cpu().numpy()
+                assert np.all(got[:, T * mid:] == 0)
+                assert O.rel_l2(got[:, :T * mid], want) < 1e-6, (geo, engine, affine, out16)
+        finally:
+            lib.dpot_patch_embed_set_engine(0)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("geo", [(2, 8, 8, 32, 4, "gelu"), (3, 4, 4, 16, 2, "tanh"), (1, 16, 8, 32, 3, "gelu"), (2, 4, 4, 8, 4, "gelu")])
+def test_out_tail_engines(geo, engine):
+    """Per-pixel output tail (models/dpot.py:317-321,397-401): warp-MMA kernel and CUDA-core kernel vs float64."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    B, h, P, old, nout, act = geo
+    rng = np.random.default_rng(sum(geo[:5]))
+    Y1 = rng.standard_normal((B * h * h, P * P * old)).astype(np.float32)
+    w2 = (rng.standard_normal((old, old)) / np.sqrt(old)).astype(np.float32)
+    b2 = rng.standard_normal(old).astype(np.float32)
+    w4 = (rng.standard_normal((nout, old)) / np.sqrt(old)).astype(np.float32)
+    b4 = rng.standard_normal(nout).astype(np.float32)
+    mu = rng.standard_normal((B, nout)).astype(np.float32)
+    sg = (1 + 0.2 * rng.standard_normal((B, nout))).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    y = Y1.astype(np.float64).reshape(B, h, h, P, P, old)
+    y = O.activation(y @ w2.T.astype(np.float64) + b2, act) @ w4.T.astype(np.float64) + b4
+    want = y.transpose(0, 1, 3, 2, 4, 5).reshape(B, h * P, h * P, nout)
+    lib.dpot_out_tail_set_engine(engine)
+    try:
+        got = ops.out_tail(t(Y1), t(w2), t(b2), t(w4), t(b4), B, h, h, P, act).cpu().numpy()
+        assert O.rel_l2(got, want) < 1e-6, (geo, engine)
+        got = ops.out_tail(t(Y1), t(w2), t(b2), t(w4), t(b4), B, h, h, P, act, mu=t(mu), sigma=t(sg), Co=nout).cpu().numpy()
+        assert O.rel_l2(got, want * sg[:, None, None, :] + mu[:, None, None, :]) < 1e-6, (geo, engine, "denorm")
+    finally:
+        lib.dpot_out_tail_set_engine(0)

@@ -18,12 +18,16 @@ def bench(M, N, K, act, out16, nb=1, nrot=6, reps=30):
     e1.record(); torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / reps
     print(f"M={M} N={N} K={K} nb={nb} act={act} out16={out16}: {t*1e6:8.1f} us  {2.0*M*N*K*nb/t/1e12:7.1f} TFLOP/s", flush=True)
-bench(8192, 1024, 1024, "gelu", True)
-bench(8192, 1024, 1024, None, False)
-bench(8192, 1024, 1024, None, True)
-bench(8192, 2048, 1024, "gelu", False)
-bench(8192, 1024, 352, None, False)
-bench(4608, 256, 256, "gelu", True, nb=8)
-bench(4608, 256, 256, None, False, nb=8)
-bench(8192, 4096, 1024, "gelu", True)
-bench(8192, 1024, 4096, None, False)
+from dpot_b200 import _lib
+for mode in ([int(a) for a in sys.argv[1:]] or [0, 1, -1]):
+  _lib.load().dpot_tc16_set_pair(mode)
+  print("pair mode", mode)
+  bench(8192, 1024, 1024, "gelu", True)
+  bench(8192, 1024, 1024, None, False)
+  bench(8192, 1024, 1024, None, True)
+  bench(8192, 2048, 1024, "gelu", False)
+  bench(8192, 1024, 352, None, False)
+  bench(4608, 256, 256, "gelu", True, nb=8)
+  bench(4608, 256, 256, None, False, nb=8)
+  bench(8192, 4096, 1024, "gelu", True)
+  bench(8192, 1024, 4096, None, False)
