@@ -45,11 +45,33 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
+// nn.GELU() (exact erf form, models/dpot.py:19) as x * Phi(x) with ONE branch-free evaluation:
+//   Phi(-t) = 0.5 erfc(t / sqrt 2) = 2^q(t),  t = min(|x|, 5.7),  q = degree-9 minimax fit of log2(0.5 erfc(t/sqrt 2))
+//   weighted by the sensitivity t * Phi(-t) of the result;  gelu(x) = x * (x > 0 ? 1 - 2^q : 2^q).
+// Max abs error vs float64 over [-8, 8]: 2.1e-7 for |x| < 3 (= fp32 rounding of the exact value), rel-L2 2.0e-8
+// (fit + check: tools/fit_gelu.py).  15 instructions instead of ~38 for the two-branch erff form.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float t = fminf(fabsf(x), 5.7f);
+  float q = 1.3804051945953688e-07f;
+  q = fmaf(q, t, -3.4098220567102544e-06f);
+  q = fmaf(q, t, 3.314594505354762e-05f);
+  q = fmaf(q, t, -0.00013128264981787652f);
+  q = fmaf(q, t, -0.00031273943022824824f);
+  q = fmaf(q, t, 0.007349733263254166f);
+  q = fmaf(q, t, -0.05274663493037224f);
+  q = fmaf(q, t, -0.4590948820114136f);
+  q = fmaf(q, t, -1.1511284112930298f);
+  q = fmaf(q, t, -0.9999985098838806f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return x * (x > 0.f ? 1.0f - e : e);
+}
+
 // ---- activations: ACTIVATION table of models/dpot.py:19 (torch module defaults) --------------
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case DPOT_ACT_GELU:  // nn.GELU() exact erf form
-      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+      return gelu_fast(x);
     case DPOT_ACT_TANH: return tanhf(x);
     case DPOT_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
     case DPOT_ACT_RELU: return fmaxf(x, 0.0f);
@@ -82,7 +104,7 @@ __device__ __forceinline__ float erf_select(float a) {
   q = fmaf(q, a, a);
   return t > 0.927734375f ? big : q;
 }
-__device__ __forceinline__ float gelu_select(float x) { return 0.5f * x * (1.0f + erf_select(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_select(float x) { return gelu_fast(x); }
 
 // derivative d act(x)/dx, used by the backward kernels
 __device__ __forceinline__ float act_grad(float x, int act) {

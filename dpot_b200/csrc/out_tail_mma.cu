@@ -14,7 +14,7 @@ namespace dpot {
 namespace {
 
 template <int OLD, int ACT_MODE>
-__global__ void __launch_bounds__(128) out_tail_mma_kernel(const float* __restrict__ Y1, const float* __restrict__ w2,
+__global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __restrict__ Y1, const float* __restrict__ w2,
                                                            const float* __restrict__ b2, const float* __restrict__ w4,
                                                            const float* __restrict__ b4, int B, int h, int w, int P,
                                                            int nout, int act, const float* __restrict__ mu,
@@ -66,29 +66,35 @@ __global__ void __launch_bounds__(128) out_tail_mma_kernel(const float* __restri
 
   const int64_t npix = (int64_t)B * h * w * P * P;
   const int64_t ntile = (npix + 15) / 16;
-  const int X = h * P, Y = w * P, PP = P * P;
+  const int X = h * P, Y = w * P;
+  const int tiles_per_patch = P * P / 16;
   const int64_t wstep = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (tid >> 5); tile < ntile; tile += wstep) {
-    const int64_t pix0 = tile * 16 + g, pix1 = pix0 + 8;
-    const bool ok0 = pix0 < npix, ok1 = pix1 < npix;
-    // ---- y1 rows -> split A fragments (row g and g+8; k = ks*16 + tg*2 (+8))
-    uint32_t ah[KS][4], al[KS][4];
-    {
-      float2 v[KS][4];
-      const float2* r0 = reinterpret_cast<const float2*>(Y1 + pix0 * OLD);
-      const float2* r1 = reinterpret_cast<const float2*>(Y1 + pix1 * OLD);
+  // y1 rows of a 16-pixel tile (row g and g+8; k = ks*16 + tg*2 (+8)); the NEXT tile's rows are in flight while
+  // this one is computed (the kernel is a stream over 67 MB with ~1 us of arithmetic per tile and warp)
+  float2 v[KS][4];
+  auto load_tile = [&](int64_t tile) {
+    const int64_t pa = tile * 16 + g, pb = pa + 8;
+    const bool oka = pa < npix, okb = pb < npix;
+    const float2* r0 = reinterpret_cast<const float2*>(Y1 + pa * OLD);
+    const float2* r1 = reinterpret_cast<const float2*>(Y1 + pb * OLD);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        v[ks][0] = ok0 ? __ldg(r0 + ks * 8 + tg) : make_float2(0.f, 0.f);
-        v[ks][1] = ok1 ? __ldg(r1 + ks * 8 + tg) : make_float2(0.f, 0.f);
-        v[ks][2] = ok0 ? __ldg(r0 + ks * 8 + 4 + tg) : make_float2(0.f, 0.f);
-        v[ks][3] = ok1 ? __ldg(r1 + ks * 8 + 4 + tg) : make_float2(0.f, 0.f);
-      }
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hl_split2(v[ks][i].x, v[ks][i].y, ah[ks][i], al[ks][i]);
+    for (int ks = 0; ks < KS; ++ks) {
+      v[ks][0] = oka ? __ldg(r0 + ks * 8 + tg) : make_float2(0.f, 0.f);
+      v[ks][1] = okb ? __ldg(r1 + ks * 8 + tg) : make_float2(0.f, 0.f);
+      v[ks][2] = oka ? __ldg(r0 + ks * 8 + 4 + tg) : make_float2(0.f, 0.f);
+      v[ks][3] = okb ? __ldg(r1 + ks * 8 + 4 + tg) : make_float2(0.f, 0.f);
     }
+  };
+  const int64_t tile_first = (int64_t)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  if (tile_first < ntile) load_tile(tile_first);
+  for (int64_t tile = tile_first; tile < ntile; tile += wstep) {
+    const int64_t pix0 = tile * 16 + g, pix1 = pix0 + 8;
+    uint32_t ah[KS][4], al[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hl_split2(v[ks][i].x, v[ks][i].y, ah[ks][i], al[ks][i]);
+    if (tile + wstep < ntile) load_tile(tile + wstep);
     // ---- layer 2
     float d1[NT][4], d2[NT][4];
 #pragma unroll
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(128) out_tail_mma_kernel(const float* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         t[j] = fmaf(d2[nt][j], HL_INV, d1[nt][j]) + bias2[nt][j & 1];
-        t[j] = ACT_MODE == 1 ? gelu_select(t[j]) : act_apply(t[j], act);
+        t[j] = ACT_MODE == 1 ? gelu_fast(t[j]) : act_apply(t[j], act);
       }
       hl_split2(t[0], t[1], yh[nt >> 1][(nt & 1) * 2], yl[nt >> 1][(nt & 1) * 2]);          // row g
       hl_split2(t[2], t[3], yh[nt >> 1][(nt & 1) * 2 + 1], yl[nt >> 1][(nt & 1) * 2 + 1]);  // row g + 8
@@ -124,26 +130,31 @@ __global__ void __launch_bounds__(128) out_tail_mma_kernel(const float* __restri
       mma_f16(e2, yh[ks], w4l[ks][0], w4l[ks][1]);
       mma_f16(e2, yl[ks], w4h[ks][0], w4h[ks][1]);
     }
-    // ---- pixel shuffle store: pix = ((b*h + p)*w + q)*P*P + u*P + v
-#pragma unroll
-    for (int hr = 0; hr < 2; ++hr) {
-      const int64_t pix = hr ? pix1 : pix0;
-      if (pix >= npix || c0 >= nout) continue;
-      const int uv = (int)(pix % PP);
-      int64_t r = pix / PP;
-      const int q = (int)(r % w); r /= w;
-      const int p = (int)(r % h); const int b = (int)(r / h);
-      const int u = uv / P, v = uv % P;
-      float y0 = fmaf(e2[hr * 2], HL_INV, e1[hr * 2]) + bias4_0;
-      float y1v = fmaf(e2[hr * 2 + 1], HL_INV, e1[hr * 2 + 1]) + bias4_1;
+    // ---- pixel shuffle store: pix = ((b*h + p)*w + q)*P*P + u*P + v.  P*P % 16 == 0 (host-checked): the 16 pixels
+    // of a tile belong to ONE patch, so (b, p, q) is a warp-uniform 32-bit computation
+    {
+      const uint32_t patch = (uint32_t)(tile / tiles_per_patch);
+      const uint32_t uv0 = (uint32_t)(tile - (int64_t)patch * tiles_per_patch) * 16u;
+      const uint32_t q = patch % (uint32_t)w, bp = patch / (uint32_t)w;
+      const uint32_t p = bp % (uint32_t)h, b = bp / (uint32_t)h;
+      float sg0 = 1.f, sg1 = 1.f, mu0 = 0.f, mu1 = 0.f;
       if (mu) {   // x * sigma + mu, channel = c % Co   (models/dpot.py:401)
         const int ca = c0 % Co, cb = (c0 + 1) % Co;
-        y0 = fmaf(y0, sigma[(int64_t)b * Co + ca], mu[(int64_t)b * Co + ca]);
-        y1v = fmaf(y1v, sigma[(int64_t)b * Co + cb], mu[(int64_t)b * Co + cb]);
+        sg0 = sigma[(int64_t)b * Co + ca]; mu0 = mu[(int64_t)b * Co + ca];
+        sg1 = sigma[(int64_t)b * Co + cb]; mu1 = mu[(int64_t)b * Co + cb];
       }
-      float* dst = out + (((int64_t)b * X + p * P + u) * Y + q * P + v) * nout + c0;
-      if ((nout & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(y0, y1v);
-      else { dst[0] = y0; if (c0 + 1 < nout) dst[1] = y1v; }
+      float* base = out + (((int64_t)b * X + p * P) * Y + q * P) * nout + c0;
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        if (c0 >= nout || (hr ? pix1 : pix0) >= npix) continue;
+        const uint32_t uv = uv0 + (uint32_t)g + (hr ? 8u : 0u);
+        const uint32_t u = uv / (uint32_t)P, v = uv - u * (uint32_t)P;
+        const float y0 = fmaf(fmaf(e2[hr * 2], HL_INV, e1[hr * 2]) + bias4_0, sg0, mu0);
+        const float y1v = fmaf(fmaf(e2[hr * 2 + 1], HL_INV, e1[hr * 2 + 1]) + bias4_1, sg1, mu1);
+        float* dst = base + ((int64_t)u * Y + v) * nout;
+        if ((nout & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(y0, y1v);
+        else { dst[0] = y0; if (c0 + 1 < nout) dst[1] = y1v; }
+      }
     }
   }
 }
@@ -155,7 +166,7 @@ int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const
                         int w, int P, int old, int nout, int act, const float* mu, const float* sigma, int Co, float* out,
                         cudaStream_t st, bool* served) {
   *served = false;
-  if (!(old == 16 || old == 32) || nout > 8 || (reinterpret_cast<uintptr_t>(Y1) % 8) != 0 ||
+  if (!(old == 16 || old == 32) || nout > 8 || (P * P) % 16 != 0 || (reinterpret_cast<uintptr_t>(Y1) % 8) != 0 ||
       ((nout & 1) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) != 0))
     return 0;
   const int64_t npix = (int64_t)B * h * w * P * P;
@@ -164,7 +175,7 @@ int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t want = (ntile + 3) / 4;
-  const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+  const unsigned grid = (unsigned)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);   // one resident wave (4 CTAs / SM)
 #define DPOT_OTM(O, AM) out_tail_mma_kernel<O, AM><<<grid, 128, 0, st>>>(Y1, w2, b2, w4, b4, B, h, w, P, nout, act, mu, sigma, Co, out)
   if (old == 32) { if (act == DPOT_ACT_GELU) DPOT_OTM(32, 1); else DPOT_OTM(32, 2); }
   else { if (act == DPOT_ACT_GELU) DPOT_OTM(16, 1); else DPOT_OTM(16, 2); }

@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const PatchArgs a) {
 // CTA = one item (b, p, QPB patches along q) x all T frames: rows r = ql*T + t, one warp per 16-row tile.
 // Per image row u the item's slab is ONE contiguous run of the field: float4 loads -> hi/lo split ->
 // shared memory [row][k] (double-buffered), ldmatrix fragments, NT8 n-tiles of 8 output channels.
-template <int NT8, bool OUT16, int NF>
-__global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a) {
+template <int NT8, bool OUT16, int KS>
+__global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a, const int nitems) {
+  constexpr int NF = KS <= 2 ? 4 : 8;      // float4 per thread per slab (host guarantees L4 <= NF * nthr)
   extern __shared__ __align__(16) uint8_t smem_mma[];
   const int KW = a.K0 + 8;                 // halves per weight row (padded: conflict-free ldmatrix)
   const int KA = a.PC + 8;                 // halves per activation row
@@ -194,152 +195,186 @@ __global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a)
   const size_t a_plane = (size_t)rows_pad * KA;
 
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
-  int item = blockIdx.x;
-  const int qs = item % a.QSPLIT; item /= a.QSPLIT;
-  const int p = item % a.h; const int b = item / a.h;
-  const int q0 = qs * a.QPB;
-  const int nq = min(a.QPB, a.w - q0);
-  const int R = nq * a.T;
   const int TC = a.T * a.C;
-  const int L4 = nq * a.P * TC / 4;        // float4 per slab run
 
-  // ---- weights -> split fp16 in shared memory (rows >= mid are zero)
-  for (int e = tid; e < NT8 * 8 * a.K0; e += nthr) {
-    const int n = e / a.K0, k = e % a.K0;
-    __half hi = __float2half_rn(0.f), lo = hi;
-    if (n < a.mid) hl_split(__ldg(a.W0p + (int64_t)n * a.K0 + k), hi, lo);
-    Wh[(size_t)n * KW + k] = hi;
-    Wl[(size_t)n * KW + k] = lo;
-  }
-  // zero the activation rows that no patch owns (read by the last warp's fragments)
-  for (int e = tid; e < 4 * (rows_pad - R) * KA; e += nthr) {
-    const int pl = e / ((rows_pad - R) * KA), rem = e % ((rows_pad - R) * KA);
-    Ab[(size_t)pl * a_plane + (size_t)R * KA + rem] = __float2half_rn(0.f);
-  }
-
-  int doff[NF];                             // NF float4 per thread per slab (host guarantees L4 <= NF * nthr)                             // destination half-offset (row*KA + k) of each float4, -1 = none
+  // ---- weights -> split fp16 in shared memory, once per (persistent) CTA; rows >= mid are zero
+  {
+    const int nvec = a.mid * a.K0 / 4;                         // K0 % 4 == 0 (C % 4 == 0)
+    const float4* W4 = reinterpret_cast<const float4*>(a.W0p);
+    for (int e0 = tid; e0 < nvec; e0 += 4 * nthr) {
+      float4 v[4];
 #pragma unroll
-  for (int it = 0; it < NF; ++it) {
-    const int f = tid + it * nthr;
-    doff[it] = -1;
-    if (f < L4) {
-      const int e = f * 4;
-      const int c = e % a.C; int r = e / a.C;
-      const int slot = r % a.T; r /= a.T;
-      const int v = r % a.P; const int ql = r / a.P;
-      int t = slot - a.t0; if (t < 0) t += a.T;
-      doff[it] = (ql * a.T + t) * KA + v * a.C + c;
-    }
-  }
-  const float* run0 = a.x + (((int64_t)b * a.X + (int64_t)p * a.P) * a.Y + (int64_t)q0 * a.P) * TC;
-  const int64_t run_stride = (int64_t)a.Y * TC;      // one image row
-  float4 pre[NF];
-  auto prefetch = [&](int u) {
-    const float4* run = reinterpret_cast<const float4*>(run0 + (int64_t)u * run_stride);
+      for (int j = 0; j < 4; ++j) v[j] = (e0 + j * nthr < nvec) ? __ldg(W4 + e0 + j * nthr) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int it = 0; it < NF; ++it)
-      if (doff[it] >= 0) pre[it] = __ldg(run + tid + it * nthr);
-  };
-  auto convert = [&](int u) {
-    __half* Ah = Ab + (size_t)(u & 1) * 2 * a_plane;
-    __half* Al = Ah + a_plane;
-    const float* scl = a.a_scale ? a.a_scale + (int64_t)b * a.K0 + u * a.PC : nullptr;
-    const float* shf = a.a_scale ? a.a_shift + (int64_t)b * a.K0 + u * a.PC : nullptr;
-#pragma unroll
-    for (int it = 0; it < NF; ++it) {
-      if (doff[it] < 0) continue;
-      float vv[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
-      if (scl) {
-        const int k = doff[it] % KA;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) vv[j] = fmaf(vv[j], scl[k + j], shf[k + j]);
+      for (int j = 0; j < 4; ++j) {
+        const int e = (e0 + j * nthr) * 4;
+        if (e >= nvec * 4) continue;
+        const int n = e / a.K0, k = e % a.K0;
+        uint32_t h0, l0, h1, l1;
+        hl_split2(v[j].x, v[j].y, h0, l0);
+        hl_split2(v[j].z, v[j].w, h1, l1);
+        *reinterpret_cast<uint2*>(Wh + (size_t)n * KW + k) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(Wl + (size_t)n * KW + k) = make_uint2(l0, l1);
       }
-      __half h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) hl_split(vv[j], h[j], l[j]);
-      *reinterpret_cast<uint2*>(Ah + doff[it]) = make_uint2(
-          (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-          (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-      *reinterpret_cast<uint2*>(Al + doff[it]) = make_uint2(
-          (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
     }
-  };
-
-  float d1[NT8][4], d2[NT8][4];
-#pragma unroll
-  for (int i = 0; i < NT8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { d1[i][j] = 0.f; d2[i][j] = 0.f; }
+    for (int e = a.mid * a.K0 + tid; e < NT8 * 8 * a.K0; e += nthr) {
+      Wh[(size_t)(e / a.K0) * KW + e % a.K0] = __float2half_rn(0.f);
+      Wl[(size_t)(e / a.K0) * KW + e % a.K0] = __float2half_rn(0.f);
+    }
+  }
+  // activation rows beyond a short item (ragged last q-run) must read as zero: clear everything once
+  for (int e = tid; e < (int)(4 * a_plane / 2); e += nthr) reinterpret_cast<uint32_t*>(Ab)[e] = 0u;
+  __syncthreads();
 
   // ldmatrix lane addressing: lane -> (matrix j = lane / 8, row i = lane % 8)
   const int lj = lane >> 3, li = lane & 7;
   const uint32_t a_lane = (uint32_t)(((warp * 16 + (lj & 1) * 8 + li) * KA + (lj >> 1) * 8) * 2);       // A: (rows, k) quads
   const uint32_t w_lane = (uint32_t)((((lj >> 1) * 8 + li) * KW + (lj & 1) * 8) * 2);                  // W: (n-tile pair, k)
   const uint32_t Ab_s = smem_u32_generic(Ab), Wh_s = smem_u32_generic(Wh), Wl_s = smem_u32_generic(Wl);
+  const int g = lane >> 2, tg = lane & 3;
 
-  prefetch(0);
-  for (int u = 0; u < a.P; ++u) {
-    convert(u);
-    if (u + 1 < a.P) prefetch(u + 1);
-    __syncthreads();
-    const uint32_t Ah_s = Ab_s + (uint32_t)((u & 1) * 2 * a_plane * 2);
-    const uint32_t Al_s = Ah_s + (uint32_t)(a_plane * 2);
-    for (int ks = 0; ks < a.PC / 16; ++ks) {
-      uint32_t ah[4], al[4];
-      ldmatrix_x4(Ah_s + a_lane + ks * 32, ah);
-      ldmatrix_x4(Al_s + a_lane + ks * 32, al);
-      const uint32_t wk = (uint32_t)((u * a.PC + ks * 16) * 2);
+  // per-thread staging map (identical for every slab and item): float4 index -> destination (row*KA + k)
+  int doff[NF];
 #pragma unroll
-      for (int np = 0; np < (NT8 + 1) / 2; ++np) {
-        uint32_t wh[4], wl[4];
-        const uint32_t wrow = (uint32_t)(np * 16 * KW * 2);
-        if (2 * np + 1 < NT8) {
-          ldmatrix_x4(Wh_s + w_lane + wrow + wk, wh);
-          ldmatrix_x4(Wl_s + w_lane + wrow + wk, wl);
-        } else {                                   // odd tail: lanes 16-31 would address rows past the table
-          ldmatrix_x2(Wh_s + w_lane + wrow + wk, wh);
-          ldmatrix_x2(Wl_s + w_lane + wrow + wk, wl);
-        }
-        mma_f16(d1[2 * np], ah, wh[0], wh[1]);
-        mma_f16(d2[2 * np], ah, wl[0], wl[1]);
-        mma_f16(d2[2 * np], al, wh[0], wh[1]);
-        if (2 * np + 1 < NT8) {
-          mma_f16(d1[2 * np + 1], ah, wh[2], wh[3]);
-          mma_f16(d2[2 * np + 1], ah, wl[2], wl[3]);
-          mma_f16(d2[2 * np + 1], al, wh[2], wh[3]);
+  for (int it = 0; it < NF; ++it) {
+    const int e = (tid + it * nthr) * 4;
+    const int c = e % a.C; int r = e / a.C;
+    const int slot = r % a.T; r /= a.T;
+    const int v = r % a.P; const int ql = r / a.P;
+    int t = slot - a.t0; if (t < 0) t += a.T;
+    doff[it] = (ql * a.T + t) * KA + v * a.C + c;              // ql >= nq of the item is masked at load time
+  }
+
+  struct Item { int b, p, q0, L4; const float* run0; };
+  auto item_of = [&](int item) {
+    Item I;
+    const int qs = item % a.QSPLIT; item /= a.QSPLIT;
+    I.p = item % a.h; I.b = item / a.h;
+    I.q0 = qs * a.QPB;
+    const int nq = min(a.QPB, a.w - I.q0);
+    I.L4 = nq * a.P * TC / 4;
+    I.run0 = a.x + (((int64_t)I.b * a.X + (int64_t)I.p * a.P) * a.Y + (int64_t)I.q0 * a.P) * TC;
+    return I;
+  };
+  const int64_t run_stride = (int64_t)a.Y * TC;      // one image row
+  float4 pre[NF];
+  auto prefetch = [&](const Item& I, int u) {
+    const float4* run = reinterpret_cast<const float4*>(I.run0 + (int64_t)u * run_stride);
+#pragma unroll
+    for (int it = 0; it < NF; ++it)
+      pre[it] = (tid + it * nthr < I.L4) ? __ldg(run + tid + it * nthr) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto convert = [&](const Item& I, int u, int buf) {
+    __half* Ah = Ab + (size_t)buf * 2 * a_plane;
+    __half* Al = Ah + a_plane;
+    const float* scl = a.a_scale ? a.a_scale + (int64_t)I.b * a.K0 + u * a.PC : nullptr;
+    const float* shf = a.a_scale ? a.a_shift + (int64_t)I.b * a.K0 + u * a.PC : nullptr;
+#pragma unroll
+    for (int it = 0; it < NF; ++it) {
+      if ((tid + it * nthr) * 4 >= a.QPB * a.P * TC) continue;       // beyond the full-size slab
+      float vv[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
+      if (scl && tid + it * nthr < I.L4) {
+        const int k = doff[it] % KA;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vv[j] = fmaf(vv[j], scl[k + j], shf[k + j]);
+      }
+      uint32_t h0, l0, h1, l1;
+      hl_split2(vv[0], vv[1], h0, l0);
+      hl_split2(vv[2], vv[3], h1, l1);
+      *reinterpret_cast<uint2*>(Ah + doff[it]) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(Al + doff[it]) = make_uint2(l0, l1);
+    }
+  };
+
+  int item = blockIdx.x;
+  if (item >= nitems) return;
+  Item cur = item_of(item);
+  prefetch(cur, 0);
+  int buf = 0;
+  while (true) {
+    float d1[NT8][4], d2[NT8][4];
+#pragma unroll
+    for (int i = 0; i < NT8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d1[i][j] = 0.f; d2[i][j] = 0.f; }
+    const int next_item = item + gridDim.x;
+    Item nxt = cur;
+    if (next_item < nitems) nxt = item_of(next_item);
+
+    for (int u = 0; u < a.P; ++u, buf ^= 1) {
+      convert(cur, u, buf);
+      if (u + 1 < a.P) prefetch(cur, u + 1);
+      else if (next_item < nitems) prefetch(nxt, 0);           // the next item's first slab flies during this item's tail
+      __syncthreads();
+      const uint32_t Ah_s = Ab_s + (uint32_t)(buf * 2 * a_plane * 2);
+      const uint32_t Al_s = Ah_s + (uint32_t)(a_plane * 2);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ah[4], al[4];
+        ldmatrix_x4(Ah_s + a_lane + ks * 32, ah);
+        ldmatrix_x4(Al_s + a_lane + ks * 32, al);
+        const uint32_t wk = (uint32_t)((u * a.PC + ks * 16) * 2);
+#pragma unroll
+        for (int np = 0; np < (NT8 + 1) / 2; ++np) {
+          uint32_t wh[4], wl[4];
+          const uint32_t wrow = (uint32_t)(np * 16 * KW * 2);
+          if (2 * np + 1 < NT8) {
+            ldmatrix_x4(Wh_s + w_lane + wrow + wk, wh);
+            ldmatrix_x4(Wl_s + w_lane + wrow + wk, wl);
+          } else {                                   // odd tail: lanes 16-31 would address rows past the table
+            ldmatrix_x2(Wh_s + w_lane + wrow + wk, wh);
+            ldmatrix_x2(Wl_s + w_lane + wrow + wk, wl);
+          }
+          mma_f16(d1[2 * np], ah, wh[0], wh[1]);
+          mma_f16(d2[2 * np], ah, wl[0], wl[1]);
+          mma_f16(d2[2 * np], al, wh[0], wh[1]);
+          if (2 * np + 1 < NT8) {
+            mma_f16(d1[2 * np + 1], ah, wh[2], wh[3]);
+            mma_f16(d2[2 * np + 1], ah, wl[2], wl[3]);
+            mma_f16(d2[2 * np + 1], al, wh[2], wh[3]);
+          }
         }
       }
     }
-  }
 
-  // ---- epilogue: + row bias (conv bias and coordinate channels), activation, store
-  const int g = lane >> 2, tg = lane & 3;
+    // ---- epilogue: + row bias (conv bias and coordinate channels), activation, store
+    const int R = min(a.QPB, a.w - cur.q0) * a.T;
+    const bool is_gelu = a.act == DPOT_ACT_GELU;
 #pragma unroll
-  for (int hrow = 0; hrow < 2; ++hrow) {
-    const int r = warp * 16 + g + hrow * 8;
-    if (r >= R) continue;
-    const int ql = r / a.T, t = r % a.T;
-    const int q = q0 + ql;
-    const int64_t tok = ((int64_t)b * a.h + p) * a.w + q;
-    const float* rb = a.rowbias0 + (((int64_t)p * a.w + q) * a.T + t) * a.mid;
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int r = warp * 16 + g + hrow * 8;
+      if (r >= R) continue;
+      const int ql = r / a.T, t = r - ql * a.T;
+      const int q = cur.q0 + ql;
+      const int64_t tok = ((int64_t)cur.b * a.h + cur.p) * a.w + q;
+      const float* rb = a.rowbias0 + (((int64_t)cur.p * a.w + q) * a.T + t) * a.mid + tg * 2;
+      float bv[NT8][2];
 #pragma unroll
-    for (int nt = 0; nt < NT8; ++nt)
+      for (int nt = 0; nt < NT8; ++nt)        // all bias loads in flight before the first use
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int m = nt * 8 + tg * 2 + j;
-        if (m >= a.mid) continue;
-        const float v = act_apply(fmaf(d2[nt][hrow * 2 + j], HL_INV, d1[nt][hrow * 2 + j]) + __ldg(rb + m), a.act);
-        if (OUT16) {
-          __half* dst = reinterpret_cast<__half*>(a.z1) + tok * (2 * (int64_t)a.Kp) + t * a.mid + m;
-          __half hi, lo;
-          hl_split(v, hi, lo);
-          dst[0] = hi;
-          dst[a.Kp] = lo;
-        } else {
-          a.z1[tok * a.Kp + t * a.mid + m] = v;
+        for (int j = 0; j < 2; ++j) bv[nt][j] = (nt * 8 + tg * 2 + j < a.mid) ? __ldg(rb + nt * 8 + j) : 0.f;
+      __half* dst16 = reinterpret_cast<__half*>(a.z1) + tok * (2 * (int64_t)a.Kp) + t * a.mid + tg * 2;
+      float* dst32 = a.z1 + tok * a.Kp + t * a.mid + tg * 2;
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (nt * 8 + tg * 2 + j >= a.mid) continue;
+          const float pre_act = fmaf(d2[nt][hrow * 2 + j], HL_INV, d1[nt][hrow * 2 + j]) + bv[nt][j];
+          const float v = is_gelu ? gelu_fast(pre_act) : act_apply(pre_act, a.act);
+          if (OUT16) {
+            __half hi, lo;
+            hl_split(v, hi, lo);
+            dst16[nt * 8 + j] = hi;
+            dst16[nt * 8 + j + a.Kp] = lo;
+          } else {
+            dst32[nt * 8 + j] = v;
+          }
         }
-      }
+    }
+    if (next_item >= nitems) break;
+    item = next_item;
+    cur = nxt;
   }
 }
 
@@ -382,7 +417,8 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
   // ---- tensor-core path (mma.sync on split fp16): needs float4-able runs and 16-deep k-steps per image row
   const int nt8 = (int)ceil_div(mid, 8);
   if (g_patch_engine != 1 && vec4 && a.PC % 16 == 0 && a.PC <= 64 && nt8 <= 9) {
-    const int nf = a.PC <= 32 ? 4 : 8;
+    const int ks = a.PC / 16;                   // k-steps per image-row slab: 1, 2 or 4
+    const int nf = ks <= 2 ? 4 : 8;
     int q = a.w, best = 0;
     for (; q >= 1; --q) {                      // largest run of patches that fits 8 warps, preferring no padded rows
       const int64_t rows = (int64_t)q * T, nw = ceil_div(rows, 16);
@@ -392,29 +428,42 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
       if (q < best / 2) break;
     }
     if (best > 0 && best == a.w && a.w >= 16 && ((int64_t)(a.w / 2) * T) % 16 == 0) best = a.w / 2;
-    if (best > 0) {
+    // instantiated (k-steps, n-tiles) combinations: mid = out_channels*P + 3 with P = 4 / 8 / 16 (models/dpot.py:278)
+    const bool inst = (ks == 1 && nt8 <= 3) || (ks == 2 && nt8 >= 2 && nt8 <= 5) || (ks == 4 && (nt8 == 3 || nt8 == 5));
+    if (best > 0 && inst) {
       PatchArgs m = a;
       m.QPB = best; m.QSPLIT = (int)ceil_div(a.w, best);
       const int nw = (int)ceil_div((int64_t)best * T, 16);
       const size_t smem_m = 2 * ((size_t)nt8 * 8 * (a.K0 + 8) * 2 + 2 * (size_t)nw * 16 * (a.PC + 8) * 2);
       if (smem_m <= 160 * 1024) {
-        const unsigned grid_m = (unsigned)((int64_t)B * a.h * m.QSPLIT);
-#define DPOT_PEM_LAUNCH(NT, O16, NFV)                                                                                   \
+        const int nitems = (int)((int64_t)B * a.h * m.QSPLIT);
+        int dev = 0, sms = 148;
+        DPOT_CUDA(cudaGetDevice(&dev));
+        DPOT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int per_sm = (int)((220 * 1024) / (smem_m + 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        const unsigned grid_m = (unsigned)(nitems < sms * per_sm ? nitems : sms * per_sm);   // persistent: weights staged once per CTA
+#define DPOT_PEM_LAUNCH(NT, O16, KSV)                                                                                   \
   do {                                                                                                                  \
     if (smem_m > 48 * 1024)                                                                                             \
-      DPOT_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<NT, O16, NFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      DPOT_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<NT, O16, KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem_m));                                                                     \
-    patch_embed_mma_kernel<NT, O16, NFV><<<grid_m, nw * 32, smem_m, st>>>(m);                                           \
+    patch_embed_mma_kernel<NT, O16, KSV><<<grid_m, nw * 32, smem_m, st>>>(m, nitems);                                   \
   } while (0)
-#define DPOT_PEM_NF(NT, O16) do { if (nf == 4) DPOT_PEM_LAUNCH(NT, O16, 4); else DPOT_PEM_LAUNCH(NT, O16, 8); } while (0)
-#define DPOT_PEM_CASE(NT) case NT: if (o16) DPOT_PEM_NF(NT, true); else DPOT_PEM_NF(NT, false); break
-        switch (nt8) {
-          DPOT_PEM_CASE(1); DPOT_PEM_CASE(2); DPOT_PEM_CASE(3); DPOT_PEM_CASE(4); DPOT_PEM_CASE(5);
-          DPOT_PEM_CASE(6); DPOT_PEM_CASE(7); DPOT_PEM_CASE(8); DPOT_PEM_CASE(9);
+#define DPOT_PEM(NT, KSV) do { if (o16) DPOT_PEM_LAUNCH(NT, true, KSV); else DPOT_PEM_LAUNCH(NT, false, KSV); } while (0)
+        switch (ks * 16 + nt8) {
+          case 16 + 1: DPOT_PEM(1, 1); break;
+          case 16 + 2: DPOT_PEM(2, 1); break;
+          case 16 + 3: DPOT_PEM(3, 1); break;
+          case 32 + 2: DPOT_PEM(2, 2); break;
+          case 32 + 3: DPOT_PEM(3, 2); break;
+          case 32 + 4: DPOT_PEM(4, 2); break;
+          case 32 + 5: DPOT_PEM(5, 2); break;
+          case 64 + 3: DPOT_PEM(3, 4); break;
+          case 64 + 5: DPOT_PEM(5, 4); break;
           default: break;
         }
-#undef DPOT_PEM_CASE
-#undef DPOT_PEM_NF
+#undef DPOT_PEM
 #undef DPOT_PEM_LAUNCH
         DPOT_LAUNCH_CHECK("patch_embed_mma_kernel");
         return 0;
