@@ -21,8 +21,8 @@
 //                                D[BA,2BA) += Wlo * Ahi^T              (N = BA)
 // TMEM: 2 x 256 columns (double-buffered tiles), so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent): warp 0 TMA producer, warp 1 MMA issuer,
-// warp 2 TMEM allocator, warps 4-11 epilogue (two per TMEM lane quarter, interleaved 8-column groups).
+// Warp roles (640 threads, 1 CTA / SM, persistent): warp 0 TMA producer, warp 1 MMA issuer,
+// warp 2 TMEM allocator, warps 4-19 epilogue (four per TMEM lane quarter, interleaved 8-column groups).
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "tc_ptx.cuh"
@@ -36,8 +36,8 @@ namespace {
 constexpr int TN = 128;            // weight rows (output channels) per CTA tile = TMEM lanes
 constexpr int TA = 128;            // max activation rows (tokens) per tile
 constexpr int BKH = 64;            // halves per k-block = one 128 B swizzle row
-constexpr int NTHREADS = 384;
-constexpr int EPI_WARP0 = 4, EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 16, EPI_PARTS = EPI_WARPS / 4;
+constexpr int NTHREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 
 constexpr uint32_t W_BYTES = TN * 128;          // 16 KB per plane
 constexpr uint32_t OFF_W_HI = 0, OFF_W_LO = W_BYTES, OFF_A = 2 * W_BYTES;   // A_hi at OFF_A, A_lo one plane later
@@ -190,7 +190,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   } else if (warp >= EPI_WARP0) {
     // ================================ epilogue ====================================
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may read
-    const int half = (warp - EPI_WARP0) >> 2;         // interleaved 8-column groups: g = half, half+2, ...
+    const int half = (warp - EPI_WARP0) >> 2;         // interleaved 8-column groups: g = half, half + EPI_PARTS, ...
     const int ngroups = BA / 8;
     __half* const Ch_base = reinterpret_cast<__half*>(g.C);
     const uint32_t tempty_leader = CG == 2 ? mapa_rank(TEMPTY(0), 0) : TEMPTY(0);
@@ -224,7 +224,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-      for (int gi = half; gi < ngroups; gi += 2) {
+      for (int gi = half; gi < ngroups; gi += EPI_PARTS) {
         if (P.dbg & 4) break;                   // experiment: no epilogue work
         const int c0 = gi * 8;
         uint32_t r1[8], r2[8];
@@ -233,7 +233,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         float rb[8], rs[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { rb[u] = SIDE ? nrb[u] : 0.f; rs[u] = SIDE ? nrs[u] : 0.f; }
-        if (gi + 2 < ngroups) load_side(gi + 2);
+        if (gi + EPI_PARTS < ngroups) load_side(gi + EPI_PARTS);
         tmem_ld_wait();
         const int m0 = mt * BA + c0;
         const int cnt = min(8, g.M - m0);
