@@ -104,6 +104,9 @@ SIGNATURES = {
     "dpot_gn_finalize": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p]),
     "dpot_afno_fft_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p]),
     "dpot_afno_fft_fwd16": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
+    "dpot_afno_fft_fwd16_gn": (C.c_int, [_p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
+    "dpot_afno_fft_inv_gn": (C.c_int, [_p, _p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "dpot_split_f16_gn": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _i32, _f, _i32, _p, _i64, _i64, _p]),
     "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _p]),
     "dpot_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),
     "dpot_colsum": (C.c_int, [_p, _i64, _i32, _i32, _p, _i32, _p]),
@@ -130,6 +133,9 @@ SIGNATURES = {
     "dpot_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p]),
     "dpot_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _p, _p, _p, _i32, _p]),
     "dpot_forward_ring": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "dpot_rollout_step": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _i32, _p]),
+    "dpot_out_tail_ring": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p,
+                                     _i32, _i32, _i32, _i32, _p]),
 }
 
 _lib = None

@@ -89,10 +89,10 @@ struct Cfg {
 //
 // OUT16: the spectrum is stored as split fp16 (DPOT_FMT_HL16; row = [hi 2E | lo 2E] halves), the operand format
 // of the f16-split tensor-core engine that consumes it.
-template <int H, bool OUT16>
+template <int H, bool OUT16, bool GN>
 __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restrict__ a, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int E, int bs, int km1,
-                                                          int km2, float* __restrict__ S, float wint) {
+                                                          int km2, float* __restrict__ S, float wint, const GnRef gn) {
   constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, HC = (H >= 2) ? H / 2 : 1, n = H * H;
   extern __shared__ __align__(16) float smem[];
   float2* R_s = reinterpret_cast<float2*>(smem);             // [H][HC][CH]; column 0 = (DC, Nyquist) real pair
@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
   const int tid = threadIdx.x, c = tid % CH, task0 = tid / CH;
   const int b = blockIdx.y, ch = blockIdx.x * CH + c;
   const bool live = ch < E;
-  const float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
-  const float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
+  float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
+  float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
+  if (GN && live) gn_affine_ref(gn, b, ch, sc, sh);      // GroupNorm-1 by reference (no finalize launch)
 
   // phase A: GroupNorm-1 applied on load; real row transforms, two rows per complex FFT
   for (int pr = task0; pr < H / 2; pr += NTASK) {
@@ -179,11 +180,12 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-template <int H>
+template <int H, bool GN>
 __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restrict__ O2, const float* __restrict__ a,
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                           int E, int bs, int km1, int km2, float* __restrict__ f,
-                                                          double* __restrict__ stats, int groups, float wint) {
+                                                          double* __restrict__ stats, int groups, float wint,
+                                                          const GnRef gn) {
   constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, HC = (H >= 2) ? H / 2 : 1, n = H * H;
   extern __shared__ __align__(16) float smem[];
   float2* Z_s = reinterpret_cast<float2*>(smem);             // [H][HC][CH]; column 0 = (x_0[p], x_{H/2}[p]) real pair
@@ -238,8 +240,9 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
 
   // skip term: the normalised block input, fetched before the barrier so that its latency overlaps phase A/C
   const float norm = 1.0f / (float)H;
-  const float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
-  const float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
+  float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
+  float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
+  if (GN && live) gn_affine_ref(gn, b, ch, sc, sh);      // GroupNorm-1 (skip term) by reference
   double s1 = 0.0, s2 = 0.0;
   float k0[H], k1v[H];
   auto load_skip = [&](int pr) {
@@ -301,29 +304,30 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
   }
 }
 
-template <int H, bool OUT16 = false>
+template <int H, bool OUT16 = false, bool GN = false>
 int launch_fwd(const float* a, const float* scale, const float* shift, int B, int E, int nb, int km1, int km2,
-               float* S, float wint, cudaStream_t st) {
+               float* S, float wint, cudaStream_t st, const GnRef gn = GnRef()) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
   const size_t smem = (size_t)H * (H >= 2 ? H / 2 : 1) * CH * 8;
   (void)KH;
-  DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H, OUT16, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_fwd_kernel<H, OUT16><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S, wint);
+  afno_fft_fwd_kernel<H, OUT16, GN><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S, wint, gn);
   DPOT_LAUNCH_CHECK("afno_fft_fwd_kernel");
   return 0;
 }
 
-template <int H>
+template <int H, bool GN = false>
 int launch_inv(const float* O2, const float* a, const float* scale, const float* shift, int B, int E, int nb,
-               int km1, int km2, float* f, double* stats, int groups, float wint, cudaStream_t st) {
+               int km1, int km2, float* f, double* stats, int groups, float wint, cudaStream_t st,
+               const GnRef gn = GnRef()) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
   size_t smem = (size_t)H * (H >= 2 ? H / 2 : 1) * CH * 8;
   (void)KH;
   if (smem < (size_t)2 * NT * 8) smem = (size_t)2 * NT * 8;
-  DPOT_CUDA(cudaFuncSetAttribute(afno_fft_inv_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DPOT_CUDA(cudaFuncSetAttribute(afno_fft_inv_kernel<H, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_inv_kernel<H><<<grid, NT, smem, st>>>(O2, a, scale, shift, E, E / nb, km1, km2, f, stats, groups, wint);
+  afno_fft_inv_kernel<H, GN><<<grid, NT, smem, st>>>(O2, a, scale, shift, E, E / nb, km1, km2, f, stats, groups, wint, gn);
   DPOT_LAUNCH_CHECK("afno_fft_inv_kernel");
   return 0;
 }
@@ -385,5 +389,42 @@ extern "C" int dpot_afno_fft_inv(const float* O2, const float* a, const float* s
     case 8: return launch_inv<8>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
     case 16: return launch_inv<16>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
     default: return launch_inv<32>(O2, a, scale, shift, B, E, nb, km1, km2, f, stats_out, groups, interior_weight, st);
+  }
+}
+
+// ---- GroupNorm-by-reference variants (the f16-split inference pipeline, forward.cu): GroupNorm-1 comes as raw
+// statistics [B, groups, 2] (double) + gamma/beta instead of finalised scale/shift tables
+extern "C" int dpot_afno_fft_fwd16_gn(const float* a, const double* stats1, const float* gamma1, const float* beta1,
+                                      int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, int32_t km1,
+                                      int32_t km2, void* S16, void* stream) {
+  DPOT_REQUIRE(a && S16 && stats1 && gamma1 && beta1, DPOT_E_BADARG, "dpot_afno_fft_fwd16_gn: null pointer");
+  DPOT_CALL(check_common(B, h, E, nb, km1, km2));
+  DPOT_REQUIRE(groups > 0 && E % groups == 0, DPOT_E_BADARG, "dpot_afno_fft_fwd16_gn: bad groups");
+  cudaStream_t st = as_stream(stream);
+  float* S = reinterpret_cast<float*>(S16);
+  const GnRef gn = make_gn_ref(stats1, gamma1, beta1, groups, eps, E, (int64_t)h * h);
+  switch (h) {
+    case 2: return launch_fwd<2, true, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, 1.0f, st, gn);
+    case 4: return launch_fwd<4, true, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, 1.0f, st, gn);
+    case 8: return launch_fwd<8, true, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, 1.0f, st, gn);
+    case 16: return launch_fwd<16, true, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, 1.0f, st, gn);
+    default: return launch_fwd<32, true, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, 1.0f, st, gn);
+  }
+}
+
+extern "C" int dpot_afno_fft_inv_gn(const float* O2, const float* a, const double* stats1, const float* gamma1,
+                                    const float* beta1, int32_t groups, float eps, int32_t B, int32_t h, int32_t E,
+                                    int32_t nb, int32_t km1, int32_t km2, float* f, double* stats_out, void* stream) {
+  DPOT_REQUIRE(O2 && a && f && stats1 && gamma1 && beta1, DPOT_E_BADARG, "dpot_afno_fft_inv_gn: null pointer");
+  DPOT_CALL(check_common(B, h, E, nb, km1, km2));
+  DPOT_REQUIRE(groups > 0 && E % groups == 0, DPOT_E_BADARG, "dpot_afno_fft_inv_gn: bad groups");
+  cudaStream_t st = as_stream(stream);
+  const GnRef gn = make_gn_ref(stats1, gamma1, beta1, groups, eps, E, (int64_t)h * h);
+  switch (h) {
+    case 2: return launch_inv<2, true>(O2, a, nullptr, nullptr, B, E, nb, km1, km2, f, stats_out, groups, 1.0f, st, gn);
+    case 4: return launch_inv<4, true>(O2, a, nullptr, nullptr, B, E, nb, km1, km2, f, stats_out, groups, 1.0f, st, gn);
+    case 8: return launch_inv<8, true>(O2, a, nullptr, nullptr, B, E, nb, km1, km2, f, stats_out, groups, 1.0f, st, gn);
+    case 16: return launch_inv<16, true>(O2, a, nullptr, nullptr, B, E, nb, km1, km2, f, stats_out, groups, 1.0f, st, gn);
+    default: return launch_inv<32, true>(O2, a, nullptr, nullptr, B, E, nb, km1, km2, f, stats_out, groups, 1.0f, st, gn);
   }
 }

@@ -99,6 +99,17 @@ static Work work_layout(const Dims& d, const dpot_config* c, int B) {
   return L;
 }
 
+// destination of the new frames when the forward is one step of an autoregressive rollout (dpot_rollout_step)
+struct RingOut { float* ring; float* pred; int slot0, Ttot, step; };
+
+static int run_tail(const float* Y, const float* w2, const float* b2, const dpot_params* prm, int B, const Dims& d, int nout,
+                    int act, const float* mu_c, const float* sg_c, float* y, const RingOut* ro, void* stream) {
+  if (ro)
+    return dpot_out_tail_ring(Y, w2, b2, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y,
+                              ro->ring, ro->pred, d.T, ro->slot0, ro->Ttot, ro->step, stream);
+  return dpot_out_tail(Y, w2, b2, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream);
+}
+
 static dpot_gemm_args gemm_args(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int M,
                                 int N, int K, const float* bias, int act, int engine) {
   dpot_gemm_args g;
@@ -137,7 +148,8 @@ static bool use_tc16(const Dims& d, int engine) {
 // epilogues -> O1 / hidden, GroupNorm-2 apply -> n2.  The residual stream, the inverse-FFT input
 // and the head stay fp32.
 static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int t0, int B,
-                        float* y, float* cls, float* ws, const Dims& d, const Packed& PL, const Work& WL, void* stream) {
+                        float* y, float* cls, float* ws, const Dims& d, const Packed& PL, const Work& WL, const RingOut* ro,
+                        void* stream) {
   cudaStream_t st = as_stream(stream);
   const int Mt = B * d.n, Ms = B * d.km1 * d.km2, act = cfg->act, R = cfg->img_size;
   const int groups = 8;
@@ -162,8 +174,10 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
   for (int i = 0; i < d.depth; ++i) {
     const dpot_block_params& bp = prm->blocks[i];
     const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
-    DPOT_CALL(dpot_gn_finalize(st1, bp.norm1_w, bp.norm1_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc1, ws + WL.sh1, stream));
-    DPOT_CALL(dpot_afno_fft_fwd16(lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.S, stream));
+    // GroupNorm by reference: the consumers derive their affines from the raw statistics (no finalize launches)
+    const bool gnref = (d.E / groups) % 8 == 0 && (reinterpret_cast<uintptr_t>(bp.norm2_w) | reinterpret_cast<uintptr_t>(bp.norm2_b)) % 16 == 0;
+    DPOT_CALL(dpot_afno_fft_fwd16_gn(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, d.km1, d.km2,
+                                     ws + WL.S, stream));
     {
       // block-diagonal complex MLP as nb real GEMMs of size [Ms, 2bs] x [2bs, 2bs]
       dpot_gemm_args g = gemm16_args(ws + WL.S, 2 * d.E, pk + PL.Wc1_16, kb, ws + WL.O1, 0, Ms, (int)kb, (int)kb, pk + PL.bc1, act);
@@ -175,10 +189,15 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       DPOT_CALL(dpot_gemm(&g, stream));     // O2 overwrites S as fp32 (the inverse FFT reads fp32)
     }
     DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
-    DPOT_CALL(dpot_afno_fft_inv(ws + WL.S, lat, ws + WL.sc1, ws + WL.sh1, B, d.h, d.E, d.nb, d.km1, d.km2, ws + WL.f, st2, groups, 1.0f, stream));
-    DPOT_CALL(dpot_gn_finalize(st2, bp.norm2_w, bp.norm2_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc2, ws + WL.sh2, stream));
+    DPOT_CALL(dpot_afno_fft_inv_gn(ws + WL.S, lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, d.km1, d.km2,
+                                   ws + WL.f, st2, stream));
     // GroupNorm-2 apply fused with the fp16 split of the channel-MLP input
-    DPOT_CALL(dpot_split_f16(ws + WL.f, d.E, Mt, d.E, ws + WL.sc2, ws + WL.sh2, d.n, ws + WL.n2, 2 * d.E, d.E, stream));
+    if (gnref) {
+      DPOT_CALL(dpot_split_f16_gn(ws + WL.f, d.E, Mt, d.E, st2, bp.norm2_w, bp.norm2_b, groups, 1e-5f, d.n, ws + WL.n2, 2 * d.E, d.E, stream));
+    } else {
+      DPOT_CALL(dpot_gn_finalize(st2, bp.norm2_w, bp.norm2_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc2, ws + WL.sh2, stream));
+      DPOT_CALL(dpot_split_f16(ws + WL.f, d.E, Mt, d.E, ws + WL.sc2, ws + WL.sh2, d.n, ws + WL.n2, 2 * d.E, d.E, stream));
+    }
     {
       dpot_gemm_args g = gemm16_args(ws + WL.n2, d.E, pk + PL.fc1_16, d.E, ws + WL.hid, 0, Mt, d.hid, d.E, bp.fc1_b, act);
       out16(g, d.hid);
@@ -218,11 +237,11 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       mu_c = mc; sg_c = sc;
     }
     if (fused_tail) {
-      DPOT_CALL(dpot_out_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+      DPOT_CALL(run_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));
     } else {
       g = gemm_args(ws + WL.Y1, d.old, prm->out2_w, d.old, ws + WL.Y2, d.old, Mt * d.P * d.P, d.old, d.old, prm->out2_b, act, DPOT_GEMM_AUTO);
       DPOT_CALL(dpot_gemm(&g, stream));
-      DPOT_CALL(dpot_out_tail(ws + WL.Y2, nullptr, nullptr, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+      DPOT_CALL(run_tail(ws + WL.Y2, nullptr, nullptr, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));
     }
   }
   return 0;
@@ -281,8 +300,31 @@ extern "C" int dpot_forward(const dpot_config* cfg, const dpot_params* prm, cons
   return dpot_forward_ring(cfg, prm, packed, x, 0, B, y, cls, ws, engine, stream);
 }
 
+static int forward_impl(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int32_t t0,
+                        int32_t B, float* y, float* cls, float* ws, int32_t engine, const dpot::RingOut* ro, void* stream);
+
 extern "C" int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                                  int32_t t0, int32_t B, float* y, float* cls, float* ws, int32_t engine, void* stream) {
+  return forward_impl(cfg, prm, packed, x, t0, B, y, cls, ws, engine, nullptr, stream);
+}
+
+// One autoregressive step on a ring window (evaluate.py:192-208): im = model(window at t0); the T_out new frames
+// replace the oldest slots (t0 + j) % T of the ring and land in pred[..., step*T_out + j, :].  The caller advances
+// t0 by T_out.  y: scratch [B,X,Y,T_out,C_out] (used only by geometries the fused tail kernel does not serve).
+extern "C" int dpot_rollout_step(const dpot_config* cfg, const dpot_params* prm, const float* packed, float* ring,
+                                 int32_t t0, int32_t B, float* y, float* cls, float* ws, int32_t engine, float* pred,
+                                 int32_t pred_frames, int32_t step, void* stream) {
+  DPOT_REQUIRE(cfg && ring && y, DPOT_E_BADARG, "dpot_rollout_step: null pointer");
+  DPOT_REQUIRE(cfg->in_channels == cfg->out_channels, DPOT_E_BADARG, "dpot_rollout_step: needs out_channels == in_channels");
+  DPOT_REQUIRE(!pred || (step >= 0 && (step + 1) * cfg->out_timesteps <= pred_frames), DPOT_E_BADARG,
+               "dpot_rollout_step: step %d outside the prediction tensor (%d frames)", step, pred_frames);
+  dpot::RingOut ro;
+  ro.ring = ring; ro.pred = pred; ro.slot0 = t0; ro.Ttot = pred_frames; ro.step = step;
+  return forward_impl(cfg, prm, packed, ring, t0, B, y, cls, ws, engine, &ro, stream);
+}
+
+static int forward_impl(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int32_t t0,
+                        int32_t B, float* y, float* cls, float* ws, int32_t engine, const dpot::RingOut* ro, void* stream) {
   Dims d;
   DPOT_CALL(make_dims(cfg, d));
   DPOT_REQUIRE(prm && packed && x && y && ws && prm->blocks && B > 0, DPOT_E_BADARG, "dpot_forward: null pointer / bad B");
@@ -311,7 +353,7 @@ extern "C" int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm,
     DPOT_CALL(dpot_gemm(&g, stream));
   }
 
-  if (tc16) return forward_tc16(cfg, prm, packed, x, t0, B, y, cls, ws, d, PL, WL, stream);
+  if (tc16) return forward_tc16(cfg, prm, packed, x, t0, B, y, cls, ws, d, PL, WL, ro, stream);
 
   // ---- PatchEmbed conv0 + act, coordinate channels folded into rowbias0
   if (d.Kp != d.T * d.mid) DPOT_CUDA(cudaMemsetAsync(ws + WL.z1, 0, sizeof(float) * (size_t)Mt * d.Kp, st));
@@ -389,11 +431,11 @@ extern "C" int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm,
       mu_c = mc; sg_c = sc;
     }
     if (fused_tail) {
-      DPOT_CALL(dpot_out_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+      DPOT_CALL(run_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));
     } else {
       g = gemm_args(ws + WL.Y1, d.old, prm->out2_w, d.old, ws + WL.Y2, d.old, Mt * d.P * d.P, d.old, d.old, prm->out2_b, act, engine);
       DPOT_CALL(dpot_gemm(&g, stream));
-      DPOT_CALL(dpot_out_tail(ws + WL.Y2, nullptr, nullptr, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream));
+      DPOT_CALL(run_tail(ws + WL.Y2, nullptr, nullptr, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));
     }
   }
   return 0;

@@ -436,7 +436,7 @@ namespace dpot {
 int g_tail_engine = 0;   // 0 auto, 1 CUDA cores only (dpot_out_tail_set_engine; tests)
 int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4, int B, int h,
                         int w, int P, int old, int nout, int act, const float* mu, const float* sigma, int Co, float* out,
-                        cudaStream_t st, bool* served);
+                        cudaStream_t st, bool* served, float* ring, float* pred, int T, int slot0, int Ttot, int step);
 }
 extern "C" void dpot_out_tail_set_engine(int32_t engine) { dpot::g_tail_engine = engine; }
 
@@ -453,7 +453,8 @@ extern "C" int dpot_out_tail(const float* Y1, const float* w2, const float* b2, 
   if (l2 && g_tail_engine != 1) {   // warp-MMA kernel (out_tail_mma.cu) when the geometry allows
     DPOT_REQUIRE(b2 != nullptr, DPOT_E_BADARG, "dpot_out_tail: b2 missing");
     bool served = false;
-    DPOT_CALL(out_tail_mma_launch(Y1, w2, b2, w4, b4, B, h, w, P, old, nout, act, mu, sigma, Co, out, st, &served));
+    DPOT_CALL(out_tail_mma_launch(Y1, w2, b2, w4, b4, B, h, w, P, old, nout, act, mu, sigma, Co, out, st, &served, nullptr,
+                                  nullptr, 0, 0, 0, 0));
     if (served) return 0;
   }
   const size_t smem = sizeof(float) * ((l2 ? (size_t)old * old + old : 0) + (size_t)nout * old + nout);
@@ -475,6 +476,26 @@ extern "C" int dpot_out_tail(const float* Y1, const float* w2, const float* b2, 
 #undef TAIL_CASE
   DPOT_LAUNCH_CHECK("out_tail_kernel");
   return 0;
+}
+
+// Output tail writing the new frames straight into the autoregressive ring window and the prediction tensor (see
+// TailRing, out_tail_mma.cu); geometries the fused kernel does not take go through y + dpot_ring_insert.
+extern "C" int dpot_out_tail_ring(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4,
+                                  int32_t B, int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act,
+                                  const float* mu, const float* sigma, int32_t Co, float* y_scratch, float* ring, float* pred,
+                                  int32_t T, int32_t slot0, int32_t Ttot, int32_t step, void* stream) {
+  DPOT_REQUIRE(Y1 && w4 && b4 && ring && y_scratch, DPOT_E_BADARG, "dpot_out_tail_ring: null pointer");
+  DPOT_REQUIRE(Co > 0 && nout % Co == 0 && slot0 >= 0 && slot0 < T && nout / Co <= T, DPOT_E_BADARG, "dpot_out_tail_ring: bad geometry");
+  cudaStream_t st = as_stream(stream);
+  if (w2 != nullptr && g_tail_engine != 1) {
+    DPOT_REQUIRE(b2 != nullptr, DPOT_E_BADARG, "dpot_out_tail_ring: b2 missing");
+    bool served = false;
+    DPOT_CALL(out_tail_mma_launch(Y1, w2, b2, w4, b4, B, h, w, P, old, nout, act, mu, sigma, Co, y_scratch, st, &served, ring,
+                                  pred, T, slot0, Ttot, step));
+    if (served) return 0;
+  }
+  DPOT_CALL(dpot_out_tail(Y1, w2, b2, w4, b4, B, h, w, P, old, nout, act, mu, sigma, Co, y_scratch, stream));
+  return dpot_ring_insert(y_scratch, ring, pred, (int64_t)B * h * P * w * P, T, nout / Co, Co, Ttot, slot0, step, stream);
 }
 
 extern "C" int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E, float* tok, void* stream) {

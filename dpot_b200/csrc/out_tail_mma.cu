@@ -13,13 +13,18 @@
 namespace dpot {
 namespace {
 
-template <int OLD, int ACT_MODE>
+// RING: instead of out[B,X,Y,nout] the T_out new frames go straight into the autoregressive window, a ring in time
+// (frame j -> slot (slot0 + j) % T of ring[B,X,Y,T,Co]), and into the prediction tensor pred[B,X,Y,Ttot,Co] at
+// frame step*T_out + j: the window advance of train_temporal.py:219 / evaluate.py:207 without a copy kernel.
+struct TailRing { float* ring; float* pred; int T, slot0, Ttot, step; };
+
+template <int OLD, int ACT_MODE, bool RING>
 __global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __restrict__ Y1, const float* __restrict__ w2,
                                                            const float* __restrict__ b2, const float* __restrict__ w4,
                                                            const float* __restrict__ b4, int B, int h, int w, int P,
                                                            int nout, int act, const float* __restrict__ mu,
                                                            const float* __restrict__ sigma, int Co,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, const TailRing rg) {
   constexpr int KS = OLD / 16, NT = OLD / 8, KW = OLD + 8;
   __shared__ __align__(16) __half s_w[2][OLD + 8][KW];      // [hi|lo][n: W2 rows, then 8 rows of W4][k]
   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, tg = lane & 3;
@@ -143,7 +148,11 @@ __global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __res
         sg0 = sigma[(int64_t)b * Co + ca]; mu0 = mu[(int64_t)b * Co + ca];
         sg1 = sigma[(int64_t)b * Co + cb]; mu1 = mu[(int64_t)b * Co + cb];
       }
-      float* base = out + (((int64_t)b * X + p * P) * Y + q * P) * nout + c0;
+      const int64_t pix_base = ((int64_t)b * X + p * P) * Y + q * P;       // linear pixel index of the patch corner
+      float* base = out + pix_base * nout + c0;
+      const int to = RING ? c0 / Co : 0, co = RING ? c0 - to * Co : 0;      // Co even: (c0, c0+1) lie in one frame
+      int slot = RING ? rg.slot0 + to : 0;
+      if (RING && slot >= rg.T) slot -= rg.T;
 #pragma unroll
       for (int hr = 0; hr < 2; ++hr) {
         if (c0 >= nout || (hr ? pix1 : pix0) >= npix) continue;
@@ -151,9 +160,16 @@ __global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __res
         const uint32_t u = uv / (uint32_t)P, v = uv - u * (uint32_t)P;
         const float y0 = fmaf(fmaf(e2[hr * 2], HL_INV, e1[hr * 2]) + bias4_0, sg0, mu0);
         const float y1v = fmaf(fmaf(e2[hr * 2 + 1], HL_INV, e1[hr * 2 + 1]) + bias4_1, sg1, mu1);
-        float* dst = base + ((int64_t)u * Y + v) * nout;
-        if ((nout & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(y0, y1v);
-        else { dst[0] = y0; if (c0 + 1 < nout) dst[1] = y1v; }
+        if (RING) {
+          const int64_t pl = pix_base + (int64_t)u * Y + v;
+          *reinterpret_cast<float2*>(rg.ring + (pl * rg.T + slot) * Co + co) = make_float2(y0, y1v);
+          if (rg.pred)
+            *reinterpret_cast<float2*>(rg.pred + (pl * rg.Ttot + (int64_t)rg.step * (nout / Co) + to) * Co + co) = make_float2(y0, y1v);
+        } else {
+          float* dst = base + ((int64_t)u * Y + v) * nout;
+          if ((nout & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(y0, y1v);
+          else { dst[0] = y0; if (c0 + 1 < nout) dst[1] = y1v; }
+        }
       }
     }
   }
@@ -164,11 +180,15 @@ __global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __res
 // *served = false: this geometry is not taken (the caller falls back to the CUDA-core kernel)
 int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4, int B, int h,
                         int w, int P, int old, int nout, int act, const float* mu, const float* sigma, int Co, float* out,
-                        cudaStream_t st, bool* served) {
+                        cudaStream_t st, bool* served, float* ring, float* pred, int T, int slot0, int Ttot, int step) {
   *served = false;
-  if (!(old == 16 || old == 32) || nout > 8 || (P * P) % 16 != 0 || (reinterpret_cast<uintptr_t>(Y1) % 8) != 0 ||
-      ((nout & 1) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) != 0))
+  if (ring && (nout % 2 != 0 || Co % 2 != 0 || nout % Co != 0 || (reinterpret_cast<uintptr_t>(ring) % 8) != 0 ||
+               (pred && (reinterpret_cast<uintptr_t>(pred) % 8) != 0)))
     return 0;
+  if (!(old == 16 || old == 32) || nout > 8 || (P * P) % 16 != 0 || (reinterpret_cast<uintptr_t>(Y1) % 8) != 0 ||
+      (!ring && (nout & 1) == 0 && (reinterpret_cast<uintptr_t>(out) % 8) != 0))
+    return 0;
+  TailRing rg; rg.ring = ring; rg.pred = pred; rg.T = T; rg.slot0 = slot0; rg.Ttot = Ttot; rg.step = step;
   const int64_t npix = (int64_t)B * h * w * P * P;
   const int64_t ntile = (npix + 15) / 16;
   int dev = 0, sms = 148;
@@ -176,10 +196,12 @@ int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t want = (ntile + 3) / 4;
   const unsigned grid = (unsigned)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);   // one resident wave (4 CTAs / SM)
-#define DPOT_OTM(O, AM) out_tail_mma_kernel<O, AM><<<grid, 128, 0, st>>>(Y1, w2, b2, w4, b4, B, h, w, P, nout, act, mu, sigma, Co, out)
+#define DPOT_OTM2(O, AM, RG) out_tail_mma_kernel<O, AM, RG><<<grid, 128, 0, st>>>(Y1, w2, b2, w4, b4, B, h, w, P, nout, act, mu, sigma, Co, out, rg)
+#define DPOT_OTM(O, AM) do { if (ring) DPOT_OTM2(O, AM, true); else DPOT_OTM2(O, AM, false); } while (0)
   if (old == 32) { if (act == DPOT_ACT_GELU) DPOT_OTM(32, 1); else DPOT_OTM(32, 2); }
   else { if (act == DPOT_ACT_GELU) DPOT_OTM(16, 1); else DPOT_OTM(16, 2); }
 #undef DPOT_OTM
+#undef DPOT_OTM2
   *served = true;
   DPOT_LAUNCH_CHECK("out_tail_mma_kernel");
   return 0;

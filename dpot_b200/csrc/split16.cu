@@ -7,9 +7,11 @@
 namespace dpot {
 namespace {
 
+template <bool GN>
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols8,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
-                                                        int rps, __half* __restrict__ dst, int64_t ldd, int64_t lo_off) {
+                                                        int rps, __half* __restrict__ dst, int64_t ldd, int64_t lo_off,
+                                                        const GnRef gn) {
   const int64_t total = rows * cols8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols8;
@@ -17,7 +19,25 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
     const float4 a = *reinterpret_cast<const float4*>(src + r * lds + c);
     const float4 b = *reinterpret_cast<const float4*>(src + r * lds + c + 4);
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    if (scale) {
+    if (GN) {     // GroupNorm by reference: the 8 columns share one group (host-checked: group size % 8 == 0)
+      const int bsm = (int)(r / rps);
+      const double* sp = gn.stats + ((int64_t)bsm * gn.groups + c / gn.gs) * 2;
+      const double mean = sp[0] * gn.inv_cnt;
+      const double var = fma(-mean, mean, sp[1] * gn.inv_cnt);
+      const float vv = fmaxf((float)var, 0.f) + gn.eps;
+      float rstd = rsqrtf(vv);
+      rstd = rstd * fmaf(-0.5f * vv * rstd, rstd, 1.5f);
+      const float nm = -(float)mean;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gn.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gn.gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(gn.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(gn.beta + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float scu = rstd * gg[u];
+        v[u] = fmaf(v[u], scu, fmaf(nm, scu, bb[u]));
+      }
+    } else if (scale) {
       const int64_t o = (r / rps) * (int64_t)(cols8 * 8) + c;
       const float4 s0 = *reinterpret_cast<const float4*>(scale + o), s1 = *reinterpret_cast<const float4*>(scale + o + 4);
       const float4 h0 = *reinterpret_cast<const float4*>(shift + o), h1 = *reinterpret_cast<const float4*>(shift + o + 4);
@@ -53,8 +73,29 @@ extern "C" int dpot_split_f16(const float* src, int64_t lds, int64_t rows, int32
   if (rows == 0) return 0;
   const int64_t total = rows * (cols / 8);
   const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
-  split_f16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, lds, rows, cols / 8, scale, shift, rows_per_sample,
-                                                        reinterpret_cast<__half*>(dst), ldd, lo_off);
+  split_f16_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, lds, rows, cols / 8, scale, shift, rows_per_sample,
+                                                               reinterpret_cast<__half*>(dst), ldd, lo_off, GnRef());
+  DPOT_LAUNCH_CHECK("split_f16_kernel");
+  return 0;
+}
+
+// GroupNorm-apply fused with the split, the normalisation given by reference (raw statistics + gamma/beta)
+extern "C" int dpot_split_f16_gn(const float* src, int64_t lds, int64_t rows, int32_t cols, const double* stats,
+                                 const float* gamma, const float* beta, int32_t groups, float eps, int32_t rows_per_sample,
+                                 void* dst, int64_t ldd, int64_t lo_off, void* stream) {
+  DPOT_REQUIRE(src && dst && stats && gamma && beta && rows >= 0 && cols > 0, DPOT_E_BADARG, "dpot_split_f16_gn: null pointer / bad shape");
+  DPOT_REQUIRE(cols % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0 && lo_off % 8 == 0, DPOT_E_ALIGN,
+               "dpot_split_f16_gn: cols, ldd, lo_off must be multiples of 8 (lds of 4)");
+  DPOT_REQUIRE((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(gamma) |
+                reinterpret_cast<uintptr_t>(beta)) % 16 == 0, DPOT_E_ALIGN, "dpot_split_f16_gn: pointers must be 16-byte aligned");
+  DPOT_REQUIRE(groups > 0 && cols % groups == 0 && (cols / groups) % 8 == 0 && rows_per_sample > 0, DPOT_E_BADARG,
+               "dpot_split_f16_gn: group size must be a multiple of 8");
+  if (rows == 0) return 0;
+  const int64_t total = rows * (cols / 8);
+  const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
+  const GnRef gn = make_gn_ref(stats, gamma, beta, groups, eps, cols, rows_per_sample);
+  split_f16_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, lds, rows, cols / 8, nullptr, nullptr, rows_per_sample,
+                                                              reinterpret_cast<__half*>(dst), ldd, lo_off, gn);
   DPOT_LAUNCH_CHECK("split_f16_kernel");
   return 0;
 }

@@ -497,6 +497,20 @@ class _InferenceEngine:
                                              torch.cuda.current_stream().cuda_stream), "dpot_forward_ring")
         return out, cls
 
+    @torch.no_grad()
+    def rollout_step(self, ring: torch.Tensor, scratch: torch.Tensor, pred: Optional[torch.Tensor], t0: int, step: int):
+        """One autoregressive step on the ring window (dpot_rollout_step): the new frames overwrite the oldest slots
+        (t0 + j) % T of `ring` and land in pred[..., step*T_out + j, :]; the caller advances t0 by T_out."""
+        dev = ring.device
+        with torch.cuda.device(dev):
+            self.refresh(dev)
+            B = ring.shape[0]
+            ws = self.workspace(B, dev)
+            check(self.lib.dpot_rollout_step(C.byref(self.cfg), C.byref(self.prm), ptr(self.packed), ptr(ring), t0, B,
+                                             ptr(scratch), None, ptr(ws), self.net.gemm_engine, ptr(pred),
+                                             pred.shape[-2] if pred is not None else 0, step,
+                                             torch.cuda.current_stream().cuda_stream), "dpot_rollout_step")
+
 
 def resize_pos_embed(posemb, posemb_new):
     """Bilinear rescale of a ViT-style [1, 1+g*g, D] position table (reference models/dpot.py:424-441;

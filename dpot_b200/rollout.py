@@ -3,9 +3,9 @@ under no_grad): im = model(xx); pred[..., t] = im; xx = cat(xx[..., T_bundle:, :
 
 Everything is enqueued on one CUDA stream without host synchronisation.  The window is a RING in
 time: logical frame t lives in slot (t + t0) % T, the model reads it through that offset
-(dpot_forward_ring) and each step only overwrites the oldest T_bundle slots with the new frames
-(dpot_ring_insert, which also scatters them into the preallocated prediction tensor) -- no
-torch.cat, no copy of the surviving T - T_bundle frames."""
+(dpot_rollout_step) and each step only overwrites the oldest T_bundle slots with the new frames:
+the output-tail kernel stores them straight into the ring slot and into the preallocated
+prediction tensor -- no torch.cat, no copy kernel, no copy of the surviving T - T_bundle frames."""
 from __future__ import annotations
 
 from typing import Optional
@@ -36,8 +36,9 @@ class RolloutEngine:
         T, Tb = self.model.in_timesteps, self.model.out_timesteps
         t0 = 0
         for s in range(self.n_steps):
-            eng.forward(self.win, out=self.im, want_cls=False, t0=t0)
-            ops.ring_insert(self.im, self.win, self.pred, slot0=t0, step=s)
+            # forward + window advance in one library call: the output tail writes the new frames straight into the
+            # ring slot and the prediction tensor (dpot_rollout_step)
+            eng.rollout_step(self.win, self.im, self.pred, t0, s)
             t0 = (t0 + Tb) % T
         return self.pred
 

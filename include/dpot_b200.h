@@ -178,6 +178,18 @@ DPOT_API int dpot_afno_fft_inv(const float* O2, const float* a, const float* sca
 /* fwd with the spectrum stored as split fp16 (DPOT_FMT_HL16): S16 row (b,k1,k2) = [hi: 2E halves | lo: 2E halves] */
 DPOT_API int dpot_afno_fft_fwd16(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
                         int32_t E, int32_t nb, int32_t km1, int32_t km2, void* S16, void* stream);
+/* GroupNorm-by-reference variants (the f16-split inference pipeline): instead of finalised scale/shift tables the
+   kernels take the raw statistics [B, groups, 2] (double sum, sum of squares) plus gamma/beta and derive the
+   per-channel affine themselves (no dpot_gn_finalize launch). */
+DPOT_API int dpot_afno_fft_fwd16_gn(const float* a, const double* stats1, const float* gamma1, const float* beta1,
+                           int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, int32_t km1,
+                           int32_t km2, void* S16, void* stream);
+DPOT_API int dpot_afno_fft_inv_gn(const float* O2, const float* a, const double* stats1, const float* gamma1,
+                         const float* beta1, int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb,
+                         int32_t km1, int32_t km2, float* f, double* stats_out, void* stream);
+DPOT_API int dpot_split_f16_gn(const float* src, int64_t lds, int64_t rows, int32_t cols, const double* stats,
+                      const float* gamma, const float* beta, int32_t groups, float eps, int32_t rows_per_sample,
+                      void* dst, int64_t ldd, int64_t lo_off, void* stream);
 /* interior_weight multiplies the spectrum columns 0 < k2 < h/2 (on output of fwd / on input of inv); 1 for the
    forward pass.  The two transforms are each other's adjoint up to that weight (Hermitian packing):
    adjoint(inv) = fwd with weight 2, adjoint(fwd) = inv with weight 1/2 -- this is the whole FFT backward.
@@ -252,6 +264,12 @@ DPOT_API int dpot_unpack_afno_grad(const float* dWc, const float* dbc, int32_t n
 DPOT_API int dpot_out_tail(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4,
                   int32_t B, int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act,
                   const float* mu, const float* sigma, int32_t Co, float* out, void* stream);
+/* dpot_out_tail whose result goes straight into the ring window (slots (slot0 + j) % T) and pred (frame step*T_out + j):
+   the window advance without a copy kernel.  y_scratch as in dpot_rollout_step. */
+DPOT_API int dpot_out_tail_ring(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4, int32_t B,
+                       int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act, const float* mu,
+                       const float* sigma, int32_t Co, float* y_scratch, float* ring, float* pred, int32_t T, int32_t slot0,
+                       int32_t Ttot, int32_t step, void* stream);
 /* engine knob (tests): 0 = auto (warp-MMA kernel for out_layer_dim in {16,32}, nout <= 8), 1 = CUDA cores only */
 DPOT_API void dpot_out_tail_set_engine(int32_t engine);
 /* spatial mean a[B*n,E] -> tok[B,E]  (models/dpot.py:394) */
@@ -340,6 +358,13 @@ DPOT_API int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const 
 /* dpot_forward on a time-ring input window (see dpot_ring_insert): logical frame t of x is slot (t + t0) % T */
 DPOT_API int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                       int32_t t0, int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
+/* One autoregressive step on a ring window (evaluate.py:192-208, train_temporal.py:262-272): im = model(window read at
+   ring offset t0); the out_timesteps new frames overwrite the oldest slots (t0 + j) % T of `ring` and are scattered into
+   pred[B,X,Y,pred_frames,C] at frame step*out_timesteps + j (pred may be NULL).  The caller advances t0 by out_timesteps.
+   y: scratch of the model-output shape (only touched for geometries the fused tail kernel does not serve). */
+DPOT_API int dpot_rollout_step(const dpot_config* cfg, const dpot_params* prm, const float* packed, float* ring, int32_t t0,
+                      int32_t B, float* y, float* cls, float* ws, int32_t engine, float* pred, int32_t pred_frames,
+                      int32_t step, void* stream);
 
 #ifdef __cplusplus
 }
