@@ -110,9 +110,10 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int KB = P.kblocks, BA = P.BA;
-  const int rows_a = BA / CG;                                  // token rows this CTA stages
-  const uint32_t a_plane = (uint32_t)rows_a * 128u;
-  const uint32_t stage_tx = 2u * W_BYTES + 2u * a_plane;       // bytes this CTA loads per stage
+  const int rows_a = BA / CG;                                  // token rows this CTA stages (a multiple of 8)
+  const uint32_t a_bytes = (uint32_t)rows_a * 128u;
+  const uint32_t a_plane = CG == 2 ? ((a_bytes + 1023u) & ~1023u) : a_bytes;   // lo plane on a swizzle-atom boundary
+  const uint32_t stage_tx = 2u * W_BYTES + 2u * a_bytes;       // bytes this CTA loads per stage
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0) {
@@ -336,7 +337,7 @@ Plan plan_for(const GemmDev& p, int batch, int cg, int sms, int divides) {
   Plan pl;
   pl.cg = cg;
   pl.n_tiles = (int)ceil_div(p.N, TN * cg);
-  const int other = pl.n_tiles * batch, units = sms / cg, step = 16 * cg;
+  const int other = pl.n_tiles * batch, units = sms / cg, step = 16;   // pairs: BA/2 rows per CTA, a multiple of 8
   const int64_t kblocks = ceil_div(p.K, BKH), ovh = cg == 2 ? 320 : 192;
   pl.BA = 0; pl.cost = -1;
   if (p.M <= TA) {
