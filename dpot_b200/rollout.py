@@ -29,10 +29,17 @@ class RolloutEngine:
         self.pred = torch.empty((batch, R, R, n_steps * Tb, Co), device=dev)
 
     @torch.no_grad()
-    def run(self, xx: torch.Tensor, non_blocking: bool = True) -> torch.Tensor:
-        """xx[B,X,Y,T,C] (host-pinned or device) -> pred[B,X,Y,n_steps*T_bundle,C] on the device."""
-        eng = self.model.engine()
+    def load(self, xx: torch.Tensor, non_blocking: bool = True) -> None:
+        """Fill the window from xx[B,X,Y,T,C] (host-pinned or device) on the current stream."""
         self.win.copy_(xx, non_blocking=non_blocking)
+
+    @torch.no_grad()
+    def run(self, xx: Optional[torch.Tensor] = None, non_blocking: bool = True) -> torch.Tensor:
+        """xx[B,X,Y,T,C] (host-pinned or device; None: the window was filled by load()) ->
+        pred[B,X,Y,n_steps*T_bundle,C] on the device."""
+        eng = self.model.engine()
+        if xx is not None:
+            self.load(xx, non_blocking)
         T, Tb = self.model.in_timesteps, self.model.out_timesteps
         t0 = 0
         for s in range(self.n_steps):
