@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
   float sc = live ? (scale ? scale[(int64_t)b * E + ch] : 1.f) : 0.f;
   float sh = (live && shift) ? shift[(int64_t)b * E + ch] : 0.f;
   if (GN && live) gn_affine_ref(gn, b, ch, sc, sh);      // GroupNorm-1 (skip term) by reference
-  double s1 = 0.0, s2 = 0.0;
+  float s1 = 0.f, s2 = 0.f;      // fp32 over this thread's 2H values; across threads / CTAs in double
   float k0[H], k1v[H];
   auto load_skip = [&](int pr) {
     const float* ap = a + ((int64_t)b * n + (2 * pr) * H) * E + ch;
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
         const float v1 = fmaf(zi[q], norm, a ? fmaf(k1v[q], sc, sh) : 0.f);
         f[base0 + (int64_t)q * E] = v0;
         f[base0 + (int64_t)(H + q) * E] = v1;
-        s1 += (double)v0 + (double)v1;
-        s2 += (double)v0 * v0 + (double)v1 * v1;
+        s1 += v0 + v1;
+        s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
       }
     }
   }
@@ -288,8 +288,8 @@ __global__ void __launch_bounds__(NT) afno_fft_inv_kernel(const float* __restric
 
   // GroupNorm-2 statistics of f: reduce over the CTA per channel, then per group
   __syncthreads();
-  red[tid] = s1;
-  red[NT + tid] = s2;
+  red[tid] = (double)s1;
+  red[NT + tid] = (double)s2;
   __syncthreads();
   if (tid < CH && live) {
     double t1 = 0.0, t2 = 0.0;

@@ -296,11 +296,15 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         for (int slot = 0; slot < 2; ++slot) {
           const int smp = smp0 + slot;
           if (slot == 1 && (mt * BA + BA <= m_next || m_next >= g.M)) break;   // uniform: the tile ends inside sample smp0
-          double d1 = nok ? (double)(slot ? st1b : st1a) : 0.0, d2 = nok ? (double)(slot ? st2b : st2a) : 0.0;
+          // fp32 warp reduction (32 partial sums of <= 64 elements each; the fp64 pipe is slow and these shuffles sit on
+          // the epilogue's critical path); the cross-tile accumulation below stays in double
+          float f1 = nok ? (slot ? st1b : st1a) : 0.f, f2 = nok ? (slot ? st2b : st2a) : 0.f;
+#pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+            f2 += __shfl_xor_sync(0xffffffffu, f2, o);
           }
+          const double d1 = (double)f1, d2 = (double)f2;
           if (lane == 0 && nok) {
             const int grp = n / (g.N / g.st_groups);
             double* dst = g.out_stats + ((int64_t)smp * g.st_groups + grp) * 2;

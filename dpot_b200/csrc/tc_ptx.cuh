@@ -136,8 +136,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // possibly remote barrier
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// arrive on a (possibly remote) barrier of the cluster.  RELAXED: a release at cluster scope makes ptxas drain every
+// outstanding global store of the thread first (ERRBAR; measured: ~15 % of the fc2 kernel); the only accesses this
+// arrival has to order are tcgen05.ld's, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into OWN shared memory whose completion is signalled on a barrier that may live in the pair's leader CTA
 __device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
