@@ -68,9 +68,12 @@ struct Tc16Params {
 };
 
 // ACT_MODE: 0 = none, 1 = GELU (erf), 2 = runtime switch.  OUT16: store the result as DPOT_FMT_HL16.
-// SIDE: the epilogue has side inputs (row-periodic bias, residual, per-sample affine); without them that code
-// (and its registers) is compiled out -- the AFNO GEMMs (K = 2*bs) are epilogue-bound.
-template <int CG, int ACT_MODE, bool OUT16, bool SIDE>
+// SIDE: side inputs of the epilogue.  0 = none (that code and its registers are compiled out -- the AFNO GEMMs,
+// K = 2*bs, are epilogue-bound); 1 = row-periodic bias only, 2 = residual only: ALL of the warp's side values of a tile
+// are requested before the accumulator is even waited for (their latency is multiple microseconds while the TMA
+// stream saturates the L2 -> SM fabric; a one-group-ahead prefetch left the epilogue latency-bound: +14 us on the
+// K = 352 time-aggregation GEMM); 3 = any combination incl. the per-sample affine, fetched one group ahead.
+template <int CG, int ACT_MODE, bool OUT16, int SIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                  const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
@@ -209,9 +212,15 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       const int m_next = (smp0 + 1) * g.st_rps;       // first token of the next sample
       // side inputs (row-periodic bias, residual) of a group are fetched one group ahead: their global-load
       // latency hides behind the arithmetic of the previous group instead of serialising the epilogue
-      float nrb[8], nrs[8];
+      constexpr bool DEEP = (SIDE == 1 || SIDE == 2);
+      constexpr int EPI_ITERS = (TA / 8 + EPI_PARTS - 1) / EPI_PARTS;      // groups per warp and tile (max)
+      float sd[DEEP ? EPI_ITERS : 1][8];                                   // DEEP: every side value of this warp's tile
+      float nrb[8], nrs[8];                                                // SIDE 3: one group ahead
+      auto side_ptr = [&](int m) -> const float* {
+        return SIDE == 1 ? g.rowbias + (int64_t)(m % g.rb_period) * g.ldrb + n : g.residual + (int64_t)m * g.ldr + n;
+      };
       auto load_side = [&](int gi) {
-        if (!SIDE) return;
+        if (SIDE != 3) return;
         const int m0 = mt * BA + gi * 8;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -220,25 +229,34 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
           nrs[u] = (g.residual && ok) ? __ldg(g.residual + (int64_t)(m0 + u) * g.ldr + n) : 0.f;
         }
       };
-      if (half < ngroups) load_side(half);
+      if (DEEP) {
+#pragma unroll
+        for (int it = 0; it < EPI_ITERS; ++it) {
+          const int m0 = mt * BA + (half + it * EPI_PARTS) * 8;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            sd[it][u] = (nok && half + it * EPI_PARTS < ngroups && m0 + u < g.M) ? __ldg(side_ptr(m0 + u)) : 0.f;
+        }
+      } else if (half < ngroups) load_side(half);
       mbar_wait(TFULL(buf), bph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * 256u + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int gi = half; gi < ngroups; gi += EPI_PARTS) {
-        if (P.dbg & 4) break;                   // experiment: no epilogue work
+      auto do_group = [&](int gi, const float (&sv)[8]) {      // sv: this group's deep-prefetched side values (DEEP only)
         const int c0 = gi * 8;
         uint32_t r1[8], r2[8];
         tmem_ld8(t_row + (uint32_t)c0, r1);
         tmem_ld8(t_row + (uint32_t)(BA + c0), r2);
         float rb[8], rs[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { rb[u] = SIDE ? nrb[u] : 0.f; rs[u] = SIDE ? nrs[u] : 0.f; }
+        for (int u = 0; u < 8; ++u) {
+          rb[u] = SIDE == 3 ? nrb[u] : (SIDE == 1 ? sv[u] : 0.f);
+          rs[u] = SIDE == 3 ? nrs[u] : (SIDE == 2 ? sv[u] : 0.f);
+        }
         if (gi + EPI_PARTS < ngroups) load_side(gi + EPI_PARTS);
         tmem_ld_wait();
         const int m0 = mt * BA + c0;
         const int cnt = min(8, g.M - m0);
-        if (cnt <= 0 || !nok) continue;
+        if (cnt <= 0 || !nok) return;
         float t[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t[u] = fmaf(__uint_as_float(r2[u]), HL_INV, __uint_as_float(r1[u])) + bias_n + rb[u];
@@ -249,7 +267,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] = act_apply(t[u], g.act);
         }
-        if (SIDE && g.c_scale) {
+        if (SIDE == 3 && g.c_scale) {
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (u < cnt) {
@@ -257,7 +275,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
               t[u] = fmaf(t[u], g.c_scale[o], g.c_shift[o]);
             }
         }
-        if (SIDE) {
+        if (SIDE >= 2) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] += rs[u];
         }
@@ -284,6 +302,16 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
           const bool nxt = m0 >= m_next;             // st_rps % 8 == 0: a group of 8 tokens never straddles samples
           st1a += nxt ? 0.f : a1; st2a += nxt ? 0.f : a2;
           st1b += nxt ? a1 : 0.f; st2b += nxt ? a2 : 0.f;
+        }
+      };
+      if (!(P.dbg & 4)) {                      // (dbg 4: experiment without epilogue work)
+        if (DEEP) {
+#pragma unroll
+          for (int it = 0; it < EPI_ITERS; ++it)
+            if (half + it * EPI_PARTS < ngroups) do_group(half + it * EPI_PARTS, sd[it]);
+        } else {
+#pragma unroll 1
+          for (int gi = half; gi < ngroups; gi += EPI_PARTS) do_group(gi, sd[0]);
         }
       }
       tc_fence_before();
@@ -429,7 +457,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   const int grid = CGn * (P.total_tiles < units ? P.total_tiles : units);
   const int am = p.act == DPOT_ACT_NONE ? 0 : (p.act == DPOT_ACT_GELU ? 1 : 2);
   const bool o16 = p.c_fmt == DPOT_FMT_HL16;
-  const bool side = p.rowbias || p.residual || p.c_scale;
+  const int side = p.c_scale || (p.rowbias && p.residual) ? 3 : (p.rowbias ? 1 : (p.residual ? 2 : 0));
 #define DPOT_TC16_LAUNCH(CGV, AM, O16, SD)                                                                             \
   do {                                                                                                                 \
     static bool attr = false;                                                                                          \
@@ -447,7 +475,13 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
     lc.attrs = at; lc.numAttrs = 1;                                                                                    \
     DPOT_CUDA(cudaLaunchKernelEx(&lc, gemm_tc16_kernel<CGV, AM, O16, SD>, mWh, mWl, mAh, mAl, P));                     \
   } while (0)
-#define DPOT_TC16_SD(CGV, AM, O16) do { if (side) DPOT_TC16_LAUNCH(CGV, AM, O16, true); else DPOT_TC16_LAUNCH(CGV, AM, O16, false); } while (0)
+#define DPOT_TC16_SD(CGV, AM, O16)                                                                                     \
+  do {                                                                                                                 \
+    if (side == 0) DPOT_TC16_LAUNCH(CGV, AM, O16, 0);                                                                  \
+    else if (side == 1) DPOT_TC16_LAUNCH(CGV, AM, O16, 1);                                                             \
+    else if (side == 2) DPOT_TC16_LAUNCH(CGV, AM, O16, 2);                                                             \
+    else DPOT_TC16_LAUNCH(CGV, AM, O16, 3);                                                                            \
+  } while (0)
 #define DPOT_TC16_O(CGV, AM) do { if (o16) DPOT_TC16_SD(CGV, AM, true); else DPOT_TC16_SD(CGV, AM, false); } while (0)
 #define DPOT_TC16_A(CGV) do { if (am == 0) DPOT_TC16_O(CGV, 0); else if (am == 1) DPOT_TC16_O(CGV, 1); else DPOT_TC16_O(CGV, 2); } while (0)
   if (CGn == 2) DPOT_TC16_A(2); else DPOT_TC16_A(1);

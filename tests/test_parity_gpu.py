@@ -383,6 +383,16 @@ def test_tc16_pair_and_single_tile_plans(shape, pair):
             if out16:
                 out = ops.unsplit_f16(out)
             assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6, (shape, pair, out16)
+        # epilogue side-input modes: row-periodic bias only / residual only (deep prefetch), and both together
+        period = 37 if M >= 37 else M
+        RB = rng.standard_normal((period, N)).astype(np.float32)
+        lin = A.astype(np.float64) @ W.T.astype(np.float64) + b
+        rbt = np.tile(RB, (M // period + 1, 1))[:M].astype(np.float64)
+        A16, W16 = ops.split_f16(t(A)), ops.split_f16(t(W))
+        for rb_, rs_ in ((True, False), (False, True), (True, True)):
+            out = ops.gemm16(A16, W16, bias=t(b), act="gelu", rowbias=t(RB) if rb_ else None, residual=t(R) if rs_ else None)
+            want = O.activation(lin + (rbt if rb_ else 0.0), "gelu") + (R if rs_ else 0.0)
+            assert O.rel_l2(out.cpu().numpy(), want) < 2e-6, (shape, pair, rb_, rs_)
     finally:
         lib.dpot_tc16_set_pair(-1)
 
@@ -479,3 +489,77 @@ def test_out_tail_engines(geo, engine):
         assert O.rel_l2(got, want * sg[:, None, None, :] + mu[:, None, None, :]) < 1e-6, (geo, engine, "denorm")
     finally:
         lib.dpot_out_tail_set_engine(0)
+
+
+def test_groupnorm_by_reference_kernels_match_table_kernels():
+    """dpot_afno_fft_fwd16_gn / dpot_afno_fft_inv_gn / dpot_split_f16_gn (GroupNorm from raw statistics + gamma/beta)
+    against the table-driven kernels fed by dpot_gn_finalize, and against float64 GroupNorm (models/dpot.py:167,175)."""
+    from dpot_b200 import _lib, ops
+    from dpot_b200._lib import ptr
+    lib = _lib.load()
+    B, h, E, nb, groups = 3, 16, 256, 4, 8
+    n, km1, km2 = h * h, 16, 9
+    rng = np.random.default_rng(21)
+    a = torch.from_numpy((rng.standard_normal((B * n, E)) * 1.7 + 0.3).astype(np.float32)).cuda()
+    gamma = torch.from_numpy((1 + 0.2 * rng.standard_normal(E)).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.3 * rng.standard_normal(E)).astype(np.float32)).cuda()
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    stats = ops.gn_stats(a, B, n, groups)
+    sc, sh = ops.gn_finalize(stats, gamma, beta, n)
+    # float64 reference of the normalised tensor
+    a64 = a.cpu().numpy().astype(np.float64).reshape(B, n, groups, E // groups)
+    mu, var = a64.mean(axis=(1, 3), keepdims=True), a64.var(axis=(1, 3), keepdims=True)
+    n1 = ((a64 - mu) / np.sqrt(var + 1e-5)).reshape(B * n, E) * gamma.cpu().numpy() + beta.cpu().numpy()
+    # split: by reference vs float64
+    out = torch.empty((B * n, 2 * E), device="cuda", dtype=torch.float16)
+    _lib.check(lib.dpot_split_f16_gn(ptr(a), E, B * n, E, ptr(stats), ptr(gamma), ptr(beta), groups, 1e-5, n, ptr(out), 2 * E, E, st()),
+               "dpot_split_f16_gn")
+    assert O.rel_l2(ops.unsplit_f16(out).cpu().numpy(), n1) < 1e-6
+    # forward FFT: by reference vs tables (both split-fp16 spectra)
+    Ms = B * km1 * km2
+    S_ref = torch.zeros((Ms, 4 * E), device="cuda", dtype=torch.float16)
+    S_gn = torch.zeros_like(S_ref)
+    _lib.check(lib.dpot_afno_fft_fwd16(ptr(a), ptr(sc), ptr(sh), B, h, E, nb, km1, km2, ptr(S_ref), st()), "fwd16")
+    _lib.check(lib.dpot_afno_fft_fwd16_gn(ptr(a), ptr(stats), ptr(gamma), ptr(beta), groups, 1e-5, B, h, E, nb, km1, km2, ptr(S_gn), st()),
+               "fwd16_gn")
+    u = lambda t_: ops.unsplit_f16(t_).cpu().numpy()
+    assert O.rel_l2(u(S_gn), u(S_ref)) < 1e-6
+    # inverse FFT + skip: by reference vs tables
+    O2 = torch.from_numpy(rng.standard_normal((Ms, 2 * E)).astype(np.float32)).cuda()
+    f_ref, st_ref = ops.afno_fft_inv(O2, a, sc, sh, B, h, nb, km1, km2)
+    f_gn = torch.empty_like(f_ref)
+    st_gn = torch.zeros_like(st_ref)
+    _lib.check(lib.dpot_afno_fft_inv_gn(ptr(O2), ptr(a), ptr(stats), ptr(gamma), ptr(beta), groups, 1e-5, B, h, E, nb, km1, km2,
+                                        ptr(f_gn), ptr(st_gn), st()), "inv_gn")
+    assert O.rel_l2(f_gn.cpu().numpy(), f_ref.cpu().numpy()) < 1e-6
+    assert O.rel_l2(st_gn.cpu().numpy(), st_ref.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("kw", [dict(img_size=64, patch_size=8, in_channels=4, out_channels=4, in_timesteps=10, out_timesteps=1,
+                                     n_blocks=4, embed_dim=128, out_layer_dim=32, depth=2, modes=32, mlp_ratio=1, n_cls=12),
+                                dict(img_size=32, patch_size=4, in_channels=2, out_channels=2, in_timesteps=6, out_timesteps=2,
+                                     n_blocks=2, embed_dim=64, out_layer_dim=16, depth=1, modes=4, mlp_ratio=2, n_cls=5),
+                                dict(img_size=32, patch_size=4, in_channels=3, out_channels=3, in_timesteps=4, out_timesteps=1,
+                                     n_blocks=2, embed_dim=64, out_layer_dim=8, depth=1, modes=32, mlp_ratio=1, n_cls=5)])
+def test_rollout_step_equals_forward_plus_window_shift(kw):
+    """dpot_rollout_step (output tail writes the new frames into the ring window and pred) against the literal loop of
+    evaluate.py:192-208: im = model(xx); pred[..., t] = im; xx = cat(xx[..., T_b:, :], im) -- fused tail kernel, its
+    fallback (out_layer_dim 8, odd channel count) and T_bundle = 2."""
+    from dpot_b200.models.dpot import DPOTNet
+    from dpot_b200.rollout import RolloutEngine
+    cfg = O.make_cfg(**kw)
+    model = DPOTNet(**cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_params(cfg, seed=7).items()})
+    model = model.cuda().eval()
+    B, steps, Tb = 2, 5, cfg["out_timesteps"]
+    xx = torch.from_numpy(O.make_input(cfg, B, seed=8)).cuda()
+    pred = RolloutEngine(model, B, steps).run(xx.clone())
+    with torch.no_grad():
+        win, outs = xx.clone(), []
+        for _ in range(steps):
+            im, _ = model(win)
+            outs.append(im)
+            win = torch.cat((win[..., Tb:, :], im), dim=-2)
+    want = torch.cat(outs, dim=-2)
+    assert pred.shape == want.shape
+    assert O.rel_l2(pred.cpu().numpy(), want.cpu().numpy()) < 1e-6
