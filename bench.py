@@ -159,10 +159,10 @@ def run_ours(args):
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     host = [torch.randn((BATCH, 128, 128, 10, 4), generator=g).pin_memory() for _ in range(NBUF)]
     devbuf = [h.to(dev) for h in host]
-    eng = RolloutEngine(model, BATCH, N_AR, device=dev)
+    eng = RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph)
     # end-to-end arm: two window/prediction buffer sets so that the H2D copy of step s+1 and the D2H read of step s-1
     # (own streams) overlap the rollout of step s; every byte still moves inside the timed region
-    engs = [eng, RolloutEngine(model, BATCH, N_AR, device=dev)]
+    engs = [eng, RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph)]
     host_out = [torch.empty((BATCH, 128, 128, N_AR, 4)).pin_memory() for _ in range(2)]
     s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -217,11 +217,10 @@ def run_ours(args):
         step_resident(s)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = lib.dpot_launch_count()
     ms = timed(step_resident, args.steps)
-    launches = lib.dpot_launch_count() - l0
+    launches = eng.launches_per_run * args.steps       # kernels of this library per rollout x rollouts (graph replays included)
     clocks = sampler.stop() if sampler else None
-    for s in range(min(args.warmup, 2)):
+    for s in range(4):
         step_e2e(s)
     torch.cuda.synchronize()
     ms_e2e = timed(step_e2e, args.steps, finish_e2e)
@@ -286,7 +285,8 @@ def run_ours(args):
                                    f"{N_AR} AR steps per bench step, no_grad",
                        "batch_per_gpu": BATCH, "ar_steps": N_AR, "field_steps_per_step": fs_per_step,
                        "l2_policy": f"{NBUF} distinct input batches rotated ({NBUF * in_bytes / 2**20:.0f} MiB > 126 MB L2)",
-                       "parallelism": f"replicas x{world} (no data-path collective)"},
+                       "parallelism": f"replicas x{world} (no data-path collective)",
+                       "launch": "eager kernel launches" if args.no_graph else "one CUDA graph per 10-step rollout (captured after an eager warm-up)"},
             "e2e": {"value": e2e, "unit": "field-steps/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -307,6 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the rollout kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--engine", type=int, default=None, help="force GEMM engine: 1 = SIMT fp32, 2 = tcgen05")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

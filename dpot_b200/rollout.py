@@ -16,9 +16,19 @@ from . import ops
 
 
 class RolloutEngine:
-    def __init__(self, model, batch: int, n_steps: int, device=None):
+    """use_graph: after one eager rollout (which also warms the library's one-time kernel attributes) the whole
+    n_steps rollout -- ~50 kernel launches per step -- is captured into ONE CUDA graph and replayed; the buffers
+    (window, prediction, workspace, packed weights) are fixed, so the recorded pointers stay valid.  The graph is
+    dropped whenever the parameters change (the packed-weight arena is re-derived then)."""
+
+    def __init__(self, model, batch: int, n_steps: int, device=None, use_graph: bool = False):
         self.model = model
         self.n_steps = n_steps
+        self.use_graph = use_graph
+        self._graph = None
+        self._graph_key = None
+        self._warm = False
+        self.launches_per_run = 0      # library kernels per rollout (counted on the eager run; a graph replay launches the same)
         dev = device or next(model.parameters()).device
         R, T, Cc = model.img_size, model.in_timesteps, model.in_channels
         Tb, Co = model.out_timesteps, model.out_channels
@@ -40,6 +50,34 @@ class RolloutEngine:
         eng = self.model.engine()
         if xx is not None:
             self.load(xx, non_blocking)
+        if not self.use_graph:
+            l0 = eng.lib.dpot_launch_count()
+            self._steps(eng)
+            self.launches_per_run = int(eng.lib.dpot_launch_count() - l0)
+            return self.pred
+        key = eng._param_key()
+        if self._graph is not None and key != self._graph_key:
+            self._graph, self._warm = None, False
+        if not self._warm:                      # first rollout: eager (also the warm-up the capture needs)
+            l0 = eng.lib.dpot_launch_count()
+            self._steps(eng)
+            self.launches_per_run = int(eng.lib.dpot_launch_count() - l0)
+            self._warm, self._graph_key = True, eng._param_key()
+            return self.pred
+        if self._graph is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=self.win.device)
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self._steps(eng)
+            cur.wait_stream(side)
+            self._graph = g
+        self._graph.replay()
+        return self.pred
+
+    def _steps(self, eng) -> None:
         T, Tb = self.model.in_timesteps, self.model.out_timesteps
         t0 = 0
         for s in range(self.n_steps):
@@ -47,7 +85,6 @@ class RolloutEngine:
             # ring slot and the prediction tensor (dpot_rollout_step)
             eng.rollout_step(self.win, self.im, self.pred, t0, s)
             t0 = (t0 + Tb) % T
-        return self.pred
 
 
 def rollout(model, xx: torch.Tensor, n_steps: int, engine: Optional[RolloutEngine] = None) -> torch.Tensor:

@@ -563,3 +563,27 @@ def test_rollout_step_equals_forward_plus_window_shift(kw):
     want = torch.cat(outs, dim=-2)
     assert pred.shape == want.shape
     assert O.rel_l2(pred.cpu().numpy(), want.cpu().numpy()) < 1e-6
+
+
+def test_rollout_cuda_graph_replay_matches_eager():
+    """RolloutEngine(use_graph=True): eager first call, captured + replayed afterwards; every call must reproduce the
+    eager engine on fresh inputs, and a parameter update must invalidate the captured graph."""
+    from dpot_b200.models.dpot import DPOTNet
+    from dpot_b200.rollout import RolloutEngine
+    cfg = O.make_cfg(img_size=64, patch_size=8, in_channels=4, out_channels=4, in_timesteps=10, out_timesteps=1,
+                     n_blocks=4, embed_dim=128, out_layer_dim=32, depth=2, modes=32, mlp_ratio=1, n_cls=12)
+    model = DPOTNet(**cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_params(cfg, seed=3).items()})
+    model = model.cuda().eval()
+    B, steps = 2, 4
+    eager, graphed = RolloutEngine(model, B, steps), RolloutEngine(model, B, steps, use_graph=True)
+    for it in range(4):
+        if it == 3:     # in-place parameter change: the packed weights are re-derived, the graph must be rebuilt
+            with torch.no_grad():
+                model.blocks[0].mlp[0].bias.add_(0.05)
+        xx = torch.from_numpy(O.make_input(cfg, B, seed=20 + it)).cuda()
+        want = eager.run(xx.clone()).clone()
+        got = graphed.run(xx.clone()).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), it
+    assert graphed.launches_per_run == eager.launches_per_run > 0
