@@ -431,6 +431,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
     DPOT_CUDA(cudaGetDevice(&dev));
     DPOT_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
   const Plan pl = make_plan(q, batch);

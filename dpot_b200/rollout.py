@@ -50,6 +50,8 @@ class RolloutEngine:
         eng = self.model.engine()
         if xx is not None:
             self.load(xx, non_blocking)
+        with torch.cuda.device(self.win.device):
+            eng.refresh(self.win.device)          # (re-)pack the weights outside the counted / captured region
         if not self.use_graph:
             l0 = eng.lib.dpot_launch_count()
             self._steps(eng)

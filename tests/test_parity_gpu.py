@@ -587,3 +587,40 @@ def test_rollout_cuda_graph_replay_matches_eager():
         torch.cuda.synchronize()
         assert torch.equal(got, want), it
     assert graphed.launches_per_run == eager.launches_per_run > 0
+
+
+@pytest.mark.parametrize("M,N,K,nb,act,out16", [(4608, 256, 256, 8, "gelu", True), (4608, 256, 256, 8, None, False),
+                                                 (5000, 128, 192, 4, "tanh", False), (5000, 512, 128, 1, "gelu", True)])
+def test_tc16_weight_stationary_plan(M, N, K, nb, act, out16):
+    """Weight-stationary short-K plan (gemm_tc16_ws.cu: resident weight tile, 64-token tiles, four TMEM buffers) against
+    float64 and against the generic plan, incl. a ragged last token tile and K of 2 / 3 k-blocks."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    if not lib.dpot_tc16_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    rng = np.random.default_rng(M + N + K + nb)
+    A = rng.standard_normal((M, nb * K)).astype(np.float32)
+    W = (rng.standard_normal((nb, N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal((nb, N)).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).cuda()
+    A16 = ops.split_f16(t(A))
+    W16 = ops.split_f16(t(W.reshape(nb * N, K)))
+    if nb > 1:
+        W16 = W16.reshape(nb, N, 2 * K)
+    bias = t(b) if nb > 1 else t(b[0])
+    ref = np.concatenate([O.activation(A[:, i * K:(i + 1) * K].astype(np.float64) @ W[i].T.astype(np.float64) + b[i], act or "none")
+                          if act else A[:, i * K:(i + 1) * K].astype(np.float64) @ W[i].T.astype(np.float64) + b[i]
+                          for i in range(nb)], axis=1)
+    outs = []
+    for ws in (-1, 0):
+        lib.dpot_tc16_set_ws(ws)
+        try:
+            l0 = lib.dpot_launch_count()
+            out = ops.gemm16(A16, W16, bias=bias, act=act, out16=out16, nb=nb)
+            assert lib.dpot_launch_count() == l0 + 1
+        finally:
+            lib.dpot_tc16_set_ws(-1)
+        out = ops.unsplit_f16(out) if out16 else out
+        outs.append(out.cpu().numpy())
+        assert O.rel_l2(outs[-1], ref) < 2e-6, (ws,)
+    assert O.rel_l2(outs[0], outs[1]) < 1e-6
