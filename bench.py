@@ -146,6 +146,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.pdl:
+        lib.dpot_set_pdl(1)
 
     cfg = O.zoo_cfg(MODEL)
     model = DPOTNet(**cfg)
@@ -308,6 +310,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels of the forward chain")
     ap.add_argument("--engine", type=int, default=None, help="force GEMM engine: 1 = SIMT fp32, 2 = tcgen05")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -7,6 +7,7 @@
 namespace dpot {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+int g_pdl = 0;
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
@@ -35,3 +36,5 @@ extern "C" int dpot_device_supported(void) {
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   return (major == 10 && minor == 0) ? 1 : 0;
 }
+
+extern "C" void dpot_set_pdl(int32_t on) { dpot::g_pdl = on ? 1 : 0; }

@@ -41,6 +41,28 @@ void count_launch();   // kernels launched by this library since load (dpot_laun
     if (rc__ != 0) return rc__;    \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// The kernels of the forward chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: each one
+// signals `launch_dependents` at its very start, so the NEXT kernel's CTAs are placed on an SM as soon as the last CTA
+// of this kernel leaves it, run their prologue there (barrier init, TMEM allocation, parameter-only loads such as
+// weight staging) while other SMs still finish this kernel, and block in `pdl_wait()` -- placed before the first read
+// or write of anything a predecessor produces -- until the predecessor grid has completed and flushed.
+// Measured on DPOT-S B=32 (bench.py --no-pdl / --no-graph): +1.1 % when kernels are launched one by one, none (-1 %,
+// noise) under CUDA-graph replay, where the launch gaps are already gone -- so it is OFF by default.
+extern int g_pdl;      // 0 = plain stream order (default), 1 = programmatic dependent launch (dpot_set_pdl)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

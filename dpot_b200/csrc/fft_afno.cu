@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
   constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, HC = (H >= 2) ? H / 2 : 1, n = H * H;
   extern __shared__ __align__(16) float smem[];
   float2* R_s = reinterpret_cast<float2*>(smem);             // [H][HC][CH]; column 0 = (DC, Nyquist) real pair
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tid = threadIdx.x, c = tid % CH, task0 = tid / CH;
   const int b = blockIdx.y, ch = blockIdx.x * CH + c;
@@ -249,6 +251,8 @@ __global__ void __launch_bounds__(NT, H <= 16 ? 3 : 1) afno_fft_inv_kernel(const
   extern __shared__ __align__(16) float smem[];
   float2* Z_s = reinterpret_cast<float2*>(smem);             // [H][HC][CH]; column 0 = (x_0[p], x_{H/2}[p]) real pair
   double* red = reinterpret_cast<double*>(smem);             // reused for the statistics (after a sync)
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tid = threadIdx.x, c = tid % CH, task0 = tid / CH;
   const int b = blockIdx.y, ch = blockIdx.x * CH + c;
@@ -371,7 +375,7 @@ int launch_fwd(const float* a, const float* scale, const float* shift, int B, in
   (void)KH;
   DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H, OUT16, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_fwd_kernel<H, OUT16, GN><<<grid, NT, smem, st>>>(a, scale, shift, E, E / nb, km1, km2, S, wint, gn);
+  DPOT_CUDA(launch_pdl(afno_fft_fwd_kernel<H, OUT16, GN>, grid, dim3(NT), smem, st, a, scale, shift, E, E / nb, km1, km2, S, wint, gn));
   DPOT_LAUNCH_CHECK("afno_fft_fwd_kernel");
   return 0;
 }
@@ -386,7 +390,7 @@ int launch_inv(const float* O2, const float* a, const float* scale, const float*
   if (smem < (size_t)2 * NT * 8) smem = (size_t)2 * NT * 8;
   DPOT_CUDA(cudaFuncSetAttribute(afno_fft_inv_kernel<H, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  afno_fft_inv_kernel<H, GN><<<grid, NT, smem, st>>>(O2, a, scale, shift, E, E / nb, km1, km2, f, stats, groups, wint, gn);
+  DPOT_CUDA(launch_pdl(afno_fft_inv_kernel<H, GN>, grid, dim3(NT), smem, st, O2, a, scale, shift, E, E / nb, km1, km2, f, stats, groups, wint, gn));
   DPOT_LAUNCH_CHECK("afno_fft_inv_kernel");
   return 0;
 }

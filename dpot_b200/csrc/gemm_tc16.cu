@@ -93,6 +93,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmDev& g = P.g;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;     // 0 = leader of the pair (issues the MMAs)
+  pdl_launch_dependents();
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&mapWh); tma_prefetch_desc(&mapWl); tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapAl);
@@ -111,6 +112,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // the prologue above overlapped the predecessor's tail; operands / side inputs are read below
 
   const int KB = P.kblocks, BA = P.BA;
   const int rows_a = BA / CG;                                  // token rows this CTA stages (a multiple of 8)
@@ -470,10 +472,12 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
     cudaLaunchConfig_t lc = {};                                                                                        \
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = Geo<CGV>::SMEM_BYTES;       \
     lc.stream = st;                                                                                                    \
-    cudaLaunchAttribute at[1];                                                                                         \
+    cudaLaunchAttribute at[2];                                                                                         \
     at[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
     at[0].val.clusterDim.x = CGV; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                              \
-    lc.attrs = at; lc.numAttrs = 1;                                                                                    \
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+    at[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;                                                  \
+    lc.attrs = at; lc.numAttrs = 2;                                                                                    \
     DPOT_CUDA(cudaLaunchKernelEx(&lc, gemm_tc16_kernel<CGV, AM, O16, SD>, mWh, mWl, mAh, mAl, P));                     \
   } while (0)
 #define DPOT_TC16_SD(CGV, AM, O16)                                                                                     \

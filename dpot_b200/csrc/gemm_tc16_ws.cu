@@ -56,6 +56,7 @@ gemm_tc16_ws_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmDev& g = P.g;
+  pdl_launch_dependents();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&mapWh); tma_prefetch_desc(&mapWl); tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapAl);
   }
@@ -71,6 +72,7 @@ gemm_tc16_ws_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   const int KB = P.kblocks;
   const int group = blockIdx.x / P.cpg, member = blockIdx.x % P.cpg;
@@ -237,7 +239,7 @@ int gemm_tc16_ws_launch(const GemmDev& p, int batch, int sms, cudaStream_t st) {
                                      (int)WS_SMEM));                                                                  \
       attr = true;                                                                                                    \
     }                                                                                                                 \
-    gemm_tc16_ws_kernel<AM, O16><<<grid, WS_NTHREADS, WS_SMEM, st>>>(mWh, mWl, mAh, mAl, P);                          \
+    DPOT_CUDA(launch_pdl(gemm_tc16_ws_kernel<AM, O16>, dim3(grid), dim3(WS_NTHREADS), WS_SMEM, st, mWh, mWl, mAh, mAl, P)); \
   } while (0)
 #define DPOT_WS_O(AM) do { if (o16) DPOT_WS_LAUNCH(AM, true); else DPOT_WS_LAUNCH(AM, false); } while (0)
   if (am == 0) DPOT_WS_O(0); else if (am == 1) DPOT_WS_O(1); else DPOT_WS_O(2);

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __res
   constexpr int KS = OLD / 16, NT = OLD / 8, KW = OLD + 8;
   __shared__ __align__(16) __half s_w[2][OLD + 8][KW];      // [hi|lo][n: W2 rows, then 8 rows of W4][k]
   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  pdl_launch_dependents();
+  // parameters only up to pdl_wait(): the weight fragments are built while the predecessor (the ConvTranspose GEMM) drains
   for (int e = tid; e < (OLD + 8) * OLD; e += blockDim.x) {
     const int n = e / OLD, k = e % OLD;
     float v = 0.f;
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(128, 4) out_tail_mma_kernel(const float* __res
   const int c0 = tg * 2;
   const float bias4_0 = c0 < nout ? b4[c0] : 0.f, bias4_1 = c0 + 1 < nout ? b4[c0 + 1] : 0.f;
 
+  pdl_wait();
   const int64_t npix = (int64_t)B * h * w * P * P;
   const int64_t ntile = (npix + 15) / 16;
   const int X = h * P, Y = w * P;
@@ -196,7 +199,7 @@ int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t want = (ntile + 3) / 4;
   const unsigned grid = (unsigned)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);   // one resident wave (4 CTAs / SM)
-#define DPOT_OTM2(O, AM, RG) out_tail_mma_kernel<O, AM, RG><<<grid, 128, 0, st>>>(Y1, w2, b2, w4, b4, B, h, w, P, nout, act, mu, sigma, Co, out, rg)
+#define DPOT_OTM2(O, AM, RG) DPOT_CUDA(launch_pdl(out_tail_mma_kernel<O, AM, RG>, dim3(grid), dim3(128), 0, st, Y1, w2, b2, w4, b4, B, h, w, P, nout, act, mu, sigma, Co, out, rg))
 #define DPOT_OTM(O, AM) do { if (ring) DPOT_OTM2(O, AM, true); else DPOT_OTM2(O, AM, false); } while (0)
   if (old == 32) { if (act == DPOT_ACT_GELU) DPOT_OTM(32, 1); else DPOT_OTM(32, 2); }
   else { if (act == DPOT_ACT_GELU) DPOT_OTM(16, 1); else DPOT_OTM(16, 2); }

@@ -196,8 +196,10 @@ __global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a,
 
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
   const int TC = a.T * a.C;
+  pdl_launch_dependents();
 
-  // ---- weights -> split fp16 in shared memory, once per (persistent) CTA; rows >= mid are zero
+  // ---- weights -> split fp16 in shared memory, once per (persistent) CTA; rows >= mid are zero.  The packed weights
+  // were produced long before the predecessor kernel: this staging runs BEFORE pdl_wait() and overlaps its tail.
   {
     const int nvec = a.mid * a.K0 / 4;                         // K0 % 4 == 0 (C % 4 == 0)
     const float4* W4 = reinterpret_cast<const float4*>(a.W0p);
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a,
   // activation rows beyond a short item (ragged last q-run) must read as zero: clear everything once
   for (int e = tid; e < (int)(4 * a_plane / 2); e += nthr) reinterpret_cast<uint32_t*>(Ab)[e] = 0u;
   __syncthreads();
+  pdl_wait();      // the field (written by the previous step's output tail) is read from here on
 
   // ldmatrix lane addressing: lane -> (matrix j = lane / 8, row i = lane % 8)
   const int lj = lane >> 3, li = lane & 7;
@@ -448,7 +451,7 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
     if (smem_m > 48 * 1024)                                                                                             \
       DPOT_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<NT, O16, KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem_m));                                                                     \
-    patch_embed_mma_kernel<NT, O16, KSV><<<grid_m, nw * 32, smem_m, st>>>(m, nitems);                                   \
+    DPOT_CUDA(launch_pdl(patch_embed_mma_kernel<NT, O16, KSV>, dim3(grid_m), dim3(nw * 32), smem_m, st, m, nitems));    \
   } while (0)
 #define DPOT_PEM(NT, KSV) do { if (o16) DPOT_PEM_LAUNCH(NT, true, KSV); else DPOT_PEM_LAUNCH(NT, false, KSV); } while (0)
         switch (ks * 16 + nt8) {

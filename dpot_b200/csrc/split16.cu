@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
                                                         int rps, __half* __restrict__ dst, int64_t ldd, int64_t lo_off,
                                                         const GnRef gn) {
   const int64_t total = rows * cols8;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols8;
     const int c = (int)(i % cols8) * 8;
@@ -73,8 +75,8 @@ extern "C" int dpot_split_f16(const float* src, int64_t lds, int64_t rows, int32
   if (rows == 0) return 0;
   const int64_t total = rows * (cols / 8);
   const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
-  split_f16_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, lds, rows, cols / 8, scale, shift, rows_per_sample,
-                                                               reinterpret_cast<__half*>(dst), ldd, lo_off, GnRef());
+  DPOT_CUDA(launch_pdl(split_f16_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), src, lds, rows, cols / 8, scale, shift,
+                       rows_per_sample, reinterpret_cast<__half*>(dst), ldd, lo_off, GnRef()));
   DPOT_LAUNCH_CHECK("split_f16_kernel");
   return 0;
 }
@@ -94,8 +96,8 @@ extern "C" int dpot_split_f16_gn(const float* src, int64_t lds, int64_t rows, in
   const int64_t total = rows * (cols / 8);
   const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
   const GnRef gn = make_gn_ref(stats, gamma, beta, groups, eps, cols, rows_per_sample);
-  split_f16_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, lds, rows, cols / 8, nullptr, nullptr, rows_per_sample,
-                                                              reinterpret_cast<__half*>(dst), ldd, lo_off, gn);
+  DPOT_CUDA(launch_pdl(split_f16_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), src, lds, rows, cols / 8,
+                       (const float*)nullptr, (const float*)nullptr, rows_per_sample, reinterpret_cast<__half*>(dst), ldd, lo_off, gn));
   DPOT_LAUNCH_CHECK("split_f16_kernel");
   return 0;
 }

@@ -147,6 +147,8 @@ DPOT_API int dpot_tc16_available(void);
 /* tile-plan knob of the f16-split engine (tests / experiments): -1 = auto (cost model), 0 = single-CTA tiles only,
    1 = CTA pairs (tcgen05 cta_group::2, UMMA M = 256) whenever N > 128 */
 DPOT_API void dpot_tc16_set_pair(int32_t mode);
+/* programmatic dependent launch between the kernels of the forward chain: 0 = plain stream order (default), 1 = on */
+DPOT_API void dpot_set_pdl(int32_t on);
 /* weight-stationary plan for short-K batched problems (K <= 256; the AFNO block MLP): -1 = auto, 0 = never */
 DPOT_API void dpot_tc16_set_ws(int32_t mode);
 /* pipeline-isolation experiments (results are garbage when non-zero): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue */

@@ -624,3 +624,35 @@ def test_tc16_weight_stationary_plan(M, N, K, nb, act, out16):
         outs.append(out.cpu().numpy())
         assert O.rel_l2(outs[-1], ref) < 2e-6, (ws,)
     assert O.rel_l2(outs[0], outs[1]) < 1e-6
+
+
+@pytest.mark.parametrize("name,kw,B", [
+    ("M", dict(embed_dim=1024, depth=2, n_blocks=8, mlp_ratio=4, out_layer_dim=32, img_size=128, patch_size=8), 2),
+    ("L", dict(embed_dim=1536, depth=2, n_blocks=16, mlp_ratio=4, out_layer_dim=128, img_size=256, patch_size=16, modes=64), 1),
+    ("H", dict(embed_dim=2048, depth=1, n_blocks=8, mlp_ratio=4, out_layer_dim=128, img_size=128, patch_size=8), 1)])
+def test_zoo_shapes_forward_matches_oracle(name, kw, B):
+    """BASELINE configs 3-5 are parity cases: the layer shapes of DPOT-M / L (256^2, patch 16, modes 64) / H at reduced depth
+    (the per-layer kernels and tile plans are the ones the full models run: K = 4096 GEMMs, 192- and 512-deep AFNO
+    blocks, out_layer_dim 128, 67-wide PatchEmbed) against the float32 numpy oracle."""
+    from dpot_b200.models.dpot import DPOTNet
+    from dpot_b200 import _lib
+    cfg = O.make_cfg(in_channels=4, out_channels=4, in_timesteps=10, out_timesteps=1, n_cls=12, **kw)
+    p = O.make_params(cfg, seed=11)
+    x = O.make_input(cfg, B, seed=12)
+    model = DPOTNet(**cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    model = model.cuda().eval()
+    with torch.no_grad():
+        y, cls = model(torch.from_numpy(x).cuda())
+    yo, co = O.dpot_forward(x, p, cfg)
+    assert O.rel_l2(y.cpu().numpy(), yo) < TOL, name
+    assert O.rel_l2(cls.cpu().numpy(), co) < TOL, name
+    lib = _lib.load()
+    lib.dpot_set_pdl(1)      # the same forward under programmatic dependent launch
+    try:
+        with torch.no_grad():
+            y2, _ = model(torch.from_numpy(x).cuda())
+        torch.cuda.synchronize()
+    finally:
+        lib.dpot_set_pdl(0)
+    assert torch.equal(y2, y), name
