@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 BATCH, N_AR, MODEL = 32, 10, "S"
 FLOP_PER_FIELD_STEP = 15.07e9      # algorithmic forward FLOPs of DPOT-S @128^2
+FC1_DRAM_BYTES = 40.3e6            # fc1 GEMM kernel, dram read + write per launch (ncu --set full, profiles/r01d_ncu_summary.txt)
 METRIC = "autoregressive field-steps/sec, DPOT-S 128x128 (10 frames in -> 1 out), fp32"
 
 
@@ -91,7 +92,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -265,14 +266,20 @@ def run_ours(args):
         div = 3.0 if tc16 else 6.0
         roof = {"bound": "tensor", "kernel": "channel-MLP fc1 GEMM M=8192 N=1024 K=1024 (bias+GELU epilogue)",
                 "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-                "traffic": None, "peak_source": pk["src"] + ", dense bf16 cuBLAS burst",
+                "traffic": FC1_DRAM_BYTES if tc16 else None, "traffic_unit": "bytes per launch",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full (cold L2), "
+                                  "profiles/r01d_ncu_summary.txt; algorithmic operand + result bytes = 71 MB (the result stays in L2)",
+                "peak_source": pk["src"] + ", dense bf16 cuBLAS burst",
                 "engine": ("tcgen05 kind::f16 on split-fp16 operands (3 MMAs per fp32 product)" if tc16 else
                            ("tcgen05 3xTF32" if (lib.dpot_tc_available() and model.gemm_engine != 1) else "fp32 CUDA cores (SIMT)")),
                 "us_per_launch": t * 1e6,
                 "frac_of_fp32_faithful_peak": ach / (pk["bf16"] / div),
                 "note": f"achieved = algorithmic 2MNK / CUDA-event time; fp32 parity costs {mmas:.0f} tensor-core MMAs per "
                         f"product, so the honest ceiling for this kernel is bf16 peak / {div:.0f}",
-                "whole_step_algorithmic_tflops": FLOP_PER_FIELD_STEP * value / world / 1e12}
+                "whole_step_algorithmic_tflops": FLOP_PER_FIELD_STEP * value / world / 1e12,
+                "whole_step_frac_of_fp32_faithful_sustained_peak": FLOP_PER_FIELD_STEP * value / world / 1e12 / (pk["bf16_sus"] / div),
+                "whole_step_note": "whole rollout step: algorithmic 15.07 GFLOP per field-step x field-steps/s per GPU, against the "
+                                   "SUSTAINED bf16 peak / 3 (a kernel inside a long step runs under the power cap)"}
 
     if rank == 0:
         cores = os.cpu_count() or 1
