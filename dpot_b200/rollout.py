@@ -72,7 +72,8 @@ class RolloutEngine:
             side.wait_stream(cur)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
-                with torch.cuda.graph(g, stream=side):
+                # thread_local: other threads (e.g. the NCCL watchdog of a multi-GPU job) may keep calling the CUDA API
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                     self._steps(eng)
             cur.wait_stream(side)
             self._graph = g
