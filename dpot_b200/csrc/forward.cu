@@ -205,6 +205,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       g = gemm16_args(ws + WL.hid, d.hid, pk + PL.fc2_16, d.hid, lat_next, d.E, Mt, d.E, d.hid, bp.fc2_b, DPOT_ACT_NONE);
       g.residual = lat; g.ldr = d.E;
       if (i + 1 < d.depth) { g.out_stats = st1; g.stats_groups = groups; g.stats_rows_per_sample = d.n; }
+      else if (!cls) { g.C = ws + WL.n2; out16(g, d.E); }   // last block, no cls head: the latent is only read by the output GEMM -> split fp16
       DPOT_CALL(dpot_gemm(&g, stream));
     }
     float* tmp = lat; lat = lat_next; lat_next = tmp;
@@ -220,8 +221,9 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
     DPOT_CALL(dpot_gemm(&g, stream));
   }
 
-  // output head: ConvTranspose as a GEMM on the split latent, then the fused per-pixel tail
-  DPOT_CALL(dpot_split_f16(lat, d.E, Mt, d.E, nullptr, nullptr, 0, ws + WL.n2, 2 * d.E, d.E, stream));
+  // output head: ConvTranspose as a GEMM on the split latent (written split by the last fc2 unless the cls head
+  // needed it in fp32), then the fused per-pixel tail
+  if (cls) DPOT_CALL(dpot_split_f16(lat, d.E, Mt, d.E, nullptr, nullptr, 0, ws + WL.n2, 2 * d.E, d.E, stream));
   {
     dpot_gemm_args g = gemm16_args(ws + WL.n2, d.E, packed + PL.WtT16, d.E, ws + WL.Y1, d.NP, Mt, d.NP, d.E, packed + PL.bias_t, act);
     DPOT_CALL(dpot_gemm(&g, stream));

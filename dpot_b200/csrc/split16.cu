@@ -57,6 +57,61 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
   }
 }
 
+// GroupNorm-by-reference split, tuned form: one thread owns ONE chunk of 8 columns for a run of consecutive rows of one
+// sample, so the statistics, gamma and beta are fetched once and the row loop keeps 4 rows (8 x 16 B) in flight.
+constexpr int SPLIT_ROWS = 8;
+__global__ void __launch_bounds__(128) split_f16_gn_rows_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols8,
+                                                                int rps, __half* __restrict__ dst, int64_t ldd, int64_t lo_off,
+                                                                const GnRef gn) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;       // column chunk
+  if (cc >= cols8) return;
+  const int c = cc * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * SPLIT_ROWS;         // rps % SPLIT_ROWS == 0: the run stays inside one sample
+  const int bsm = (int)(r0 / rps);
+  const double* sp = gn.stats + ((int64_t)bsm * gn.groups + c / gn.gs) * 2;
+  const double mean = sp[0] * gn.inv_cnt;
+  const double var = fma(-mean, mean, sp[1] * gn.inv_cnt);
+  const float vv = fmaxf((float)var, 0.f) + gn.eps;
+  float rstd = rsqrtf(vv);
+  rstd = rstd * fmaf(-0.5f * vv * rstd, rstd, 1.5f);
+  const float nm = -(float)mean;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gn.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gn.gamma + c + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(gn.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(gn.beta + c + 4));
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float sc[8], sh[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { sc[u] = rstd * gg[u]; sh[u] = fmaf(nm, sc[u], bb[u]); }
+  const int64_t rend = r0 + SPLIT_ROWS < rows ? r0 + SPLIT_ROWS : rows;
+  for (int64_t r = r0; r < rend; r += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r + j < rend) {
+        a[j] = __ldcs(reinterpret_cast<const float4*>(src + (r + j) * lds + c));
+        b[j] = __ldcs(reinterpret_cast<const float4*>(src + (r + j) * lds + c + 4));
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r + j < rend) {
+        const float v[8] = {a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float x0 = fmaf(v[2 * u], sc[2 * u], sh[2 * u]), x1 = fmaf(v[2 * u + 1], sc[2 * u + 1], sh[2 * u + 1]);
+          const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+          const __half l0 = __float2half_rn((x0 - __half2float(h0)) * HL_SCALE), l1 = __float2half_rn((x1 - __half2float(h1)) * HL_SCALE);
+          hi[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lo[u] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4*>(dst + (r + j) * ldd + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + (r + j) * ldd + c + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+  }
+}
+
 }  // namespace
 }  // namespace dpot
 
@@ -96,6 +151,13 @@ extern "C" int dpot_split_f16_gn(const float* src, int64_t lds, int64_t rows, in
   const int64_t total = rows * (cols / 8);
   const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
   const GnRef gn = make_gn_ref(stats, gamma, beta, groups, eps, cols, rows_per_sample);
+  if (rows_per_sample % SPLIT_ROWS == 0 && rows % SPLIT_ROWS == 0 && rows / SPLIT_ROWS <= 65535) {
+    dim3 g2((unsigned)ceil_div(cols / 8, 128), (unsigned)(rows / SPLIT_ROWS));
+    DPOT_CUDA(launch_pdl(split_f16_gn_rows_kernel, g2, dim3(128), 0, as_stream(stream), src, lds, rows, cols / 8, rows_per_sample,
+                         reinterpret_cast<__half*>(dst), ldd, lo_off, gn));
+    DPOT_LAUNCH_CHECK("split_f16_gn_rows_kernel");
+    return 0;
+  }
   DPOT_CUDA(launch_pdl(split_f16_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), src, lds, rows, cols / 8,
                        (const float*)nullptr, (const float*)nullptr, rows_per_sample, reinterpret_cast<__half*>(dst), ldd, lo_off, gn));
   DPOT_LAUNCH_CHECK("split_f16_kernel");
