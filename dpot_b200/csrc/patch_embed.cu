@@ -182,20 +182,29 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const PatchArgs a) {
 // CTA = one item (b, p, QPB patches along q) x all T frames: rows r = ql*T + t, one warp per 16-row tile.
 // Per image row u the item's slab is ONE contiguous run of the field: float4 loads -> hi/lo split ->
 // shared memory [row][k] (double-buffered), ldmatrix fragments, NT8 n-tiles of 8 output channels.
+// Warp-specialised, persistent: warp 0 is a producer that streams the item's image-row slabs (ONE contiguous run of
+// the field each) into a ring of shared-memory stages with cp.async.bulk + mbarriers; warps 1..NW own one 16-row
+// tile of the item each: they wait for a slab, pull their mma A fragments straight out of the raw fp32 slab (one
+// float2 = one pixel's channel pair per register pair), release the stage, split to hi/lo in registers and run the
+// MMAs against the weight table (ldmatrix).  No CTA-wide barrier after the one-time weight staging.
+constexpr int PE_STAGES = 6;
 template <int NT8, bool OUT16, int KS>
-__global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a, const int nitems) {
-  constexpr int NF = KS <= 2 ? 4 : 8;      // float4 per thread per slab (host guarantees L4 <= NF * nthr)
-  extern __shared__ __align__(16) uint8_t smem_mma[];
+__global__ void __launch_bounds__(288) patch_embed_mma_kernel(const PatchArgs a, const int nitems) {
+  extern __shared__ __align__(128) uint8_t smem_mma[];
   const int KW = a.K0 + 8;                 // halves per weight row (padded: conflict-free ldmatrix)
-  const int KA = a.PC + 8;                 // halves per activation row
-  const int rows_pad = (int)(blockDim.x >> 5) * 16;
+  const int NW = (int)(blockDim.x >> 5) - 1;                   // consumer warps = 16-row tiles per item
+  const int TC = a.T * a.C;
+  const uint32_t slab_bytes = (uint32_t)(a.QPB * a.P * TC * 4);   // full-size slab (a multiple of 16)
   __half* Wh = reinterpret_cast<__half*>(smem_mma);            // [NT8*8][KW]
   __half* Wl = Wh + (size_t)NT8 * 8 * KW;
-  __half* Ab = Wl + (size_t)NT8 * 8 * KW;                      // [2 buffers][hi, lo][rows_pad][KA]
-  const size_t a_plane = (size_t)rows_pad * KA;
+  const uint32_t w_bytes = (uint32_t)(2 * NT8 * 8 * KW * 2);
+  const uint32_t ring_off = (w_bytes + 127u) & ~127u;
+  float* ring = reinterpret_cast<float*>(smem_mma + ring_off);                      // [PE_STAGES][slab]
+  const uint32_t bar0 = smem_u32_generic(smem_mma + ring_off + PE_STAGES * slab_bytes);   // full[S], empty[S]
+  auto FULL = [&](int st) -> uint32_t { return bar0 + 8u * st; };
+  auto EMPTY = [&](int st) -> uint32_t { return bar0 + 8u * (PE_STAGES + st); };
 
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
-  const int TC = a.T * a.C;
   pdl_launch_dependents();
 
   // ---- weights -> split fp16 in shared memory, once per (persistent) CTA; rows >= mid are zero.  The packed weights
@@ -224,98 +233,118 @@ __global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a,
       Wl[(size_t)(e / a.K0) * KW + e % a.K0] = __float2half_rn(0.f);
     }
   }
-  // activation rows beyond a short item (ragged last q-run) must read as zero: clear everything once
-  for (int e = tid; e < (int)(4 * a_plane / 2); e += nthr) reinterpret_cast<uint32_t*>(Ab)[e] = 0u;
+  if (tid == 0) {
+    for (int st = 0; st < PE_STAGES; ++st) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(FULL(st)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(st)), "r"(NW));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   pdl_wait();      // the field (written by the previous step's output tail) is read from here on
 
-  // ldmatrix lane addressing: lane -> (matrix j = lane / 8, row i = lane % 8)
-  const int lj = lane >> 3, li = lane & 7;
-  const uint32_t a_lane = (uint32_t)(((warp * 16 + (lj & 1) * 8 + li) * KA + (lj >> 1) * 8) * 2);       // A: (rows, k) quads
-  const uint32_t w_lane = (uint32_t)((((lj >> 1) * 8 + li) * KW + (lj & 1) * 8) * 2);                  // W: (n-tile pair, k)
-  const uint32_t Ab_s = smem_u32_generic(Ab), Wh_s = smem_u32_generic(Wh), Wl_s = smem_u32_generic(Wl);
-  const int g = lane >> 2, tg = lane & 3;
-
-  // per-thread staging map (identical for every slab and item): float4 index -> destination (row*KA + k)
-  int doff[NF];
-#pragma unroll
-  for (int it = 0; it < NF; ++it) {
-    const int e = (tid + it * nthr) * 4;
-    const int c = e % a.C; int r = e / a.C;
-    const int slot = r % a.T; r /= a.T;
-    const int v = r % a.P; const int ql = r / a.P;
-    int t = slot - a.t0; if (t < 0) t += a.T;
-    doff[it] = (ql * a.T + t) * KA + v * a.C + c;              // ql >= nq of the item is masked at load time
-  }
-
-  struct Item { int b, p, q0, L4; const float* run0; };
-  auto item_of = [&](int item) {
-    Item I;
-    const int qs = item % a.QSPLIT; item /= a.QSPLIT;
-    I.p = item % a.h; I.b = item / a.h;
-    I.q0 = qs * a.QPB;
-    const int nq = min(a.QPB, a.w - I.q0);
-    I.L4 = nq * a.P * TC / 4;
-    I.run0 = a.x + (((int64_t)I.b * a.X + (int64_t)I.p * a.P) * a.Y + (int64_t)I.q0 * a.P) * TC;
-    return I;
-  };
-  const int64_t run_stride = (int64_t)a.Y * TC;      // one image row
-  float4 pre[NF];
-  auto prefetch = [&](const Item& I, int u) {
-    const float4* run = reinterpret_cast<const float4*>(I.run0 + (int64_t)u * run_stride);
-#pragma unroll
-    for (int it = 0; it < NF; ++it)
-      pre[it] = (tid + it * nthr < I.L4) ? __ldg(run + tid + it * nthr) : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  auto convert = [&](const Item& I, int u, int buf) {
-    __half* Ah = Ab + (size_t)buf * 2 * a_plane;
-    __half* Al = Ah + a_plane;
-    const float* scl = a.a_scale ? a.a_scale + (int64_t)I.b * a.K0 + u * a.PC : nullptr;
-    const float* shf = a.a_scale ? a.a_shift + (int64_t)I.b * a.K0 + u * a.PC : nullptr;
-#pragma unroll
-    for (int it = 0; it < NF; ++it) {
-      if ((tid + it * nthr) * 4 >= a.QPB * a.P * TC) continue;       // beyond the full-size slab
-      float vv[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
-      if (scl && tid + it * nthr < I.L4) {
-        const int k = doff[it] % KA;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) vv[j] = fmaf(vv[j], scl[k + j], shf[k + j]);
-      }
-      uint32_t h0, l0, h1, l1;
-      hl_split2(vv[0], vv[1], h0, l0);
-      hl_split2(vv[2], vv[3], h1, l1);
-      *reinterpret_cast<uint2*>(Ah + doff[it]) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(Al + doff[it]) = make_uint2(l0, l1);
+  auto mbar_wait_ = [&](uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; !ok; ++it) {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      if (it > 20000000u) __trap();          // a protocol bug must fail loudly, never hang the GPU
     }
   };
+  const int64_t run_stride = (int64_t)a.Y * TC;      // one image row
 
-  int item = blockIdx.x;
-  if (item >= nitems) return;
-  Item cur = item_of(item);
-  prefetch(cur, 0);
-  int buf = 0;
-  while (true) {
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        int it = item;
+        const int qs = it % a.QSPLIT; it /= a.QSPLIT;
+        const int p = it % a.h, b = it / a.h;
+        const int q0 = qs * a.QPB;
+        const uint32_t bytes = (uint32_t)(min(a.QPB, a.w - q0) * a.P * TC * 4);
+        const float* run0 = a.x + (((int64_t)b * a.X + (int64_t)p * a.P) * a.Y + (int64_t)q0 * a.P) * TC;
+        for (int u = 0; u < a.P; ++u) {
+          mbar_wait_(EMPTY(st), ph ^ 1);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(st)), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32_generic(ring) + (uint32_t)st * slab_bytes), "l"(run0 + (int64_t)u * run_stride), "r"(bytes),
+                         "r"(FULL(st)) : "memory");
+          if (++st == PE_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================ consumers ================================
+  const int cw = warp - 1;                                     // 16-row tile of the item
+  const int lj = lane >> 3, li = lane & 7;
+  const uint32_t w_lane = (uint32_t)((((lj >> 1) * 8 + li) * KW + (lj & 1) * 8) * 2);                  // W: (n-tile pair, k)
+  const uint32_t Wh_s = smem_u32_generic(Wh), Wl_s = smem_u32_generic(Wl);
+  const int g = lane >> 2, tg = lane & 3;
+  // float offset of this lane's float2 inside a slab, per (k-step, k-half): pixel column v = ks*4 + tg/2 + 2j, channels (tg&1)*2
+  int voff[KS][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) voff[ks][j] = (ks * 4 + (tg >> 1) + 2 * j) * TC + (tg & 1) * 2;
+  // this lane's two rows r = (q_local, t): float offset of (pixel column 0, channel 0) of the row inside a slab
+  int roff[2], rq[2], rt[2];
+#pragma unroll
+  for (int hr = 0; hr < 2; ++hr) {
+    const int r = cw * 16 + g + hr * 8;
+    rq[hr] = r / a.T; rt[hr] = r - rq[hr] * a.T;
+    int slot = rt[hr] + a.t0; if (slot >= a.T) slot -= a.T;
+    roff[hr] = (rq[hr] * a.P * a.T + slot) * a.C;
+  }
+  const bool is_gelu = a.act == DPOT_ACT_GELU;
+
+  int st = 0; uint32_t ph = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    int it = item;
+    const int qs = it % a.QSPLIT; it /= a.QSPLIT;
+    const int p = it % a.h, b = it / a.h;
+    const int q0 = qs * a.QPB;
+    const int R = min(a.QPB, a.w - q0) * a.T;        // live rows of this item
+    const bool rok[2] = {cw * 16 + g < R, cw * 16 + g + 8 < R};
     float d1[NT8][4], d2[NT8][4];
 #pragma unroll
     for (int i = 0; i < NT8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { d1[i][j] = 0.f; d2[i][j] = 0.f; }
-    const int next_item = item + gridDim.x;
-    Item nxt = cur;
-    if (next_item < nitems) nxt = item_of(next_item);
 
-    for (int u = 0; u < a.P; ++u, buf ^= 1) {
-      convert(cur, u, buf);
-      if (u + 1 < a.P) prefetch(cur, u + 1);
-      else if (next_item < nitems) prefetch(nxt, 0);           // the next item's first slab flies during this item's tail
-      __syncthreads();
-      const uint32_t Ah_s = Ab_s + (uint32_t)(buf * 2 * a_plane * 2);
-      const uint32_t Al_s = Ah_s + (uint32_t)(a_plane * 2);
+    for (int u = 0; u < a.P; ++u) {
+      mbar_wait_(FULL(st), ph);
+      const float* slab = ring + (size_t)st * (slab_bytes / 4);
+      float2 v[KS][4];                               // [k-step][row g klo, row g+8 klo, row g khi, row g+8 khi]
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          v[ks][i] = rok[i & 1] ? *reinterpret_cast<const float2*>(slab + roff[i & 1] + voff[ks][i >> 1]) : make_float2(0.f, 0.f);
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(EMPTY(st)) : "memory");   // slab consumed
+      if (++st == PE_STAGES) { st = 0; ph ^= 1; }
+      if (a.a_scale) {                               // input normalisation tables (normalize=True), k = (u, v, c)
+        const float* scl = a.a_scale + (int64_t)b * a.K0 + u * a.PC;
+        const float* shf = a.a_shift + (int64_t)b * a.K0 + u * a.PC;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = (ks * 4 + (tg >> 1) + 2 * (i >> 1)) * a.C + (tg & 1) * 2;
+            if (rok[i & 1]) {
+              v[ks][i].x = fmaf(v[ks][i].x, scl[k], shf[k]);
+              v[ks][i].y = fmaf(v[ks][i].y, scl[k + 1], shf[k + 1]);
+            }
+          }
+      }
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t ah[4], al[4];
-        ldmatrix_x4(Ah_s + a_lane + ks * 32, ah);
-        ldmatrix_x4(Al_s + a_lane + ks * 32, al);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hl_split2(v[ks][i].x, v[ks][i].y, ah[i], al[i]);
         const uint32_t wk = (uint32_t)((u * a.PC + ks * 16) * 2);
 #pragma unroll
         for (int np = 0; np < (NT8 + 1) / 2; ++np) {
@@ -341,16 +370,12 @@ __global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a,
     }
 
     // ---- epilogue: + row bias (conv bias and coordinate channels), activation, store
-    const int R = min(a.QPB, a.w - cur.q0) * a.T;
-    const bool is_gelu = a.act == DPOT_ACT_GELU;
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
-      const int r = warp * 16 + g + hrow * 8;
-      if (r >= R) continue;
-      const int ql = r / a.T, t = r - ql * a.T;
-      const int q = cur.q0 + ql;
-      const int64_t tok = ((int64_t)cur.b * a.h + cur.p) * a.w + q;
-      const float* rb = a.rowbias0 + (((int64_t)cur.p * a.w + q) * a.T + t) * a.mid + tg * 2;
+      if (!rok[hrow]) continue;
+      const int q = q0 + rq[hrow], t = rt[hrow];
+      const int64_t tok = ((int64_t)b * a.h + p) * a.w + q;
+      const float* rb = a.rowbias0 + (((int64_t)p * a.w + q) * a.T + t) * a.mid + tg * 2;
       float bv[NT8][2];
 #pragma unroll
       for (int nt = 0; nt < NT8; ++nt)        // all bias loads in flight before the first use
@@ -364,20 +389,17 @@ __global__ void __launch_bounds__(256) patch_embed_mma_kernel(const PatchArgs a,
         for (int j = 0; j < 2; ++j) {
           if (nt * 8 + tg * 2 + j >= a.mid) continue;
           const float pre_act = fmaf(d2[nt][hrow * 2 + j], HL_INV, d1[nt][hrow * 2 + j]) + bv[nt][j];
-          const float v = is_gelu ? gelu_fast(pre_act) : act_apply(pre_act, a.act);
+          const float vv = is_gelu ? gelu_fast(pre_act) : act_apply(pre_act, a.act);
           if (OUT16) {
             __half hi, lo;
-            hl_split(v, hi, lo);
+            hl_split(vv, hi, lo);
             dst16[nt * 8 + j] = hi;
             dst16[nt * 8 + j + a.Kp] = lo;
           } else {
-            dst32[nt * 8 + j] = v;
+            dst32[nt * 8 + j] = vv;
           }
         }
     }
-    if (next_item >= nitems) break;
-    item = next_item;
-    cur = nxt;
   }
 }
 
@@ -419,13 +441,13 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
 
   // ---- tensor-core path (mma.sync on split fp16): needs float4-able runs and 16-deep k-steps per image row
   const int nt8 = (int)ceil_div(mid, 8);
-  if (g_patch_engine != 1 && vec4 && a.PC % 16 == 0 && a.PC <= 64 && nt8 <= 9) {
+  if (g_patch_engine != 1 && vec4 && C == 4 && a.PC % 16 == 0 && a.PC <= 64 && nt8 <= 9) {
     const int ks = a.PC / 16;                   // k-steps per image-row slab: 1, 2 or 4
-    const int nf = ks <= 2 ? 4 : 8;
-    int q = a.w, best = 0;
-    for (; q >= 1; --q) {                      // largest run of patches that fits 8 warps, preferring no padded rows
-      const int64_t rows = (int64_t)q * T, nw = ceil_div(rows, 16);
-      if (nw > 8 || (int64_t)q * P * T * C / 4 > nf * 32 * nw) continue;
+    // items = runs of QPB patches along q: at most 8 tiles of 16 rows, preferring runs without padded rows
+    int best = 0;
+    for (int q = a.w; q >= 1; --q) {
+      const int64_t rows = (int64_t)q * T;
+      if (ceil_div(rows, 16) > 8) continue;
       if (best == 0) best = q;
       if (rows % 16 == 0) { best = q; break; }
       if (q < best / 2) break;
@@ -437,13 +459,15 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
       PatchArgs m = a;
       m.QPB = best; m.QSPLIT = (int)ceil_div(a.w, best);
       const int nw = (int)ceil_div((int64_t)best * T, 16);
-      const size_t smem_m = 2 * ((size_t)nt8 * 8 * (a.K0 + 8) * 2 + 2 * (size_t)nw * 16 * (a.PC + 8) * 2);
-      if (smem_m <= 160 * 1024) {
+      const size_t slab = (size_t)best * P * T * C * 4;
+      const size_t w_b = ((size_t)2 * nt8 * 8 * (a.K0 + 8) * 2 + 127) & ~(size_t)127;
+      const size_t smem_m = w_b + PE_STAGES * slab + 2 * PE_STAGES * 8 + 128;
+      if (smem_m <= 200 * 1024 && slab % 16 == 0) {
         const int nitems = (int)((int64_t)B * a.h * m.QSPLIT);
         int dev = 0, sms = 148;
         DPOT_CUDA(cudaGetDevice(&dev));
         DPOT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        int per_sm = (int)((220 * 1024) / (smem_m + 1024));
+        int per_sm = (int)((224 * 1024) / (smem_m + 1024));
         per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
         const unsigned grid_m = (unsigned)(nitems < sms * per_sm ? nitems : sms * per_sm);   // persistent: weights staged once per CTA
 #define DPOT_PEM_LAUNCH(NT, O16, KSV)                                                                                   \
@@ -451,7 +475,7 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
     if (smem_m > 48 * 1024)                                                                                             \
       DPOT_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<NT, O16, KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem_m));                                                                     \
-    DPOT_CUDA(launch_pdl(patch_embed_mma_kernel<NT, O16, KSV>, dim3(grid_m), dim3(nw * 32), smem_m, st, m, nitems));    \
+    DPOT_CUDA(launch_pdl(patch_embed_mma_kernel<NT, O16, KSV>, dim3(grid_m), dim3((nw + 1) * 32), smem_m, st, m, nitems)); \
   } while (0)
 #define DPOT_PEM(NT, KSV) do { if (o16) DPOT_PEM_LAUNCH(NT, true, KSV); else DPOT_PEM_LAUNCH(NT, false, KSV); } while (0)
         switch (ks * 16 + nt8) {
