@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdpot_b200.so")
 ACT_IDS = {"gelu": 0, "tanh": 1, "sigmoid": 2, "relu": 3, "leaky_relu": 4, "softplus": 5, "ELU": 6, "silu": 7}
 ACT_NONE = -1
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TC16 = 0, 1, 2, 3
-FMT_F32, FMT_HL16 = 0, 1
+FMT_F32, FMT_HL16, FMT_HL16G32 = 0, 1, 2
 A_PLAIN, A_PATCH = 0, 1
 
 c_f32p = C.c_void_p  # device pointers travel as integers
@@ -136,6 +136,9 @@ SIGNATURES = {
     "dpot_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _p, _p, _p, _i32, _p]),
     "dpot_forward_ring": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _i32, _p, _p, _p, _i32, _p]),
     "dpot_rollout_step": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _i32, _p]),
+    "dpot_out_tail_tc": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p,
+                                   _i32, _i32, _i32, _i32, _p]),
+    "dpot_out_tail_tc_supported": (C.c_int, [_i32, _i32, _i32]),
     "dpot_out_tail_ring": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p,
                                      _i32, _i32, _i32, _i32, _p]),
 }

@@ -226,8 +226,13 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
   if (cls) DPOT_CALL(dpot_split_f16(lat, d.E, Mt, d.E, nullptr, nullptr, 0, ws + WL.n2, 2 * d.E, d.E, stream));
   {
     dpot_gemm_args g = gemm16_args(ws + WL.n2, d.E, packed + PL.WtT16, d.E, ws + WL.Y1, d.NP, Mt, d.NP, d.E, packed + PL.bias_t, act);
-    DPOT_CALL(dpot_gemm(&g, stream));
     const int nout = d.Co * d.To;
+    // tcgen05 tail: the GEMM writes one [hi 32 | lo 32] record per pixel (DPOT_FMT_HL16G32), the tail's TMA operand
+    const bool tc_tail = d.old == 32 && dpot_out_tail_tc_supported(d.old, nout, d.Co) &&
+                         (reinterpret_cast<uintptr_t>(y) % 16 == 0) && (!ro || (reinterpret_cast<uintptr_t>(ro->ring) % 16 == 0 &&
+                                                                               (!ro->pred || reinterpret_cast<uintptr_t>(ro->pred) % 16 == 0)));
+    if (tc_tail) { g.c_fmt = DPOT_FMT_HL16G32; g.ldc = 2 * (int64_t)d.NP; }
+    DPOT_CALL(dpot_gemm(&g, stream));
     const bool fused_tail = (d.old == 4 || d.old == 8 || d.old == 16 || d.old == 32);
     if (cfg->normalize) DPOT_REQUIRE(d.C == d.Co, DPOT_E_UNSUPPORTED, "normalize=True needs in_channels == out_channels");
     const float* mu_c = nullptr; const float* sg_c = nullptr;
@@ -237,6 +242,12 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       DPOT_CUDA(cudaMemcpy2DAsync(mc, sizeof(float) * d.C, mu, sizeof(float) * 2 * d.C, sizeof(float) * d.C, B, cudaMemcpyDeviceToDevice, st));
       DPOT_CUDA(cudaMemcpy2DAsync(sc, sizeof(float) * d.C, mu + d.C, sizeof(float) * 2 * d.C, sizeof(float) * d.C, B, cudaMemcpyDeviceToDevice, st));
       mu_c = mc; sg_c = sc;
+    }
+    if (tc_tail) {
+      DPOT_CALL(dpot_out_tail_tc(ws + WL.Y1, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act,
+                                 mu_c, sg_c, d.Co, y, ro ? ro->ring : nullptr, ro ? ro->pred : nullptr, d.T, ro ? ro->slot0 : 0,
+                                 ro ? ro->Ttot : 0, ro ? ro->step : 0, stream));
+      return 0;
     }
     if (fused_tail) {
       DPOT_CALL(run_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));

@@ -34,7 +34,11 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   p.a_fmt = a->a_fmt; p.w_fmt = a->w_fmt; p.c_fmt = a->c_fmt; p.a_lo = a->a_lo_off; p.w_lo = a->w_lo_off; p.c_lo = a->c_lo_off;
   DPOT_REQUIRE((a->a_fmt == DPOT_FMT_F32 || a->a_fmt == DPOT_FMT_HL16) && a->a_fmt == a->w_fmt, DPOT_E_BADARG,
                "dpot_gemm: a_fmt and w_fmt must both be F32 or both HL16");
-  DPOT_REQUIRE(a->c_fmt == DPOT_FMT_F32 || a->c_fmt == DPOT_FMT_HL16, DPOT_E_BADARG, "dpot_gemm: bad c_fmt");
+  DPOT_REQUIRE(a->c_fmt == DPOT_FMT_F32 || a->c_fmt == DPOT_FMT_HL16 || a->c_fmt == DPOT_FMT_HL16G32, DPOT_E_BADARG, "dpot_gemm: bad c_fmt");
+  if (a->c_fmt == DPOT_FMT_HL16G32)
+    DPOT_REQUIRE(a->a_fmt == DPOT_FMT_HL16 && a->N % 32 == 0 && a->ldc >= 2 * (int64_t)a->N && a->batch == 1 && !a->C_pre &&
+                 !a->dact_src && a->c_mode == DPOT_A_PLAIN && !a->out_stats, DPOT_E_BADARG,
+                 "dpot_gemm: the grouped split-fp16 output needs split-fp16 operands, N %% 32 == 0 and ldc >= 2N halves");
   if (a->c_fmt == DPOT_FMT_HL16)
     DPOT_REQUIRE(!a->C_pre && !a->dact_src && a->c_mode == DPOT_A_PLAIN && !a->out_stats && a->c_lo_off > 0, DPOT_E_BADARG,
                  "dpot_gemm: split-fp16 output excludes C_pre/dact_src/patch scatter/out_stats");

@@ -282,14 +282,16 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
           for (int u = 0; u < 8; ++u) t[u] += rs[u];
         }
         if (OUT16) {
-          __half* __restrict__ cp = Ch_base + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + n;
+          const bool grp = g.c_fmt == DPOT_FMT_HL16G32;            // [hi 32 | lo 32] record per 32-column group
+          const int64_t ncol = grp ? (int64_t)((n >> 5) << 6) + (n & 31) : n, lo_off = grp ? 32 : g.c_lo;
+          __half* __restrict__ cp = Ch_base + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + ncol;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (u < cnt) {
               __half hi, lo;
               hl_split(t[u], hi, lo);
               cp[(int64_t)u * g.ldc] = hi;
-              cp[(int64_t)u * g.ldc + g.c_lo] = lo;
+              cp[(int64_t)u * g.ldc + lo_off] = lo;
             }
         } else {
           float* __restrict__ cp = g.C + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + n;
@@ -459,7 +461,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   const int units = g_sm_count / CGn;
   const int grid = CGn * (P.total_tiles < units ? P.total_tiles : units);
   const int am = p.act == DPOT_ACT_NONE ? 0 : (p.act == DPOT_ACT_GELU ? 1 : 2);
-  const bool o16 = p.c_fmt == DPOT_FMT_HL16;
+  const bool o16 = p.c_fmt != DPOT_FMT_F32;
   const int side = p.c_scale || (p.rowbias && p.residual) ? 3 : (p.rowbias ? 1 : (p.residual ? 2 : 0));
 #define DPOT_TC16_LAUNCH(CGV, AM, O16, SD)                                                                             \
   do {                                                                                                                 \

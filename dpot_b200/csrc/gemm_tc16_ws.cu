@@ -203,6 +203,7 @@ int g_ws_mode = -1;    // -1 auto, 0 never (dpot_tc16_set_ws; tests / experiment
 // that have no epilogue side inputs; every (batch, n-tile) group gets the same number of CTAs.
 bool gemm_tc16_ws_takes(const GemmDev& p, int batch, int sms) {
   if (g_ws_mode == 0) return false;
+  if (p.c_fmt == DPOT_FMT_HL16G32) return false;
   if (p.K > WS_KB_MAX * WS_BKH || p.rowbias || p.residual || p.c_scale || p.out_stats) return false;
   const int groups = (int)ceil_div(p.N, WS_TN) * batch;
   if (groups < 2 || groups > sms) return false;

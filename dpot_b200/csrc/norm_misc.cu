@@ -438,7 +438,9 @@ int out_tail_mma_launch(const float* Y1, const float* w2, const float* b2, const
                         int w, int P, int old, int nout, int act, const float* mu, const float* sigma, int Co, float* out,
                         cudaStream_t st, bool* served, float* ring, float* pred, int T, int slot0, int Ttot, int step);
 }
-extern "C" void dpot_out_tail_set_engine(int32_t engine) { dpot::g_tail_engine = engine; }
+namespace dpot { extern int g_tail_tc; }
+// 0 = auto (tcgen05 tail where the forward can feed it, else warp-MMA, else CUDA cores), 1 = CUDA cores only, 2 = no tcgen05 tail
+extern "C" void dpot_out_tail_set_engine(int32_t engine) { dpot::g_tail_engine = engine == 2 ? 0 : engine; dpot::g_tail_tc = engine == 0 ? 1 : 0; }
 
 extern "C" int dpot_out_tail(const float* Y1, const float* w2, const float* b2, const float* w4, const float* b4,
                              int32_t B, int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act,

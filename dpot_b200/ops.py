@@ -87,7 +87,10 @@ def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residua
     assert Kt == nb * K
     Nt = nb * N
     g = GemmArgs()
-    if out16:
+    if out16 == "g32":      # one [hi 32 | lo 32] record per (row, 32-column group): DPOT_FMT_HL16G32
+        out = torch.empty((M, 2 * Nt), device=A16.device, dtype=torch.float16)
+        g.C, g.ldc, g.c_fmt = ptr(out), 2 * Nt, _lib.FMT_HL16G32
+    elif out16:
         out = torch.empty((M, 2 * Nt), device=A16.device, dtype=torch.float16)
         g.C, g.ldc, g.c_fmt, g.c_lo_off = ptr(out), 2 * Nt, _lib.FMT_HL16, Nt
     else:
@@ -190,6 +193,36 @@ def out_tail(Y1: torch.Tensor, w2, b2, w4, b4, B: int, h: int, w: int, P: int, a
     out = torch.empty((B, h * P, w * P, nout), device=Y1.device, dtype=torch.float32)
     check(_lib.load().dpot_out_tail(ptr(Y1), ptr(w2), ptr(b2), ptr(w4), ptr(b4), B, h, w, P, old, nout, act_id(act),
                                     ptr(mu), ptr(sigma), Co or nout, ptr(out), _stream()), "dpot_out_tail")
+    return out
+
+
+def to_g32(y: torch.Tensor) -> torch.Tensor:
+    """fp32 [R, 32*G] -> DPOT_FMT_HL16G32 halves [R, 64*G] (test helper, plain torch arithmetic)."""
+    R, N = y.shape
+    hi = y.half()
+    lo = ((y - hi.float()) * 2048.0).half()
+    return torch.cat([hi.reshape(R, N // 32, 32), lo.reshape(R, N // 32, 32)], dim=2).reshape(R, 2 * N).contiguous()
+
+
+def from_g32(g: torch.Tensor) -> torch.Tensor:
+    R, N2 = g.shape
+    r = g.reshape(R, N2 // 64, 64)
+    return (r[:, :, :32].float() + r[:, :, 32:].float() / 2048.0).reshape(R, N2 // 2)
+
+
+def out_tail_tc(Y1g: torch.Tensor, w2, b2, w4, b4, B: int, h: int, w: int, P: int, act, *, mu=None, sigma=None, Co: int = 0,
+                ring=None, pred=None, slot0: int = 0, step: int = 0):
+    """dpot_out_tail_tc: Y1g = per-pixel [hi 32 | lo 32] records (DPOT_FMT_HL16G32) -> out[B, h*P, w*P, nout], or into the
+    ring window / prediction tensor when `ring` is given."""
+    _need_cuda(w2, b2, w4, b4, mu, sigma, ring, pred)
+    assert Y1g.is_cuda and Y1g.dtype == torch.float16 and Y1g.is_contiguous()
+    nout, old = w4.shape[0], w4.shape[1]
+    out = None if ring is not None else torch.empty((B, h * P, w * P, nout), device=Y1g.device, dtype=torch.float32)
+    T = ring.shape[-2] if ring is not None else 0
+    Ttot = pred.shape[-2] if pred is not None else 0
+    check(_lib.load().dpot_out_tail_tc(ptr(Y1g), ptr(w2), ptr(b2), ptr(w4), ptr(b4), B, h, w, P, old, nout, act_id(act),
+                                       ptr(mu), ptr(sigma), Co or nout, ptr(out), ptr(ring), ptr(pred), T, slot0, Ttot, step,
+                                       _stream()), "dpot_out_tail_tc")
     return out
 
 

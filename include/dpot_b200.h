@@ -58,7 +58,11 @@ enum { DPOT_GEMM_AUTO = 0, DPOT_GEMM_SIMT = 1, DPOT_GEMM_TC = 2, DPOT_GEMM_TC16 
  * hi*hi into one TMEM accumulator, hi*lo + lo*hi into a second one scaled by 2^-11), written
  * directly by the kernels that produce activations, so the GEMM needs no conversion pass.
  * Range: |x| <= 65504 (fp16); larger magnitudes become inf/NaN (loud, never silent). */
-enum { DPOT_FMT_F32 = 0, DPOT_FMT_HL16 = 1 };
+enum { DPOT_FMT_F32 = 0, DPOT_FMT_HL16 = 1,
+       /* output only (f16-split engine): split fp16 interleaved per group of 32 columns -- element (m, n) at half index
+          m*ldc + (n/32)*64 + n%32 (hi) and +32 (lo): a 128-byte [hi 32 | lo 32] record per (row, 32-column group), the
+          operand layout of the tcgen05 output-tail kernel (one record = one pixel's out_layer_dim = 32 channels) */
+       DPOT_FMT_HL16G32 = 2 };
 
 DPOT_API int         dpot_abi_version(void);
 DPOT_API const char* dpot_last_error_string(void);
@@ -274,7 +278,15 @@ DPOT_API int dpot_out_tail_ring(const float* Y1, const float* w2, const float* b
                        int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act, const float* mu,
                        const float* sigma, int32_t Co, float* y_scratch, float* ring, float* pred, int32_t T, int32_t slot0,
                        int32_t Ttot, int32_t step, void* stream);
-/* engine knob (tests): 0 = auto (warp-MMA kernel for out_layer_dim in {16,32}, nout <= 8), 1 = CUDA cores only */
+/* Output tail on tcgen05: Y1g = the ConvTranspose GEMM's result stored as DPOT_FMT_HL16G32 (one [hi 32 | lo 32] record
+   per pixel; out_layer_dim must be 32).  Writes out[B,X,Y,nout] or, when ring != NULL, the ring window / pred as
+   dpot_out_tail_ring does.  dpot_out_tail_tc_supported tells whether a geometry is served. */
+DPOT_API int dpot_out_tail_tc(const void* Y1g, const float* w2, const float* b2, const float* w4, const float* b4, int32_t B,
+                     int32_t h, int32_t w, int32_t P, int32_t old, int32_t nout, int32_t act, const float* mu,
+                     const float* sigma, int32_t Co, float* out, float* ring, float* pred, int32_t T, int32_t slot0,
+                     int32_t Ttot, int32_t step, void* stream);
+DPOT_API int dpot_out_tail_tc_supported(int32_t old, int32_t nout, int32_t Co);
+/* engine knob (tests): 0 = auto, 1 = CUDA cores only, 2 = warp-MMA allowed but no tcgen05 tail */
 DPOT_API void dpot_out_tail_set_engine(int32_t engine);
 /* spatial mean a[B*n,E] -> tok[B,E]  (models/dpot.py:394) */
 DPOT_API int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E, float* tok, void* stream);

@@ -656,3 +656,66 @@ def test_zoo_shapes_forward_matches_oracle(name, kw, B):
     finally:
         lib.dpot_set_pdl(0)
     assert torch.equal(y2, y), name
+
+
+@pytest.mark.parametrize("geo", [(2, 8, 8, 4, "gelu"), (1, 16, 8, 4, "gelu"), (3, 4, 4, 2, "tanh"), (1, 5, 8, 8, "gelu"), (2, 4, 4, 3, "silu")])
+def test_out_tail_tcgen05(geo):
+    """tcgen05 output tail (out_tail_tc.cu: pixels as UMMA M, [hi|lo] records as a K' = 64 operand, fp32 projection) vs
+    float64, incl. de-normalisation, a ragged last 128-pixel tile, odd nout, and the ring / prediction destinations."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    B, h, P, nout, act = geo
+    old = 32
+    if not lib.dpot_out_tail_tc_supported(old, nout, nout):
+        pytest.skip("tcgen05 tail unavailable")
+    rng = np.random.default_rng(sum(geo[:4]))
+    Y1 = rng.standard_normal((B * h * h, P * P * old)).astype(np.float32)
+    w2 = (rng.standard_normal((old, old)) / np.sqrt(old)).astype(np.float32)
+    b2 = rng.standard_normal(old).astype(np.float32)
+    w4 = (rng.standard_normal((nout, old)) / np.sqrt(old)).astype(np.float32)
+    b4 = rng.standard_normal(nout).astype(np.float32)
+    mu = rng.standard_normal((B, nout)).astype(np.float32)
+    sg = (1 + 0.2 * rng.standard_normal((B, nout))).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    Y1g = ops.to_g32(t(Y1))
+    assert O.rel_l2(ops.from_g32(Y1g).cpu().numpy(), Y1) < 2e-7
+    y = Y1.astype(np.float64).reshape(B, h, h, P, P, old)
+    y = O.activation(y @ w2.T.astype(np.float64) + b2, act) @ w4.T.astype(np.float64) + b4
+    want = y.transpose(0, 1, 3, 2, 4, 5).reshape(B, h * P, h * P, nout)
+    got = ops.out_tail_tc(Y1g, t(w2), t(b2), t(w4), t(b4), B, h, h, P, act).cpu().numpy()
+    assert O.rel_l2(got, want) < 1e-6, geo
+    got = ops.out_tail_tc(Y1g, t(w2), t(b2), t(w4), t(b4), B, h, h, P, act, mu=t(mu), sigma=t(sg), Co=nout).cpu().numpy()
+    assert O.rel_l2(got, want * sg[:, None, None, :] + mu[:, None, None, :]) < 1e-6, (geo, "denorm")
+    # ring + prediction destinations (T_out = 1 and, for even nout, T_out = 2)
+    for To in ((1, 2) if nout % 2 == 0 else (1,)):
+        Co, T, Ttot, slot0, step = nout // To, 5, 3 * To, 3, 1
+        ring = torch.zeros((B, h * P, h * P, T, Co), device="cuda")
+        pred = torch.zeros((B, h * P, h * P, Ttot, Co), device="cuda")
+        ops.out_tail_tc(Y1g, t(w2), t(b2), t(w4), t(b4), B, h, h, P, act, Co=Co, ring=ring, pred=pred, slot0=slot0, step=step)
+        w5 = want.reshape(B, h * P, h * P, To, Co)
+        for j in range(To):
+            assert O.rel_l2(ring[..., (slot0 + j) % T, :].cpu().numpy(), w5[..., j, :]) < 1e-6, (geo, To, j)
+            assert O.rel_l2(pred[..., step * To + j, :].cpu().numpy(), w5[..., j, :]) < 1e-6, (geo, To, j)
+        assert float(ring.abs().sum()) == pytest.approx(float(ring[..., [(slot0 + j) % T for j in range(To)], :].abs().sum()))
+
+
+def test_tc16_grouped_split_output():
+    """DPOT_FMT_HL16G32 output of the f16-split GEMM (the tail's operand format), single-CTA and pair tiles."""
+    from dpot_b200 import _lib, ops
+    lib = _lib.load()
+    if not lib.dpot_tc16_available():
+        pytest.skip("tcgen05 engine unavailable on this device")
+    rng = np.random.default_rng(9)
+    M, N, K = 700, 256, 128
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).cuda()
+    ref = O.activation(A.astype(np.float64) @ W.T.astype(np.float64) + b, "gelu")
+    for pair in (0, 1):
+        lib.dpot_tc16_set_pair(pair)
+        try:
+            out = ops.gemm16(ops.split_f16(t(A)), ops.split_f16(t(W)), bias=t(b), act="gelu", out16="g32")
+        finally:
+            lib.dpot_tc16_set_pair(-1)
+        assert O.rel_l2(ops.from_g32(out).cpu().numpy(), ref) < 2e-6, pair
