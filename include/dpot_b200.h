@@ -318,7 +318,8 @@ DPOT_API int dpot_ring_insert(const float* im, float* ring, float* pred, int64_t
 DPOT_API int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, const float* rowbias0, const float* a_scale,
                      const float* a_shift, int32_t B, int32_t X, int32_t Y, int32_t T, int32_t C, int32_t P,
                      int32_t mid, int32_t act, void* z1, int32_t Kp, int32_t out_fmt, void* stream);
-/* engine knob (tests): 0 = auto (warp-MMA on split fp16 when the geometry allows), 1 = fp32 CUDA cores, 2 = warp-MMA only */
+/* engine knob (tests): 0 = auto (warp-MMA on split fp16 when the geometry allows, else CUDA cores), 1 = fp32 CUDA cores,
+   2 = warp-MMA only, 3 = tcgen05 only (P*C = 32, mid <= 48; measured slower than warp-MMA, kept as a tested alternative) */
 DPOT_API void dpot_patch_embed_set_engine(int32_t engine);
 
 /* ------------------------------------------------------------------------------------------

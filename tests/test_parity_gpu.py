@@ -424,14 +424,17 @@ def test_tc16_fused_groupnorm_statistics(M, N, K, rps, pair):
     assert np.abs(st[..., 1] / s2 - 1).max() < 1e-5
 
 
-@pytest.mark.parametrize("engine", [1, 2])
-@pytest.mark.parametrize("geo", [(2, 64, 8, 10, 4, 35, 3), (3, 32, 4, 6, 4, 19, 0), (1, 128, 8, 10, 4, 35, 7), (2, 32, 8, 5, 4, 11, 2)])
+@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("geo", [(2, 64, 8, 10, 4, 35, 3), (3, 32, 4, 6, 4, 19, 0), (1, 128, 8, 10, 4, 35, 7), (2, 32, 8, 5, 4, 11, 2),
+                                 (2, 48, 8, 10, 4, 27, 9)])
 def test_patch_embed_engines(geo, engine):
     """PatchEmbed conv0 + GELU from the ring-in-time field layout: fp32 CUDA-core kernel and the warp-MMA kernel on
     split fp16 against float64 (models/dpot.py:199-200,375), incl. ring offset and input-normalisation tables."""
     from dpot_b200 import _lib, ops
     lib = _lib.load()
     B, R, P, T, Cc, mid, t0 = geo
+    if engine == 3 and P * Cc != 32:
+        pytest.skip("the tcgen05 PatchEmbed serves P*C = 32")
     h = R // P
     rng = np.random.default_rng(sum(geo))
     x = rng.standard_normal((B, R, R, T, Cc)).astype(np.float32)
