@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 BATCH, N_AR, MODEL = 32, 10, "S"
 FLOP_PER_FIELD_STEP = 15.07e9      # algorithmic forward FLOPs of DPOT-S @128^2
-FC1_DRAM_BYTES = 40.3e6            # fc1 GEMM kernel, dram read + write per launch (ncu --set full, profiles/r01d_ncu_summary.txt)
+FC1_DRAM_BYTES = 39.5e6            # fc1 GEMM kernel, dram read + write per launch (ncu --set full, profiles/r01f_ncu_summary.txt)
 METRIC = "autoregressive field-steps/sec, DPOT-S 128x128 (10 frames in -> 1 out), fp32"
 
 
@@ -268,7 +268,7 @@ def run_ours(args):
                 "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
                 "traffic": FC1_DRAM_BYTES if tc16 else None, "traffic_unit": "bytes per launch",
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full (cold L2), "
-                                  "profiles/r01d_ncu_summary.txt; algorithmic operand + result bytes = 71 MB (the result stays in L2)",
+                                  "profiles/r01f_ncu_summary.txt; algorithmic operand + result bytes = 71 MB (the result stays in L2)",
                 "peak_source": pk["src"] + ", dense bf16 cuBLAS burst",
                 "engine": ("tcgen05 kind::f16 on split-fp16 operands (3 MMAs per fp32 product)" if tc16 else
                            ("tcgen05 3xTF32" if (lib.dpot_tc_available() and model.gemm_engine != 1) else "fp32 CUDA cores (SIMT)")),
