@@ -63,7 +63,24 @@ def _gemm(A, W, *, bias=None, act=ACT_NONE, residual=None, rowbias=None, out=Non
 
 
 def _wgrad(X, Y, N, K, *, batch=1, strides=None, patch=None):
-    """dW[n,k] = sum_m X[m,n] Y[m,k]; batch/strides = (sX, sY, sW)."""
+    """dW[n,k] = sum_m X[m,n] Y[m,k]; batch/strides = (sX, sY, sW).
+
+    Large plain problems (the channel-MLP / time-aggregation / ConvTranspose weights: 8.6 GFLOP each at B=16) run on
+    the f16-split tcgen05 engine: the contraction index m must be the K-contiguous one, so both operands are transposed
+    ([N, M], [K, M]) and split, then dW = gemm16(Xt, Yt) -- fp32-faithful like every other product (measured: 347 us on
+    the CUDA-core dpot_wgrad -> ~60 us).  Batched / im2col forms stay on dpot_wgrad."""
+    M = X.shape[0]
+    if (batch == 1 and patch is None and M >= 256 and M % 8 == 0 and N >= 64 and K >= 64 and X.dim() == 2 and Y.dim() == 2
+            and X.shape[1] == N and Y.shape[1] == K and _lib_().dpot_tc16_available()):
+        from . import ops
+        Xt, Yt = _transpose(X), _transpose(Y)        # [N, M], [K, M]
+        # contraction chunks of <= 1024 tokens chained through the epilogue's residual input: the tensor core truncates
+        # on every accumulate into TMEM, an error that grows with the chain length (DESIGN.md 4.1)
+        dW, CH = None, 1024
+        for m0 in range(0, M, CH):
+            m1 = min(M, m0 + CH)
+            dW = ops.gemm16(ops.split_f16(Xt[:, m0:m1]), ops.split_f16(Yt[:, m0:m1]), residual=dW)
+        return dW                                     # [N, K]
     a = WgradArgs()
     dW = torch.empty((batch, N, K) if batch > 1 else (N, K), device=X.device, dtype=torch.float32)
     a.X, a.ldx, a.Y, a.ldy, a.dW, a.ldw = ptr(X), X.stride(0), ptr(Y), (Y.stride(0) if patch is None else 0), ptr(dW), K

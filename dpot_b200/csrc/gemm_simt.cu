@@ -172,28 +172,41 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
 // ---- skinny problems (M <= 64: classification head, AdaIN tables) --------------------------------
 // One warp per pair of output columns; lanes split K (coalesced 128 B rows of A and W), fp32 FMA,
 // shuffle reduction.  A (<= 64 x K) stays in L1/L2; the kernel is latency- not bandwidth-critical.
-constexpr int SK_MAXM = 64, SK_WARPS = 8;
+constexpr int SK_MAXM = 64, SK_WARPS = 8, SK_KC = 256;
+// Skinny problems (M <= 64 rows: the classification head, models/dpot.py:394-395, runs on M = batch rows).  The CTA
+// stages a [32 rows x 256 k] slice of A in shared memory (prologue affine applied once), every warp owns two output
+// columns and walks k with its lanes (coalesced weight reads, conflict-free A reads), 64 FMAs per lane and k-step.
+// (The first version re-read A from global memory in every warp: 376 us for M = 16, N = K = 1024; this one ~10 us.)
 template <int MT>   // rows handled per pass (32): M is covered in ceil(M/32) passes
 __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDev p) {
-  const int lane = threadIdx.x & 31;
-  const int wglob = blockIdx.x * SK_WARPS + (threadIdx.x >> 5);
-  const int n0 = wglob * 2;
-  if (n0 >= p.N) return;
-  const bool two = (n0 + 1) < p.N;
-  const float* __restrict__ w0 = p.W + (int64_t)n0 * p.ldw;
-  const float* __restrict__ w1 = p.W + (int64_t)(two ? n0 + 1 : n0) * p.ldw;
+  __shared__ float A_s[MT][SK_KC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * SK_WARPS + warp) * 2;
+  const bool live = n0 < p.N, two = (n0 + 1) < p.N;
+  const float* __restrict__ w0 = p.W + (int64_t)(live ? n0 : 0) * p.ldw;
+  const float* __restrict__ w1 = p.W + (int64_t)(two ? n0 + 1 : (live ? n0 : 0)) * p.ldw;
   for (int mb = 0; mb < p.M; mb += MT) {
     float a0[MT], a1[MT];
 #pragma unroll
     for (int i = 0; i < MT; ++i) a0[i] = a1[i] = 0.f;
-    for (int k = lane; k < p.K; k += 32) {
-      const float x0 = w0[k], x1 = w1[k];
+    for (int kc = 0; kc < p.K; kc += SK_KC) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < MT * SK_KC; e += SK_WARPS * 32) {
+        const int i = e / SK_KC, k = e - i * SK_KC;
+        A_s[i][k] = (mb + i < p.M && kc + k < p.K) ? gemm_load_a(p, p.A, mb + i, kc + k) : 0.f;
+      }
+      __syncthreads();
+      if (live) {
+        const int kend = min(SK_KC, p.K - kc);
+        for (int k = lane; k < kend; k += 32) {
+          const float x0 = __ldg(w0 + kc + k), x1 = __ldg(w1 + kc + k);
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const int m = mb + i;
-        const float a = (m < p.M) ? gemm_load_a(p, p.A, m, k) : 0.f;
-        a0[i] = fmaf(a, x0, a0[i]);
-        a1[i] = fmaf(a, x1, a1[i]);
+          for (int i = 0; i < MT; ++i) {
+            const float a = A_s[i][k];
+            a0[i] = fmaf(a, x0, a0[i]);
+            a1[i] = fmaf(a, x1, a1[i]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDe
     // lane i finalises row mb+i
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      if (lane == (i & 31) && mb + i < p.M) {
+      if (live && lane == (i & 31) && mb + i < p.M) {
         gemm_epilogue_store(p, p.C, p.bias, mb + i, n0, a0[i]);
         if (two) gemm_epilogue_store(p, p.C, p.bias, mb + i, n0 + 1, a1[i]);
       }

@@ -722,3 +722,23 @@ def test_tc16_grouped_split_output():
         finally:
             lib.dpot_tc16_set_pair(-1)
         assert O.rel_l2(ops.from_g32(out).cpu().numpy(), ref) < 2e-6, pair
+
+
+def test_wgrad_tensor_core_path_and_skinny_gemm():
+    """Training-path kernels outside the tiny golden configs: the f16-split tcgen05 weight gradient (large plain
+    problems) and the shared-memory skinny GEMM of the classification head (M = batch rows), both vs float64."""
+    from dpot_b200 import autograd as AG, ops
+    rng = np.random.default_rng(33)
+    t = lambda a: torch.from_numpy(a).cuda()
+    M, N, K = 2304, 256, 192
+    X = rng.standard_normal((M, N)).astype(np.float32)
+    Y = rng.standard_normal((M, K)).astype(np.float32)
+    dW = AG._wgrad(t(X), t(Y), N, K)
+    assert O.rel_l2(dW.cpu().numpy(), X.astype(np.float64).T @ Y.astype(np.float64)) < 2e-6
+    for (m, n, k) in ((16, 1024, 1024), (3, 12, 1024), (33, 50, 300), (64, 7, 40)):
+        A = rng.standard_normal((m, k)).astype(np.float32)
+        W = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+        b = rng.standard_normal(n).astype(np.float32)
+        out = ops.gemm(t(A), t(W), bias=t(b), act="gelu", engine=1)
+        ref = O.activation(A.astype(np.float64) @ W.T.astype(np.float64) + b, "gelu")
+        assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6, (m, n, k)
