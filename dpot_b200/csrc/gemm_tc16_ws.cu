@@ -72,7 +72,10 @@ gemm_tc16_ws_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();
+  // PDL: the weight tile is a parameter (packed long before the predecessor kernel), so the producer requests it
+  // BEFORE pdl_wait(): on a ~20 us kernel the prologue + 128 KB weight load (~3 us) overlap the predecessor's tail.
+  // Everything that touches activations is behind the wait: the producer's token loads directly, the MMAs and the
+  // epilogue's stores through the barrier chain that starts at those loads.
 
   const int KB = P.kblocks;
   const int group = blockIdx.x / P.cpg, member = blockIdx.x % P.cpg;
@@ -86,6 +89,7 @@ gemm_tc16_ws_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_cons
         tma_load_3d(smem0 + (uint32_t)kb * 2u * WS_W_PLANE, &mapWh, WFULL, kb * WS_BKH, nt * WS_TN, bz);           // (k, n, batch)
         tma_load_3d(smem0 + (uint32_t)kb * 2u * WS_W_PLANE + WS_W_PLANE, &mapWl, WFULL, kb * WS_BKH, nt * WS_TN, bz);
       }
+      pdl_wait();
       int s = 0; uint32_t ph = 0;
       for (int mt = member; mt < P.m_tiles; mt += P.cpg) {
         for (int kb = 0; kb < KB; ++kb) {
@@ -138,6 +142,7 @@ gemm_tc16_ws_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_cons
     const int n = nt * WS_TN + quarter * 32 + lane;
     const bool nok = n < g.N;
     const float bias_n = (g.bias && nok) ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+    pdl_wait();
     uint32_t tc = 0;
     for (int mt = member; mt < P.m_tiles; mt += P.cpg, ++tc) {
       const uint32_t buf = tc % WS_NBUF, bph = (tc / WS_NBUF) & 1u;
@@ -195,7 +200,8 @@ gemm_tc16_ws_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_cons
   }
 }
 
-int g_ws_mode = -1;    // -1 auto, 0 never (dpot_tc16_set_ws; tests / experiments)
+int g_ws_mode = -1;    // -1 auto, 0 never, 2 auto without the early (PDL) start (dpot_tc16_set_ws; tests / experiments)
+int g_ws_pdl = 1;      // launch with programmatic stream serialization so that prologue + weight load start early
 
 }  // namespace
 
@@ -240,7 +246,7 @@ int gemm_tc16_ws_launch(const GemmDev& p, int batch, int sms, cudaStream_t st) {
                                      (int)WS_SMEM));                                                                  \
       attr = true;                                                                                                    \
     }                                                                                                                 \
-    DPOT_CUDA(launch_pdl(gemm_tc16_ws_kernel<AM, O16>, dim3(grid), dim3(WS_NTHREADS), WS_SMEM, st, mWh, mWl, mAh, mAl, P)); \
+    DPOT_CUDA(launch_pdl_if(g_pdl != 0 || g_ws_pdl != 0, gemm_tc16_ws_kernel<AM, O16>, dim3(grid), dim3(WS_NTHREADS), WS_SMEM, st, mWh, mWl, mAh, mAl, P)); \
   } while (0)
 #define DPOT_WS_O(AM) do { if (o16) DPOT_WS_LAUNCH(AM, true); else DPOT_WS_LAUNCH(AM, false); } while (0)
   if (am == 0) DPOT_WS_O(0); else if (am == 1) DPOT_WS_O(1); else DPOT_WS_O(2);
@@ -252,4 +258,4 @@ int gemm_tc16_ws_launch(const GemmDev& p, int batch, int sms, cudaStream_t st) {
 
 }  // namespace dpot
 
-extern "C" void dpot_tc16_set_ws(int32_t mode) { dpot::g_ws_mode = mode; }
+extern "C" void dpot_tc16_set_ws(int32_t mode) { dpot::g_ws_mode = mode == 2 ? -1 : mode; dpot::g_ws_pdl = mode == 2 ? 0 : 1; }
