@@ -140,3 +140,28 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("oracle/", "oracle/") or f == "build.py" or "import oracle" not in txt
                 assert "from oracle" not in txt and "import oracle" not in txt, os.path.join(dp, f)
+
+
+def test_gelu_polynomial_accuracy():
+    """The single-branch GELU of the CUDA kernels (common.cuh::gelu_fast: x * Phi(x), Phi(-t) = 2^q(t)) evaluated in
+    float32 numpy from the coefficients in the source: the documented accuracy against the exact erf form."""
+    import numpy as np
+    src = open(os.path.join(ROOT, "dpot_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_fast(float x)"):]
+    body = body[:body.index("asm(")]
+    coef = [np.float32(c) for c in re.findall(r"(-?\d\.\d+e?-?\d*)f[;\)]", body)]
+    tmax, coef = coef[0], coef[1:]
+    assert len(coef) == 10 and abs(float(tmax) - 5.7) < 1e-6
+    x = np.concatenate([np.linspace(-8, 8, 400001), np.random.default_rng(0).standard_normal(200000) * 2]).astype(np.float32)
+    t = np.minimum(np.abs(x), tmax).astype(np.float32)
+    q = np.full_like(t, coef[0])
+    for c in coef[1:]:
+        q = (q * t + c).astype(np.float32)
+    e = np.exp2(q.astype(np.float64)).astype(np.float32)
+    got = (x * np.where(x > 0, np.float32(1) - e, e)).astype(np.float32)
+    from oracle import dpot_oracle as O
+    ref = O.activation(x.astype(np.float64), "gelu")
+    err = np.abs(got - ref)
+    assert err[np.abs(x) < 3].max() < 3e-7
+    assert err.max() < 6e-7                       # = fp32 rounding of values up to 8
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 5e-8
