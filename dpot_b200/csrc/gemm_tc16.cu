@@ -397,6 +397,7 @@ Plan make_plan(const GemmDev& p, int batch) {
   Plan one = plan_for(p, batch, 1, sms, divides);
   // pairs need >= 256 output channels to fill both CTAs and enough tokens to split
   if (g_pair_mode == 0 || p.N <= TN || p.M < 32 || sms % 2 != 0) return one;
+  if ((g_dbg & 3) == 3) return one;   // experiment "no TMA + no MMA": a pair commit with nothing in flight never reaches the peer (measured: trap)
   Plan two = plan_for(p, batch, 2, sms, divides);
   if (two.cost < 0) return one;
   if (one.cost < 0 || g_pair_mode == 1) return two;
