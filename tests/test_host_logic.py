@@ -99,6 +99,49 @@ def test_drop_in_against_reference_module():
     assert str(inspect.signature(ref.Block.__init__)) == str(inspect.signature(ours.Block.__init__))
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_reference_checkpoint_utilities_work_on_our_model():
+    """The reference's OWN checkpoint helpers (utils/utilities.py:99-166: DDP 'module.' prefixes, component-wise loading
+    used by finetune.py) operate on our DPOTNet unchanged -- same attribute names, sub-module state dicts and keys."""
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    try:
+        import importlib
+        ref = importlib.import_module("models.dpot")
+        src = open(os.path.join(REF, "utils", "utilities.py")).read()
+    finally:
+        sys.path.remove(REF)
+        os.chdir(cwd)
+    # utils/utilities.py imports plotting / dataset modules at module level; take the two loaders' source as is
+    import collections
+    import torch.nn as nn
+    ns = {"OrderedDict": collections.OrderedDict, "nn": nn, "torch": torch}
+    for fn in ("load_model_from_checkpoint", "load_components_from_pretrained"):
+        start = src.index(f"def {fn}(")
+        end = src.index("\ndef ", start + 1)
+        exec(src[start:end], ns)
+    from dpot_b200.models import dpot as ours
+    kw = dict(img_size=32, patch_size=4, in_channels=3, out_channels=3, in_timesteps=5, out_timesteps=2, n_blocks=4,
+              embed_dim=32, out_layer_dim=16, depth=2, modes=3, mlp_ratio=2, n_cls=5, normalize=True)
+    torch.manual_seed(1)
+    a = ref.DPOTNet(**kw)
+    sd = a.state_dict()
+    torch.manual_seed(2)
+    b = ours.DPOTNet(**kw)
+    ns["load_model_from_checkpoint"](b, collections.OrderedDict(("module." + k, v.clone()) for k, v in sd.items()))
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    torch.manual_seed(3)
+    c = ours.DPOTNet(**kw)
+    before = {k: v.clone() for k, v in c.state_dict().items()}
+    comps = ["patch_embed", "pos", "blocks", "time_agg", "scale_feats"]
+    ns["load_components_from_pretrained"](c, collections.OrderedDict((k, v.clone()) for k, v in sd.items()), components=comps)
+    for k, v in c.state_dict().items():
+        loaded = k.startswith(("patch_embed.", "pos_embed", "blocks.", "time_agg_layer.", "scale_feats_"))
+        assert torch.equal(v, sd[k] if loaded else before[k]), k
+
+
 def test_constructor_rejects_unbuilt_configs_loudly():
     from dpot_b200.models.dpot import DPOTNet
     with pytest.raises(NotImplementedError):
