@@ -97,3 +97,98 @@ class GradArena:
         for p, v in zip(live, views):
             p.grad = v
         return total
+
+
+class OverlappedGradArena:
+    """The gradient exchange of GradArena, overlapped with backward (reverse-layer buckets on a
+    communication stream): parameters are laid out in REVERSE registration order -- the order their gradients become
+    ready -- in buckets of ~bucket_mb; a post-accumulate-grad hook copies each fresh gradient into its arena slot,
+    makes .grad a view of the arena and, when the last expected gradient of a bucket has arrived, starts that bucket's
+    asynchronous all-reduce while autograd keeps running the earlier layers.  finish() (after loss.backward(), before
+    clip_grad_norm_ / optimizer.step()) starts whatever is left, waits and leaves DDP-averaged gradients behind.
+
+    The set of parameters that receive gradients is learned on the first step (e.g. cls_head gets none in
+    train_temporal.py:226): from then on buckets do not wait for them.  A gradient that shows up after its bucket has
+    been launched is exchanged on its own in finish().  All ranks run the same graph, so every rank takes the same
+    decisions and issues the same collectives in the same order."""
+
+    def __init__(self, params: Iterable[torch.Tensor], bucket_mb: float = 64.0):
+        self.params: List[torch.Tensor] = [p for p in params if p.requires_grad][::-1]
+        cap = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.slots, self.buckets, o, start, members = {}, [], 0, 0, []
+        for p in self.params:
+            n = (p.numel() + 63) // 64 * 64
+            self.slots[p] = (len(self.buckets), o, p.numel())
+            members.append(p)
+            o += n
+            if o - start >= cap:
+                self.buckets.append(dict(start=start, end=o, params=members, expect=len(members), pending=len(members),
+                                         handle=None))
+                start, members = o, []
+        if members:
+            self.buckets.append(dict(start=start, end=o, params=members, expect=len(members), pending=len(members), handle=None))
+        self.total = o
+        self.buf: Optional[torch.Tensor] = None
+        self.seen, self.late, self.steps = set(), [], 0
+        self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    def _world(self) -> int:
+        return dist.get_world_size() if dist.is_initialized() else 1
+
+    def _launch(self, b) -> None:
+        if self._world() > 1:
+            op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+            b["handle"] = dist.all_reduce(self.buf[b["start"]:b["end"]], op=op, async_op=True)
+        else:
+            b["handle"] = True
+
+    @torch.no_grad()
+    def _hook(self, p: torch.Tensor) -> None:
+        if self.buf is None or self.buf.device != p.grad.device:
+            self.buf = torch.zeros(self.total, device=p.grad.device, dtype=torch.float32)
+        bi, o, n = self.slots[p]
+        b = self.buckets[bi]
+        self.seen.add(p)
+        if b["handle"] is not None:            # its bucket is already on the wire: exchange this one separately
+            self.late.append(p)
+            return
+        view = self.buf[o:o + n].view_as(p)
+        view.copy_(p.grad)
+        p.grad = view
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    @torch.no_grad()
+    def finish(self) -> int:
+        """Start the exchanges that are still pending, wait for all of them; returns the fp32 elements exchanged."""
+        world, gloo = self._world(), dist.is_initialized() and dist.get_backend() != "nccl"
+        for b in self.buckets:
+            if b["handle"] is None and any(p.grad is not None for p in b["params"]):
+                self._launch(b)
+        n = 0
+        for b in self.buckets:
+            if b["handle"] is None:
+                continue
+            if b["handle"] is not True:
+                b["handle"].wait()
+            if world > 1 and gloo:
+                self.buf[b["start"]:b["end"]].div_(world)
+            n += b["end"] - b["start"]
+        for p in self.late:
+            if world > 1:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                p.grad.div_(world)
+            n += p.numel()
+        # re-arm: from the second step on a bucket only waits for the parameters that really receive gradients
+        self.steps += 1
+        for b in self.buckets:
+            b["expect"] = sum(1 for p in b["params"] if p in self.seen) or len(b["params"])
+            b["pending"], b["handle"] = b["expect"], None
+        self.late = []
+        return n
+
+    def close(self) -> None:
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
