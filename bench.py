@@ -28,6 +28,8 @@ BATCH, N_AR, MODEL = 32, 10, "S"
 FLOP_PER_FIELD_STEP = 15.07e9      # algorithmic forward FLOPs of DPOT-S @128^2
 FC1_DRAM_BYTES = 39.5e6            # fc1 GEMM kernel, dram read + write per launch (ncu --set full, profiles/r01f_ncu_summary.txt)
 METRIC = "autoregressive field-steps/sec, DPOT-S 128x128 (10 frames in -> 1 out), fp32"
+WORKLOAD = (f"DPOT-{MODEL} (30.8M) 10->1 autoregressive rollout, 128x128x10x4, batch {BATCH}/GPU, "
+            f"{N_AR} AR steps per bench step, no_grad")      # the same workload name in both arms
 
 
 def peaks():
@@ -73,7 +75,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fs, "unit": "field-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DPOT-{MODEL} 128x128x10x4 forward, bounded sample B={B} per step", "batch": B},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "ar_steps": N_AR,
+                   "sample": f"bounded sample of that workload: one step = one {B}-sample forward (= {B} field-steps) on the host cores"},
         "cpu_baseline": {"value": fs, "unit": "field-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} forwards of B={B} (oracle port of models/dpot.py on torch CPU operators, all host threads)"},
         "e2e": {"value": fs, "unit": "field-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -292,8 +295,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "field-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"DPOT-{MODEL} (30.8M) 10->1 autoregressive rollout, 128x128x10x4, batch {BATCH}/GPU, "
-                                   f"{N_AR} AR steps per bench step, no_grad",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": BATCH, "ar_steps": N_AR, "field_steps_per_step": fs_per_step,
                        "l2_policy": f"{NBUF} distinct input batches rotated ({NBUF * in_bytes / 2**20:.0f} MiB > 126 MB L2)",
                        "parallelism": f"replicas x{world} (no data-path collective)",
