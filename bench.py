@@ -2,7 +2,7 @@
 """bench.py -- autoregressive field-steps/sec for DPOT-Small 128^2 (BASELINE.json config C2).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the unmodified reference (baseline/_ref) on the host cores
 
 One "step" = one 10-step autoregressive rollout (evaluate.py:192-208) of a batch of 32 synthetic
 128x128x10x4 fields on each GPU = 320 field-steps per GPU per step.  Multi-GPU = independent
@@ -25,8 +25,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH, N_AR, MODEL = 32, 10, "S"
-FLOP_PER_FIELD_STEP = 15.07e9      # algorithmic forward FLOPs of DPOT-S @128^2
-FC1_DRAM_BYTES = 39.5e6            # fc1 GEMM kernel, dram read + write per launch (ncu --set full, profiles/r01f_ncu_summary.txt)
 METRIC = "autoregressive field-steps/sec, DPOT-S 128x128 (10 frames in -> 1 out), fp32"
 WORKLOAD = (f"DPOT-{MODEL} (30.8M) 10->1 autoregressive rollout, 128x128x10x4, batch {BATCH}/GPU, "
             f"{N_AR} AR steps per bench step, no_grad")      # the same workload name in both arms
@@ -41,26 +39,79 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
-# ------------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_leg(nthreads: int, B: int, steps: int, warmup: int):
-    """The reference algorithm on the host cores.  The reference is a Python/PyTorch program that cannot travel to
-    the GPU box, so this times the oracle port on the SAME CPU operator library the reference runs on (ATen conv2d /
-    group_norm / rfft2 / einsum: oracle/dpot_oracle_torch.py, checked against the numpy oracle in tests/), with all
-    host threads.  Returns (field-steps/s, ms/step)."""
+def captured_traffic():
+    """dram bytes per launch of the dominant kernel from this round's `ncu --set full` capture (tools/ncu_traffic.py
+    writes profiles/dominant_kernel_traffic.json from the raw csv): (bytes, provenance) or (None, why)."""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if not os.path.exists(p):
+        return None, "no ncu --set full capture committed for this round"
+    d = json.load(open(p))
+    return float(d["dram_bytes_per_launch"]), d.get("source", p)
+
+
+# ------------------------------------------------------------------------------------------ reference legs
+def reference_model(device="cpu"):
+    """(model, kind, note): the UNMODIFIED reference DPOTNet from baseline/_ref (staged by baseline/install_ref.py,
+    kind 'reference'), with the bench's synthetic weights; when it is absent, None."""
     import torch
-    from oracle import dpot_oracle as O
-    from oracle import dpot_oracle_torch as OT
+    from baseline.install_ref import import_reference
+    from dpot_b200 import zoo
+    ref = import_reference()
+    if ref is None:
+        return None, "port", "baseline/_ref is absent"
+    RefNet, _, _, manifest = ref
+    torch.manual_seed(0)
+    model = RefNet(**zoo.zoo_cfg(MODEL))
+    zoo.synthetic_weights_(model, seed=0)
+    return model.to(device).eval(), "reference", "models/dpot.py sha256 " + manifest.get("models/dpot.py", "?")[:16]
+
+
+def reference_rollout(model, xx, n_ar):
+    """evaluate.py:192-208 verbatim in structure: im,_ = model(xx); pred = cat(pred, im); xx = cat(xx[..., 1:, :], im)."""
+    import torch
+    pred = None
+    for _ in range(n_ar):
+        im, _ = model(xx)
+        pred = im if pred is None else torch.cat((pred, im), -2)
+        xx = torch.cat((xx[..., im.shape[-2]:, :], im), dim=-2)
+    return pred
+
+
+def cpu_reference_leg(nthreads: int, B: int, n_ar: int, steps: int, warmup: int, budget_s: float = 0.0):
+    """The reference's own CPU path on the host cores: the unmodified reference DPOTNet (baseline/_ref) when staged,
+    else the oracle port on the same ATen CPU operators (oracle/dpot_oracle_torch.py).  One step = one n_ar-step
+    rollout of B samples.  budget_s > 0 bounds the run: after the warm-up the number of timed steps is cut so that the
+    whole leg stays within the budget.  Returns (field-steps/s, ms/step, kind, note, steps actually timed)."""
+    import torch
     torch.set_num_threads(max(1, nthreads))
-    cfg = O.zoo_cfg(MODEL)
-    params = OT.to_torch(O.make_params(cfg, seed=0))
-    x = torch.from_numpy(O.make_input(cfg, B, seed=0))
-    for _ in range(warmup):
-        OT.dpot_forward(x, params, cfg)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        OT.dpot_forward(x, params, cfg)
-    dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.randn((B, 128, 128, 10, 4), generator=g)
+    model, kind, note = reference_model("cpu")
+    if model is not None:
+        run = lambda: reference_rollout(model, x, n_ar)
+    else:
+        from oracle import dpot_oracle as O
+        from oracle import dpot_oracle_torch as OT
+        cfg = O.zoo_cfg(MODEL)
+        params = OT.to_torch(O.make_params(cfg, seed=0))
+
+        def run():
+            xx = x
+            for _ in range(n_ar):
+                im, _ = OT.dpot_forward(xx, params, cfg)
+                xx = torch.cat((xx[..., 1:, :], im), dim=-2)
+    with torch.no_grad():
+        tw = time.perf_counter()
+        for _ in range(warmup):
+            run()
+        tw = time.perf_counter() - tw
+        if budget_s > 0 and warmup > 0:
+            steps = max(1, min(steps, int((budget_s - tw) / (tw / warmup))))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run()
+        dt = time.perf_counter() - t0
+    return B * n_ar * steps / dt, dt / steps * 1e3, kind, note, steps
 
 
 def run_reference(args):
@@ -68,20 +119,57 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    B = 8
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    fs, ms = cpu_reference_leg(cores, B, steps, warmup)
+    # the SAME workload as the GPU arm: every step is a full 10-step rollout of 32 samples (320 field-steps, ~5 s of
+    # host time); only the number of steps is bounded so that the run ends within a few minutes
+    steps, warmup = max(1, min(args.steps, 20)), max(0, min(args.warmup, 3))
+    fs, ms, kind, note, steps = cpu_reference_leg(cores, BATCH, N_AR, steps, warmup, budget_s=170.0)
+    what = ("unmodified reference DPOTNet (baseline/_ref, " + note + ")") if kind == "reference" else \
+        "oracle port of models/dpot.py on torch CPU operators (baseline/_ref absent)"
     line = {
         "impl": "reference", "metric": METRIC, "value": fs, "unit": "field-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "ar_steps": N_AR,
-                   "sample": f"bounded sample of that workload: one step = one {B}-sample forward (= {B} field-steps) on the host cores"},
-        "cpu_baseline": {"value": fs, "unit": "field-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} forwards of B={B} (oracle port of models/dpot.py on torch CPU operators, all host threads)"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "ar_steps": N_AR, "field_steps_per_step": BATCH * N_AR,
+                   "sample": f"{steps} full rollouts (B={BATCH}, {N_AR} AR steps each) of the same workload on the host cores"},
+        "cpu_baseline": {"value": fs, "unit": "field-steps/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} rollouts of B={BATCH} x {N_AR} AR steps, {what}, all host threads"},
         "e2e": {"value": fs, "unit": "field-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_leg(dev, xs):
+    """The thing users of the reference actually run: the unmodified reference DPOTNet, eager PyTorch (cuBLAS / cuDNN /
+    cuFFT) on THIS GPU, same weights, same B=32 10-step rollout (evaluate.py:192-208), CUDA-event timed.  Two settings:
+    PyTorch defaults (cuDNN convolutions may use TF32 -> not fp32-faithful) and allow_tf32=False (the fp32 parity bar)."""
+    import torch
+    model, kind, note = reference_model(dev)
+    if model is None:
+        return {"unavailable": note}
+    out = {"impl": "reference DPOTNet eager on this GPU (" + note + ")", "unit": "field-steps/s",
+           "sample": f"3 rollouts of B={BATCH} x {N_AR} AR steps after 2 warm-up rollouts, CUDA events"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for label, tf32 in (("default_flags", None), ("allow_tf32_false", False)):
+            if tf32 is not None:
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for i in range(2):
+                    reference_rollout(model, xs[i % len(xs)], N_AR)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(3):
+                    pred = reference_rollout(model, xs[i % len(xs)], N_AR)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out[label] = {"value": BATCH * N_AR / (ms * 1e-3), "ms_per_step": ms}
+        out["last_pred"] = pred
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -135,10 +223,9 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from dpot_b200 import _lib, ops
+    from dpot_b200 import _lib, ops, zoo
     from dpot_b200.models.dpot import DPOTNet
     from dpot_b200.rollout import RolloutEngine
-    from oracle import dpot_oracle as O   # synthetic weights/inputs + the cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -155,10 +242,8 @@ def run_ours(args):
     if args.ws_mode is not None:
         lib.dpot_tc16_set_ws(args.ws_mode)
 
-    cfg = O.zoo_cfg(MODEL)
-    model = DPOTNet(**cfg)
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_params(cfg, seed=0).items()})
-    model = model.to(dev).eval()
+    cfg = zoo.zoo_cfg(MODEL)
+    model = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).eval()
     if args.engine is not None:
         model.gemm_engine = args.engine
 
@@ -167,10 +252,12 @@ def run_ours(args):
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     host = [torch.randn((BATCH, 128, 128, 10, 4), generator=g).pin_memory() for _ in range(NBUF)]
     devbuf = [h.to(dev) for h in host]
-    eng = RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph)
+    # want_cls: the classification head runs on every step, as in the reference's model(xx) (evaluate.py:198)
+    eng = RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph, want_cls=True)
+    eng_nocls = RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph, want_cls=False)
     # end-to-end arm: two window/prediction buffer sets so that the H2D copy of step s+1 and the D2H read of step s-1
     # (own streams) overlap the rollout of step s; every byte still moves inside the timed region
-    engs = [eng, RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph)]
+    engs = [eng, RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph, want_cls=True)]
     host_out = [torch.empty((BATCH, 128, 128, N_AR, 4)).pin_memory() for _ in range(2)]
     s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -232,6 +319,9 @@ def run_ours(args):
         step_e2e(s)
     torch.cuda.synchronize()
     ms_e2e = timed(step_e2e, args.steps, finish_e2e)
+    for s in range(3):
+        eng_nocls.run(devbuf[s % NBUF])
+    ms_nocls = timed(lambda s: eng_nocls.run(devbuf[s % NBUF]), args.steps)
 
     fs_per_step = BATCH * N_AR * world
     value = fs_per_step * args.steps / (ms * 1e-3)
@@ -267,28 +357,47 @@ def run_ours(args):
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) * 1e-3 / reps
         ach = 2.0 * M * N * K / t / 1e12
-        mmas = 3.0
         div = 3.0 if tc16 else 6.0
+        fl = zoo.forward_flops(cfg)
+        per_gpu = value / world
+        traffic, traffic_src = captured_traffic() if tc16 else (None, "not captured for this engine")
         roof = {"bound": "tensor", "kernel": "channel-MLP fc1 GEMM M=8192 N=1024 K=1024 (bias+GELU epilogue)",
                 "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-                "traffic": FC1_DRAM_BYTES if tc16 else None, "traffic_unit": "bytes per launch",
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full (cold L2), "
-                                  "profiles/r01f_ncu_summary.txt; algorithmic operand + result bytes = 71 MB (the result stays in L2)",
+                "traffic": traffic, "traffic_unit": "bytes per launch",
+                "traffic_source": traffic_src + "; algorithmic operand + result bytes = 71 MB (the split-fp16 result mostly stays in L2)",
                 "peak_source": pk["src"] + ", dense bf16 cuBLAS burst",
                 "engine": ("tcgen05 kind::f16 on split-fp16 operands (3 MMAs per fp32 product)" if tc16 else
                            ("tcgen05 3xTF32" if (lib.dpot_tc_available() and model.gemm_engine != 1) else "fp32 CUDA cores (SIMT)")),
                 "us_per_launch": t * 1e6,
                 "frac_of_fp32_faithful_peak": ach / (pk["bf16"] / div),
-                "note": f"achieved = algorithmic 2MNK / CUDA-event time; fp32 parity costs {mmas:.0f} tensor-core MMAs per "
+                "note": f"achieved = algorithmic 2MNK / CUDA-event time; fp32 parity costs {div:.0f} tensor-core MMAs per "
                         f"product, so the honest ceiling for this kernel is bf16 peak / {div:.0f}",
-                "whole_step_algorithmic_tflops": FLOP_PER_FIELD_STEP * value / world / 1e12,
-                "whole_step_frac_of_fp32_faithful_sustained_peak": FLOP_PER_FIELD_STEP * value / world / 1e12 / (pk["bf16_sus"] / div),
-                "whole_step_note": "whole rollout step: algorithmic 15.07 GFLOP per field-step x field-steps/s per GPU, against the "
-                                   "SUSTAINED bf16 peak / 3 (a kernel inside a long step runs under the power cap)"}
+                "whole_step": {
+                    "algorithmic_gflop_per_field_step": fl["algorithmic"] / 1e9, "executed_gflop_per_field_step": fl["executed"] / 1e9,
+                    "algorithmic_tflops": fl["algorithmic"] * per_gpu / 1e12, "executed_tflops": fl["executed"] * per_gpu / 1e12,
+                    "frac_algorithmic_of_fp32_faithful_sustained_peak": fl["algorithmic"] * per_gpu / 1e12 / (pk["bf16_sus"] / div),
+                    "frac_executed_of_fp32_faithful_sustained_peak": fl["executed"] * per_gpu / 1e12 / (pk["bf16_sus"] / div),
+                    "frac_executed_of_raw_bf16_sustained_peak": fl["executed"] * per_gpu / 1e12 / pk["bf16_sus"],
+                    "note": "per GPU; algorithmic = the reference's formulation (SURVEY 8d), executed = after folding conv1x1 + "
+                            "pos_embed + time aggregation into one K=350 contraction; against the SUSTAINED bf16 peak / 3 "
+                            "(a kernel inside a long step runs under the power cap)"}}
 
     if rank == 0:
         cores = os.cpu_count() or 1
-        cb_fs, _ = cpu_reference_leg(cores, 8, 12, 1)
+        cb_steps = 2
+        cb_fs, _, cb_kind, cb_note, _ = cpu_reference_leg(cores, BATCH, N_AR, cb_steps, 0)
+        eager = gpu_eager_leg(dev, devbuf)
+        parity = None
+        if isinstance(eager, dict) and "last_pred" in eager:
+            # same weights, same inputs: our prediction of the last timed eager input vs the reference's (fp32, tf32 off)
+            ref_pred = eager.pop("last_pred")
+            ours = eng.run(devbuf[2 % NBUF]).clone()
+            torch.cuda.synchronize()
+            parity = {"rel_l2_step1": float((ours[..., :1, :] - ref_pred[..., :1, :]).norm() / ref_pred[..., :1, :].norm()),
+                      "rel_l2_full_rollout": float((ours - ref_pred).norm() / ref_pred.norm()),
+                      "against": "reference DPOTNet eager on this GPU, allow_tf32=False (cuBLAS/cuDNN fp32), B=32, 10 AR steps"}
+            eager["speedup_vs_default_flags"] = per_gpu / eager["default_flags"]["value"]
+            eager["speedup_vs_allow_tf32_false"] = per_gpu / eager["allow_tf32_false"]["value"]
         in_bytes = BATCH * 128 * 128 * 10 * 4 * 4
         out_bytes = BATCH * 128 * 128 * N_AR * 4 * 4
         line = {
@@ -297,16 +406,22 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "batch_per_gpu": BATCH, "ar_steps": N_AR, "field_steps_per_step": fs_per_step,
+                       "cls_head": "computed on every step (as the reference's model(xx) does)",
                        "l2_policy": f"{NBUF} distinct input batches rotated ({NBUF * in_bytes / 2**20:.0f} MiB > 126 MB L2)",
                        "parallelism": f"replicas x{world} (no data-path collective)",
                        "launch": "eager kernel launches" if args.no_graph else "one CUDA graph per 10-step rollout (captured after an eager warm-up)"},
             "e2e": {"value": e2e, "unit": "field-steps/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": ms_e2e / args.steps},
+            "value_without_cls_head": fs_per_step * args.steps / (ms_nocls * 1e-3),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
-            "cpu_baseline": {"value": cb_fs, "unit": "field-steps/s", "cores": cores, "kind": "port",
-                             "sample": "12 forwards of B=8 DPOT-S 128^2 = 96 field-steps (oracle port on torch CPU operators, all host threads), rank 0"},
+            "cpu_baseline": {"value": cb_fs, "unit": "field-steps/s", "cores": cores, "kind": cb_kind,
+                             "sample": f"{cb_steps} rollouts of B={BATCH} x {N_AR} AR steps = {cb_steps * BATCH * N_AR} field-steps "
+                                       f"({'unmodified reference DPOTNet from baseline/_ref, ' + cb_note if cb_kind == 'reference' else 'oracle port on torch CPU operators'}, "
+                                       "all host threads), rank 0"},
+            "gpu_eager_baseline": eager,
+            "parity_in_run": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -124,6 +124,7 @@ SIGNATURES = {
     "dpot_pack_out": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "dpot_out_tail": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "dpot_spatial_mean": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "dpot_spatial_mean16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "dpot_input_stats": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p]),
     "dpot_window_advance": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "dpot_ring_insert": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -354,9 +354,13 @@ class SpatialMeanFn(Function):
 # ------------------------------------------------------------------------------------------------ model
 def dpot_forward_train(net, x):
     """Differentiable DPOTNet.forward (models/dpot.py:364-403) on the kernels of libdpot_b200."""
-    if net.normalize:
-        raise NotImplementedError("dpot_b200: the training path with normalize=True is not built yet "
-                                  "(no shipped config uses it); inference supports it")
+    # the reference scripts address cuda:{args.gpu} without set_device (train_temporal.py:90): make x's device current
+    # for every launch of the forward (backward runs on autograd's per-device thread, which already does)
+    with torch.cuda.device(x.device):
+        return _forward_train(net, x)
+
+
+def _forward_train(net, x):
     if x.dtype != torch.float32:
         x = x.float()
     dev = x.device
@@ -366,6 +370,18 @@ def dpot_forward_train(net, x):
     n = h * h
     act = ACT_IDS[net.act_name]
     km1, km2 = min(net.modes, h), min(net.modes, h // 2 + 1)
+
+    # ---- input normalisation (normalize=True, models/dpot.py:366-370).  No shipped config trains with it, so the
+    # per-sample statistics, the AdaIN affine below and the de-normalisation of the output are plain differentiable
+    # torch ops (five elementwise / reduction kernels); the inference engine has its own fused kernels for them.
+    mu = sigma = scale_mu = scale_sigma = None
+    if net.normalize:
+        mu = x.mean(dim=(1, 2, 3), keepdim=True)
+        sigma = x.std(dim=(1, 2, 3), keepdim=True) + 1e-6
+        x = (x - mu) / sigma
+        ms = torch.cat([mu, sigma], dim=-1).reshape(B, 2 * Cc)
+        scale_mu = LinearFn.apply(ms, net.scale_feats_mu.weight, net.scale_feats_mu.bias, None, None, ACT_NONE)
+        scale_sigma = LinearFn.apply(ms, net.scale_feats_sigma.weight, net.scale_feats_sigma.bias, None, None, ACT_NONE)
 
     # ---- weight-space re-parameterisations (differentiable torch ops on parameter-sized tensors)
     pe0, pe2 = net.patch_embed.proj[0], net.patch_embed.proj[2]
@@ -394,6 +410,8 @@ def dpot_forward_train(net, x):
     # ---- PatchEmbed conv0 + folded aggregation
     z1 = PatchGemmFn.apply(x, W0p, rowbias0, P, act)                       # [(b,pq,t), mid]
     a = LinearFn.apply(z1.view(B * n, T * mid), WeffT, None, bias_eff, None, ACT_NONE)
+    if net.normalize:                                                      # AdaIN, models/dpot.py:386-387
+        a = (a.view(B, n, E) * scale_sigma.view(B, 1, E) + scale_mu.view(B, 1, E)).reshape(B * n, E)
 
     # ---- blocks (models/dpot.py:165-180, double_skip=False)
     for blk in net.blocks:
@@ -427,4 +445,6 @@ def dpot_forward_train(net, x):
     y2 = LinearFn.apply(y1, ol[2].weight.reshape(old, old), ol[2].bias, None, None, act)
     y3 = LinearFn.apply(y2, ol[4].weight.reshape(Co * To, old), ol[4].bias, None, None, ACT_NONE)
     out = PixelShuffleFn.apply(y3, B, h, P).view(B, R, R, To, Co)
+    if net.normalize:                                                      # models/dpot.py:400-401
+        out = out * sigma + mu
     return out, cls_pred

@@ -8,6 +8,16 @@ namespace dpot {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 int g_pdl = 0;
+int sm_count_cur() {
+  static int cache[64] = {0};
+  const int d = cur_dev();
+  if (cache[d] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
+    cache[d] = n;
+  }
+  return cache[d];
+}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {

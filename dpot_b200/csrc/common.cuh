@@ -67,6 +67,16 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   return launch_pdl_if(g_pdl != 0, kern, grid, block, smem, st, args...);
 }
 
+// Per-device caches: function attributes (opt-in shared memory) and the SM count are properties of a DEVICE; a process
+// that drives several GPUs (train_temporal.py --gpu N, tests on multi-GPU boxes) must not reuse device 0's.
+static inline int cur_dev() { int d = 0; cudaGetDevice(&d); return d < 0 ? 0 : (d > 63 ? 63 : d); }
+int sm_count_cur();    // SM count of the current device (cached per device ordinal)
+struct DevOnce {       // "done once per device" flag set for one kernel instantiation
+  unsigned long long mask = 0;
+  bool need() const { return !((mask >> cur_dev()) & 1ull); }
+  void done() { mask |= 1ull << cur_dev(); }
+};
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

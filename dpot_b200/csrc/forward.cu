@@ -205,14 +205,15 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       g = gemm16_args(ws + WL.hid, d.hid, pk + PL.fc2_16, d.hid, lat_next, d.E, Mt, d.E, d.hid, bp.fc2_b, DPOT_ACT_NONE);
       g.residual = lat; g.ldr = d.E;
       if (i + 1 < d.depth) { g.out_stats = st1; g.stats_groups = groups; g.stats_rows_per_sample = d.n; }
-      else if (!cls) { g.C = ws + WL.n2; out16(g, d.E); }   // last block, no cls head: the latent is only read by the output GEMM -> split fp16
+      else { g.C = ws + WL.n2; out16(g, d.E); }   // last block: the latent is only read by the output GEMM (and the cls mean) -> split fp16
       DPOT_CALL(dpot_gemm(&g, stream));
     }
     float* tmp = lat; lat = lat_next; lat_next = tmp;
   }
 
   if (cls) {   // classification head (M = B rows: skinny CUDA-core GEMMs)
-    DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, stream));
+    if (d.depth > 0) DPOT_CALL(dpot_spatial_mean16(ws + WL.n2, B, d.n, d.E, ws + WL.tok, stream));
+    else DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, stream));
     dpot_gemm_args g = gemm_args(ws + WL.tok, d.E, prm->cls0_w, d.E, ws + WL.c1, d.E, B, d.E, d.E, prm->cls0_b, act, DPOT_GEMM_AUTO);
     DPOT_CALL(dpot_gemm(&g, stream));
     g = gemm_args(ws + WL.c1, d.E, prm->cls2_w, d.E, ws + WL.c2, d.E, B, d.E, d.E, prm->cls2_b, act, DPOT_GEMM_AUTO);
@@ -223,7 +224,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
 
   // output head: ConvTranspose as a GEMM on the split latent (written split by the last fc2 unless the cls head
   // needed it in fp32), then the fused per-pixel tail
-  if (cls) DPOT_CALL(dpot_split_f16(lat, d.E, Mt, d.E, nullptr, nullptr, 0, ws + WL.n2, 2 * d.E, d.E, stream));
+  if (d.depth == 0) DPOT_CALL(dpot_split_f16(lat, d.E, Mt, d.E, nullptr, nullptr, 0, ws + WL.n2, 2 * d.E, d.E, stream));
   {
     dpot_gemm_args g = gemm16_args(ws + WL.n2, d.E, packed + PL.WtT16, d.E, ws + WL.Y1, d.NP, Mt, d.NP, d.E, packed + PL.bias_t, act);
     const int nout = d.Co * d.To;

@@ -476,16 +476,13 @@ int gemm_tc_launch(const GemmDev& p, int batch, cudaStream_t st) {
   DPOT_CALL(encode_map(&mapA, p.A, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 4, BK, 1,
                        (uint32_t)P.BA));
 
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    DPOT_CUDA(cudaGetDevice(&dev));
-    DPOT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const int sm_count = sm_count_cur();
+  static DevOnce attr_set;
+  if (attr_set.need()) {
     DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     DPOT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
+    attr_set.done();
   }
   const int grid = P.total_tiles < sm_count ? P.total_tiles : sm_count;
   if (p.act == DPOT_ACT_NONE)

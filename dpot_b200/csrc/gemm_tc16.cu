@@ -431,11 +431,7 @@ bool gemm_tc16_fuses_stats(const GemmDev& p) {
 int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
-  if (g_sm_count == 0) {
-    int dev = 0;
-    DPOT_CUDA(cudaGetDevice(&dev));
-    DPOT_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  g_sm_count = sm_count_cur();
   if (gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
@@ -466,11 +462,11 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   const int side = p.c_scale || (p.rowbias && p.residual) ? 3 : (p.rowbias ? 1 : (p.residual ? 2 : 0));
 #define DPOT_TC16_LAUNCH(CGV, AM, O16, SD)                                                                             \
   do {                                                                                                                 \
-    static bool attr = false;                                                                                          \
-    if (!attr) {                                                                                                       \
+    static DevOnce attr;                                                                                          \
+    if (attr.need()) {                                                                                                       \
       DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_kernel<CGV, AM, O16, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                      (int)Geo<CGV>::SMEM_BYTES));                                                      \
-      attr = true;                                                                                                     \
+      attr.done();                                                                                                     \
     }                                                                                                                  \
     cudaLaunchConfig_t lc = {};                                                                                        \
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(NTHREADS); lc.dynamicSmemBytes = Geo<CGV>::SMEM_BYTES;       \

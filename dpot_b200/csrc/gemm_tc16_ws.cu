@@ -240,11 +240,11 @@ int gemm_tc16_ws_launch(const GemmDev& p, int batch, int sms, cudaStream_t st) {
   const bool o16 = p.c_fmt == DPOT_FMT_HL16;
 #define DPOT_WS_LAUNCH(AM, O16)                                                                                       \
   do {                                                                                                                \
-    static bool attr = false;                                                                                         \
-    if (!attr) {                                                                                                      \
+    static DevOnce attr;                                                                                         \
+    if (attr.need()) {                                                                                                      \
       DPOT_CUDA(cudaFuncSetAttribute(gemm_tc16_ws_kernel<AM, O16>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)WS_SMEM));                                                                  \
-      attr = true;                                                                                                    \
+      attr.done();                                                                                                    \
     }                                                                                                                 \
     DPOT_CUDA(launch_pdl_if(g_pdl != 0 || g_ws_pdl != 0, gemm_tc16_ws_kernel<AM, O16>, dim3(grid), dim3(WS_NTHREADS), WS_SMEM, st, mWh, mWl, mAh, mAl, P)); \
   } while (0)

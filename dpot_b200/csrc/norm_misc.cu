@@ -1,6 +1,7 @@
 // GroupNorm statistics, weight packing / folding, output-head tail, rollout window advance.
 // All of these are HBM/L2-bound streaming kernels: coalesced along the channel axis.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace dpot {
 namespace {
@@ -259,6 +260,28 @@ __global__ void spatial_mean_kernel(const float* __restrict__ a, int n, int E, f
   tok[(int64_t)b * E + e] = (float)(acc / (double)n);
 }
 
+// split-fp16 rows [hi E | lo E]: 64 channels x 4 row slices per CTA, fp32 partial sums (<= n/4 terms) combined in double
+__global__ void __launch_bounds__(256) spatial_mean16_kernel(const __half* __restrict__ a, int n, int E, float* __restrict__ tok) {
+  __shared__ float red[2][4][64];
+  const int c = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + c, b = blockIdx.y;
+  float s_hi = 0.f, s_lo = 0.f;
+  if (e < E) {
+    const __half* p = a + (int64_t)b * n * 2 * E + e;
+    for (int r = sl; r < n; r += 4) {
+      s_hi += __half2float(p[(int64_t)r * 2 * E]);
+      s_lo += __half2float(p[(int64_t)r * 2 * E + E]);
+    }
+  }
+  red[0][sl][c] = s_hi; red[1][sl][c] = s_lo;
+  __syncthreads();
+  if (sl == 0 && e < E) {
+    double hi = 0.0, lo = 0.0;
+    for (int k = 0; k < 4; ++k) { hi += (double)red[0][k][c]; lo += (double)red[1][k][c]; }
+    tok[(int64_t)b * E + e] = (float)((hi + lo * (1.0 / 2048.0)) / (double)n);
+  }
+}
+
 // ---------------------------------------------------------------------------- input statistics
 constexpr int IS_CMAX = 16;
 __global__ void __launch_bounds__(1024) input_stats_kernel(const float* __restrict__ x, int64_t per_sample, int C,
@@ -504,6 +527,14 @@ extern "C" int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E
   DPOT_REQUIRE(a && tok && B > 0 && n > 0 && E > 0, DPOT_E_BADARG, "dpot_spatial_mean: bad args");
   spatial_mean_kernel<<<dim3((unsigned)ceil_div(E, 128), (unsigned)B), 128, 0, as_stream(stream)>>>(a, n, E, tok);
   DPOT_LAUNCH_CHECK("spatial_mean_kernel");
+  return 0;
+}
+
+extern "C" int dpot_spatial_mean16(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* stream) {
+  DPOT_REQUIRE(a16 && tok && B > 0 && n > 0 && E > 0, DPOT_E_BADARG, "dpot_spatial_mean16: bad args");
+  spatial_mean16_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(a16), n, E, tok);
+  DPOT_LAUNCH_CHECK("spatial_mean16_kernel");
   return 0;
 }
 

@@ -235,10 +235,10 @@ int out_tail_tc_launch(const void* y1g, const float* w2, const float* b2, const 
   const int grid = Pm.ntiles < sms ? Pm.ntiles : sms;
 #define DPOT_OTT(AM, RG)                                                                                               \
   do {                                                                                                                 \
-    static bool attr = false;                                                                                          \
-    if (!attr) {                                                                                                       \
+    static DevOnce attr;                                                                                          \
+    if (attr.need()) {                                                                                                       \
       DPOT_CUDA(cudaFuncSetAttribute(out_tail_tc_kernel<AM, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OT_SMEM)); \
-      attr = true;                                                                                                     \
+      attr.done();                                                                                                     \
     }                                                                                                                  \
     DPOT_CUDA(launch_pdl(out_tail_tc_kernel<AM, RG>, dim3(grid), dim3(OT_NTHREADS), OT_SMEM, st, mY, Pm));             \
   } while (0)

@@ -473,8 +473,18 @@ class _InferenceEngine:
             if nfl <= 0:
                 raise RuntimeError("dpot_workspace_floats: " + self.lib.dpot_last_error_string().decode())
             ws = torch.empty(nfl, device=device, dtype=torch.float32)
-            self.ws = {B: ws}  # keep one batch size resident
+            # a few batch sizes stay resident (train batch, eval batch, last partial batch); the oldest goes first.
+            # Captured CUDA graphs never point here: RolloutEngine owns its workspace (new_workspace).
+            self.ws = {k: v for k, v in list(self.ws.items())[-2:] if v.device == device}
+            self.ws[B] = ws
         return ws
+
+    def new_workspace(self, B: int, device) -> torch.Tensor:
+        """A workspace the caller owns (RolloutEngine: its pointer is baked into a captured graph)."""
+        nfl = self.lib.dpot_workspace_floats(C.byref(self.cfg), B)
+        if nfl <= 0:
+            raise RuntimeError("dpot_workspace_floats: " + self.lib.dpot_last_error_string().decode())
+        return torch.empty(nfl, device=device, dtype=torch.float32)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, want_cls: bool = True, t0: int = 0):
@@ -498,16 +508,18 @@ class _InferenceEngine:
         return out, cls
 
     @torch.no_grad()
-    def rollout_step(self, ring: torch.Tensor, scratch: torch.Tensor, pred: Optional[torch.Tensor], t0: int, step: int):
+    def rollout_step(self, ring: torch.Tensor, scratch: torch.Tensor, pred: Optional[torch.Tensor], t0: int, step: int,
+                     ws: Optional[torch.Tensor] = None, want_cls: Optional[torch.Tensor] = None):
         """One autoregressive step on the ring window (dpot_rollout_step): the new frames overwrite the oldest slots
         (t0 + j) % T of `ring` and land in pred[..., step*T_out + j, :]; the caller advances t0 by T_out."""
         dev = ring.device
         with torch.cuda.device(dev):
             self.refresh(dev)
             B = ring.shape[0]
-            ws = self.workspace(B, dev)
+            if ws is None:
+                ws = self.workspace(B, dev)
             check(self.lib.dpot_rollout_step(C.byref(self.cfg), C.byref(self.prm), ptr(self.packed), ptr(ring), t0, B,
-                                             ptr(scratch), None, ptr(ws), self.net.gemm_engine, ptr(pred),
+                                             ptr(scratch), ptr(want_cls), ptr(ws), self.net.gemm_engine, ptr(pred),
                                              pred.shape[-2] if pred is not None else 0, step,
                                              torch.cuda.current_stream().cuda_stream), "dpot_rollout_step")
 

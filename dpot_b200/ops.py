@@ -5,6 +5,7 @@ or a missing library raises."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional
 
 import torch
@@ -17,6 +18,32 @@ GROUPS = 8  # torch.nn.GroupNorm(8, width), models/dpot.py:142,152
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _first_cuda(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+        elif isinstance(a, (list, tuple)):
+            t = _first_cuda(a)
+            if t is not None:
+                return t
+    return None
+
+
+def _on_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA tensor argument current: the reference scripts address
+    cuda:{args.gpu} without ever calling set_device (train_temporal.py:90), and a kernel launched while another
+    device is current would run against foreign pointers on the wrong GPU's stream."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        t = _first_cuda(args) or _first_cuda(tuple(kw.values()))
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kw)
+    return wrapped
 
 
 def _need_cuda(*ts):
@@ -34,6 +61,7 @@ def act_id(act) -> int:
     return ACT_IDS[act]
 
 
+@_on_device
 def gemm(A: torch.Tensor, W: torch.Tensor, *, bias=None, act=None, residual=None, rowbias=None,
          a_scale=None, a_shift=None, a_rows_per_sample=0, c_scale=None, c_shift=None, c_rows_per_sample=0,
          out: Optional[torch.Tensor] = None, engine: int = GEMM_AUTO) -> torch.Tensor:
@@ -63,6 +91,7 @@ def gemm(A: torch.Tensor, W: torch.Tensor, *, bias=None, act=None, residual=None
     return out
 
 
+@_on_device
 def split_f16(x: torch.Tensor, scale=None, shift=None, rows_per_sample: int = 0) -> torch.Tensor:
     """fp32 [M,K] -> split fp16 [M, 2K] (DPOT_FMT_HL16: columns [0,K) = hi, [K,2K) = lo * 2048)."""
     _need_cuda(x, scale, shift)
@@ -74,6 +103,7 @@ def split_f16(x: torch.Tensor, scale=None, shift=None, rows_per_sample: int = 0)
     return out
 
 
+@_on_device
 def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residual=None, rowbias=None, c_scale=None,
            c_shift=None, c_rows_per_sample=0, out16: bool = False, nb: int = 1, stats=None):
     """The f16-split tcgen05 engine on pre-split operands A16[M, 2*Kt], W16[nb*N, 2*K] (see split_f16).
@@ -124,6 +154,7 @@ def unsplit_f16(x16: torch.Tensor) -> torch.Tensor:
     return x16[:, :K].float() + x16[:, K:].float() / 2048.0
 
 
+@_on_device
 def gemm_batched_cols(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, nb: int, *, act=None,
                       out: Optional[torch.Tensor] = None, engine: int = GEMM_AUTO) -> torch.Tensor:
     """Block-diagonal GEMM of the AFNO spectral MLP: A[M, nb*k], W[nb, n, k], bias[nb, n] -> C[M, nb*n]."""
@@ -143,6 +174,7 @@ def gemm_batched_cols(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, nb: 
     return out
 
 
+@_on_device
 def patch_gemm(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: int, act, Kp: int, *,
                a_scale=None, a_shift=None, engine: int = GEMM_AUTO) -> torch.Tensor:
     """PatchEmbed conv0 + act as an im2col GEMM: x[B,X,Y,T,C] -> z1[B*n, Kp] (column t*mid+m)."""
@@ -166,6 +198,7 @@ def patch_gemm(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: in
     return z1
 
 
+@_on_device
 def patch_embed(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: int, act, Kp: int, *, t0: int = 0,
                 a_scale=None, a_shift=None, out16: bool = False) -> torch.Tensor:
     """dpot_patch_embed: x[B,X,Y,T,C] (a ring in time, logical frame t = slot (t+t0)%T) -> z1[B*n, Kp] fp32, or the
@@ -185,6 +218,7 @@ def patch_embed(x: torch.Tensor, W0p: torch.Tensor, rowbias0: torch.Tensor, P: i
     return z1
 
 
+@_on_device
 def out_tail(Y1: torch.Tensor, w2, b2, w4, b4, B: int, h: int, w: int, P: int, act, *, mu=None, sigma=None,
              Co: int = 0) -> torch.Tensor:
     """dpot_out_tail: Y1[(b,p,q), (u,v,o)] -> per-pixel act(W2 y + b2) -> W4 . + b4 -> out[B, h*P, w*P, nout]."""
@@ -210,6 +244,7 @@ def from_g32(g: torch.Tensor) -> torch.Tensor:
     return (r[:, :, :32].float() + r[:, :, 32:].float() / 2048.0).reshape(R, N2 // 2)
 
 
+@_on_device
 def out_tail_tc(Y1g: torch.Tensor, w2, b2, w4, b4, B: int, h: int, w: int, P: int, act, *, mu=None, sigma=None, Co: int = 0,
                 ring=None, pred=None, slot0: int = 0, step: int = 0):
     """dpot_out_tail_tc: Y1g = per-pixel [hi 32 | lo 32] records (DPOT_FMT_HL16G32) -> out[B, h*P, w*P, nout], or into the
@@ -226,6 +261,7 @@ def out_tail_tc(Y1g: torch.Tensor, w2, b2, w4, b4, B: int, h: int, w: int, P: in
     return out
 
 
+@_on_device
 def gn_stats(x: torch.Tensor, B: int, n: int, groups: int = GROUPS) -> torch.Tensor:
     _need_cuda(x)
     E = x.shape[-1]
@@ -234,6 +270,7 @@ def gn_stats(x: torch.Tensor, B: int, n: int, groups: int = GROUPS) -> torch.Ten
     return stats
 
 
+@_on_device
 def gn_finalize(stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n: int, eps: float = 1e-5):
     B, groups, _ = stats.shape
     E = gamma.numel()
@@ -244,6 +281,7 @@ def gn_finalize(stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, n:
     return scale, shift
 
 
+@_on_device
 def afno_fft_fwd(a, scale, shift, B, h, nb, km1, km2):
     _need_cuda(a, scale, shift)
     E = a.shape[-1]
@@ -253,6 +291,7 @@ def afno_fft_fwd(a, scale, shift, B, h, nb, km1, km2):
     return S
 
 
+@_on_device
 def afno_fft_inv(O2, a, scale, shift, B, h, nb, km1, km2, want_stats=True, groups: int = GROUPS):
     _need_cuda(O2, a, scale, shift)
     E = a.shape[-1]
@@ -263,6 +302,7 @@ def afno_fft_inv(O2, a, scale, shift, B, h, nb, km1, km2, want_stats=True, group
     return f, stats
 
 
+@_on_device
 def pack_afno(w: torch.Tensor, b: torch.Tensor):
     _need_cuda(w, b)
     _, nb, bs, _ = w.shape
@@ -273,6 +313,7 @@ def pack_afno(w: torch.Tensor, b: torch.Tensor):
     return Wc, bc
 
 
+@_on_device
 def window_advance(xx, im, xx_next, pred=None, step=0):
     _need_cuda(xx, im, xx_next, pred)
     B, X, Y, T, Cc = xx.shape
@@ -283,6 +324,7 @@ def window_advance(xx, im, xx_next, pred=None, step=0):
     return xx_next
 
 
+@_on_device
 def ring_insert(im, ring, pred=None, slot0=0, step=0):
     """ring[..., (slot0+j) % T, :] = im[..., j, :]; pred[..., step*Tb+j, :] = im[..., j, :]."""
     _need_cuda(im, ring, pred)
@@ -294,6 +336,7 @@ def ring_insert(im, ring, pred=None, slot0=0, step=0):
     return ring
 
 
+@_on_device
 def adam_step_multi(params, grads, ms, vs, vmaxs, steps, *, lr, beta1, beta2, eps, weight_decay, decoupled,
                     grad_scale=1.0):
     n = len(params)

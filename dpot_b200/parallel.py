@@ -129,7 +129,7 @@ class OverlappedGradArena:
             self.buckets.append(dict(start=start, end=o, params=members, expect=len(members), pending=len(members), handle=None))
         self.total = o
         self.buf: Optional[torch.Tensor] = None
-        self.seen, self.late, self.steps = set(), [], 0
+        self.seen, self.late, self.steps, self.arrived = set(), [], 0, set()
         self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
 
     def _world(self) -> int:
@@ -149,9 +149,16 @@ class OverlappedGradArena:
         bi, o, n = self.slots[p]
         b = self.buckets[bi]
         self.seen.add(p)
-        if b["handle"] is not None:            # its bucket is already on the wire: exchange this one separately
+        if b["handle"] is not None:            # its bucket is already on the wire
+            if p in self.arrived:
+                # a SECOND gradient for a parameter whose bucket is in flight (gradient accumulation, two backward
+                # passes before finish()): autograd has just accumulated in place into the buffer NCCL is reducing
+                raise RuntimeError("OverlappedGradArena: a parameter received a second gradient before finish(); "
+                                   "the contract is one backward pass per finish() (train_temporal_parallel.py:243-245)")
+            self.arrived.add(p)
             self.late.append(p)
             return
+        self.arrived.add(p)
         view = self.buf[o:o + n].view_as(p)
         view.copy_(p.grad)
         p.grad = view
@@ -186,6 +193,7 @@ class OverlappedGradArena:
             b["expect"] = sum(1 for p in b["params"] if p in self.seen) or len(b["params"])
             b["pending"], b["handle"] = b["expect"], None
         self.late = []
+        self.arrived = set()
         return n
 
     def close(self) -> None:

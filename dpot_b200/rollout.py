@@ -21,7 +21,7 @@ class RolloutEngine:
     (window, prediction, workspace, packed weights) are fixed, so the recorded pointers stay valid.  The graph is
     dropped whenever the parameters change (the packed-weight arena is re-derived then)."""
 
-    def __init__(self, model, batch: int, n_steps: int, device=None, use_graph: bool = False):
+    def __init__(self, model, batch: int, n_steps: int, device=None, use_graph: bool = False, want_cls: bool = False):
         self.model = model
         self.n_steps = n_steps
         self.use_graph = use_graph
@@ -37,6 +37,13 @@ class RolloutEngine:
         self.win = torch.empty((batch, R, R, T, Cc), device=dev)
         self.im = torch.empty((batch, R, R, Tb, Co), device=dev)
         self.pred = torch.empty((batch, R, R, n_steps * Tb, Co), device=dev)
+        # want_cls: also evaluate the classification head on every step, as the reference's model(xx) does
+        # (evaluate.py:198 discards it); cls[s] = cls_pred of step s
+        self.cls = torch.empty((n_steps, batch, model.n_cls), device=dev) if want_cls else None
+        # the workspace is owned here: a captured graph holds its address, so it must not be shared with (or evicted
+        # by) other batch sizes running through the model's engine
+        with torch.cuda.device(dev):
+            self.ws = model.engine().new_workspace(batch, dev)
 
     @torch.no_grad()
     def load(self, xx: torch.Tensor, non_blocking: bool = True) -> None:
@@ -57,14 +64,14 @@ class RolloutEngine:
             self._steps(eng)
             self.launches_per_run = int(eng.lib.dpot_launch_count() - l0)
             return self.pred
-        key = eng._param_key()
+        key = (eng._param_key(), eng.packed.data_ptr())
         if self._graph is not None and key != self._graph_key:
             self._graph, self._warm = None, False
         if not self._warm:                      # first rollout: eager (also the warm-up the capture needs)
             l0 = eng.lib.dpot_launch_count()
             self._steps(eng)
             self.launches_per_run = int(eng.lib.dpot_launch_count() - l0)
-            self._warm, self._graph_key = True, eng._param_key()
+            self._warm, self._graph_key = True, (eng._param_key(), eng.packed.data_ptr())
             return self.pred
         if self._graph is None:
             cur = torch.cuda.current_stream()
@@ -86,7 +93,8 @@ class RolloutEngine:
         for s in range(self.n_steps):
             # forward + window advance in one library call: the output tail writes the new frames straight into the
             # ring slot and the prediction tensor (dpot_rollout_step)
-            eng.rollout_step(self.win, self.im, self.pred, t0, s)
+            eng.rollout_step(self.win, self.im, self.pred, t0, s, ws=self.ws,
+                             want_cls=self.cls[s] if self.cls is not None else None)
             t0 = (t0 + Tb) % T
 
 

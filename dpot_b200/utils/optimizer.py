@@ -76,9 +76,17 @@ class _FusedAdamBase(Optimizer):
                 if group['amsgrad']:
                     xs.append(st['max_exp_avg_sq'])
                 steps.append(int(st['step']))
-            ops.adam_step_multi(ps, gs, ms, vs, xs if group['amsgrad'] else None, steps, lr=float(group['lr']),
-                                beta1=beta1, beta2=beta2, eps=group['eps'], weight_decay=group['weight_decay'],
-                                decoupled=self._decoupled, grad_scale=self.grad_scale)
+            if not ps:
+                continue
+            # one process may drive a GPU other than the current one (train_temporal.py --gpu N never calls set_device)
+            with torch.cuda.device(ps[0].device):
+                ops.adam_step_multi(ps, gs, ms, vs, xs if group['amsgrad'] else None, steps, lr=float(group['lr']),
+                                    beta1=beta1, beta2=beta2, eps=group['eps'], weight_decay=group['weight_decay'],
+                                    decoupled=self._decoupled, grad_scale=self.grad_scale)
+            # the kernel updates the parameters through raw pointers: bump their autograd version counters so that
+            # everything keyed on (data_ptr, _version) -- the inference engine's packed-weight arena, captured rollout
+            # graphs, autograd's saved-tensor checks -- sees the change, exactly as p.addcdiv_() would have
+            torch.autograd.graph.increment_version(ps)
         return loss
 
 

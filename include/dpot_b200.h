@@ -290,6 +290,9 @@ DPOT_API int dpot_out_tail_tc_supported(int32_t old, int32_t nout, int32_t Co);
 DPOT_API void dpot_out_tail_set_engine(int32_t engine);
 /* spatial mean a[B*n,E] -> tok[B,E]  (models/dpot.py:394) */
 DPOT_API int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E, float* tok, void* stream);
+/* the same on a split-fp16 latent (DPOT_FMT_HL16 rows [hi E | lo E], as the last block's fc2 writes it for the output
+   GEMM): the cls head then costs no extra fp32 copy of the latent. */
+DPOT_API int dpot_spatial_mean16(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* stream);
 /* per (sample, channel) mean and unbiased std + 1e-6 over (X,Y,T)  (models/dpot.py:367);
    writes musig[B, 2C] = [mu | sigma] and the im2col prologue tables a_scale/a_shift[B, P*P*C]. */
 DPOT_API int dpot_input_stats(const float* x, int32_t B, int64_t per_sample, int32_t C, int32_t PP,

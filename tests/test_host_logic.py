@@ -238,3 +238,41 @@ def test_gelu_polynomial_accuracy():
     assert err[np.abs(x) < 3].max() < 3e-7
     assert err.max() < 6e-7                       # = fp32 rounding of values up to 8
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 5e-8
+
+
+def test_zoo_synthetic_weights_equal_oracle_make_params():
+    """bench.py's product arm draws its weights from dpot_b200.zoo (no oracle import); they must be the weights the
+    golden fixtures were generated with (oracle.make_params), for ours and for the reference's schema alike."""
+    import torch
+    from dpot_b200 import zoo
+    from dpot_b200.models.dpot import DPOTNet
+    for cfg_z, cfg_o in [(zoo.zoo_cfg("Ti", img_size=64), O.zoo_cfg("Ti", img_size=64)),
+                         (zoo.zoo_cfg("S", depth=1), O.zoo_cfg("S", depth=1))]:
+        m = zoo.synthetic_weights_(DPOTNet(**cfg_z), seed=0)
+        p = O.make_params(cfg_o, seed=0)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(p.keys())
+        for k in sd:
+            assert torch.equal(sd[k], torch.from_numpy(p[k])), k
+    fl = zoo.forward_flops(zoo.zoo_cfg("S"))
+    assert abs(fl["algorithmic"] / 1e9 - 15.07) < 0.05 and abs(fl["executed"] / 1e9 - 9.66) < 0.1   # SURVEY 8(d), DESIGN 3
+
+
+def test_bench_reference_arm_uses_the_staged_reference():
+    """baseline/install_ref.py stages the unmodified reference files (sha256 manifest) and bench.py's reference arm
+    builds the reference's own DPOTNet from them."""
+    import hashlib, importlib.util, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("install_ref", os.path.join(root, "baseline", "install_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not os.path.isdir(mod.SRC) and not os.path.exists(os.path.join(mod.DST, "models", "dpot.py")):
+        pytest.skip("no reference tree here and nothing staged")
+    assert mod.install(verbose=False)
+    man = json.load(open(os.path.join(mod.DST, "MANIFEST.json")))
+    for rel, dig in man.items():
+        assert hashlib.sha256(open(os.path.join(mod.DST, rel), "rb").read()).hexdigest() == dig
+        if os.path.isdir(mod.SRC):
+            assert open(os.path.join(mod.SRC, rel), "rb").read() == open(os.path.join(mod.DST, rel), "rb").read(), rel
+    RefNet, RefAdam, RefLoss, _ = mod.import_reference()
+    assert RefNet.__module__.endswith("models.dpot") and "dpot_b200" not in RefNet.__module__
