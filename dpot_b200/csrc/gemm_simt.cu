@@ -169,59 +169,72 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmDev p) {
 }
 
 
-// ---- skinny problems (M <= 64: classification head, AdaIN tables) --------------------------------
-// One warp per pair of output columns; lanes split K (coalesced 128 B rows of A and W), fp32 FMA,
-// shuffle reduction.  A (<= 64 x K) stays in L1/L2; the kernel is latency- not bandwidth-critical.
-constexpr int SK_MAXM = 64, SK_WARPS = 8, SK_KC = 256;
-// Skinny problems (M <= 64 rows: the classification head, models/dpot.py:394-395, runs on M = batch rows).  The CTA
-// stages a [32 rows x 256 k] slice of A in shared memory (prologue affine applied once), every warp owns two output
-// columns and walks k with its lanes (coalesced weight reads, conflict-free A reads), 64 FMAs per lane and k-step.
-// (The first version re-read A from global memory in every warp: 376 us for M = 16, N = K = 1024; this one ~10 us.)
+// ---- skinny problems (M <= 64 rows: the classification head, models/dpot.py:394-395, runs on M = batch rows; AdaIN
+// tables).  The problem is a weight STREAM (N x K fp32, e.g. 4 MB for the 1024 x 1024 head layers, usually from HBM)
+// against a tiny A, so the kernel is built for bytes in flight: one warp per output column, the warp's lanes walk K in
+// float4s and request a whole SK_KC-wide slice of the weight row (4 independent 512 B warp loads) -- and the NEXT
+// slice -- before touching the current one; the CTA stages the matching [32 rows x SK_KC] slice of A in shared memory
+// (prologue affine applied once), 32 register accumulators per lane, one shuffle reduction per row at the end.
+// History: v1 re-read A from global memory in every warp (376 us for M = 16, N = K = 1024); v2 staged A but kept two
+// scalar weight loads in flight per warp on 64 CTAs (~100 us per head at B = 32: 21 % of the whole rollout step).
+constexpr int SK_MAXM = 64, SK_WARPS = 8, SK_KC = 512, SK_V = SK_KC / 128;   // SK_V float4 per lane and slice
 template <int MT>   // rows handled per pass (32): M is covered in ceil(M/32) passes
 __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDev p) {
-  __shared__ float A_s[MT][SK_KC];
+  extern __shared__ __align__(16) float A_s[];          // [MT][SK_KC]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n0 = (blockIdx.x * SK_WARPS + warp) * 2;
-  const bool live = n0 < p.N, two = (n0 + 1) < p.N;
-  const float* __restrict__ w0 = p.W + (int64_t)(live ? n0 : 0) * p.ldw;
-  const float* __restrict__ w1 = p.W + (int64_t)(two ? n0 + 1 : (live ? n0 : 0)) * p.ldw;
-  for (int mb = 0; mb < p.M; mb += MT) {
-    float a0[MT], a1[MT];
+  const int n0 = blockIdx.x * SK_WARPS + warp;
+  const bool live = n0 < p.N;
+  const float* __restrict__ wrow = p.W + (int64_t)(live ? n0 : 0) * p.ldw;
+  const bool vec = (p.ldw % 4 == 0) && (reinterpret_cast<uintptr_t>(p.W) % 16 == 0);
+  auto load_w = [&](int kc, float4 (&w)[SK_V]) {
 #pragma unroll
-    for (int i = 0; i < MT; ++i) a0[i] = a1[i] = 0.f;
+    for (int v = 0; v < SK_V; ++v) {
+      const int k = kc + v * 128 + lane * 4;
+      if (!live || k >= p.K) { w[v] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+      if (vec && k + 3 < p.K) w[v] = __ldg(reinterpret_cast<const float4*>(wrow + k));
+      else {
+        w[v].x = __ldg(wrow + k);
+        w[v].y = k + 1 < p.K ? __ldg(wrow + k + 1) : 0.f;
+        w[v].z = k + 2 < p.K ? __ldg(wrow + k + 2) : 0.f;
+        w[v].w = k + 3 < p.K ? __ldg(wrow + k + 3) : 0.f;
+      }
+    }
+  };
+  for (int mb = 0; mb < p.M; mb += MT) {
+    float acc[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) acc[i] = 0.f;
+    float4 wc[SK_V], wn[SK_V];
+    load_w(0, wc);
     for (int kc = 0; kc < p.K; kc += SK_KC) {
+      if (kc + SK_KC < p.K) load_w(kc + SK_KC, wn);          // next slice in flight while this one is consumed
       __syncthreads();
       for (int e = threadIdx.x; e < MT * SK_KC; e += SK_WARPS * 32) {
         const int i = e / SK_KC, k = e - i * SK_KC;
-        A_s[i][k] = (mb + i < p.M && kc + k < p.K) ? gemm_load_a(p, p.A, mb + i, kc + k) : 0.f;
+        A_s[e] = (mb + i < p.M && kc + k < p.K) ? gemm_load_a(p, p.A, mb + i, kc + k) : 0.f;
       }
       __syncthreads();
-      if (live) {
-        const int kend = min(SK_KC, p.K - kc);
-        for (int k = lane; k < kend; k += 32) {
-          const float x0 = __ldg(w0 + kc + k), x1 = __ldg(w1 + kc + k);
 #pragma unroll
-          for (int i = 0; i < MT; ++i) {
-            const float a = A_s[i][k];
-            a0[i] = fmaf(a, x0, a0[i]);
-            a1[i] = fmaf(a, x1, a1[i]);
-          }
+      for (int i = 0; i < MT; ++i) {
+        const float4* ar = reinterpret_cast<const float4*>(A_s + i * SK_KC) + lane;
+        float a = acc[i];
+#pragma unroll
+        for (int v = 0; v < SK_V; ++v) {
+          const float4 x = ar[v * 32];
+          a = fmaf(x.x, wc[v].x, fmaf(x.y, wc[v].y, fmaf(x.z, wc[v].z, fmaf(x.w, wc[v].w, a))));
         }
+        acc[i] = a;
       }
+#pragma unroll
+      for (int v = 0; v < SK_V; ++v) wc[v] = wn[v];
     }
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-      a0[i] = warp_sum(a0[i]);
-      a1[i] = warp_sum(a1[i]);
-    }
-    // lane i finalises row mb+i
+    for (int i = 0; i < MT; ++i) acc[i] = warp_sum(acc[i]);
+    // lane i finalises row mb+i (MT == 32: one row per lane)
+    float mine = 0.f;
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-      if (live && lane == (i & 31) && mb + i < p.M) {
-        gemm_epilogue_store(p, p.C, p.bias, mb + i, n0, a0[i]);
-        if (two) gemm_epilogue_store(p, p.C, p.bias, mb + i, n0 + 1, a1[i]);
-      }
-    }
+    for (int i = 0; i < MT; ++i) mine = (lane == i) ? acc[i] : mine;
+    if (live && mb + lane < p.M) gemm_epilogue_store(p, p.C, p.bias, mb + lane, n0, mine);
   }
 }
 
@@ -235,8 +248,13 @@ int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st) {
                        (!p.a_scale || (reinterpret_cast<uintptr_t>(p.a_scale) % 16 == 0 &&
                                        reinterpret_cast<uintptr_t>(p.a_shift) % 16 == 0));
   if (p.M <= SK_MAXM && batch == 1 && p.a_mode == DPOT_A_PLAIN) {
-    const int warps = (p.N + 1) / 2;
-    gemm_skinny_kernel<32><<<(unsigned)ceil_div(warps, SK_WARPS), SK_WARPS * 32, 0, st>>>(p);
+    constexpr int smem = 32 * SK_KC * 4;
+    static DevOnce attr;
+    if (attr.need()) {
+      DPOT_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr.done();
+    }
+    gemm_skinny_kernel<32><<<(unsigned)ceil_div(p.N, SK_WARPS), SK_WARPS * 32, smem, st>>>(p);
     DPOT_LAUNCH_CHECK("gemm_skinny_kernel");
     return 0;
   }

@@ -38,7 +38,9 @@ def _on_device(fn):
     device is current would run against foreign pointers on the wrong GPU's stream."""
     @functools.wraps(fn)
     def wrapped(*args, **kw):
-        t = _first_cuda(args) or _first_cuda(tuple(kw.values()))
+        t = _first_cuda(args)
+        if t is None:
+            t = _first_cuda(tuple(kw.values()))
         if t is None or t.device.index == torch.cuda.current_device():
             return fn(*args, **kw)
         with torch.cuda.device(t.device):
