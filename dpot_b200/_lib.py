@@ -108,6 +108,11 @@ SIGNATURES = {
     "dpot_afno_fft_fwd16": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_afno_fft_fwd16_gn": (C.c_int, [_p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_afno_fft_inv_gn": (C.c_int, [_p, _p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "dpot_afno_fused_supported": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "dpot_afno_fused_packed_floats": (C.c_int64, [_i32]),
+    "dpot_afno_fused_pack": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p]),
+    "dpot_afno_fused": (C.c_int, [_p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
+    "dpot_afno_set_fused": (None, [_i32]),
     "dpot_split_f16_gn": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _i32, _f, _i32, _p, _i64, _i64, _p]),
     "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _p]),
     "dpot_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),

@@ -34,10 +34,16 @@ static int make_dims(const dpot_config* c, Dims& d) {
 
 static inline int64_t slot(int64_t n) { return round_up(n, 64); }  // 256 B granules
 
+// geometry served by the fused AFNO mixer kernel (afno_fused.cu): latent 16 x 16, block size 128, no mode truncation
+static inline bool fused_geometry(const Dims& d) {
+  return d.h == 16 && d.bs == 128 && d.km1 == 16 && d.km2 == 9 && (d.E / 8) % 32 == 0;
+}
+
 struct Packed {
   int64_t W0p, rowbias0, WeffT, bias_eff, blocks, blk_stride, Wc1, bc1, Wc2, bc2, WtT, bias_t, total;
   // split-fp16 (DPOT_FMT_HL16) copies for the f16-split tensor-core engine; same float counts as the fp32 originals
   int64_t WeffT16, WtT16, Wc1_16, Wc2_16, fc1_16, fc2_16;   // the last four are offsets inside a block slab
+  int64_t Wfus;                                             // fused AFNO mixer arena inside a block slab (afno_fused.cu)
 };
 static Packed packed_layout(const Dims& d) {
   Packed L; int64_t o = 0;
@@ -55,6 +61,7 @@ static Packed packed_layout(const Dims& d) {
   L.Wc2_16 = b; b += slot((int64_t)d.nb * 4 * d.bs * d.bs);
   L.fc1_16 = b; b += slot((int64_t)d.hid * d.E);
   L.fc2_16 = b; b += slot((int64_t)d.hid * d.E);
+  L.Wfus = b; b += fused_geometry(d) ? slot(dpot_afno_fused_packed_floats(d.nb)) : 0;
   L.blk_stride = b; o += b * d.depth;
   L.WtT = o; o += slot((int64_t)d.NP * d.E);
   L.bias_t = o; o += slot(d.NP);
@@ -176,6 +183,12 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
     const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
     // GroupNorm by reference: the consumers derive their affines from the raw statistics (no finalize launches)
     const bool gnref = (d.E / groups) % 8 == 0 && (reinterpret_cast<uintptr_t>(bp.norm2_w) | reinterpret_cast<uintptr_t>(bp.norm2_b)) % 16 == 0;
+    if (fused_geometry(d) && dpot_afno_fused_supported(d.h, d.E, d.nb, d.km1, d.km2, groups)) {
+      // the whole mixer in one launch: spectrum and hidden layer stay on chip
+      DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
+      DPOT_CALL(dpot_afno_fused(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, pk + PL.Wfus, act,
+                                ws + WL.f, st2, nullptr, stream));
+    } else {
     DPOT_CALL(dpot_afno_fft_fwd16_gn(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, d.km1, d.km2,
                                      ws + WL.S, stream));
     {
@@ -191,6 +204,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
     DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
     DPOT_CALL(dpot_afno_fft_inv_gn(ws + WL.S, lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, d.km1, d.km2,
                                    ws + WL.f, st2, stream));
+    }
     // GroupNorm-2 apply fused with the fp16 split of the channel-MLP input
     if (gnref) {
       DPOT_CALL(dpot_split_f16_gn(ws + WL.f, d.E, Mt, d.E, st2, bp.norm2_w, bp.norm2_b, groups, 1e-5f, d.n, ws + WL.n2, 2 * d.E, d.E, stream));
@@ -304,6 +318,7 @@ extern "C" int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm,
       DPOT_CALL(dpot_split_f16(base + L.Wc2, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc2_16, 2 * kb, kb, stream));
       DPOT_CALL(dpot_split_f16(b.fc1_w, d.E, d.hid, d.E, nullptr, nullptr, 0, base + L.fc1_16, 2 * d.E, d.E, stream));
       DPOT_CALL(dpot_split_f16(b.fc2_w, d.hid, d.E, d.hid, nullptr, nullptr, 0, base + L.fc2_16, 2 * d.hid, d.hid, stream));
+      if (fused_geometry(d)) DPOT_CALL(dpot_afno_fused_pack(b.w1, b.b1, b.w2, b.b2, d.nb, d.bs, base + L.Wfus, stream));
     }
   }
   return 0;

@@ -305,6 +305,29 @@ def afno_fft_inv(O2, a, scale, shift, B, h, nb, km1, km2, want_stats=True, group
 
 
 @_on_device
+def afno_fused(lat: torch.Tensor, stats1: torch.Tensor, gamma1, beta1, w1, b1, w2, b2, B: int, h: int, act="gelu",
+               eps: float = 1e-5, groups: int = GROUPS, want_stats: bool = True, debug: bool = False):
+    """dpot_afno_fused: the whole AFNO2D mixer of one block (GroupNorm-1 by reference -> rfft2 -> complex block MLP ->
+    irfft2 -> + skip) in one kernel.  lat[B*h*h, E]; stats1[B, groups, 2] (double); w1/w2 (2, nb, bs, bs), b1/b2 (2, nb, bs).
+    Returns (f, stats2[, dbg]) -- dbg = per-unit images of the X and O1 operand tiles (test hook)."""
+    _need_cuda(lat, gamma1, beta1, w1, b1, w2, b2)
+    lib = _lib.load()
+    E = lat.shape[1]
+    nb, bs = w1.shape[1], w1.shape[2]
+    if not lib.dpot_afno_fused_supported(h, E, nb, h, h // 2 + 1, groups):
+        raise RuntimeError(f"dpot_afno_fused: geometry h={h} E={E} nb={nb} is not served by the fused mixer")
+    packed = torch.empty(lib.dpot_afno_fused_packed_floats(nb), device=lat.device, dtype=torch.float32)
+    check(lib.dpot_afno_fused_pack(ptr(w1.contiguous()), ptr(b1.contiguous()), ptr(w2.contiguous()), ptr(b2.contiguous()),
+                                   nb, bs, ptr(packed), _stream()), "dpot_afno_fused_pack")
+    f = torch.empty_like(lat)
+    stats2 = torch.zeros((B, groups, 2), device=lat.device, dtype=torch.float64) if want_stats else None
+    dbg = torch.zeros((B * nb, 2 * 147456 // 4), device=lat.device, dtype=torch.float32) if debug else None
+    check(lib.dpot_afno_fused(ptr(lat), ptr(stats1), ptr(gamma1), ptr(beta1), groups, eps, B, h, E, nb, ptr(packed),
+                              act_id(act), ptr(f), ptr(stats2), ptr(dbg), _stream()), "dpot_afno_fused")
+    return (f, stats2, dbg) if debug else (f, stats2)
+
+
+@_on_device
 def pack_afno(w: torch.Tensor, b: torch.Tensor):
     _need_cuda(w, b)
     _, nb, bs, _ = w.shape

@@ -186,6 +186,28 @@ DPOT_API int dpot_afno_fft_inv(const float* O2, const float* a, const float* sca
 /* fwd with the spectrum stored as split fp16 (DPOT_FMT_HL16): S16 row (b,k1,k2) = [hi: 2E halves | lo: 2E halves] */
 DPOT_API int dpot_afno_fft_fwd16(const float* a, const float* scale, const float* shift, int32_t B, int32_t h,
                         int32_t E, int32_t nb, int32_t km1, int32_t km2, void* S16, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * The fused AFNO2D mixer: GroupNorm-1 by reference -> rfft2 -> block-diagonal complex MLP (two layers, tcgen05) ->
+ * irfft2 -> + skip -> f, with the GroupNorm-2 statistics of f, in ONE kernel per block; the spectrum and the hidden
+ * layer stay in shared memory / TMEM.  Replaces AFNO2D.forward, models/dpot.py:51-110, together with the GroupNorm
+ * calls around it (:167,175).  Geometry served: latent 16 x 16, block size 128 (E = 128 * nb), no mode truncation --
+ * DPOT-Ti/S/M at 128^2 -- query dpot_afno_fused_supported; other geometries run the four-kernel path
+ * (dpot_afno_fft_fwd16_gn -> 2 x dpot_gemm -> dpot_afno_fft_inv_gn).
+ *   packed: dpot_afno_fused_packed_floats(nb) floats written by dpot_afno_fused_pack from the block's
+ *           filter.w1/b1/w2/b2 (three pre-swizzled fp16 planes of s*w per 16 KB chunk, biases, 1/s per layer).
+ *   stats1: GroupNorm-1 statistics [B, groups, 2] (double: sum, sum of squares) of `lat`; stats2 (may be NULL):
+ *           receives the statistics of f, ACCUMULATED (zero it first).  dbg: NULL (test hook: operand-tile images).
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int     dpot_afno_fused_supported(int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, int32_t groups);
+DPOT_API int64_t dpot_afno_fused_packed_floats(int32_t nb);
+DPOT_API int     dpot_afno_fused_pack(const float* w1, const float* b1, const float* w2, const float* b2, int32_t nb,
+                                      int32_t bs, float* packed, void* stream);
+DPOT_API int     dpot_afno_fused(const float* lat, const double* stats1, const float* gamma1, const float* beta1,
+                                 int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
+                                 int32_t act, float* f, double* stats2, float* dbg, void* stream);
+/* knob (tests / A-B measurements): -1 = fused whenever supported (default), 0 = never */
+DPOT_API void    dpot_afno_set_fused(int32_t mode);
+
 /* GroupNorm-by-reference variants (the f16-split inference pipeline): instead of finalised scale/shift tables the
    kernels take the raw statistics [B, groups, 2] (double sum, sum of squares) plus gamma/beta and derive the
    per-channel affine themselves (no dpot_gn_finalize launch). */
