@@ -113,6 +113,7 @@ SIGNATURES = {
     "dpot_afno_fused_pack": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p]),
     "dpot_afno_fused": (C.c_int, [_p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "dpot_afno_set_fused": (None, [_i32]),
+    "dpot_afno_fused_set_trace": (None, [C.c_void_p]),
     "dpot_split_f16_gn": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _i32, _f, _i32, _p, _i64, _i64, _p]),
     "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _p]),
     "dpot_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),
@@ -136,6 +137,13 @@ SIGNATURES = {
     "dpot_patch_embed": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
     "dpot_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _d, _i32, _i32, _d, _p]),
     "dpot_adam_step_multi": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _p, _i32, _d, _p]),
+    "dpot_adam_step_multi_clip": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _p, _i32, _d, _p, _d, _p]),
+    "dpot_grad_sqnorm": (C.c_int, [_p, _p, _i32, _p, _p]),
+    "dpot_chan_sumsq": (C.c_int, [_p, _i32, _i64, _i32, _p, _p]),
+    "dpot_noise_inject": (C.c_int, [_p, _i32, _i64, _i32, _f, C.c_uint64, C.c_uint64, _p, _p, _p]),
+    "dpot_noise_inject_bwd": (C.c_int, [_p, _p, _i32, _i64, _i32, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p]),
+    "dpot_lp_loss": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "dpot_lp_loss_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p]),
     "dpot_packed_floats": (C.c_int64, [C.POINTER(Config)]),
     "dpot_workspace_floats": (C.c_int64, [C.POINTER(Config), _i32]),
     "dpot_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p]),

@@ -9,6 +9,9 @@ namespace {
 struct AdamConst {
   float beta1, beta2, one_m_beta1, one_m_beta2, eps, wd, decay_mul, grad_scale;
   int decoupled;
+  // clip_grad_norm_ folded into the step (train_temporal.py:228): sqnorm = device double holding sum g^2 over ALL
+  // gradients (dpot_grad_sqnorm), max_norm the clip threshold; nullptr = no clipping
+  const double* sqnorm; float max_norm;
 };
 
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float* vmax, const AdamConst& c,
@@ -36,7 +39,13 @@ struct MultiArgs {
 
 constexpr int ADAM_NT = 256, ADAM_PER_BLOCK = ADAM_NT * 4 * 4;  // 4 float4 per thread
 
-__global__ void __launch_bounds__(ADAM_NT) adam_multi_kernel(const MultiArgs a, const AdamConst c) {
+__global__ void __launch_bounds__(ADAM_NT) adam_multi_kernel(const MultiArgs a, AdamConst c) {
+  if (c.sqnorm) {
+    // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1, in fp32; the norm is
+    // that of the gradients AFTER the data-parallel average (grad_scale)
+    const float total = (float)sqrt(*c.sqnorm) * c.grad_scale;
+    c.grad_scale *= fminf(1.0f, c.max_norm / (total + 1e-6f));
+  }
   // locate the tensor of this block (<= 32 entries: linear scan)
   int ti = 0;
   while (ti + 1 < a.count && (int)blockIdx.x >= a.blk_start[ti + 1]) ++ti;
@@ -86,6 +95,15 @@ extern "C" int dpot_adam_step_multi(float* const* p, const float* const* g, floa
                                     float* const* vmax, const int64_t* n, int32_t count, double lr, double beta1,
                                     double beta2, double eps, double weight_decay, const int32_t* steps,
                                     int32_t decoupled, double grad_scale, void* stream) {
+  return dpot_adam_step_multi_clip(p, g, m, v, vmax, n, count, lr, beta1, beta2, eps, weight_decay, steps, decoupled,
+                                   grad_scale, nullptr, 0.0, stream);
+}
+
+extern "C" int dpot_adam_step_multi_clip(float* const* p, const float* const* g, float* const* m, float* const* v,
+                                         float* const* vmax, const int64_t* n, int32_t count, double lr, double beta1,
+                                         double beta2, double eps, double weight_decay, const int32_t* steps,
+                                         int32_t decoupled, double grad_scale, const double* grad_sqnorm, double max_norm,
+                                         void* stream) {
   DPOT_REQUIRE(count >= 0, DPOT_E_BADARG, "dpot_adam_step_multi: negative count");
   if (count == 0) return 0;
   DPOT_REQUIRE(p && g && m && v && n && steps, DPOT_E_BADARG, "dpot_adam_step_multi: null array");
@@ -94,6 +112,7 @@ extern "C" int dpot_adam_step_multi(float* const* p, const float* const* g, floa
   c.one_m_beta1 = (float)(1.0 - beta1); c.one_m_beta2 = (float)(1.0 - beta2);  // python-float arithmetic, then fp32
   c.eps = (float)eps; c.wd = (float)weight_decay; c.decay_mul = (float)(1.0 - lr * weight_decay);
   c.grad_scale = (float)grad_scale; c.decoupled = decoupled;
+  c.sqnorm = grad_sqnorm; c.max_norm = (float)max_norm;
   cudaStream_t st = as_stream(stream);
   int t = 0;
   while (t < count) {

@@ -52,7 +52,6 @@ constexpr uint32_t AF_SMEM = AF_OFF_BAR + 128 + 1024;
 static_assert(AF_SMEM <= 232448, "shared memory budget");
 static_assert(AF_OFF_SCR + 65536 == AF_OFF_BAR, "scratch = stages 1-2 + 32 KB");
 static_assert(16 * 8 * 128 * 8 <= AF_OPER, "inverse-transform scratch lives in the dead operand tile");
-constexpr uint32_t AF_TCOL_RE = 0, AF_TCOL_IM = AF_MODES;        // TMEM columns of the two accumulators
 
 // packed-weight arena of one block (floats): [2 layers][nb][12 chunks][4096] | bias [2][nb][2][128] | inv_s[2] (+ amax scratch)
 __host__ __device__ inline int64_t af_chunk_floats() { return AF_WCHUNK / 4; }
@@ -91,24 +90,37 @@ struct AfArgs {
   GnRef gn;                // GroupNorm-1 by reference
   int B, E, nb, act, groups;
   float* dbg;              // test hook: units x (X operand | O1 operand) images, 2 * AF_OPER bytes per unit, or nullptr
+  long long* trace;        // profiling hook: clock64() of CTA 0 / thread 0 at the phase boundaries, 8 per unit, or nullptr
 };
 
-template <int ACT_MODE>
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// TMEM columns: layer 1 accumulates D_re at 0 and D_im at 144; layer 2 accumulates D_re at 0 (layer 1's D_re has been
+// consumed by then) and D_im at 288, so that its first half can run while E1 still reads layer 1's D_im.
+constexpr uint32_t AF_T_RE = 0, AF_T_IM1 = AF_MODES, AF_T_IM2 = 2 * AF_MODES;
+
+// ESPEC: embed_dim as a compile-time constant (0 = run time): every global load / store of a transform then uses an
+// immediate offset instead of 64-bit address arithmetic.
+template <int ACT_MODE, int ESPEC>
 __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  uint8_t* const S = smem_raw + (smem0 - smem_u32(smem_raw));        // generic view of the aligned base (shared space)
   const uint32_t bar0 = smem0 + AF_OFF_BAR;
   auto FULL = [&](int s) -> uint32_t { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) -> uint32_t { return bar0 + 8u * (AF_NST + s); };
-  const uint32_t XRDY = bar0 + 8u * (2 * AF_NST), M1DONE = XRDY + 8u, O1RDY = XRDY + 16u, M2DONE = XRDY + 24u;
-  const uint32_t tmem_slot = XRDY + 32u;
+  const uint32_t XRDY = bar0 + 8u * (2 * AF_NST), M1DONE = XRDY + 8u, O1RE = XRDY + 16u, O1IM = XRDY + 24u, M2DONE = XRDY + 32u;
+  const uint32_t tmem_slot = XRDY + 40u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (warp == AF_CWARPS && elect_one()) {
     for (int s = 0; s < AF_NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-    mbar_init(XRDY, AF_CWARPS); mbar_init(M1DONE, 1); mbar_init(O1RDY, AF_CWARPS); mbar_init(M2DONE, 1);
+    mbar_init(XRDY, AF_CWARPS); mbar_init(M1DONE, 1); mbar_init(O1RE, AF_CWARPS); mbar_init(O1IM, AF_CWARPS); mbar_init(M2DONE, 1);
     fence_barrier_init();
   }
   if (warp == AF_CWARPS + 1) tmem_alloc(tmem_slot, 512);
@@ -119,22 +131,27 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();
 
-  const int nb = P.nb, E = P.E;
+  const int E = ESPEC ? ESPEC : P.E;
+  const int nb = ESPEC ? ESPEC / AF_BS : P.nb;
   const int units = P.B * nb;
   const float* const bias_all = P.packed + af_bias_off(nb);
   const float inv_s1 = P.packed[af_scale_off(nb)], inv_s2 = P.packed[af_scale_off(nb) + 1];
 
   if (warp == AF_CWARPS) {
     // ======================================= weight producer =======================================
+    // per unit and layer: 12 chunks of 16 KB, each feeding both accumulators.  (Measured: streaming layer 2's chunks
+    // twice so that its Re(hidden) products could overlap E1 made things slower -- the MMA phases already run at the
+    // ~30 B/clk/SM the L2 -> SM fabric delivers, 576 tensor-clocks per chunk.)
     if (elect_one()) {
       int s = 0; uint32_t ph = 0; uint32_t it = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
         const int kap = u % nb;
-        for (int layer = 0; layer < 2; ++layer) {
+        for (int pass = 0; pass < 2; ++pass) {
+          const int layer = pass;
           const float* src = P.packed + ((int64_t)(layer * nb + kap) * AF_CHUNKS) * (AF_WCHUNK / 4);
           for (int ci = 0; ci < AF_CHUNKS; ++ci) {
             // ring stages 1 and 2 are FFT scratch until this unit's spectrum is complete
-            if (layer == 0 && ci == 1) mbar_wait(XRDY, it & 1u);
+            if (pass == 0 && ci == 1) mbar_wait(XRDY, it & 1u);
             mbar_wait(EMPTY(s), ph ^ 1u);
             mbar_expect_tx(FULL(s), AF_WCHUNK);
             bulk_g2s(smem0 + AF_OFF_W + (uint32_t)s * AF_WCHUNK, src + (int64_t)ci * (AF_WCHUNK / 4), AF_WCHUNK, FULL(s));
@@ -147,11 +164,12 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
     // ========================================= MMA issuer ==========================================
     if (elect_one()) {
       int s = 0; uint32_t ph = 0; uint32_t it = 0;
-      const uint32_t d_re = tmem_base + AF_TCOL_RE, d_im = tmem_base + AF_TCOL_IM;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        // layer 1 accumulates into (D_re @ 0, D_im @ 144), layer 2 into (D_re @ 0, D_im @ 288)
         for (int layer = 0; layer < 2; ++layer) {
-          mbar_wait(layer == 0 ? XRDY : O1RDY, it & 1u);
+          mbar_wait(layer == 0 ? XRDY : O1IM, it & 1u);
           tc_fence_after();
+          const uint32_t d_re = tmem_base + AF_T_RE, d_im = tmem_base + (layer == 0 ? AF_T_IM1 : AF_T_IM2);
           for (int ci = 0; ci < AF_CHUNKS; ++ci) {
             const int T = ci / 6, kb = (ci / 3) & 1, plane = ci % 3;
             mbar_wait(FULL(s), ph);
@@ -185,20 +203,27 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
       const uint32_t par = it & 1u;
       const float* const lat_u = P.lat + (int64_t)b * 256 * E + (int64_t)kap * AF_BS;
       float* const f_u = P.f + (int64_t)b * 256 * E + (int64_t)kap * AF_BS;
+      const bool tr = P.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+      long long* const trow_t = P.trace + (int64_t)it * 8;
+      if (tr) trow_t[0] = clock64();
 
       // ---------------- phase A: GroupNorm-1 + rfft2 -> operand tile X (two passes of 64 channels) ----------------
       {
         const int c = (warp & 1) * 32 + lane, task = warp >> 1;                       // channel in pass, task 0..7
-        const uint32_t scr = smem0 + AF_OFF_SCR;                                      // float2 [16 p][8 kc][64 c]
-        uint32_t sw[8];
+        float2* const R = reinterpret_cast<float2*>(S + AF_OFF_SCR);                  // [16 p][8 kc][64 c]
+        // second pass of this unit: pull its 64 KB towards L2 while the first pass computes (one 128 B line per thread)
+        prefetch_l2(lat_u + (int64_t)(threadIdx.x >> 1) * E + 64 + (threadIdx.x & 1) * 32);
+        // 128B-swizzle byte offset of this thread's channel inside a row whose index is j modulo 8, plus that row
+        uint32_t swr[8];
 #pragma unroll
-        for (int jx = 0; jx < 8; ++jx) sw[jx] = ((((uint32_t)c >> 3) ^ (uint32_t)jx) << 4) + ((uint32_t)c & 7u) * 2u;
+        for (int jx = 0; jx < 8; ++jx)
+          swr[jx] = ((((uint32_t)c >> 3) ^ (uint32_t)jx) << 4) + ((uint32_t)c & 7u) * 2u + (uint32_t)jx * 128u + (uint32_t)task * 2048u;
 #pragma unroll 1
         for (int cp = 0; cp < 2; ++cp) {
           const int chb = cp * 64 + c;
           float sc = 1.f, sh = 0.f;
           gn_affine_ref(P.gn, b, kap * AF_BS + chb, sc, sh);
-          {   // A1: row pair `task`
+          {   // A1: row pair `task`; the halving of the two-for-one untangling is folded into A2's normalisation
             float zr[16], zi[16];
             const float* ap = lat_u + (int64_t)(2 * task) * 16 * E + chb;
 #pragma unroll
@@ -209,14 +234,15 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
 #pragma unroll
             for (int q = 0; q < 16; ++q) { zr[q] = fmaf(zr[q], sc, sh); zi[q] = fmaf(zi[q], sc, sh); }
             fft_reg<16, -1>(zr, zi);
-            const uint32_t r0 = scr + (uint32_t)(((2 * task) * 8) * 64 + c) * 8u, r1 = r0 + 8u * 64u * 8u;
-            sts_f2(r0, zr[0], zr[8]);
-            sts_f2(r1, zi[0], zi[8]);
+            float2* r0 = R + ((2 * task) * 8) * 64 + c;
+            float2* r1 = r0 + 8 * 64;
+            r0[0] = make_float2(zr[0], zr[8]);
+            r1[0] = make_float2(zi[0], zi[8]);
 #pragma unroll
             for (int k = 1; k < 8; ++k) {
               const int kn = 16 - k;
-              sts_f2(r0 + (uint32_t)k * 64u * 8u, 0.5f * (zr[k] + zr[kn]), 0.5f * (zi[k] - zi[kn]));
-              sts_f2(r1 + (uint32_t)k * 64u * 8u, 0.5f * (zi[k] + zi[kn]), -0.5f * (zr[k] - zr[kn]));
+              r0[k * 64] = make_float2(zr[k] + zr[kn], zi[k] - zi[kn]);          // 2 x (spectrum of row 2*task)
+              r1[k * 64] = make_float2(zi[k] + zi[kn], zr[kn] - zr[k]);          // 2 x (spectrum of row 2*task + 1)
             }
           }
           named_bar_sync(1, AF_CTHREADS);
@@ -224,102 +250,126 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
             float zr[16], zi[16];
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-              const float2 v = lds_f2(scr + (uint32_t)((p * 8 + task) * 64 + c) * 8u);
+              const float2 v = R[(p * 8 + task) * 64 + c];
               zr[p] = v.x; zi[p] = v.y;
             }
             fft_reg<16, -1>(zr, zi);
-            const float norm = 1.0f / 16.0f;
-            const uint32_t re_hi = smem0 + (uint32_t)(cp * 2) * AF_PLANE, im_hi = smem0 + (uint32_t)((2 + cp) * 2) * AF_PLANE;
-            auto put = [&](uint32_t row_off, int k1, float re, float im) {   // row_off = byte offset of row (k2*16) in a plane
-              const uint32_t o = row_off + (uint32_t)k1 * 128u + sw[k1 & 7];
-              __half hi, lo;
-              hl_split(re, hi, lo);
-              sts_u16(re_hi + o, hi); sts_u16(re_hi + AF_PLANE + o, lo);
-              hl_split(im, hi, lo);
-              sts_u16(im_hi + o, hi); sts_u16(im_hi + AF_PLANE + o, lo);
-            };
+            uint8_t* const re_hi = S + (uint32_t)(cp * 2) * AF_PLANE;                  // k-block cp (re); im: k-block 2 + cp
+            constexpr uint32_t IM = 4u * AF_PLANE, LO = AF_PLANE;
             if (task > 0) {
-              const uint32_t ro = (uint32_t)task * 2048u;
+              const float norm = 0.5f / 16.0f;
 #pragma unroll
-              for (int k1 = 0; k1 < 16; ++k1) put(ro, k1, zr[k1] * norm, zi[k1] * norm);
+              for (int k1 = 0; k1 < 16; ++k1) {
+                uint8_t* const o = re_hi + swr[k1 & 7] + (k1 >> 3) * 1024;
+                __half hi, lo;
+                hl_split(zr[k1] * norm, hi, lo);
+                *reinterpret_cast<__half*>(o) = hi; *reinterpret_cast<__half*>(o + LO) = lo;
+                hl_split(zi[k1] * norm, hi, lo);
+                *reinterpret_cast<__half*>(o + IM) = hi; *reinterpret_cast<__half*>(o + IM + LO) = lo;
+              }
             } else {
               // F = FFT(col_0 + i col_8) -> X_0[k1] = (F[k1] + conj F[-k1]) / 2,  X_8[k1] = (F[k1] - conj F[-k1]) / 2i
+              const float norm = 0.5f / 16.0f;
 #pragma unroll
               for (int k1 = 0; k1 < 16; ++k1) {
                 const int kn = (16 - k1) & 15;
-                put(0u, k1, 0.5f * (zr[k1] + zr[kn]) * norm, 0.5f * (zi[k1] - zi[kn]) * norm);
-                put(8u * 2048u, k1, 0.5f * (zi[k1] + zi[kn]) * norm, -0.5f * (zr[k1] - zr[kn]) * norm);
+                uint8_t* const o = re_hi + swr[k1 & 7] + (k1 >> 3) * 1024;           // task == 0: row k1 (k2 = 0)
+                __half hi, lo;
+                hl_split((zr[k1] + zr[kn]) * norm, hi, lo);
+                *reinterpret_cast<__half*>(o) = hi; *reinterpret_cast<__half*>(o + LO) = lo;
+                hl_split((zi[k1] - zi[kn]) * norm, hi, lo);
+                *reinterpret_cast<__half*>(o + IM) = hi; *reinterpret_cast<__half*>(o + IM + LO) = lo;
+                uint8_t* const o8 = o + 8 * 2048;                                    // row 128 + k1 (k2 = 8)
+                hl_split((zi[k1] + zi[kn]) * norm, hi, lo);
+                *reinterpret_cast<__half*>(o8) = hi; *reinterpret_cast<__half*>(o8 + LO) = lo;
+                hl_split((zr[kn] - zr[k1]) * norm, hi, lo);
+                *reinterpret_cast<__half*>(o8 + IM) = hi; *reinterpret_cast<__half*>(o8 + IM + LO) = lo;
               }
             }
           }
           if (cp == 0) named_bar_sync(1, AF_CTHREADS);       // the scratch is rewritten by the second pass
         }
       }
-      tc_fence_before();            // this unit's TMEM reads of the previous iteration precede the new MMAs
+      tc_fence_before();            // this warp's TMEM reads of the previous unit precede the new MMAs
       fence_proxy_async();          // generic-proxy operand writes -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(XRDY);
+      if (tr) trow_t[1] = clock64();
 
       if (P.dbg) {                  // test hook: image of the X operand tile (E1 overwrites it: barrier on both sides)
         named_bar_sync(1, AF_CTHREADS);
         float* dst = P.dbg + (int64_t)u * (2 * AF_OPER / 4);
-        for (uint32_t i = threadIdx.x; i < AF_OPER / 4; i += AF_CTHREADS) dst[i] = reinterpret_cast<const float*>(smem_gen)[i];
+        for (uint32_t i = threadIdx.x; i < AF_OPER / 4; i += AF_CTHREADS) dst[i] = reinterpret_cast<const float*>(S)[i];
         named_bar_sync(1, AF_CTHREADS);
+      }
+      // next unit of this CTA: pull its first 64 channels towards L2 while the tensor core works (one line per thread)
+      if (u + (int)gridDim.x < units) {
+        const int un = u + (int)gridDim.x;
+        prefetch_l2(P.lat + (int64_t)(un / nb) * 256 * E + (int64_t)(un % nb) * AF_BS + (int64_t)(threadIdx.x >> 1) * E + (threadIdx.x & 1) * 32);
       }
 
       // ---------------- E1: layer-1 accumulators -> + b1 -> act -> split fp16 -> operand tile O1 ----------------
+      // All 16 warps convert the real half, then the imaginary half; slot sl of a lane quarter owns 36 of the 144 modes.
       {
-        const int part = sl >> 1, mb = (sl & 1) * 72;                                 // re | im accumulator, first mode
         const int j = q4 * 32 + lane;
-        const float bias = __ldg(bias_all + ((int64_t)(0 * nb + kap) * 2 + part) * AF_BS + j);
-        const uint32_t kblk = (uint32_t)(part * 2 + (q4 >> 1));
         const uint32_t chunk = (uint32_t)((q4 & 1) * 4 + (lane >> 3));
-        uint32_t sw[8];
+        const int mb = sl * 36;                                                       // first mode; mb & 7 = 4 * (sl & 1)
+        uint32_t swr[8];
 #pragma unroll
-        for (int jx = 0; jx < 8; ++jx) sw[jx] = ((chunk ^ (uint32_t)jx) << 4) + ((uint32_t)lane & 7u) * 2u;
-        const uint32_t o_hi = smem0 + kblk * 2u * AF_PLANE + (uint32_t)mb * 128u, o_lo = o_hi + AF_PLANE;
-        const uint32_t tcol = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(part * AF_MODES + mb);
+        for (int jx = 0; jx < 8; ++jx) {
+          const uint32_t rj = (uint32_t)((jx + 4 * (sl & 1)) & 7);                    // row index modulo 8 of local row jx
+          swr[jx] = ((chunk ^ rj) << 4) + ((uint32_t)lane & 7u) * 2u + (uint32_t)(mb + jx) * 128u;
+        }
         mbar_wait(M1DONE, par);
         tc_fence_after();
+        if (tr) trow_t[2] = clock64();
 #pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-          uint32_t v[3][8];
-          tmem_ld8(tcol + (uint32_t)(r * 24), v[0]);
-          tmem_ld8(tcol + (uint32_t)(r * 24 + 8), v[1]);
-          tmem_ld8(tcol + (uint32_t)(r * 24 + 16), v[2]);
-          tmem_ld_wait();
-          const uint32_t oh = o_hi + (uint32_t)(r * 24) * 128u, ol = o_lo + (uint32_t)(r * 24) * 128u;
+        for (int part = 0; part < 2; ++part) {
+          const float bias = __ldg(bias_all + ((int64_t)(0 * nb + kap) * 2 + part) * AF_BS + j);
+          uint8_t* const o_hi = S + (uint32_t)((part * 2 + (q4 >> 1)) * 2) * AF_PLANE;
+          const uint32_t tcol = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(part * AF_MODES + mb);
+          uint32_t v[36];
+          {
+            uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
+            uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
+            uint32_t (&v2)[4] = *reinterpret_cast<uint32_t (*)[4]>(&v[32]);
+            tmem_ld16(tcol, v0);
+            tmem_ld16(tcol + 16u, v1);
+            tmem_ld4(tcol + 32u, v2);
+            tmem_ld_wait();
+          }
 #pragma unroll
-          for (int gi = 0; gi < 3; ++gi)
-#pragma unroll
-            for (int uu = 0; uu < 8; ++uu) {
-              float x = fmaf(__uint_as_float(v[gi][uu]), inv_s1, bias);
-              x = ACT_MODE == 1 ? gelu_select(x) : act_apply(x, P.act);
-              __half hi, lo;
-              hl_split(x, hi, lo);
-              const uint32_t o = (uint32_t)(gi * 8 + uu) * 128u + sw[uu];
-              sts_u16(oh + o, hi);
-              sts_u16(ol + o, lo);
-            }
+          for (int i = 0; i < 36; ++i) {
+            float x = fmaf(__uint_as_float(v[i]), inv_s1, bias);
+            x = ACT_MODE == 1 ? gelu_select(x) : act_apply(x, P.act);
+            __half hi, lo;
+            hl_split(x, hi, lo);
+            uint8_t* const o = o_hi + swr[i & 7] + (i >> 3) * 1024;
+            *reinterpret_cast<__half*>(o) = hi;
+            *reinterpret_cast<__half*>(o + AF_PLANE) = lo;
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(part == 0 ? O1RE : O1IM);
         }
       }
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(O1RDY);
+      if (tr) trow_t[3] = clock64();
 
-      if (P.dbg) {                  // test hook: image of the O1 operand tile (the inverse transform reuses the tile)
+      if (P.dbg) {                  // test hook: image of the O1 operand tile (read while layer 2 reads it, before E2 reuses it)
         named_bar_sync(1, AF_CTHREADS);
         float* dst = P.dbg + (int64_t)u * (2 * AF_OPER / 4) + AF_OPER / 4;
-        for (uint32_t i = threadIdx.x; i < AF_OPER / 4; i += AF_CTHREADS) dst[i] = reinterpret_cast<const float*>(smem_gen)[i];
+        for (uint32_t i = threadIdx.x; i < AF_OPER / 4; i += AF_CTHREADS) dst[i] = reinterpret_cast<const float*>(S)[i];
         named_bar_sync(1, AF_CTHREADS);
       }
 
       // ---------------- E2: layer-2 accumulators -> inverse transforms -> + skip -> f, GroupNorm-2 statistics -----
       const int j = q4 * 32 + lane;                                                   // channel in block = TMEM lane
-      const uint32_t zs = smem0;                                                      // float2 [16 p][8 kc][128 j] over the dead operand
+      float2* const Z = reinterpret_cast<float2*>(S);                                 // [16 p][8 kc][128 j] over the dead operand
+      // the skip rows of this thread's first row pair: requested before the wait, consumed in E2b
       mbar_wait(M2DONE, par);
       tc_fence_after();
+      if (tr) trow_t[4] = clock64();
       {
         const float b2r = __ldg(bias_all + ((int64_t)(1 * nb + kap) * 2 + 0) * AF_BS + j);
         const float b2i = __ldg(bias_all + ((int64_t)(1 * nb + kap) * 2 + 1) * AF_BS + j);
@@ -330,8 +380,8 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
           float zr[16], zi[16];
           {
             uint32_t rr[16], ri[16];
-            tmem_ld16(trow + AF_TCOL_RE + (uint32_t)(kc * 16), rr);
-            tmem_ld16(trow + AF_TCOL_IM + (uint32_t)(kc * 16), ri);
+            tmem_ld16(trow + AF_T_RE + (uint32_t)(kc * 16), rr);
+            tmem_ld16(trow + AF_T_IM2 + (uint32_t)(kc * 16), ri);
             tmem_ld_wait();
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) {
@@ -343,8 +393,8 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
             // Nyquist column (k2 = 8), then pack the Hermitian parts: W = Herm(col_0) + i Herm(col_8)
             // (torch.fft.irfft2 ignores the imaginary part of the k1-inverse of these two columns)
             uint32_t rr[16], ri[16];
-            tmem_ld16(trow + AF_TCOL_RE + 128u, rr);
-            tmem_ld16(trow + AF_TCOL_IM + 128u, ri);
+            tmem_ld16(trow + AF_T_RE + 128u, rr);
+            tmem_ld16(trow + AF_T_IM2 + 128u, ri);
             tmem_ld_wait();
             float wr[16], wi[16];
 #pragma unroll
@@ -361,12 +411,14 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
             for (int k1 = 0; k1 < 16; ++k1) { zr[k1] = wr[k1]; zi[k1] = wi[k1]; }
           }
           fft_reg<16, +1>(zr, zi);
+          float2* zo = Z + kc * 128 + j;
 #pragma unroll
-          for (int p = 0; p < 16; ++p) sts_f2(zs + (uint32_t)((p * 8 + kc) * 128 + j) * 8u, zr[p], zi[p]);
+          for (int p = 0; p < 16; ++p) zo[p * 8 * 128] = make_float2(zr[p], zi[p]);
         }
       }
       tc_fence_before();
       named_bar_sync(1, AF_CTHREADS);                      // Z complete
+      if (tr) trow_t[5] = clock64();
       {
         float sc = 1.f, sh = 0.f;
         gn_affine_ref(P.gn, b, kap * AF_BS + j, sc, sh);
@@ -383,15 +435,16 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
             k1v[q] = __ldg(ap + (int64_t)(16 + q) * E);
           }
           float zr[16], zi[16];
-          const uint32_t za = zs + (uint32_t)(((2 * pr) * 8) * 128 + j) * 8u, zb = za + 8u * 128u * 8u;
+          const float2* za = Z + ((2 * pr) * 8) * 128 + j;
+          const float2* zb = za + 8 * 128;
           {
-            const float2 A = lds_f2(za), Bv = lds_f2(zb);
+            const float2 A = za[0], Bv = zb[0];
             zr[0] = A.x; zi[0] = Bv.x;                 // c2r ignores Im of the DC and Nyquist columns
             zr[8] = A.y; zi[8] = Bv.y;
           }
 #pragma unroll
           for (int k = 1; k < 8; ++k) {
-            const float2 A = lds_f2(za + (uint32_t)k * 128u * 8u), Bv = lds_f2(zb + (uint32_t)k * 128u * 8u);
+            const float2 A = za[k * 128], Bv = zb[k * 128];
             zr[k] = A.x - Bv.y; zi[k] = A.y + Bv.x;
             zr[16 - k] = A.x + Bv.y; zi[16 - k] = -A.y + Bv.x;
           }
@@ -417,6 +470,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
         }
       }
       named_bar_sync(1, AF_CTHREADS);                      // Z (the operand tile) is free for the next unit's spectrum
+      if (tr) trow_t[6] = clock64();
     }
   }
 
@@ -483,6 +537,7 @@ __global__ void af_pack_kernel(const float* __restrict__ w1, const float* __rest
 }
 
 int g_fused_mode = -1;     // -1 auto (fused when supported), 0 never
+long long* g_fused_trace = nullptr;
 
 }  // namespace
 }  // namespace dpot
@@ -490,6 +545,7 @@ int g_fused_mode = -1;     // -1 auto (fused when supported), 0 never
 using namespace dpot;
 
 extern "C" void dpot_afno_set_fused(int32_t mode) { dpot::g_fused_mode = mode; }
+extern "C" void dpot_afno_fused_set_trace(long long* dev_buf) { dpot::g_fused_trace = dev_buf; }
 
 extern "C" int dpot_afno_fused_supported(int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, int32_t groups) {
   if (dpot::g_fused_mode == 0 || !tc_device_ok()) return 0;
@@ -528,27 +584,25 @@ extern "C" int dpot_afno_fused(const float* lat, const double* stats1, const flo
                "dpot_afno_fused: geometry h=%d E=%d nb=%d groups=%d is not served by the fused mixer", h, E, nb, groups);
   DPOT_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0, DPOT_E_ALIGN, "dpot_afno_fused: packed must be 16-byte aligned");
   AfArgs P;
-  P.lat = lat; P.f = f; P.packed = packed; P.stats2 = stats2; P.dbg = dbg;
+  P.lat = lat; P.f = f; P.packed = packed; P.stats2 = stats2; P.dbg = dbg; P.trace = g_fused_trace;
   P.gn = make_gn_ref(stats1, gamma1, beta1, groups, eps, E, (int64_t)h * h);
   P.B = B; P.E = E; P.nb = nb; P.act = act; P.groups = groups;
   const int units = B * nb, sms = sm_count_cur();
   const int grid = units < sms ? units : sms;
   cudaStream_t st = as_stream(stream);
-  if (act == DPOT_ACT_GELU) {
-    static DevOnce attr;
-    if (attr.need()) {
-      DPOT_CUDA(cudaFuncSetAttribute(afno_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_SMEM));
-      attr.done();
-    }
-    DPOT_CUDA(launch_pdl(afno_fused_kernel<1>, dim3(grid), dim3(AF_THREADS), AF_SMEM, st, P));
-  } else {
-    static DevOnce attr;
-    if (attr.need()) {
-      DPOT_CUDA(cudaFuncSetAttribute(afno_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_SMEM));
-      attr.done();
-    }
-    DPOT_CUDA(launch_pdl(afno_fused_kernel<2>, dim3(grid), dim3(AF_THREADS), AF_SMEM, st, P));
-  }
+#define DPOT_AF_LAUNCH(AM, ES)                                                                                         \
+  do {                                                                                                                 \
+    static DevOnce attr;                                                                                               \
+    if (attr.need()) {                                                                                                 \
+      DPOT_CUDA(cudaFuncSetAttribute(afno_fused_kernel<AM, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AF_SMEM)); \
+      attr.done();                                                                                                     \
+    }                                                                                                                  \
+    DPOT_CUDA(launch_pdl(afno_fused_kernel<AM, ES>, dim3(grid), dim3(AF_THREADS), AF_SMEM, st, P));                    \
+  } while (0)
+#define DPOT_AF_E(AM) do { if (E == 1024) DPOT_AF_LAUNCH(AM, 1024); else if (E == 512) DPOT_AF_LAUNCH(AM, 512); else DPOT_AF_LAUNCH(AM, 0); } while (0)
+  if (act == DPOT_ACT_GELU) DPOT_AF_E(1); else DPOT_AF_E(2);
+#undef DPOT_AF_E
+#undef DPOT_AF_LAUNCH
   DPOT_LAUNCH_CHECK("afno_fused_kernel");
   return 0;
 }

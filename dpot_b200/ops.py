@@ -362,8 +362,76 @@ def ring_insert(im, ring, pred=None, slot0=0, step=0):
 
 
 @_on_device
+def grad_sqnorm(grads, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sum of squares over a list of gradient tensors -> one device double (no host sync): the norm half of
+    torch.nn.utils.clip_grad_norm_ (train_temporal.py:228)."""
+    grads = [g for g in grads if g is not None]
+    _need_cuda(*grads)
+    n = len(grads)
+    if out is None:
+        out = torch.zeros(1, device=grads[0].device if n else "cuda", dtype=torch.float64)
+    if n == 0:
+        return out.zero_()
+    ga = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+    na = (C.c_int64 * n)(*[g.numel() for g in grads])
+    check(_lib.load().dpot_grad_sqnorm(ga, na, n, ptr(out), _stream()), "dpot_grad_sqnorm")
+    return out
+
+
+@_on_device
+def noise_inject(x: torch.Tensor, scale: float, seed: int, offset: int, out: Optional[torch.Tensor] = None):
+    """out = x + scale * ||x||_{(X,Y,T)} * randn  (train_temporal.py:205); returns (out, sumsq[B, C] double)."""
+    _need_cuda(x)
+    assert x.dim() == 5 and x.is_contiguous()
+    B, X, Y, T, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    sumsq = torch.empty((B, Cc), device=x.device, dtype=torch.float64)
+    check(_lib.load().dpot_noise_inject(ptr(x), B, X * Y * T, Cc, float(scale), seed, offset, ptr(sumsq), ptr(out), _stream()),
+          "dpot_noise_inject")
+    return out, sumsq
+
+
+@_on_device
+def noise_inject_bwd(x, dy, scale, seed, offset, sumsq):
+    B, X, Y, T, Cc = x.shape
+    dx = torch.empty_like(x)
+    dot = torch.empty((B, Cc), device=x.device, dtype=torch.float64)
+    check(_lib.load().dpot_noise_inject_bwd(ptr(x), ptr(dy.contiguous()), B, X * Y * T, Cc, float(scale), seed, offset,
+                                            ptr(sumsq), ptr(dot), ptr(dx), _stream()), "dpot_noise_inject_bwd")
+    return dx
+
+
+@_on_device
+def lp_loss(x: torch.Tensor, y: torch.Tensor, mask: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
+            accumulate: bool = False):
+    """SimpleLpLoss(size_average=False)(x, y, mask) (utils/criterion.py:38-59) -> (loss[1] on the device, coef[B, C])."""
+    _need_cuda(x, y, mask)
+    assert x.shape == y.shape and x.dim() == 5 and x.is_contiguous() and y.is_contiguous()
+    B, X, Y, T, Cc = x.shape
+    if mask is not None:
+        assert tuple(mask.shape) == (B, X, Y, 1, Cc) and mask.is_contiguous()
+    partial = torch.empty((B, Cc, 3), device=x.device, dtype=torch.float64)
+    coef = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    if loss is None:
+        loss = torch.zeros(1, device=x.device, dtype=torch.float32)
+    check(_lib.load().dpot_lp_loss(ptr(x), ptr(y), ptr(mask), B, X * Y, T, Cc, ptr(partial), ptr(coef), ptr(loss),
+                                   1 if accumulate else 0, _stream()), "dpot_lp_loss")
+    return loss, coef
+
+
+@_on_device
+def lp_loss_bwd(x, y, mask, coef, gscale: Optional[torch.Tensor] = None):
+    B, X, Y, T, Cc = x.shape
+    dx = torch.empty_like(x)
+    check(_lib.load().dpot_lp_loss_bwd(ptr(x), ptr(y), ptr(mask), ptr(coef), ptr(gscale), B, X * Y, T, Cc, ptr(dx), _stream()),
+          "dpot_lp_loss_bwd")
+    return dx
+
+
+@_on_device
 def adam_step_multi(params, grads, ms, vs, vmaxs, steps, *, lr, beta1, beta2, eps, weight_decay, decoupled,
-                    grad_scale=1.0):
+                    grad_scale=1.0, grad_sqnorm=None, max_norm=0.0):
     n = len(params)
     if n == 0:
         return
@@ -376,5 +444,6 @@ def adam_step_multi(params, grads, ms, vs, vmaxs, steps, *, lr, beta1, beta2, ep
     xa = VP(*[x.data_ptr() for x in vmaxs]) if vmaxs else None
     na = (C.c_int64 * n)(*[p.numel() for p in params])
     sa = (C.c_int32 * n)(*steps)
-    check(_lib.load().dpot_adam_step_multi(pa, ga, ma, va, xa, na, n, lr, beta1, beta2, eps, weight_decay, sa,
-                                           1 if decoupled else 0, grad_scale, _stream()), "dpot_adam_step_multi")
+    check(_lib.load().dpot_adam_step_multi_clip(pa, ga, ma, va, xa, na, n, lr, beta1, beta2, eps, weight_decay, sa,
+                                                1 if decoupled else 0, grad_scale, ptr(grad_sqnorm), float(max_norm),
+                                                _stream()), "dpot_adam_step_multi")

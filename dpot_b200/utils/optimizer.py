@@ -37,6 +37,9 @@ class _FusedAdamBase(Optimizer):
             raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
         self.grad_scale = 1.0  # set to 1/world_size to fold the DDP average into the step
+        # clip_grad_norm_ folded into the step: set by dpot_b200.utils.clip.clip_grad_norm_(..., optimizer=self) --
+        # (device double holding sum g^2, max_norm); consumed (and cleared) by the next step()
+        self._pending_clip = None
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -49,6 +52,7 @@ class _FusedAdamBase(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        clip, self._pending_clip = self._pending_clip, None
         for group in self.param_groups:
             ps, gs, ms, vs, xs, steps = [], [], [], [], [], []
             beta1, beta2 = group['betas']
@@ -82,7 +86,8 @@ class _FusedAdamBase(Optimizer):
             with torch.cuda.device(ps[0].device):
                 ops.adam_step_multi(ps, gs, ms, vs, xs if group['amsgrad'] else None, steps, lr=float(group['lr']),
                                     beta1=beta1, beta2=beta2, eps=group['eps'], weight_decay=group['weight_decay'],
-                                    decoupled=self._decoupled, grad_scale=self.grad_scale)
+                                    decoupled=self._decoupled, grad_scale=self.grad_scale,
+                                    grad_sqnorm=clip[0] if clip else None, max_norm=clip[1] if clip else 0.0)
             # the kernel updates the parameters through raw pointers: bump their autograd version counters so that
             # everything keyed on (data_ptr, _version) -- the inference engine's packed-weight arena, captured rollout
             # graphs, autograd's saved-tensor checks -- sees the change, exactly as p.addcdiv_() would have

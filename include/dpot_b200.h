@@ -207,6 +207,9 @@ DPOT_API int     dpot_afno_fused(const float* lat, const double* stats1, const f
                                  int32_t act, float* f, double* stats2, float* dbg, void* stream);
 /* knob (tests / A-B measurements): -1 = fused whenever supported (default), 0 = never */
 DPOT_API void    dpot_afno_set_fused(int32_t mode);
+/* profiling aid: device buffer of 8 int64 per unit of CTA 0 receiving clock64() at the phase boundaries of the fused
+   mixer (start, spectrum ready, layer-1 done, hidden ready, layer-2 done, column inverse done, unit done); NULL = off */
+DPOT_API void    dpot_afno_fused_set_trace(long long* dev_buf);
 
 /* GroupNorm-by-reference variants (the f16-split inference pipeline): instead of finalised scale/shift tables the
    kernels take the raw statistics [B, groups, 2] (double sum, sum of squares) plus gamma/beta and derive the
@@ -362,6 +365,42 @@ DPOT_API int dpot_adam_step_multi(float* const* p, const float* const* g, float*
                          float* const* vmax, const int64_t* n, int32_t count, double lr, double beta1,
                          double beta2, double eps, double weight_decay, const int32_t* steps,
                          int32_t decoupled, double grad_scale, void* stream);
+/* the same with torch.nn.utils.clip_grad_norm_ (train_temporal.py:228) folded in: grad_sqnorm = device double with the
+   sum of squares of ALL gradients (dpot_grad_sqnorm), the kernel scales every gradient by
+   grad_scale * min(1, max_norm / (grad_scale * sqrt(sum) + 1e-6)) on load -- gradients are read once per step and never
+   rewritten.  grad_sqnorm = NULL: no clipping. */
+DPOT_API int dpot_adam_step_multi_clip(float* const* p, const float* const* g, float* const* m, float* const* v,
+                                       float* const* vmax, const int64_t* n, int32_t count, double lr, double beta1,
+                                       double beta2, double eps, double weight_decay, const int32_t* steps,
+                                       int32_t decoupled, double grad_scale, const double* grad_sqnorm, double max_norm,
+                                       void* stream);
+/* global gradient norm: out_sq[0] = sum over `count` tensors of sum g^2 (double accumulation; zeroed by the call).
+   Replaces the norm computation of clip_grad_norm_, train_temporal.py:228. */
+DPOT_API int dpot_grad_sqnorm(const float* const* g, const int64_t* n, int32_t count, double* out_sq, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The autoregressive training loop around model(xx), train_temporal.py:201-230.
+ * Fields are x[B, X, Y, T, C] with the channel innermost; npos = X*Y*T, nxy = X*Y; C <= 16.
+ * ---------------------------------------------------------------------------------------- */
+/* out[b, c] = sum over (X, Y, T) of x^2   (double; zeroed by the call) */
+DPOT_API int dpot_chan_sumsq(const float* x, int32_t B, int64_t npos, int32_t C, double* out, void* stream);
+/* noise injection, train_temporal.py:205:  out = x + scale * sqrt(sumsq[b, c]) * N(0, 1), normals from a counter-based
+   Philox-4x32-10 stream (seed, offset) -- no generator state; sumsq[B, C] (double) is written by the call and kept for
+   the backward pass.  out may alias x. */
+DPOT_API int dpot_noise_inject(const float* x, int32_t B, int64_t npos, int32_t C, float scale, uint64_t seed,
+                               uint64_t offset, double* sumsq, float* out, void* stream);
+/* its backward (the reference differentiates through the norm):  dx = dy + scale * x / ||x||_bc * sum_pos(dy * eps),
+   eps regenerated from (seed, offset); dot[B, C] (double) is scratch. */
+DPOT_API int dpot_noise_inject_bwd(const float* x, const float* dy, int32_t B, int64_t npos, int32_t C, float scale,
+                                   uint64_t seed, uint64_t offset, const double* sumsq, double* dot, float* dx, void* stream);
+/* SimpleLpLoss(size_average=False).forward(x, y, mask), utils/criterion.py:38-59: loss[0] (=|+=, `accumulate`)
+   sum_b ( sum_c ||(x - y) m||_2 / (||y m||_2 + 1e-8) ) / #active channels of b;  mask[B, X, Y, 1, C] or NULL.
+   partial[B, C, 3] (double) is scratch; coef[B, C] receives the backward coefficients. */
+DPOT_API int dpot_lp_loss(const float* x, const float* y, const float* mask, int32_t B, int64_t nxy, int32_t T, int32_t C,
+                          double* partial, float* coef, float* loss, int32_t accumulate, void* stream);
+/* dx = gscale[0] * coef[b, c] * m^2 * (x - y)   (gscale = upstream gradient of the scalar loss on the device, NULL = 1) */
+DPOT_API int dpot_lp_loss_bwd(const float* x, const float* y, const float* mask, const float* coef, const float* gscale,
+                              int32_t B, int64_t nxy, int32_t T, int32_t C, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-model inference forward: DPOTNet.forward under no_grad (models/dpot.py:364-403).

@@ -1,0 +1,136 @@
+"""Kernels either side of model(xx) in the training loop (csrc/train_fused.cu, adam.cu): global gradient norm + clip folded
+into the fused Adam (train_temporal.py:228-229), noise injection (:205), SimpleLpLoss forward / backward
+(utils/criterion.py:38-59).  Oracles: torch CPU / numpy restatements of the reference lines, the golden loss fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dpot_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_grad_sqnorm_ragged_tensors():
+    from dpot_b200 import ops
+    rng = np.random.default_rng(0)
+    sizes = [1, 3, 7, 4096, 32768 + 5, 1 << 20, 0, 513] + [17 * k + 1 for k in range(70)]
+    gs = [torch.from_numpy(rng.standard_normal(n).astype(np.float32) * (1 + i % 5)).cuda() for i, n in enumerate(sizes)]
+    want = sum(float((g.double() ** 2).sum()) for g in gs)
+    got = float(ops.grad_sqnorm(gs))
+    assert got == pytest.approx(want, rel=1e-6)
+    # unaligned views
+    base = torch.from_numpy(rng.standard_normal(1000).astype(np.float32)).cuda()
+    views = [base[1:400], base[401:999]]
+    assert float(ops.grad_sqnorm(views)) == pytest.approx(sum(float((v.double() ** 2).sum()) for v in views), rel=1e-6)
+
+
+@pytest.mark.parametrize("max_norm", [1e4, 0.05])
+def test_clip_folded_into_adam_matches_torch_clip_then_reference_adam(max_norm):
+    """clip_grad_norm_ + Adam.step of the reference loop vs. our deferred clip inside the fused Adam kernel."""
+    from dpot_b200.utils.clip import clip_grad_norm_
+    from dpot_b200.utils.optimizer import Adam
+    rng = np.random.default_rng(1)
+    shapes = [(33,), (64, 7), (1024,), (5, 5, 5), (2, 300)]
+    p0 = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    ps = [torch.nn.Parameter(torch.from_numpy(a.copy()).cuda()) for a in p0]
+    opt = Adam(ps, lr=2e-3, betas=(0.9, 0.9), weight_decay=1e-6)
+    pr = [a.copy() for a in p0]
+    ms = [np.zeros_like(a) for a in p0]
+    vs = [np.zeros_like(a) for a in p0]
+    for step in (1, 2, 3):
+        gs = [rng.standard_normal(s).astype(np.float32) * 0.01 * step for s in shapes]
+        for p, g in zip(ps, gs):
+            p.grad = torch.from_numpy(g.copy()).cuda()
+        total = clip_grad_norm_(ps, max_norm, optimizer=opt)
+        opt.step()
+        tn = np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in gs))
+        assert float(total) == pytest.approx(tn, rel=1e-6)
+        coef = min(1.0, max_norm / (np.float32(tn) + np.float32(1e-6)))
+        for a, g, m, v in zip(pr, gs, ms, vs):
+            O.adam_step(a, (g * np.float32(coef)).astype(np.float32), m, v, step, lr=2e-3, beta1=0.9, beta2=0.9, eps=1e-8,
+                        weight_decay=1e-6)
+        for p, g in zip(ps, gs):      # deferred clipping leaves .grad untouched
+            assert torch.equal(p.grad.cpu(), torch.from_numpy(g))
+    for p, a in zip(ps, pr):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), a, rtol=3e-6, atol=3e-7)
+    # without an optimizer: torch semantics (in-place scaling)
+    for p, s in zip(ps, shapes):
+        p.grad = torch.ones(s, device="cuda")
+    n_el = sum(int(np.prod(s)) for s in shapes)
+    total = clip_grad_norm_(ps, 1.0)
+    assert float(total) == pytest.approx(np.sqrt(n_el), rel=1e-6)
+    assert float(ps[0].grad[0]) == pytest.approx(1.0 / (np.sqrt(n_el) + 1e-6), rel=1e-5)
+
+
+def test_noise_injection_statistics_and_backward():
+    """xx + s * ||xx||_{(X,Y,T)} * randn (train_temporal.py:205): moments per (sample, channel), determinism in
+    (seed, offset), independence across offsets, and the backward through the norm against torch autograd."""
+    from dpot_b200 import ops
+    rng = np.random.default_rng(2)
+    B, X, Y, T, C = 3, 64, 64, 10, 4
+    x = torch.from_numpy((rng.standard_normal((B, X, Y, T, C)) * np.array([1.0, 2.0, 0.5, 3.0])).astype(np.float32)).cuda()
+    s = 0.05
+    y, sumsq = ops.noise_inject(x, s, seed=1234, offset=7)
+    y2, _ = ops.noise_inject(x, s, seed=1234, offset=7)
+    y3, _ = ops.noise_inject(x, s, seed=1234, offset=8)
+    assert torch.equal(y, y2) and not torch.equal(y, y3)
+    nrm = torch.sum(x.double() ** 2, dim=(1, 2, 3), keepdim=True) ** 0.5
+    np.testing.assert_allclose(sumsq.cpu().numpy(), (nrm ** 2).reshape(B, C).cpu().numpy(), rtol=1e-6)
+    eps = ((y.double() - x.double()) / (s * nrm))                       # should be N(0, 1)
+    eps3 = ((y3.double() - x.double()) / (s * nrm))
+    n = X * Y * T
+    m = eps.mean(dim=(1, 2, 3)).abs().max().item()
+    v = eps.var(dim=(1, 2, 3)).sub(1).abs().max().item()
+    assert m < 5 / np.sqrt(n) and v < 8 * np.sqrt(2 / n), (m, v)
+    k4 = (eps ** 4).mean().item()
+    assert abs(k4 - 3.0) < 0.05                                        # Gaussian kurtosis
+    assert abs((eps * eps3).mean().item()) < 5 / np.sqrt(B * n * C)    # streams of different offsets are uncorrelated
+    assert abs((eps[..., 0] * eps[..., 1]).mean().item()) < 5 / np.sqrt(B * n)
+    # backward: d/dx of x + s * ||x|| * eps with eps constant
+    dy = torch.from_numpy(rng.standard_normal((B, X, Y, T, C)).astype(np.float32)).cuda()
+    dx = ops.noise_inject_bwd(x, dy, s, 1234, 7, sumsq)
+    xr = x.double().requires_grad_(True)
+    yr = xr + s * torch.sum(xr ** 2, dim=(1, 2, 3), keepdim=True) ** 0.5 * eps.detach()
+    yr.backward(dy.double())
+    assert O.rel_l2(dx.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-6
+
+
+def test_simple_lp_loss_forward_backward():
+    from dpot_b200 import ops
+    z = np.load(os.path.join(G, "train_grads_tiny.npz"))
+    a, b, mk = (torch.from_numpy(z[k]).cuda() for k in ("loss.a", "loss.b", "loss.mask"))
+    loss, _ = ops.lp_loss(a, b, mk)
+    assert float(loss) == pytest.approx(float(z["loss.masked"]), rel=2e-6)
+    loss, _ = ops.lp_loss(a, b, None)
+    assert float(loss) == pytest.approx(float(z["loss.nomask"]), rel=2e-6)
+    # accumulate over AR steps + backward against torch autograd of the restated formula
+    rng = np.random.default_rng(3)
+    B, X, T, C = 4, 32, 2, 4
+    x = torch.from_numpy(rng.standard_normal((B, X, X, T, C)).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.standard_normal((B, X, X, T, C)).astype(np.float32)).cuda()
+    msk = torch.ones((B, X, X, 1, C), device="cuda")
+    msk[1, ..., 2] = 0
+    msk[3, ..., :3] = 0
+
+    def ref(xx):
+        n = xx.shape[0]
+        xm, ym = xx * msk, y.double() * msk
+        nch = msk.sum(dim=(1, 2, 3)).count_nonzero(dim=-1)
+        d = torch.norm(xm.reshape(n, -1, C) - ym.reshape(n, -1, C), 2, dim=1)
+        yn = torch.norm(ym.reshape(n, -1, C), 2, dim=1) + 1e-8
+        return torch.sum(torch.sum(d / yn, dim=-1) / nch)
+    xr = x.double().requires_grad_(True)
+    lr = ref(xr)
+    lr.backward()
+    loss, coef = ops.lp_loss(x, y, msk)
+    assert float(loss) == pytest.approx(float(lr), rel=2e-6)
+    dx = ops.lp_loss_bwd(x, y, msk, coef)
+    assert O.rel_l2(dx.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-6
+    loss2, _ = ops.lp_loss(x, y, msk, loss=loss, accumulate=True)
+    assert float(loss2) == pytest.approx(2 * float(lr), rel=2e-6)
+    g = torch.full((1,), 0.5, device="cuda")
+    assert O.rel_l2(ops.lp_loss_bwd(x, y, msk, coef, g).cpu().numpy(), 0.5 * xr.grad.cpu().numpy()) < 2e-6
