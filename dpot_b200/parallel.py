@@ -123,10 +123,11 @@ class OverlappedGradArena:
             o += n
             if o - start >= cap:
                 self.buckets.append(dict(start=start, end=o, params=members, expect=len(members), pending=len(members),
-                                         handle=None))
+                                         handle=None, arrived=[]))
                 start, members = o, []
         if members:
-            self.buckets.append(dict(start=start, end=o, params=members, expect=len(members), pending=len(members), handle=None))
+            self.buckets.append(dict(start=start, end=o, params=members, expect=len(members), pending=len(members), handle=None,
+                                     arrived=[]))
         self.total = o
         self.buf: Optional[torch.Tensor] = None
         self.seen, self.late, self.steps, self.arrived = set(), [], 0, set()
@@ -134,6 +135,19 @@ class OverlappedGradArena:
 
     def _world(self) -> int:
         return dist.get_world_size() if dist.is_initialized() else 1
+
+    def _pack(self, b) -> None:
+        """Move the bucket's fresh gradients into their arena slots with ONE multi-tensor copy and make .grad views of
+        the arena.  (The copy is 8 B per parameter on top of the 28 B/param optimizer step -- S: 123 MB in + out, about
+        40 us per step; autograd owns the gradient buffers it hands to the hook, so writing them in place would need
+        every backward kernel to target the arena.)"""
+        ps = [p for p in b["arrived"] if p.grad is not None and p.grad.data_ptr() != self.buf[self.slots[p][1]:].data_ptr()]
+        if ps:
+            views = [self.buf[self.slots[p][1]:self.slots[p][1] + self.slots[p][2]].view_as(p) for p in ps]
+            torch._foreach_copy_(views, [p.grad for p in ps])
+            for p, v in zip(ps, views):
+                p.grad = v
+        b["arrived"] = []
 
     def _launch(self, b) -> None:
         if self._world() > 1:
@@ -159,11 +173,10 @@ class OverlappedGradArena:
             self.late.append(p)
             return
         self.arrived.add(p)
-        view = self.buf[o:o + n].view_as(p)
-        view.copy_(p.grad)
-        p.grad = view
+        b["arrived"].append(p)
         b["pending"] -= 1
         if b["pending"] == 0:
+            self._pack(b)
             self._launch(b)
 
     @torch.no_grad()
@@ -172,6 +185,8 @@ class OverlappedGradArena:
         world, gloo = self._world(), dist.is_initialized() and dist.get_backend() != "nccl"
         for b in self.buckets:
             if b["handle"] is None and any(p.grad is not None for p in b["params"]):
+                b["arrived"] = [p for p in b["params"] if p.grad is not None]
+                self._pack(b)
                 self._launch(b)
         n = 0
         for b in self.buckets:
@@ -182,11 +197,16 @@ class OverlappedGradArena:
             if world > 1 and gloo:
                 self.buf[b["start"]:b["end"]].div_(world)
             n += b["end"] - b["start"]
-        for p in self.late:
+        if self.late:                               # gradients that arrived after their bucket was on the wire: one exchange
+            flat = torch.cat([p.grad.reshape(-1) for p in self.late])
             if world > 1:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
-                p.grad.div_(world)
-            n += p.numel()
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.div_(world)
+            o = 0
+            for p in self.late:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+                o += p.numel()
+            n += flat.numel()
         # re-arm: from the second step on a bucket only waits for the parameters that really receive gradients
         self.steps += 1
         for b in self.buckets:

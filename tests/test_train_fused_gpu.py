@@ -134,3 +134,31 @@ def test_simple_lp_loss_forward_backward():
     assert float(loss2) == pytest.approx(2 * float(lr), rel=2e-6)
     g = torch.full((1,), 0.5, device="cuda")
     assert O.rel_l2(ops.lp_loss_bwd(x, y, msk, coef, g).cpu().numpy(), 0.5 * xr.grad.cpu().numpy()) < 2e-6
+
+
+def test_ar_train_step_fast_path_matches_reference_trajectory():
+    """dpot_b200.train.ar_train_step (loss kernel, deferred clip inside the fused Adam, no host sync) over the 3-step
+    reference trajectory fixture (train_temporal.py:189-230 with noise off): losses and final weights."""
+    from dpot_b200.models.dpot import DPOTNet
+    from dpot_b200.train import ar_train_step
+    from dpot_b200.utils.optimizer import Adam
+    z = np.load(os.path.join(G, "train_traj_tiny.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    m = DPOTNet(**cfg)
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in O.make_params(cfg, seed=0).items()})
+    m = m.cuda().train()
+    opt = Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.9), weight_decay=1e-6)
+    msk = torch.ones((int(z["B"]), cfg["img_size"], cfg["img_size"], 1, cfg["out_channels"]), device="cuda")
+    for it in range(3):
+        opt.param_groups[0]["lr"] = float(z["lrs"][it])
+        loss = ar_train_step(m, opt, torch.from_numpy(z["xs"][it]).cuda(), torch.from_numpy(z["ys"][it]).cuda(), msk,
+                             T_bundle=cfg["out_timesteps"], noise_scale=0.0, grad_clip=10000.0, step=it)
+        assert float(loss) == pytest.approx(float(z["losses"][it]), rel=5e-5), it
+    for k, v in m.state_dict().items():
+        ref = z["final." + k]
+        err = np.abs(v.cpu().numpy() - ref).max()
+        assert err < 2e-4 * max(1.0, np.abs(ref).max()), (k, err)
+    # with noise: the step runs, the loss stays finite and differs from the noise-free one
+    l_noise = ar_train_step(m, opt, torch.from_numpy(z["xs"][0]).cuda(), torch.from_numpy(z["ys"][0]).cuda(), msk,
+                            T_bundle=cfg["out_timesteps"], noise_scale=5e-4, grad_clip=10000.0, seed=3, step=9)
+    assert torch.isfinite(l_noise)
