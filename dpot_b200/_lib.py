@@ -42,6 +42,9 @@ class GemmArgs(C.Structure):
         ("C_pre", c_f32p), ("dact_src", c_f32p), ("dact", C.c_int32), ("c_mode", C.c_int32),
         ("a_fmt", C.c_int32), ("w_fmt", C.c_int32), ("c_fmt", C.c_int32),
         ("a_lo_off", C.c_int64), ("w_lo_off", C.c_int64), ("c_lo_off", C.c_int64),
+        ("a_trans", C.c_int32), ("w_trans", C.c_int32),
+        ("k_split", C.c_int32), ("k_chunk", C.c_int64), ("strideC_split", C.c_int64),
+        ("ld_pre", C.c_int64), ("stride_pre", C.c_int64), ("ld_dact", C.c_int64), ("stride_dact", C.c_int64),
     ]
 
 
@@ -183,7 +186,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.dpot_abi_version() != 1:
+        if lib.dpot_abi_version() != 2:
             raise DpotLibraryError("libdpot_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -32,6 +32,14 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   if (a->a_mode == DPOT_A_PATCH) { p.ph = a->pX / (a->pP > 0 ? a->pP : 1); p.pw = a->pY / (a->pP > 0 ? a->pP : 1); }
   p.C_pre = a->C_pre; p.dact_src = a->dact_src; p.dact = a->dact; p.c_mode = a->c_mode;
   p.a_fmt = a->a_fmt; p.w_fmt = a->w_fmt; p.c_fmt = a->c_fmt; p.a_lo = a->a_lo_off; p.w_lo = a->w_lo_off; p.c_lo = a->c_lo_off;
+  p.a_tr = a->a_trans; p.w_tr = a->w_trans; p.ksplit = a->k_split > 1 ? a->k_split : 1; p.kchunk = a->k_chunk; p.sC2 = a->strideC_split;
+  p.ldpre = a->ld_pre; p.sPre = a->stride_pre; p.lddact = a->ld_dact; p.sDact = a->stride_dact;
+  const bool bw_form = a->a_trans || a->w_trans || a->k_split > 1;
+  DPOT_REQUIRE(!bw_form || a->a_fmt == DPOT_FMT_HL16, DPOT_E_BADARG, "dpot_gemm: a_trans / w_trans / k_split need split-fp16 operands");
+  if (a->k_split > 1)
+    DPOT_REQUIRE(a->k_chunk > 0 && a->k_chunk % 64 == 0 && (int64_t)a->k_split * a->k_chunk >= a->K && !a->bias && !a->rowbias &&
+                 !a->residual && a->act == DPOT_ACT_NONE && !a->c_scale && !a->out_stats && !a->C_pre && !a->dact_src,
+                 DPOT_E_BADARG, "dpot_gemm: k_split needs k_chunk %% 64 == 0 covering K and a plain epilogue");
   DPOT_REQUIRE((a->a_fmt == DPOT_FMT_F32 || a->a_fmt == DPOT_FMT_HL16) && a->a_fmt == a->w_fmt, DPOT_E_BADARG,
                "dpot_gemm: a_fmt and w_fmt must both be F32 or both HL16");
   DPOT_REQUIRE(a->c_fmt == DPOT_FMT_F32 || a->c_fmt == DPOT_FMT_HL16 || a->c_fmt == DPOT_FMT_HL16G32, DPOT_E_BADARG, "dpot_gemm: bad c_fmt");
@@ -40,8 +48,13 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
                  !a->dact_src && a->c_mode == DPOT_A_PLAIN && !a->out_stats, DPOT_E_BADARG,
                  "dpot_gemm: the grouped split-fp16 output needs split-fp16 operands, N %% 32 == 0 and ldc >= 2N halves");
   if (a->c_fmt == DPOT_FMT_HL16)
-    DPOT_REQUIRE(!a->C_pre && !a->dact_src && a->c_mode == DPOT_A_PLAIN && !a->out_stats && a->c_lo_off > 0, DPOT_E_BADARG,
-                 "dpot_gemm: split-fp16 output excludes C_pre/dact_src/patch scatter/out_stats");
+    DPOT_REQUIRE(((!a->C_pre && !a->dact_src) || a->a_fmt == DPOT_FMT_HL16) && a->c_mode == DPOT_A_PLAIN && !a->out_stats && a->c_lo_off > 0,
+                 DPOT_E_BADARG, "dpot_gemm: split-fp16 output excludes patch scatter/out_stats (and C_pre/dact_src off the TC16 engine)");
+  if (a->a_fmt == DPOT_FMT_HL16 && (a->C_pre || a->dact_src)) {
+    DPOT_REQUIRE(!a->C_pre || a->ld_pre >= a->N, DPOT_E_BADARG, "dpot_gemm: C_pre on the TC16 engine needs ld_pre");
+    DPOT_REQUIRE(!a->dact_src || (a->ld_dact >= a->N && !a->residual && !a->rowbias && !a->c_scale), DPOT_E_BADARG,
+                 "dpot_gemm: dact_src on the TC16 engine needs ld_dact and excludes residual / rowbias / c_scale");
+  }
   if (a->c_mode == DPOT_A_PATCH) {
     DPOT_REQUIRE(a->a_mode == DPOT_A_PLAIN && a->pP > 0 && a->pX % a->pP == 0 && a->pY % a->pP == 0 &&
                  a->N == a->pP * a->pP * a->pC && a->batch == 1 && !a->C_pre && !a->dact_src && !a->residual,

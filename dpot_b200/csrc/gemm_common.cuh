@@ -22,6 +22,9 @@ struct GemmDev {
   double* out_stats; int st_groups, st_rps;   // fused GroupNorm statistics (tcgen05 engine only)
   float* C_pre; const float* dact_src; int dact; int c_mode;   // training extras
   int a_fmt, w_fmt, c_fmt; int64_t a_lo, w_lo, c_lo;           // DPOT_FMT_* storage (strides in halves when HL16)
+  // backward-pass forms of the f16-split engine (dpot_gemm_args ABI 2): transposed operand storage, contraction split
+  int a_tr, w_tr, ksplit; int64_t kchunk, sC2;
+  int64_t ldpre, sPre, lddact, sDact;                           // C_pre / dact_src geometry on the f16-split engine
 };
 
 // split fp16 storage (include/dpot_b200.h, DPOT_FMT_HL16): x ~= hi + lo / 2048

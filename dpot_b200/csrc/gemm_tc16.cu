@@ -56,8 +56,23 @@ struct Geo {
 };
 
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=m, N=n
-__host__ __device__ constexpr uint32_t make_idesc16(uint32_t n, uint32_t m = 128u) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// bit 15 / 16: the UMMA A (weight role) / B (token role) operand tile is MN-major (transposed storage)
+__host__ __device__ constexpr uint32_t make_idesc16(uint32_t n, uint32_t m = 128u, uint32_t a_mn = 0u, uint32_t b_mn = 0u) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// MN-major, 128B-swizzled operand tile as two-dimensional TMA boxes of (64 MN elements = 128 B) x (64 k rows) leave it:
+// the 8 x 128 B swizzle atoms of one box follow each other along k (SBO = 1024 B), the next 64 MN elements are the
+// next box (LBO = 8192 B).  One MMA (k = 16) covers two atoms: the k-step inside a stage is 2048 B.
+constexpr uint32_t MN_BOX_BYTES = 64 * 128;
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(MN_BOX_BYTES >> 4) << 16;          // leading byte offset: between 64-element MN chunks
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: between 8-row k groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 struct Tc16Params {
@@ -65,6 +80,7 @@ struct Tc16Params {
   int BA;            // activation rows per tile, multiple of 16, <= 128
   int n_tiles, m_tiles, total_tiles, kblocks;
   int dbg;           // experiment mask (dpot_tc16_set_debug): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
+  int batch;         // independent problems; total_tiles also spans the g.ksplit contraction chunks (bz = b + batch * chunk)
 };
 
 // ACT_MODE: 0 = none, 1 = GELU (erf), 2 = runtime switch.  OUT16: store the result as DPOT_FMT_HL16.
@@ -130,24 +146,43 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
         const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
         const int n0 = (nt * CG + (int)rank) * TN, m0 = mt * BA + (int)rank * rows_a;
+        const int bb = bz % P.batch, k00 = (bz / P.batch) * (int)g.kchunk;     // problem of the batch, contraction chunk
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(EMPTY(s), ph ^ 1);
           const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
+          const int k0 = k00 + kb * BKH;
           if (P.dbg & 1) {                      // experiment: the MMA pipeline alone (operands = whatever is in smem)
             if (rank == 0) mbar_arrive(FULL(s));
-          } else if (CG == 2) {
-            if (rank == 0) mbar_expect_tx(FULL(s), 2u * stage_tx);   // the leader's barrier collects both CTAs' bytes
-            const uint32_t fb = full_leader + 8u * s;
-            tma_load_3d_2cta(sb + OFF_W_HI, &mapWh, fb, kb * BKH, n0, bz);         // dims (k, n, batch)
-            tma_load_3d_2cta(sb + OFF_W_LO, &mapWl, fb, kb * BKH, n0, bz);
-            tma_load_3d_2cta(sb + OFF_A, &mapAh, fb, kb * BKH, bz, m0);            // dims (k, batch, m)
-            tma_load_3d_2cta(sb + OFF_A + a_plane, &mapAl, fb, kb * BKH, bz, m0);
           } else {
-            mbar_expect_tx(FULL(s), stage_tx);
-            tma_load_3d(sb + OFF_W_HI, &mapWh, FULL(s), kb * BKH, n0, bz);
-            tma_load_3d(sb + OFF_W_LO, &mapWl, FULL(s), kb * BKH, n0, bz);
-            tma_load_3d(sb + OFF_A, &mapAh, FULL(s), kb * BKH, bz, m0);
-            tma_load_3d(sb + OFF_A + a_plane, &mapAl, FULL(s), kb * BKH, bz, m0);
+            uint32_t fb = FULL(s);
+            if (CG == 2) {
+              if (rank == 0) mbar_expect_tx(FULL(s), 2u * stage_tx);   // the leader's barrier collects both CTAs' bytes
+              fb = full_leader + 8u * s;
+            } else {
+              mbar_expect_tx(FULL(s), stage_tx);
+            }
+            auto ld = [&](uint32_t dst, const CUtensorMap* mp, int c0, int c1, int c2) {
+              if (CG == 2) tma_load_3d_2cta(dst, mp, fb, c0, c1, c2); else tma_load_3d(dst, mp, fb, c0, c1, c2);
+            };
+            if (g.w_tr) {                       // stored [K, N]: dims (n, k, batch), two boxes of 64 channels per plane
+#pragma unroll
+              for (int j = 0; j < TN / 64; ++j) {
+                ld(sb + OFF_W_HI + j * MN_BOX_BYTES, &mapWh, n0 + 64 * j, k0, bb);
+                ld(sb + OFF_W_LO + j * MN_BOX_BYTES, &mapWl, n0 + 64 * j, k0, bb);
+              }
+            } else {
+              ld(sb + OFF_W_HI, &mapWh, k0, n0, bb);                   // dims (k, n, batch)
+              ld(sb + OFF_W_LO, &mapWl, k0, n0, bb);
+            }
+            if (g.a_tr) {                       // stored [K, M]: dims (m, k, batch), rows_a / 64 boxes per plane
+              for (int j = 0; j < rows_a / 64; ++j) {
+                ld(sb + OFF_A + j * MN_BOX_BYTES, &mapAh, m0 + 64 * j, k0, bb);
+                ld(sb + OFF_A + a_plane + j * MN_BOX_BYTES, &mapAl, m0 + 64 * j, k0, bb);
+              }
+            } else {
+              ld(sb + OFF_A, &mapAh, k0, bb, m0);                      // dims (k, batch, m)
+              ld(sb + OFF_A + a_plane, &mapAl, k0, bb, m0);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -156,8 +191,10 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (rank == 0 && elect_one()) {
-      const uint32_t idesc_2ba = make_idesc16((uint32_t)(2 * BA));         // CG 1: [hi ; lo] token rows in one MMA
-      const uint32_t idesc_ba = make_idesc16((uint32_t)BA, 128u * CG);
+      const uint32_t wmn = g.w_tr ? 1u : 0u, amn = g.a_tr ? 1u : 0u;
+      const uint32_t idesc_2ba = make_idesc16((uint32_t)(2 * BA), 128u, wmn, amn);   // CG 1: [hi ; lo] token rows in one MMA
+      const uint32_t idesc_ba = make_idesc16((uint32_t)BA, 128u * CG, wmn, amn);
+      const uint32_t w_kstep = g.w_tr ? 2048u : 32u, a_kstep = g.a_tr ? 2048u : 32u;
       int s = 0; uint32_t ph = 0; uint32_t tc = 0;
       for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++tc) {
         const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
@@ -171,14 +208,15 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
           const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
 #pragma unroll
           for (int k4 = 0; k4 < BKH / 16; ++k4) {
-            const uint64_t w_hi = make_smem_desc(sb + OFF_W_HI + k4 * 32);
-            const uint64_t w_lo = make_smem_desc(sb + OFF_W_LO + k4 * 32);
-            const uint64_t a_hi = make_smem_desc(sb + OFF_A + k4 * 32);      // CG 1: rows [0,BA) = hi, [BA,2BA) = lo
+            const uint64_t w_hi = g.w_tr ? make_smem_desc_mn(sb + OFF_W_HI + k4 * w_kstep) : make_smem_desc(sb + OFF_W_HI + k4 * w_kstep);
+            const uint64_t w_lo = g.w_tr ? make_smem_desc_mn(sb + OFF_W_LO + k4 * w_kstep) : make_smem_desc(sb + OFF_W_LO + k4 * w_kstep);
+            // CG 1: rows [0,BA) = hi, [BA,2BA) = lo
+            const uint64_t a_hi = g.a_tr ? make_smem_desc_mn(sb + OFF_A + k4 * a_kstep) : make_smem_desc(sb + OFF_A + k4 * a_kstep);
             const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
             if (P.dbg & 2) {                    // experiment: the load pipeline alone
             } else if (CG == 2) {
               // the pair's token operand: first BA/2 rows from the leader's shared memory, the rest from the peer's
-              const uint64_t a_lo = make_smem_desc(sb + OFF_A + a_plane + k4 * 32);
+              const uint64_t a_lo = g.a_tr ? make_smem_desc_mn(sb + OFF_A + a_plane + k4 * a_kstep) : make_smem_desc(sb + OFF_A + a_plane + k4 * a_kstep);
               umma_f16_2cta(d1, w_hi, a_hi, idesc_ba, acc);
               umma_f16_2cta(d2, w_hi, a_lo, idesc_ba, acc);
               umma_f16_2cta(d2, w_lo, a_hi, idesc_ba, 1u);
@@ -207,7 +245,10 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
       const int n = (nt * CG + (int)rank) * TN + quarter * 32 + lane;
       const bool nok = n < g.N;
-      const float bias_n = (g.bias && nok) ? g.bias[(int64_t)bz * g.sBias + n] : 0.f;
+      const int bb = bz % P.batch;
+      const int64_t c_boff = (int64_t)bb * g.sC + (int64_t)(bz / P.batch) * g.sC2;   // problem of the batch + contraction chunk
+      const bool dact_on = SIDE == 2 && g.dact_src != nullptr;   // side value = pre-activation whose act' multiplies the result
+      const float bias_n = (g.bias && nok) ? g.bias[(int64_t)bb * g.sBias + n] : 0.f;
       // fused GroupNorm statistics: a tile of <= 128 tokens touches at most two samples (slot 0 / slot 1)
       float st1a = 0.f, st2a = 0.f, st1b = 0.f, st2b = 0.f;
       const int smp0 = g.out_stats ? (mt * BA) / g.st_rps : 0;
@@ -219,7 +260,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       float sd[DEEP ? EPI_ITERS : 1][8];                                   // DEEP: every side value of this warp's tile
       float nrb[8], nrs[8];                                                // SIDE 3: one group ahead
       auto side_ptr = [&](int m) -> const float* {
-        return SIDE == 1 ? g.rowbias + (int64_t)(m % g.rb_period) * g.ldrb + n : g.residual + (int64_t)m * g.ldr + n;
+        return SIDE == 1 ? g.rowbias + (int64_t)(m % g.rb_period) * g.ldrb + n
+                         : (dact_on ? g.dact_src + (int64_t)bb * g.sDact + (int64_t)m * g.lddact + n : g.residual + (int64_t)m * g.ldr + n);
       };
       auto load_side = [&](int gi) {
         if (SIDE != 3) return;
@@ -262,6 +304,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         float t[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t[u] = fmaf(__uint_as_float(r2[u]), HL_INV, __uint_as_float(r1[u])) + bias_n + rb[u];
+        if (g.C_pre) {                                   // training: keep the pre-activation (fp32) for the backward pass
+          float* __restrict__ pp = g.C_pre + (int64_t)bb * g.sPre + (int64_t)m0 * g.ldpre + n;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (u < cnt) pp[(int64_t)u * g.ldpre] = t[u];
+        }
         if (ACT_MODE == 1) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] = gelu_select(t[u]);
@@ -277,14 +325,17 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
               t[u] = fmaf(t[u], g.c_scale[o], g.c_shift[o]);
             }
         }
-        if (SIDE >= 2) {
+        if (SIDE == 2 && dact_on) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] *= act_grad(rs[u], g.dact);
+        } else if (SIDE >= 2) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] += rs[u];
         }
         if (OUT16) {
           const bool grp = g.c_fmt == DPOT_FMT_HL16G32;            // [hi 32 | lo 32] record per 32-column group
           const int64_t ncol = grp ? (int64_t)((n >> 5) << 6) + (n & 31) : n, lo_off = grp ? 32 : g.c_lo;
-          __half* __restrict__ cp = Ch_base + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + ncol;
+          __half* __restrict__ cp = Ch_base + c_boff + (int64_t)m0 * g.ldc + ncol;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (u < cnt) {
@@ -294,7 +345,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
               cp[(int64_t)u * g.ldc + lo_off] = lo;
             }
         } else {
-          float* __restrict__ cp = g.C + (int64_t)bz * g.sC + (int64_t)m0 * g.ldc + n;
+          float* __restrict__ cp = g.C + c_boff + (int64_t)m0 * g.ldc + n;
           float a1 = 0.f, a2 = 0.f;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
@@ -374,9 +425,15 @@ Plan plan_for(const GemmDev& p, int batch, int cg, int sms, int divides) {
   pl.cg = cg;
   pl.n_tiles = (int)ceil_div(p.N, TN * cg);
   const int other = pl.n_tiles * batch, units = sms / cg, step = 16;   // pairs: BA/2 rows per CTA, a multiple of 8
-  const int64_t kblocks = ceil_div(p.K, BKH), ovh = cg == 2 ? 320 : 192;
+  const int64_t kblocks = ceil_div(p.ksplit > 1 ? p.kchunk : p.K, BKH), ovh = cg == 2 ? 320 : 192;
   pl.BA = 0; pl.cost = -1;
-  if (p.M <= TA) {
+  if (p.a_tr) {   // transposed token operand: whole 64-row TMA boxes (a pair stages BA / 2 rows per CTA)
+    for (int ba = TA; ba >= (cg == 2 ? 128 : 64); ba -= 64) {
+      const int64_t tiles = ceil_div(p.M, ba) * other;
+      const int64_t cost = ceil_div(tiles, units) * (ba * kblocks + ovh);
+      if (pl.cost < 0 || cost < pl.cost) { pl.BA = ba; pl.cost = cost; }
+    }
+  } else if (p.M <= TA) {
     pl.BA = (int)round_up(p.M, step);
     pl.cost = ceil_div(other, units) * (pl.BA * kblocks + ovh);
   } else {
@@ -396,7 +453,7 @@ Plan make_plan(const GemmDev& p, int batch) {
   const int divides = (p.st_groups > 0 && p.st_rps > 0 && !stats_any_ba(p)) ? p.st_rps : 0;
   Plan one = plan_for(p, batch, 1, sms, divides);
   // pairs need >= 256 output channels to fill both CTAs and enough tokens to split
-  if (g_pair_mode == 0 || p.N <= TN || p.M < 32 || sms % 2 != 0) return one;
+  if (g_pair_mode == 0 || p.N <= TN || p.M < 32 || sms % 2 != 0 || (p.a_tr && p.M < 128)) return one;
   if ((g_dbg & 3) == 3) return one;   // experiment "no TMA + no MMA": a pair commit with nothing in flight never reaches the peer (measured: trap)
   Plan two = plan_for(p, batch, 2, sms, divides);
   if (two.cost < 0) return one;
@@ -410,8 +467,11 @@ bool gemm_tc16_supports(const GemmDev& p, int batch) {
   if (!tc_device_ok()) return false;
   if (p.a_fmt != DPOT_FMT_HL16 || p.w_fmt != DPOT_FMT_HL16) return false;
   if (p.a_mode != DPOT_A_PLAIN || p.c_mode != DPOT_A_PLAIN) return false;
-  if (p.a_scale || p.C_pre || p.dact_src || p.c_group) return false;
-  if (p.K < 8 || p.K % 8 != 0 || p.M < 1 || p.N < 1) return false;
+  if (p.a_scale || p.c_group) return false;
+  if (p.K < 8 || p.M < 1 || p.N < 1) return false;
+  if (!p.a_tr && !p.w_tr && p.K % 8 != 0) return false;      // K-major rows must keep TMA's 16-byte pitch
+  if (p.a_tr && p.M % 8 != 0) return false;                  // transposed storage: the row is the M / N axis
+  if (p.w_tr && p.N % 8 != 0) return false;
   if (p.lda % 8 || p.ldw % 8 || p.a_lo % 8 || p.w_lo % 8) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W)) % 16) return false;
   if (batch > 1) {
@@ -432,34 +492,51 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
   g_sm_count = sm_count_cur();
-  if (gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
+  const bool bw_form = p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src;
+  if (!bw_form && gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
-  const Plan pl = make_plan(q, batch);
+  const Plan pl = make_plan(q, batch * p.ksplit);
   const int CGn = pl.cg;
   P.n_tiles = pl.n_tiles;
   P.BA = pl.BA;
   P.m_tiles = pl.m_tiles;
-  P.total_tiles = P.n_tiles * P.m_tiles * batch;
-  P.kblocks = (int)ceil_div(p.K, BKH);
+  P.total_tiles = P.n_tiles * P.m_tiles * batch * p.ksplit;
+  P.kblocks = (int)ceil_div(p.ksplit > 1 ? p.kchunk : p.K, BKH);
   P.dbg = g_dbg;
+  P.batch = batch;
+  if (p.ksplit <= 1) { P.g.kchunk = 0; P.g.sC2 = 0; P.g.ksplit = 1; }
 
   const __half* Ah = reinterpret_cast<const __half*>(p.A);
   const __half* Wh = reinterpret_cast<const __half*>(p.W);
   alignas(64) CUtensorMap mWh, mWl, mAh, mAl;
   const uint64_t sWb = batch > 1 ? (uint64_t)p.sW * 2 : (uint64_t)p.ldw * 2 * (uint64_t)p.N;
-  DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
-  DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
+  if (p.w_tr) {   // stored [K, N] (row stride ldw): dims (n, k, batch), boxes of 64 channels x 64 k rows
+    const uint64_t sWt = batch > 1 ? (uint64_t)p.sW * 2 : (uint64_t)p.ldw * 2 * (uint64_t)p.K;
+    DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.ldw * 2, sWt, 64, BKH, 1));
+    DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.ldw * 2, sWt, 64, BKH, 1));
+  } else {
+    DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
+    DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
+  }
   const uint64_t sAb = batch > 1 ? (uint64_t)p.sA * 2 : (uint64_t)p.lda * 2;
   const uint32_t box_m = (uint32_t)(P.BA / CGn);
-  DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
-  DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
+  if (p.a_tr) {   // stored [K, M] (row stride lda): dims (m, k, batch)
+    const uint64_t sAt = batch > 1 ? (uint64_t)p.sA * 2 : (uint64_t)p.lda * 2 * (uint64_t)p.K;
+    DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.lda * 2, sAt, 64, BKH, 1));
+    DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.lda * 2, sAt, 64, BKH, 1));
+  } else {
+    DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
+    DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
+  }
 
   const int units = g_sm_count / CGn;
   const int grid = CGn * (P.total_tiles < units ? P.total_tiles : units);
   const int am = p.act == DPOT_ACT_NONE ? 0 : (p.act == DPOT_ACT_GELU ? 1 : 2);
   const bool o16 = p.c_fmt != DPOT_FMT_F32;
-  const int side = p.c_scale || (p.rowbias && p.residual) ? 3 : (p.rowbias ? 1 : (p.residual ? 2 : 0));
+  const int side = p.c_scale || (p.rowbias && p.residual) ? 3 : (p.rowbias ? 1 : ((p.residual || p.dact_src) ? 2 : 0));
+  if (P.g.C_pre && P.g.ldpre <= 0) { P.g.ldpre = p.ldc; P.g.sPre = p.sC; }          // fp32 result: C's geometry
+  if (P.g.dact_src && P.g.lddact <= 0) { P.g.lddact = p.ldc; P.g.sDact = p.sC; }
 #define DPOT_TC16_LAUNCH(CGV, AM, O16, SD)                                                                             \
   do {                                                                                                                 \
     static DevOnce attr;                                                                                          \

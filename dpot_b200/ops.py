@@ -150,6 +150,60 @@ def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residua
     return out if st is None else (out, st)
 
 
+@_on_device
+def gemm16_bw(A16: torch.Tensor, W16: torch.Tensor, M: int, N: int, K: int, *, a_trans=False, w_trans=False, nb: int = 1,
+              k_chunk: int = 0, out16: bool = False, dact_src=None, dact=None, pre: bool = False, act=None, bias=None):
+    """The backward-pass forms of the f16-split engine (dpot_gemm_args a_trans / w_trans / k_split, ABI 2).
+    Per problem C[M, N] = A[M, K] W[N, K]^T with A16 stored [M, 2*nb*K] (or transposed [K, 2*nb*M]), W16 stored
+    [nb*N, 2K] (or transposed [K, 2*nb*N]); nb problems side by side (block-diagonal AFNO weights, except W16 plain:
+    [nb, N, 2K]).  k_chunk > 0: the contraction is cut into ceil(K / k_chunk) chunks -> returns the partial results
+    [chunks, ...] (the caller sums them).  dact_src [M, nb*N] fp32: result *= act'(dact_src).  pre: also return the
+    fp32 pre-activation."""
+    g = GemmArgs()
+    dev = A16.device
+    Nt = nb * N
+    ks = (K + k_chunk - 1) // k_chunk if k_chunk > 0 else 1
+    if w_trans and nb > 1 and not a_trans:      # dgrad of the block-diagonal layer: C[M, nb*N]
+        shape = (M, Nt)
+    elif a_trans:                                # wgrad: one [M, N] matrix per problem
+        shape = (nb, M, N)
+    else:
+        shape = (M, Nt)
+    lead = (ks,) if ks > 1 else ()
+    if out16:
+        out = torch.empty(lead + shape[:-1] + (2 * shape[-1],), device=dev, dtype=torch.float16)
+        g.c_fmt, g.c_lo_off = _lib.FMT_HL16, shape[-1]
+        g.ldc = 2 * shape[-1]
+    else:
+        out = torch.empty(lead + shape, device=dev, dtype=torch.float32)
+        g.ldc = shape[-1]
+    g.C = ptr(out)
+    g.M, g.N, g.K = M, N, K
+    g.a_fmt = g.w_fmt = _lib.FMT_HL16
+    g.A, g.W = ptr(A16), ptr(W16)
+    g.lda, g.a_lo_off = A16.stride(0), A16.shape[1] // 2
+    g.ldw, g.w_lo_off = W16.stride(0), W16.shape[-1] // 2
+    g.a_trans, g.w_trans = int(a_trans), int(w_trans)
+    g.batch, g.engine, g.a_mode = nb, _lib.GEMM_TC16, _lib.A_PLAIN
+    g.act = act_id(act)
+    g.bias = ptr(bias)
+    if nb > 1:
+        g.strideA = M if a_trans else K
+        g.strideW = N if (w_trans and a_trans) else (K * 2 * N if w_trans else N * 2 * K)   # activation columns / stacked weights
+        g.strideC = M * N * (2 if out16 else 1) if a_trans else N
+        g.strideBias = N
+    if ks > 1:
+        g.k_split, g.k_chunk, g.strideC_split = ks, k_chunk, out[0].numel()
+    pre_t = None
+    if pre:
+        pre_t = torch.empty(shape, device=dev, dtype=torch.float32)
+        g.C_pre, g.ld_pre, g.stride_pre = ptr(pre_t), shape[-1], (M * N if a_trans else N)
+    if dact_src is not None:
+        g.dact_src, g.ld_dact, g.stride_dact, g.dact = ptr(dact_src), dact_src.stride(0), N, act_id(dact)
+    check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(tc16 backward form)")
+    return (out, pre_t) if pre else out
+
+
 def unsplit_f16(x16: torch.Tensor) -> torch.Tensor:
     """Inverse of split_f16 (test helper: plain torch arithmetic on the stored halves)."""
     K = x16.shape[1] // 2

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DPOT_ABI_VERSION 1
+#define DPOT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DPOT_API __attribute__((visibility("default")))
@@ -136,6 +136,19 @@ typedef struct dpot_gemm_args {
      except out_stats on TC16. */
   int32_t a_fmt, w_fmt, c_fmt;
   int64_t a_lo_off, w_lo_off, c_lo_off;
+  /* ---- ABI version 2: the backward-pass forms of the DPOT_GEMM_TC16 engine (zero = the plain forward form) ----
+     a_trans / w_trans = 1: the operand is STORED TRANSPOSED, A as [K, M] (row stride lda) / W as [K, N] (row stride
+     ldw); the tensor core reads it as an MN-major tile, so neither the data-gradient (dx = g W: w_trans) nor the
+     weight-gradient (dW = g^T x: both) needs a transposed copy.  With a_trans the token tile is 64 or 128 rows.
+     k_split > 1: the contraction is cut into k_split chunks of k_chunk (a multiple of 64); chunk c writes its partial
+     result at C + c * strideC_split (a tensor-core accumulation chain is kept <= 1024 deep; the chunks
+     also fill the SMs when the output is small).  No bias / activation / side inputs with k_split > 1.
+     ld_pre / stride_pre, ld_dact / stride_dact: leading dimension and batch stride (floats) of C_pre / dact_src on the
+     TC16 engine (there they are allowed with c_fmt = HL16: the fc2 data-gradient leaves the engine already multiplied
+     by act'(pre) and split, ready to be the operand of the next two contractions). */
+  int32_t a_trans, w_trans;
+  int32_t k_split; int64_t k_chunk; int64_t strideC_split;
+  int64_t ld_pre, stride_pre, ld_dact, stride_dact;
 } dpot_gemm_args;
 
 DPOT_API int dpot_gemm(const dpot_gemm_args* args, void* stream);

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dpot_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.dpot_abi_version() == 1
+    assert lib.dpot_abi_version() == 2
 
 
 def test_ctypes_struct_sizes_match_header():
