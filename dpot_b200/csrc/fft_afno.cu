@@ -346,6 +346,23 @@ extern "C" int dpot_afno_fft_fwd16(const float* a, const float* scale, const flo
   }
 }
 
+// fwd16 without GroupNorm and with the interior-column weight: the adjoint of the inverse transform (weight 2) that the
+// backward pass feeds straight into the f16-split contractions
+extern "C" int dpot_afno_fft_fwd16w(const float* a, int32_t B, int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2,
+                                    void* S16, float interior_weight, void* stream) {
+  DPOT_REQUIRE(a && S16, DPOT_E_BADARG, "dpot_afno_fft_fwd16w: null pointer");
+  DPOT_CALL(check_common(B, h, E, nb, km1, km2));
+  cudaStream_t st = as_stream(stream);
+  float* S = reinterpret_cast<float*>(S16);
+  switch (h) {
+    case 2: return launch_fwd<2, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
+    case 4: return launch_fwd<4, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
+    case 8: return launch_fwd<8, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
+    case 16: return launch_fwd<16, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
+    default: return launch_fwd<32, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
+  }
+}
+
 extern "C" int dpot_afno_fft_inv(const float* O2, const float* a, const float* scale, const float* shift, int32_t B,
                                  int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2, float* f,
                                  double* stats_out, int32_t groups, float interior_weight, void* stream) {

@@ -44,7 +44,7 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
                "dpot_gemm: a_fmt and w_fmt must both be F32 or both HL16");
   DPOT_REQUIRE(a->c_fmt == DPOT_FMT_F32 || a->c_fmt == DPOT_FMT_HL16 || a->c_fmt == DPOT_FMT_HL16G32, DPOT_E_BADARG, "dpot_gemm: bad c_fmt");
   if (a->c_fmt == DPOT_FMT_HL16G32)
-    DPOT_REQUIRE(a->a_fmt == DPOT_FMT_HL16 && a->N % 32 == 0 && a->ldc >= 2 * (int64_t)a->N && a->batch == 1 && !a->C_pre &&
+    DPOT_REQUIRE(a->a_fmt == DPOT_FMT_HL16 && a->N % 32 == 0 && a->ldc >= 2 * (int64_t)a->N && a->batch == 1 &&
                  !a->dact_src && a->c_mode == DPOT_A_PLAIN && !a->out_stats, DPOT_E_BADARG,
                  "dpot_gemm: the grouped split-fp16 output needs split-fp16 operands, N %% 32 == 0 and ldc >= 2N halves");
   if (a->c_fmt == DPOT_FMT_HL16)

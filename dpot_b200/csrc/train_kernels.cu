@@ -1,0 +1,867 @@
+// Kernels of the training step that are not dense contractions: gradient scaling, column sums, GroupNorm backward,
+// partial-result reduction + un-packing of weight gradients, the output-head tail backward, the PatchEmbed conv0
+// backward and the time-aggregation fold helpers.  Host orchestration: train_step.cu.  Reference: autograd of
+// models/dpot.py:364-403 (train_temporal.py:227 loss.backward()).
+#include "train_kernels.cuh"
+#include "gemm_common.cuh"
+
+namespace dpot {
+namespace {
+
+__device__ __forceinline__ float inv_of(const float* inv_scale) { return inv_scale ? __ldg(inv_scale) : 1.0f; }
+
+// d act(x)/dx with the branch-free erf of common.cuh (GELU: Phi(x) + x phi(x); abs error ~1e-7)
+__device__ __forceinline__ float act_grad_fast(float x, int act) {
+  if (act == DPOT_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + erf_select(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return fmaf(x, pdf, cdf);
+  }
+  return act_grad(x, act);
+}
+
+// ------------------------------------------------------------------------------------------------ gradient scale
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ bits) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[i]);
+    m = (v == v) ? fmaxf(m, v) : INFINITY;          // NaN -> inf: the scale falls back to 1 and the NaN stays loud
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(bits, __float_as_uint(m));
+}
+__global__ void scale_from_max_kernel(const unsigned* __restrict__ bits, float* __restrict__ scale) {
+  const float m = __uint_as_float(*bits);
+  float S = 1.f;
+  if (m > 0.f && m < INFINITY) {
+    int ex;
+    frexpf(m, &ex);                                  // m = f * 2^ex, f in [0.5, 1)  ->  m * 2^(1 - ex) in [1, 2)
+    int k = 1 - ex;
+    k = k < -60 ? -60 : (k > 60 ? 60 : k);
+    S = ldexpf(1.f, k);
+  }
+  scale[0] = S;
+  scale[1] = 1.f / S;
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+template <bool F16>
+__global__ void __launch_bounds__(128) colsum2_kernel(const void* __restrict__ Xv, int64_t ld, int64_t lo_off, int M, int N,
+                                                      int rows_per_block, double* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (F16) {
+    const __half* X = reinterpret_cast<const __half*>(Xv);
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m)
+      acc += fmaf(__half2float(X[(int64_t)m * ld + n + lo_off]), HL_INV, __half2float(X[(int64_t)m * ld + n]));
+  } else {
+    const float* X = reinterpret_cast<const float*>(Xv);
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m) acc += X[(int64_t)m * ld + n];
+  }
+  atomicAdd(out + n, (double)acc);
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm backward
+// per (sample, channel): A1 = sum_pos dy, A2 = sum_pos dy * x (raw x; the centring happens in the group kernel)
+__global__ void __launch_bounds__(256) gn_bwd_reduce2_kernel(const float* __restrict__ dy, const float* __restrict__ x, int n, int E,
+                                                             float* __restrict__ A1, float* __restrict__ A2) {
+  __shared__ float2 r1[8][32], r2[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.y, c = blockIdx.x * 64 + lane * 2;
+  float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+  if (c < E) {
+    const int64_t base = (int64_t)b * n * E + c;
+#pragma unroll 4
+    for (int pos = w; pos < n; pos += 8) {
+      const float2 g = *reinterpret_cast<const float2*>(dy + base + (int64_t)pos * E);
+      const float2 xv = *reinterpret_cast<const float2*>(x + base + (int64_t)pos * E);
+      s1.x += g.x; s1.y += g.y;
+      s2.x = fmaf(g.x, xv.x, s2.x); s2.y = fmaf(g.y, xv.y, s2.y);
+    }
+  }
+  r1[w][lane] = s1; r2[w][lane] = s2;
+  __syncthreads();
+  if (w == 0 && c < E) {
+    float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t1.x += r1[k][lane].x; t1.y += r1[k][lane].y; t2.x += r2[k][lane].x; t2.y += r2[k][lane].y; }
+    *reinterpret_cast<float2*>(A1 + (int64_t)b * E + c) = t1;
+    *reinterpret_cast<float2*>(A2 + (int64_t)b * E + c) = t2;
+  }
+}
+
+// blocks [0, gblocks): one warp per (sample, group) -> dx coefficient tables; blocks after: one thread per channel -> dgamma/dbeta
+//   dx = coefA[b,c]*dy + coefBC[b,g,0]*x + coefBC[b,g,1]
+__global__ void __launch_bounds__(128) gn_bwd_group2_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
+                                                            const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                            int B, int n, int E, int groups, float eps, int gblocks,
+                                                            const float* __restrict__ inv_scale, float* __restrict__ coefA,
+                                                            float* __restrict__ coefBC, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
+  const int gs = E / groups;
+  const double cnt = (double)gs * n;
+  if ((int)blockIdx.x < gblocks) {
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid >= B * groups) return;
+    const int b = wid / groups, g = wid % groups;
+    const double* st = stats + (int64_t)wid * 2;
+    const double mean = st[0] / cnt;
+    double var = st[1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    double g1 = 0.0, g2 = 0.0;
+    for (int c = g * gs + lane; c < (g + 1) * gs; c += 32) {
+      const double gm = (double)gamma[c], a1 = (double)A1[(int64_t)b * E + c], a2 = (double)A2[(int64_t)b * E + c];
+      g1 += gm * a1;
+      g2 += gm * (a2 - mean * a1) * rstd;            // sum gamma * dy * xhat
+      coefA[(int64_t)b * E + c] = (float)(rstd * gm);
+    }
+    g1 = warp_sum(g1); g2 = warp_sum(g2);
+    if (lane == 0) {
+      coefBC[2 * wid] = (float)(-rstd * rstd * g2 / cnt);
+      coefBC[2 * wid + 1] = (float)((rstd * rstd * g2 * mean - rstd * g1) / cnt);
+    }
+  } else {
+    const int c = ((int)blockIdx.x - gblocks) * blockDim.x + threadIdx.x;
+    if (c >= E) return;
+    const int g = c / gs;
+    double d1 = 0.0, d2 = 0.0;
+    for (int b = 0; b < B; ++b) {
+      const double* st = stats + ((int64_t)b * groups + g) * 2;
+      const double mean = st[0] / cnt;
+      double var = st[1] / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double rstd = 1.0 / sqrt(var + (double)eps);
+      const double a1 = (double)A1[(int64_t)b * E + c], a2 = (double)A2[(int64_t)b * E + c];
+      d1 += a1;
+      d2 += (a2 - mean * a1) * rstd;
+    }
+    const double inv = (double)inv_of(inv_scale);
+    dbeta[c] = (float)(d1 * inv);
+    dgamma[c] = (float)(d2 * inv);
+  }
+}
+
+template <bool OUT16>
+__global__ void __launch_bounds__(256) gn_bwd_apply2_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ coefA, const float* __restrict__ coefBC,
+                                                            const float* __restrict__ add, int64_t total4, int n, int E, int gs,
+                                                            int groups, float* __restrict__ dx, __half* __restrict__ dx16,
+                                                            int64_t ld16, int64_t lo16) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int64_t i = i4 * 4;
+  const int64_t row = i / E; const int c = (int)(i % E);
+  const int b = (int)(row / n), g = c / gs;
+  const float4 gv = __ldcs(reinterpret_cast<const float4*>(dy + i));
+  const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + i));
+  const float4 ca = __ldg(reinterpret_cast<const float4*>(coefA + (int64_t)b * E + c));
+  const float2 bc = __ldg(reinterpret_cast<const float2*>(coefBC + 2 * ((int64_t)b * groups + g)));
+  float4 o;
+  o.x = fmaf(ca.x, gv.x, fmaf(bc.x, xv.x, bc.y));
+  o.y = fmaf(ca.y, gv.y, fmaf(bc.x, xv.y, bc.y));
+  o.z = fmaf(ca.z, gv.z, fmaf(bc.x, xv.z, bc.y));
+  o.w = fmaf(ca.w, gv.w, fmaf(bc.x, xv.w, bc.y));
+  if (add) {
+    const float4 av = __ldcs(reinterpret_cast<const float4*>(add + i));
+    o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
+  }
+  *reinterpret_cast<float4*>(dx + i) = o;
+  if (OUT16) {
+    const float v[4] = {o.x, o.y, o.z, o.w};
+    alignas(8) __half hi[4];
+    alignas(8) __half lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hl_split(v[u], hi[u], lo[u]);
+    *reinterpret_cast<uint2*>(dx16 + row * ld16 + c) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(dx16 + row * ld16 + c + lo16) = *reinterpret_cast<const uint2*>(lo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gradient finishing
+__global__ void slab_reduce_kernel(const float* __restrict__ slabs, int nslab, int64_t stride, int64_t count4,
+                                   const float* __restrict__ inv_scale, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  float4 a = *reinterpret_cast<const float4*>(slabs + i * 4);
+  for (int s = 1; s < nslab; ++s) {
+    const float4 b = *reinterpret_cast<const float4*>(slabs + (int64_t)s * stride + i * 4);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  const float inv = inv_of(inv_scale);
+  a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+  *reinterpret_cast<float4*>(dst + i * 4) = a;
+}
+__global__ void slab_reduce1_kernel(const float* __restrict__ slabs, int nslab, int64_t stride, int64_t count,
+                                    const float* __restrict__ inv_scale, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float a = slabs[i];
+  for (int s = 1; s < nslab; ++s) a += slabs[(int64_t)s * stride + i];
+  dst[i] = a * inv_of(inv_scale);
+}
+__global__ void finish_double_kernel(const double* __restrict__ src, int64_t count, const float* __restrict__ inv_scale,
+                                     float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = (float)(src[i] * (double)inv_of(inv_scale));
+}
+__global__ void scale_copy_kernel(const float* __restrict__ src, int64_t count, const float* __restrict__ inv_scale,
+                                  float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = src[i] * inv_of(inv_scale);
+}
+
+// dWc[nb, 2bs(out), 2bs(in)] partials -> dw[2, nb, bs(in), bs(out)], dbc -> db[2, nb, bs]   (transpose of pack_afno_kernel)
+__global__ void unpack_afno_grad2_kernel(const float* __restrict__ dWc, int nslab, int64_t stride, const double* __restrict__ dbc,
+                                         int nb, int bs, const float* __restrict__ inv_scale, float* __restrict__ dw,
+                                         float* __restrict__ db) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)nb * bs * bs;
+  const float inv = inv_of(inv_scale);
+  if (i < per) {
+    const int o = (int)(i % bs), ki = (int)((i / bs) % bs), kap = (int)(i / ((int64_t)bs * bs));
+    const int64_t L = 2 * bs;
+    float re = 0.f, im = 0.f;
+    for (int s = 0; s < nslab; ++s) {
+      const float* Wk = dWc + (int64_t)s * stride + (int64_t)kap * 4 * bs * bs;
+      // Wc[n=o][k=ki] = wr, Wc[o][ki+bs] = -wi, Wc[o+bs][ki] = wi, Wc[o+bs][ki+bs] = wr
+      re += Wk[(int64_t)o * L + ki] + Wk[(int64_t)(o + bs) * L + ki + bs];
+      im += -Wk[(int64_t)o * L + ki + bs] + Wk[(int64_t)(o + bs) * L + ki];
+    }
+    dw[i] = re * inv;
+    dw[per + i] = im * inv;
+  }
+  if (i < (int64_t)nb * bs) {
+    const int o = (int)(i % bs), kap = (int)(i / bs);
+    db[i] = (float)(dbc[(int64_t)kap * 2 * bs + o] * (double)inv);
+    db[(int64_t)nb * bs + i] = (float)(dbc[(int64_t)kap * 2 * bs + bs + o] * (double)inv);
+  }
+}
+
+// dWtT[(uv, o), e] partials -> dwt[e, o, uv]: a 32 x 32 (uv, e) tile transpose per o;  grid (E/32, ceil(PP/32), old)
+__global__ void unpack_out_grad_kernel(const float* __restrict__ dWtT, int nslab, int64_t stride, int E, int old, int PP,
+                                       const float* __restrict__ inv_scale, float* __restrict__ dwt) {
+  __shared__ float tile[32][33];
+  const int e0 = blockIdx.x * 32, uv0 = blockIdx.y * 32, o = blockIdx.z;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int uv = uv0 + i, e = e0 + threadIdx.x;
+    float a = 0.f;
+    if (uv < PP && e < E)
+      for (int s = 0; s < nslab; ++s) a += dWtT[(int64_t)s * stride + ((int64_t)uv * old + o) * E + e];
+    tile[i][threadIdx.x] = a;
+  }
+  __syncthreads();
+  const float inv = inv_of(inv_scale);
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int e = e0 + i, uv = uv0 + threadIdx.x;
+    if (e < E && uv < PP) dwt[((int64_t)e * old + o) * PP + uv] = tile[threadIdx.x][i] * inv;
+  }
+}
+__global__ void out_bias_grad_kernel(const double* __restrict__ dbias_t, int old, int PP, const float* __restrict__ inv_scale,
+                                     float* __restrict__ db) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= old) return;
+  double a = 0.0;
+  for (int uv = 0; uv < PP; ++uv) a += dbias_t[(int64_t)uv * old + o];
+  db[o] = (float)(a * (double)inv_of(inv_scale));
+}
+
+// ------------------------------------------------------------------------------------------------ output tail backward
+// One thread per pixel (32 channels in registers), the two 32 x 32 weight products against broadcast shared-memory reads;
+// the parameter gradients (outer products summed over pixels) are taken from shared-memory copies of the block's 128
+// pixels by a second mapping (8 entries of dW2 per thread) and accumulated in registers across the tiles of a
+// persistent block, then added once per block with double atomics.
+constexpr int TB_PIX = 128, TB_OLD = 32, TB_NOUT_MAX = 8;
+struct TailBwdArgs {
+  const float* Y1pre; const float* dout; const float* scale; const float* w2; const float* b2; const float* w4;
+  __half* g1; double* acc;
+  int B, h, w, P, nout, act; int64_t ntiles;
+};
+__global__ void __launch_bounds__(TB_PIX) tail_bwd_kernel(const TailBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* W2s = sm;                          // [32][32]  (n, k)
+  float* W4s = W2s + 32 * 32;               // [nout][32]
+  float* b2s = W4s + TB_NOUT_MAX * 32;      // [32]
+  float* y1s = b2s + 32;                    // [128][33]
+  float* y2s = y1s + TB_PIX * 33;           // [128][33]
+  float* g2s = y2s + TB_PIX * 33;           // [128][33]
+  float* g3s = g2s + TB_PIX * 33;           // [128][8]
+  const int tid = threadIdx.x;
+  const int PP = a.P * a.P, NP = PP * TB_OLD, nout = a.nout;
+  for (int i = tid; i < 32 * 32; i += TB_PIX) W2s[i] = a.w2[i];
+  for (int i = tid; i < nout * 32; i += TB_PIX) W4s[i] = a.w4[i];
+  if (tid < 32) b2s[tid] = a.b2[tid];
+  const float S = a.scale ? __ldg(a.scale) : 1.f;
+  // second mapping: dW2 entries (n2, k2..k2+7); dW4 entry (j4, n4) for tid < nout*32 (nout <= 4 -> one pass; else two)
+  const int n2 = tid >> 2, k2 = (tid & 3) * 8;
+  float dW2r[8], db2r = 0.f, dW4r[2] = {0.f, 0.f}, db4r = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) dW2r[u] = 0.f;
+  __syncthreads();
+  const int R = a.h * a.P;                  // field height
+  const int Wd = a.w * a.P;
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int64_t pix = tile * TB_PIX + tid;                 // pixel = (tok, uv)
+    const int64_t tok = pix / PP; const int uv = (int)(pix % PP);
+    const int u_ = uv / a.P, v_ = uv % a.P;
+    const int q = (int)(tok % a.w); const int64_t r_ = tok / a.w;
+    const int p = (int)(r_ % a.h); const int b = (int)(r_ / a.h);
+    const bool live = b < a.B;
+    float y1[32], t2[32];
+    const float* yp = a.Y1pre + tok * NP + (int64_t)uv * 32;
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(yp + k));
+        y1[k] = v.x; y1[k + 1] = v.y; y1[k + 2] = v.z; y1[k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) y1[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { y1[k] = act_apply(y1[k], a.act); y1s[tid * 33 + k] = y1[k]; }
+    // pre2 = W2 y1 + b2
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      float acc = b2s[n];
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(W2s + n * 32 + k);
+        acc = fmaf(wv.x, y1[k], acc); acc = fmaf(wv.y, y1[k + 1], acc); acc = fmaf(wv.z, y1[k + 2], acc); acc = fmaf(wv.w, y1[k + 3], acc);
+      }
+      t2[n] = acc;
+    }
+    float g3[TB_NOUT_MAX];
+    {
+      const float* dp = a.dout + ((((int64_t)b * R + p * a.P + u_) * Wd) + q * a.P + v_) * nout;
+#pragma unroll
+      for (int j = 0; j < TB_NOUT_MAX; ++j) {
+        g3[j] = (live && j < nout) ? dp[j] * S : 0.f;
+        g3s[tid * 8 + j] = g3[j];
+      }
+    }
+    // y2 = act(pre2) -> smem; g2 = (W4^T g3) * act'(pre2)
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float pre = t2[n];
+      y2s[tid * 33 + n] = act_apply(pre, a.act);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < TB_NOUT_MAX; ++j)
+        if (j < nout) acc = fmaf(W4s[j * 32 + n], g3[j], acc);
+      t2[n] = live ? acc * act_grad_fast(pre, a.act) : 0.f;
+      g2s[tid * 33 + n] = t2[n];
+    }
+    // g1 = (W2^T g2) * act'(y1pre)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) y1[k] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float gn = t2[n];
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(W2s + n * 32 + k);
+        y1[k] = fmaf(wv.x, gn, y1[k]); y1[k + 1] = fmaf(wv.y, gn, y1[k + 1]);
+        y1[k + 2] = fmaf(wv.z, gn, y1[k + 2]); y1[k + 3] = fmaf(wv.w, gn, y1[k + 3]);
+      }
+    }
+    if (live) {
+      __half* gp = a.g1 + tok * (2 * (int64_t)NP) + (int64_t)uv * 32;
+#pragma unroll
+      for (int k = 0; k < 32; k += 8) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(yp + k)), p1 = __ldg(reinterpret_cast<const float4*>(yp + k + 4));
+        const float pre[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        alignas(16) __half hi[8];
+        alignas(16) __half lo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) hl_split(y1[k + u] * act_grad_fast(pre[u], a.act), hi[u], lo[u]);
+        *reinterpret_cast<uint4*>(gp + k) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(gp + k + NP) = *reinterpret_cast<const uint4*>(lo);
+      }
+    }
+    __syncthreads();
+    // parameter gradients of this tile from the shared copies
+#pragma unroll 4
+    for (int pp = 0; pp < TB_PIX; ++pp) {
+      const float g2v = g2s[pp * 33 + n2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dW2r[u] = fmaf(g2v, y1s[pp * 33 + k2 + u], dW2r[u]);
+    }
+    if (tid < 32) {
+      float s = 0.f;
+      for (int pp = 0; pp < TB_PIX; ++pp) s += g2s[pp * 33 + tid];
+      db2r += s;
+    } else if (tid < 32 + TB_NOUT_MAX) {
+      const int j = tid - 32;
+      float s = 0.f;
+      for (int pp = 0; pp < TB_PIX; ++pp) s += g3s[pp * 8 + j];
+      db4r += s;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int e = tid + half * TB_PIX;           // entry (j, n) of dW4
+      if (e < nout * 32) {
+        const int j = e >> 5, n = e & 31;
+        float s = 0.f;
+        for (int pp = 0; pp < TB_PIX; ++pp) s = fmaf(g3s[pp * 8 + j], y2s[pp * 33 + n], s);
+        dW4r[half] += s;
+      }
+    }
+    __syncthreads();
+  }
+  double* acc = a.acc;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) atomicAdd(acc + n2 * 32 + k2 + u, (double)dW2r[u]);
+  if (tid < 32) atomicAdd(acc + 1024 + tid, (double)db2r);
+  else if (tid < 32 + TB_NOUT_MAX && tid - 32 < nout) atomicAdd(acc + 1024 + 32 + nout * 32 + (tid - 32), (double)db4r);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int e = tid + half * TB_PIX;
+    if (e < nout * 32) atomicAdd(acc + 1024 + 32 + e, (double)dW4r[half]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ PatchEmbed conv0 backward
+constexpr int PB_MID = 40, PB_T = 10, PB_NT = 256;
+struct PatchBwdArgs {
+  const float* gz; const float* x; const float* W0p; const float* inv_scale; double* dW0p; float* dx;
+  int B, X, Y, T, C, P, mid, Kp, K0, h, w;
+};
+__global__ void __launch_bounds__(PB_NT) patch_bwd_kernel(const PatchBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* gzs = sm;                              // [T][mid]  (<= 400 floats)
+  float* xs = sm + PB_T * PB_MID;               // patch tile [u][(v, t, c)] = P * (P*T*C) floats; reused for dx
+  const int tid = threadIdx.x, K0 = a.K0, T = a.T, mid = a.mid, C = a.C, P = a.P;
+  const int run = P * T * C;                    // contiguous floats of one patch row u
+  const bool kon = tid < K0;
+  const int c = tid % C, uv = tid / C, v = uv % P, u = uv / P;
+  float wcol[PB_MID], dW[PB_MID];
+#pragma unroll
+  for (int m = 0; m < PB_MID; ++m) {
+    wcol[m] = (kon && m < mid && a.dx) ? a.W0p[(int64_t)m * K0 + tid] : 0.f;
+    dW[m] = 0.f;
+  }
+  const float inv = inv_of(a.inv_scale);
+  const int64_t npatch = (int64_t)a.B * a.h * a.w;
+  for (int64_t pt = blockIdx.x; pt < npatch; pt += gridDim.x) {
+    const int q = (int)(pt % a.w); const int64_t r_ = pt / a.w;
+    const int p = (int)(r_ % a.h); const int b = (int)(r_ / a.h);
+    for (int i = tid; i < T * mid; i += PB_NT) gzs[i] = a.gz[pt * a.Kp + i];
+    for (int i = tid; i < P * run; i += PB_NT) {
+      const int uu = i / run, rr = i % run;
+      xs[i] = a.x[(((int64_t)b * a.X + p * P + uu) * a.Y + (int64_t)q * P) * T * C + rr];
+    }
+    __syncthreads();
+    float xk[PB_T], dxk[PB_T];
+#pragma unroll
+    for (int t = 0; t < PB_T; ++t) {
+      xk[t] = (kon && t < T) ? xs[u * run + (v * T + t) * C + c] : 0.f;
+      dxk[t] = 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < PB_MID; ++m) {
+      if (m < mid) {
+#pragma unroll
+        for (int t = 0; t < PB_T; ++t) {
+          if (t < T) {
+            const float gv = gzs[t * mid + m];
+            dW[m] = fmaf(gv, xk[t], dW[m]);
+            dxk[t] = fmaf(gv, wcol[m], dxk[t]);
+          }
+        }
+      }
+    }
+    if (a.dx) {
+      __syncthreads();
+      if (kon) {
+#pragma unroll
+        for (int t = 0; t < PB_T; ++t)
+          if (t < T) xs[u * run + (v * T + t) * C + c] = dxk[t] * inv;
+      }
+      __syncthreads();
+      for (int i = tid; i < P * run; i += PB_NT) {
+        const int uu = i / run, rr = i % run;
+        a.dx[(((int64_t)b * a.X + p * P + uu) * a.Y + (int64_t)q * P) * T * C + rr] = xs[i];
+      }
+    }
+    __syncthreads();
+  }
+  if (kon) {
+#pragma unroll
+    for (int m = 0; m < PB_MID; ++m)
+      if (m < mid) atomicAdd(a.dW0p + (int64_t)m * K0 + tid, (double)dW[m]);
+  }
+}
+
+// dpe0_w[m, c, u, v] / dpe0_b[m] from dW0p[m, (u,v,c)] and drb[(p,q), t*mid + m] (row pitch Kp): one block per m
+__global__ void __launch_bounds__(256) unpack_patch_grad_kernel(const double* __restrict__ dW0p, const double* __restrict__ drb,
+                                                                const float* __restrict__ gx, const float* __restrict__ gy,
+                                                                const float* __restrict__ gt, int mid, int C, int P, int h, int w,
+                                                                int T, int Kp, const float* __restrict__ inv_scale,
+                                                                float* __restrict__ dw0, float* __restrict__ db0) {
+  __shared__ double red[256];
+  __shared__ double sums[2 * 32 + 2];           // [u: x-channel | v: y-channel | t-channel | bias], P <= 32
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const double inv = (double)inv_of(inv_scale);
+  const int PP = P * P, K0 = PP * C;
+  for (int i = tid; i < K0; i += blockDim.x) {
+    const int c = i % C, uv = i / C;
+    dw0[((int64_t)m * (C + 3) + c) * PP + uv] = (float)(dW0p[(int64_t)m * K0 + i] * inv);
+  }
+  const int nitem = h * w * T;
+  for (int which = 0; which < 2 * P + 2; ++which) {
+    double acc = 0.0;
+    for (int i = tid; i < nitem; i += blockDim.x) {
+      const int t = i % T; const int pq = i / T; const int q = pq % w, p = pq / w;
+      const double g = drb[(int64_t)pq * Kp + t * mid + m];
+      double f;
+      if (which < P) f = (double)gx[p * P + which];
+      else if (which < 2 * P) f = (double)gy[q * P + (which - P)];
+      else if (which == 2 * P) f = (double)gt[t];
+      else f = 1.0;
+      acc += g * f;
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (tid < s) red[tid] += red[tid + s];
+      __syncthreads();
+    }
+    if (tid == 0) sums[which] = red[0];
+    __syncthreads();
+  }
+  for (int i = tid; i < PP; i += blockDim.x) {
+    const int u = i / P, v = i % P;
+    dw0[((int64_t)m * (C + 3) + C) * PP + i] = (float)(sums[u] * inv);
+    dw0[((int64_t)m * (C + 3) + C + 1) * PP + i] = (float)(sums[P + v] * inv);
+    dw0[((int64_t)m * (C + 3) + C + 2) * PP + i] = (float)(sums[2 * P] * inv);
+  }
+  if (tid == 0) db0[m] = (float)(sums[2 * P + 1] * inv);
+}
+
+// ------------------------------------------------------------------------------------------------ time aggregation fold
+// wts[t,i,j] = w[t,i,j] * temb[t,i];  wtsT[t,j,i] the transpose.  grid (E/32, E/32, T), block (32, 8)
+__global__ void tagg_scale_kernel(const float* __restrict__ w, const float* __restrict__ temb, int E, float* __restrict__ wts,
+                                  float* __restrict__ wtsT) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int64_t base = (int64_t)t * E * E;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    float v = 0.f;
+    if (i < E && j < E) {
+      v = w[base + (int64_t)i * E + j] * temb[(int64_t)t * E + i];
+      wts[base + (int64_t)i * E + j] = v;
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = j0 + r, i = i0 + threadIdx.x;
+    if (i < E && j < E) wtsT[base + (int64_t)j * E + i] = tile[threadIdx.x][r];
+  }
+}
+__global__ void sum_over_t_kernel(const float* __restrict__ a, const float* __restrict__ b, int T, int64_t per,
+                                  float* __restrict__ sa, float* __restrict__ sb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  double x = 0.0, y = 0.0;
+  for (int t = 0; t < T; ++t) { x += (double)a[(int64_t)t * per + i]; y += (double)b[(int64_t)t * per + i]; }
+  sa[i] = (float)x; sb[i] = (float)y;
+}
+__global__ void tagg_bp_kernel(const float* __restrict__ b2, const float* __restrict__ pos, int E, int n, float* __restrict__ bp,
+                               float* __restrict__ bpT) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)E * n) return;
+  const int i = (int)(idx / n), p = (int)(idx % n);
+  const float v = b2[i] + pos[idx];
+  bp[idx] = v;
+  bpT[(int64_t)p * E + i] = v;
+}
+// one warp per (t, i) row
+__global__ void __launch_bounds__(256) tagg_finish_kernel(const float* __restrict__ dwt, const float* __restrict__ w,
+                                                          const float* __restrict__ temb, int64_t rows, int E,
+                                                          const float* __restrict__ inv_scale, float* __restrict__ dw,
+                                                          float* __restrict__ dtemb) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float te = temb[row] * inv_of(inv_scale);
+  double acc = 0.0;
+  for (int j = lane; j < E; j += 32) {
+    const float g = dwt[row * E + j];
+    acc += (double)g * (double)w[row * E + j];
+    dw[row * E + j] = g * te;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) dtemb[row] = (float)acc;
+}
+__global__ void tagg_gamma_grad_kernel(const float* __restrict__ dtemb, const float* __restrict__ gamma, int T, int E,
+                                       const float* __restrict__ inv_scale, float* __restrict__ dgamma) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  double acc = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const double tt = T > 1 ? (double)t / (double)(T - 1) : 0.0;     // torch.linspace(0, 1, T)
+    const float arg = (float)tt * gamma[i];                          // the forward's fp32 product tt * gamma
+    acc += (double)dtemb[(int64_t)t * E + i] * (-sin((double)arg)) * tt;
+  }
+  dgamma[i] = (float)(acc * (double)inv_of(inv_scale));
+}
+__global__ void __launch_bounds__(256) rowsum_scale_kernel(const float* __restrict__ X, int rows, int cols,
+                                                           const float* __restrict__ inv_scale, float* __restrict__ rowsum,
+                                                           float* __restrict__ scaled) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float inv = inv_of(inv_scale);
+  double acc = 0.0;
+  for (int j = lane; j < cols; j += 32) {
+    const float v = X[(int64_t)row * cols + j];
+    acc += (double)v;
+    scaled[(int64_t)row * cols + j] = v * inv;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) rowsum[row] = (float)(acc * (double)inv);
+}
+__global__ void transpose2_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? src[(int64_t)r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) dst[(int64_t)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+__global__ void add_mean_grad_kernel(const float* __restrict__ dtok, int64_t total4, int n, int E, float* __restrict__ g) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int64_t i = i4 * 4;
+  const int64_t row = i / E; const int c = (int)(i % E);
+  const int b = (int)(row / n);
+  const float s = 1.0f / (float)n;
+  const float4 d = *reinterpret_cast<const float4*>(dtok + (int64_t)b * E + c);
+  float4 v = *reinterpret_cast<float4*>(g + i);
+  v.x = fmaf(d.x, s, v.x); v.y = fmaf(d.y, s, v.y); v.z = fmaf(d.z, s, v.z); v.w = fmaf(d.w, s, v.w);
+  *reinterpret_cast<float4*>(g + i) = v;
+}
+__global__ void __launch_bounds__(256) split_scaled_kernel(const float* __restrict__ src, int64_t rows, int cols8,
+                                                           const float* __restrict__ factor, __half* __restrict__ dst,
+                                                           int64_t ldd, int64_t lo_off) {
+  const int64_t total = rows * cols8;
+  const float f = factor ? __ldg(factor) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols8;
+    const int c = (int)(i % cols8) * 8;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(src + (r * cols8) * 8 + c));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(src + (r * cols8) * 8 + c + 4));
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    alignas(16) __half hi[8];
+    alignas(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) hl_split(v[u] * f, hi[u], lo[u]);
+    *reinterpret_cast<uint4*>(dst + r * ldd + c) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + r * ldd + c + lo_off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+inline unsigned blocks_for(int64_t total, int per) { return (unsigned)ceil_div(total, per); }
+
+}  // namespace
+
+// ================================================================================================ host launchers
+int tk_grad_scale(const float* dy, int64_t n, unsigned* bits, float* scale, cudaStream_t st) {
+  DPOT_CUDA(cudaMemsetAsync(bits, 0, sizeof(unsigned), st));
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+  absmax_kernel<<<grid, 256, 0, st>>>(dy, n, bits);
+  DPOT_LAUNCH_CHECK("absmax_kernel");
+  scale_from_max_kernel<<<1, 1, 0, st>>>(bits, scale);
+  DPOT_LAUNCH_CHECK("scale_from_max_kernel");
+  return 0;
+}
+
+int tk_colsum(const void* X, bool f16, int64_t ld, int64_t lo_off, int M, int N, double* out, cudaStream_t st) {
+  if (M <= 0) return 0;
+  const int rpb = M >= 4096 ? 64 : (M >= 256 ? 32 : M);
+  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, rpb));
+  if (f16) colsum2_kernel<true><<<grid, 128, 0, st>>>(X, ld, lo_off, M, N, rpb, out);
+  else colsum2_kernel<false><<<grid, 128, 0, st>>>(X, ld, lo_off, M, N, rpb, out);
+  DPOT_LAUNCH_CHECK("colsum2_kernel");
+  return 0;
+}
+
+int tk_gn_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* add, int B, int n, int E,
+              int groups, float eps, const float* inv_scale, float* scratch, float* dx, __half* dx16, float* dgamma,
+              float* dbeta, cudaStream_t st) {
+  DPOT_REQUIRE(E % groups == 0 && (E / groups) % 4 == 0 && E % 2 == 0, DPOT_E_BADARG, "gn_bwd: group size must be a multiple of 4");
+  float* A1 = scratch; float* A2 = A1 + (int64_t)B * E; float* coefA = A2 + (int64_t)B * E; float* coefBC = coefA + (int64_t)B * E;
+  gn_bwd_reduce2_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B), 256, 0, st>>>(dy, x, n, E, A1, A2);
+  DPOT_LAUNCH_CHECK("gn_bwd_reduce2_kernel");
+  const int gblocks = (int)ceil_div(B * groups, 4);
+  gn_bwd_group2_kernel<<<(unsigned)(gblocks + ceil_div(E, 128)), 128, 0, st>>>(A1, A2, stats, gamma, B, n, E, groups, eps, gblocks,
+                                                                              inv_scale, coefA, coefBC, dgamma, dbeta);
+  DPOT_LAUNCH_CHECK("gn_bwd_group2_kernel");
+  const int64_t total4 = (int64_t)B * n * E / 4;
+  if (dx16)
+    gn_bwd_apply2_kernel<true><<<blocks_for(total4, 256), 256, 0, st>>>(dy, x, coefA, coefBC, add, total4, n, E, E / groups, groups, dx,
+                                                                       dx16, 2 * (int64_t)E, E);
+  else
+    gn_bwd_apply2_kernel<false><<<blocks_for(total4, 256), 256, 0, st>>>(dy, x, coefA, coefBC, add, total4, n, E, E / groups, groups,
+                                                                        dx, nullptr, 0, 0);
+  DPOT_LAUNCH_CHECK("gn_bwd_apply2_kernel");
+  return 0;
+}
+
+int tk_slab_reduce(const float* slabs, int nslab, int64_t stride, int64_t count, const float* inv_scale, float* dst, cudaStream_t st) {
+  if (count % 4 == 0 && stride % 4 == 0 && (reinterpret_cast<uintptr_t>(slabs) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0)
+    slab_reduce_kernel<<<blocks_for(count / 4, 256), 256, 0, st>>>(slabs, nslab, stride, count / 4, inv_scale, dst);
+  else
+    slab_reduce1_kernel<<<blocks_for(count, 256), 256, 0, st>>>(slabs, nslab, stride, count, inv_scale, dst);
+  DPOT_LAUNCH_CHECK("slab_reduce_kernel");
+  return 0;
+}
+
+int tk_finish_double(const double* src, int64_t count, const float* inv_scale, float* dst, cudaStream_t st) {
+  finish_double_kernel<<<blocks_for(count, 256), 256, 0, st>>>(src, count, inv_scale, dst);
+  DPOT_LAUNCH_CHECK("finish_double_kernel");
+  return 0;
+}
+
+int tk_scale_copy(const float* src, int64_t count, const float* inv_scale, float* dst, cudaStream_t st) {
+  scale_copy_kernel<<<blocks_for(count, 256), 256, 0, st>>>(src, count, inv_scale, dst);
+  DPOT_LAUNCH_CHECK("scale_copy_kernel");
+  return 0;
+}
+
+int tk_unpack_afno_grad(const float* dWc, int nslab, int64_t stride, const double* dbc, int nb, int bs, const float* inv_scale,
+                        float* dw, float* db, cudaStream_t st) {
+  const int64_t per = (int64_t)nb * bs * bs;
+  unpack_afno_grad2_kernel<<<blocks_for(per, 256), 256, 0, st>>>(dWc, nslab, stride, dbc, nb, bs, inv_scale, dw, db);
+  DPOT_LAUNCH_CHECK("unpack_afno_grad2_kernel");
+  return 0;
+}
+
+int tk_unpack_out_grad(const float* dWtT, int nslab, int64_t stride, const double* dbias_t, int E, int old, int P,
+                       const float* inv_scale, float* dwt, float* db, cudaStream_t st) {
+  const int PP = P * P;
+  DPOT_REQUIRE(old <= 65535, DPOT_E_BADARG, "unpack_out_grad: out_layer_dim too large");
+  unpack_out_grad_kernel<<<dim3((unsigned)ceil_div(E, 32), (unsigned)ceil_div(PP, 32), (unsigned)old), dim3(32, 8), 0, st>>>(
+      dWtT, nslab, stride, E, old, PP, inv_scale, dwt);
+  DPOT_LAUNCH_CHECK("unpack_out_grad_kernel");
+  out_bias_grad_kernel<<<(unsigned)ceil_div(old, 64), 64, 0, st>>>(dbias_t, old, PP, inv_scale, db);
+  DPOT_LAUNCH_CHECK("out_bias_grad_kernel");
+  return 0;
+}
+
+int tk_tail_bwd_supported(int old, int nout) { return old == TB_OLD && nout >= 1 && nout <= TB_NOUT_MAX; }
+int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const float* w2, const float* b2, const float* w4,
+                int B, int h, int w, int P, int nout, int act, __half* g1, double* acc, cudaStream_t st) {
+  DPOT_REQUIRE(tk_tail_bwd_supported(TB_OLD, nout), DPOT_E_UNSUPPORTED, "tail_bwd: nout %d unsupported", nout);
+  const int64_t npix = (int64_t)B * h * w * P * P;
+  TailBwdArgs a;
+  a.Y1pre = Y1pre; a.dout = dout; a.scale = scale; a.w2 = w2; a.b2 = b2; a.w4 = w4; a.g1 = g1; a.acc = acc;
+  a.B = B; a.h = h; a.w = w; a.P = P; a.nout = nout; a.act = act; a.ntiles = ceil_div(npix, TB_PIX);
+  const size_t smem = sizeof(float) * (32 * 32 + TB_NOUT_MAX * 32 + 32 + 3 * TB_PIX * 33 + TB_PIX * 8);
+  static DevOnce attr;
+  if (attr.need()) {
+    DPOT_CUDA(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr.done();
+  }
+  const int sms = sm_count_cur();
+  const unsigned grid = (unsigned)std::min<int64_t>(a.ntiles, (int64_t)sms * 3);
+  tail_bwd_kernel<<<grid, TB_PIX, smem, st>>>(a);
+  DPOT_LAUNCH_CHECK("tail_bwd_kernel");
+  return 0;
+}
+
+int tk_patch_bwd_supported(int mid, int T, int K0) { return mid <= PB_MID && T <= PB_T && K0 <= PB_NT; }
+int tk_patch_bwd(const float* gz, const float* x, const float* W0p, int B, int X, int Y, int T, int C, int P, int mid, int Kp,
+                 const float* inv_scale, double* dW0p, float* dx, cudaStream_t st) {
+  DPOT_REQUIRE(tk_patch_bwd_supported(mid, T, P * P * C), DPOT_E_UNSUPPORTED, "patch_bwd: geometry unsupported");
+  PatchBwdArgs a;
+  a.gz = gz; a.x = x; a.W0p = W0p; a.inv_scale = inv_scale; a.dW0p = dW0p; a.dx = dx;
+  a.B = B; a.X = X; a.Y = Y; a.T = T; a.C = C; a.P = P; a.mid = mid; a.Kp = Kp; a.K0 = P * P * C; a.h = X / P; a.w = Y / P;
+  const size_t smem = sizeof(float) * (PB_T * PB_MID + (size_t)P * P * T * C);
+  static DevOnce attr;
+  if (attr.need()) {
+    DPOT_CUDA(cudaFuncSetAttribute(patch_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr.done();
+  }
+  DPOT_REQUIRE(smem <= 64 * 1024, DPOT_E_UNSUPPORTED, "patch_bwd: patch tile too large");
+  const int64_t npatch = (int64_t)B * a.h * a.w;
+  const unsigned grid = (unsigned)std::min<int64_t>(npatch, (int64_t)sm_count_cur() * 4);
+  patch_bwd_kernel<<<grid, PB_NT, smem, st>>>(a);
+  DPOT_LAUNCH_CHECK("patch_bwd_kernel");
+  return 0;
+}
+
+int tk_unpack_patch_grad(const double* dW0p, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
+                         int P, int h, int w, int T, int Kp, const float* inv_scale, float* dw0, float* db0, cudaStream_t st) {
+  DPOT_REQUIRE(P <= 32, DPOT_E_UNSUPPORTED, "unpack_patch_grad: patch_size > 32");
+  unpack_patch_grad_kernel<<<(unsigned)mid, 256, 0, st>>>(dW0p, drb, gx, gy, gt, mid, C, P, h, w, T, Kp, inv_scale, dw0, db0);
+  DPOT_LAUNCH_CHECK("unpack_patch_grad_kernel");
+  return 0;
+}
+
+int tk_tagg_scale(const float* w, const float* temb, int T, int E, float* wts, float* wtsT, float* Wsum, float* WsumT, cudaStream_t st) {
+  tagg_scale_kernel<<<dim3((unsigned)ceil_div(E, 32), (unsigned)ceil_div(E, 32), (unsigned)T), dim3(32, 8), 0, st>>>(w, temb, E, wts, wtsT);
+  DPOT_LAUNCH_CHECK("tagg_scale_kernel");
+  const int64_t per = (int64_t)E * E;
+  sum_over_t_kernel<<<blocks_for(per, 256), 256, 0, st>>>(wts, wtsT, T, per, Wsum, WsumT);
+  DPOT_LAUNCH_CHECK("sum_over_t_kernel");
+  return 0;
+}
+int tk_tagg_bp(const float* b2, const float* pos, int E, int n, float* bp, float* bpT, cudaStream_t st) {
+  tagg_bp_kernel<<<blocks_for((int64_t)E * n, 256), 256, 0, st>>>(b2, pos, E, n, bp, bpT);
+  DPOT_LAUNCH_CHECK("tagg_bp_kernel");
+  return 0;
+}
+int tk_tagg_finish(const float* dwt, const float* w, const float* temb, int T, int E, const float* inv_scale, float* dw,
+                   float* dtemb, cudaStream_t st) {
+  const int64_t rows = (int64_t)T * E;
+  tagg_finish_kernel<<<blocks_for(rows, 8), 256, 0, st>>>(dwt, w, temb, rows, E, inv_scale, dw, dtemb);
+  DPOT_LAUNCH_CHECK("tagg_finish_kernel");
+  return 0;
+}
+int tk_tagg_gamma_grad(const float* dtemb, const float* gamma, int T, int E, const float* inv_scale, float* dgamma, cudaStream_t st) {
+  tagg_gamma_grad_kernel<<<(unsigned)ceil_div(E, 128), 128, 0, st>>>(dtemb, gamma, T, E, inv_scale, dgamma);
+  DPOT_LAUNCH_CHECK("tagg_gamma_grad_kernel");
+  return 0;
+}
+int tk_rowsum_scale(const float* X, int rows, int cols, const float* inv_scale, float* rowsum, float* scaled, cudaStream_t st) {
+  rowsum_scale_kernel<<<blocks_for(rows, 8), 256, 0, st>>>(X, rows, cols, inv_scale, rowsum, scaled);
+  DPOT_LAUNCH_CHECK("rowsum_scale_kernel");
+  return 0;
+}
+int tk_transpose(const float* src, int64_t lds, float* dst, int64_t ldd, int R, int Cc, cudaStream_t st) {
+  transpose2_kernel<<<dim3((unsigned)ceil_div(Cc, 32), (unsigned)ceil_div(R, 32)), dim3(32, 8), 0, st>>>(src, lds, dst, ldd, R, Cc);
+  DPOT_LAUNCH_CHECK("transpose2_kernel");
+  return 0;
+}
+int tk_add_mean_grad(const float* dtok, int B, int n, int E, float* g, cudaStream_t st) {
+  DPOT_REQUIRE(E % 4 == 0, DPOT_E_BADARG, "add_mean_grad: E %% 4");
+  const int64_t total4 = (int64_t)B * n * E / 4;
+  add_mean_grad_kernel<<<blocks_for(total4, 256), 256, 0, st>>>(dtok, total4, n, E, g);
+  DPOT_LAUNCH_CHECK("add_mean_grad_kernel");
+  return 0;
+}
+int tk_split_scaled(const float* src, int64_t rows, int cols, const float* factor, __half* dst, int64_t ldd, int64_t lo_off,
+                    cudaStream_t st) {
+  DPOT_REQUIRE(cols % 8 == 0, DPOT_E_BADARG, "split_scaled: cols %% 8");
+  const int64_t total = rows * (cols / 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+  split_scaled_kernel<<<grid, 256, 0, st>>>(src, rows, cols / 8, factor, dst, ldd, lo_off);
+  DPOT_LAUNCH_CHECK("split_scaled_kernel");
+  return 0;
+}
+
+}  // namespace dpot

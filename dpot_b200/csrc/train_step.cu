@@ -1,0 +1,544 @@
+// The training step of DPOTNet as three stream-ordered calls (no allocation, no synchronisation):
+//   dpot_train_prepare   -- once per optimizer step: packed / folded / split weights (models/dpot.py:183-232 folds)
+//   dpot_train_forward   -- DPOTNet.forward (models/dpot.py:364-403) keeping what backward needs on a caller-owned tape
+//   dpot_train_backward  -- its autograd (train_temporal.py:227 loss.backward()): every parameter gradient and dL/dx
+// Every dense contraction of forward AND backward runs on the f16-split tcgen05 engine (gemm_tc16.cu): data gradients
+// read the weights in their forward layout (w_trans), weight gradients read both token-major activations as stored
+// (a_trans + w_trans) in <= 1024-token chunks whose partial results are summed by the un-packing kernels; the
+// activation derivative rides in the data-gradient epilogue and its result leaves the engine already split.
+// Gradients are carried scaled by a power of two S (S * max|dL/dy| in [1, 2)) so that small gradient entries keep full
+// fp16 significands in the split operands; every final gradient is multiplied by 1 / S as it is written.
+#include "common.cuh"
+#include "model_layout.cuh"
+#include "train_kernels.cuh"
+#include <string.h>
+
+namespace dpot {
+namespace {
+
+constexpr int GROUPS = 8;
+constexpr float GN_EPS = 1e-5f;
+
+struct Bump {   // bump allocator over a float arena (sizes in floats, 256-byte granules)
+  int64_t o = 0;
+  int64_t take(int64_t n) { const int64_t r = o; o += slot(n); return r; }
+};
+
+struct TapeL {
+  int64_t z1, blocks, blk_stride, alat16, Y1pre, tok, c1pre, c2pre, c1, c2, total;
+  // offsets inside a block slab
+  int64_t lat, st1, st2, S, O1pre, O1, f, n2, hpre, hid;
+};
+TapeL tape_layout(const Dims& d, int B) {
+  TapeL L; Bump a;
+  const int64_t Mt = (int64_t)B * d.n, Ms = (int64_t)B * d.km1 * d.km2;
+  L.z1 = a.take(Mt * d.Kp);
+  Bump b;
+  L.lat = b.take(Mt * d.E);
+  L.st1 = b.take((int64_t)B * GROUPS * 4);
+  L.st2 = b.take((int64_t)B * GROUPS * 4);
+  L.S = b.take(Ms * 2 * d.E);
+  L.O1pre = b.take(Ms * 2 * d.E);
+  L.O1 = b.take(Ms * 2 * d.E);
+  L.f = b.take(Mt * d.E);
+  L.n2 = b.take(Mt * d.E);
+  L.hpre = b.take(Mt * d.hid);
+  L.hid = b.take(Mt * d.hid);
+  L.blk_stride = b.o;
+  L.blocks = a.take(b.o * d.depth);
+  L.alat16 = a.take(Mt * d.E);
+  L.Y1pre = a.take(Mt * d.NP);
+  L.tok = a.take((int64_t)B * d.E);
+  L.c1pre = a.take((int64_t)B * d.E);
+  L.c2pre = a.take((int64_t)B * d.E);
+  L.c1 = a.take((int64_t)B * d.E);
+  L.c2 = a.take((int64_t)B * d.E);
+  L.total = a.o;
+  return L;
+}
+
+struct PrepL { int64_t wts, Wsum, bp, total; };              // fold intermediates the backward needs
+PrepL prep_layout(const Dims& d) {
+  PrepL L; Bump a;
+  L.wts = a.take((int64_t)d.T * d.E * d.E);
+  L.Wsum = a.take((int64_t)d.E * d.E);
+  L.bp = a.take((int64_t)d.E * d.n);
+  L.total = a.o;
+  return L;
+}
+
+int64_t kchunk_for(int64_t K, int64_t tiles) {   // contraction chunk: <= 1024 deep, smaller when the output alone cannot fill the SMs
+  if (K <= 1024 && tiles >= 96) return 0;        // one chunk
+  int64_t ch = 1024;
+  while (ch > 256 && tiles * ceil_div(K, ch) < 148) ch /= 2;
+  return ch;
+}
+int64_t nchunks(int64_t K, int64_t ch) { return ch > 0 ? ceil_div(K, ch) : 1; }
+
+struct ScratchL {
+  // prepare
+  int64_t wtsT, WsumT, bpT, W2T;
+  // forward
+  int64_t O2, Y1g;
+  // backward
+  int64_t gA, gB, g16, g1_16, dn2, df, dO2, dO1, dS, dn1, slabs, g1t, z1pre, gz, dWeffT, dWeffT_T, dbe, dbeT, dWsum, dwt,
+      dW2acc, dbp, dtemb, gn, cls, dbl, scale;
+  // double accumulators (offsets in DOUBLES from dbl): per block [db2 E | db1 hid | dbc2 2E | dbc1 2E], then the rest
+  int64_t d_blk, d_blk_stride, d_tail, d_bias_t, d_be, d_rb, d_W0p, d_total;
+  int64_t total;
+};
+ScratchL scratch_layout(const Dims& d, int B) {
+  ScratchL L; memset(&L, 0, sizeof(L));
+  const int64_t Mt = (int64_t)B * d.n, Ms = (int64_t)B * d.km1 * d.km2, E = d.E;
+  int64_t mx = 0;
+  { Bump a;   // prepare
+    L.wtsT = a.take((int64_t)d.T * E * E); L.WsumT = a.take(E * E); L.bpT = a.take((int64_t)d.n * E); L.W2T = a.take((int64_t)d.mid * E);
+    mx = a.o; }
+  { Bump a;   // forward
+    L.O2 = a.take(Ms * 2 * E); L.Y1g = a.take(Mt * d.NP);
+    if (a.o > mx) mx = a.o; }
+  { Bump a;   // backward
+    const int64_t W = E > d.hid ? E : d.hid;
+    L.gA = a.take(Mt * E); L.gB = a.take(Mt * E); L.g16 = a.take(Mt * E); L.g1_16 = a.take(Mt * W);
+    L.dn2 = a.take(Mt * E); L.df = a.take(Mt * E); L.dO2 = a.take(Ms * 2 * E); L.dO1 = a.take(Ms * 2 * E); L.dS = a.take(Ms * 2 * E);
+    L.dn1 = a.take(Mt * E);
+    const int64_t kt = 8 + ceil_div(Mt, 256), ks = 8 + ceil_div(Ms, 256);   // generous chunk counts (kchunk_for >= 256)
+    int64_t sl = kt * (int64_t)d.hid * E;
+    if (kt * (int64_t)d.NP * E > sl) sl = kt * (int64_t)d.NP * E;
+    if (kt * E * d.Kp > sl) sl = kt * E * d.Kp;
+    if (ks * (int64_t)d.nb * 4 * d.bs * d.bs > sl) sl = ks * (int64_t)d.nb * 4 * d.bs * d.bs;
+    L.slabs = a.take(sl);
+    L.g1t = a.take(Mt * d.NP); L.z1pre = a.take(Mt * d.Kp); L.gz = a.take(Mt * d.Kp);
+    L.dWeffT = a.take(E * d.Kp); L.dWeffT_T = a.take(E * d.Kp); L.dbe = a.take((int64_t)d.n * E); L.dbeT = a.take((int64_t)d.n * E);
+    L.dWsum = a.take(E * E); L.dwt = a.take((int64_t)d.T * E * E); L.dW2acc = a.take(E * d.mid); L.dbp = a.take(E * d.n);
+    L.dtemb = a.take((int64_t)d.T * E);
+    L.gn = a.take(3 * (int64_t)B * E + 2 * (int64_t)B * GROUPS);
+    L.cls = a.take(8 * (int64_t)B * E + 3 * E * E + (int64_t)d.ncls * E + 4096);
+    L.scale = a.take(64);
+    // doubles
+    int64_t q = 0;
+    L.d_blk = q; L.d_blk_stride = E + d.hid + 4 * E; q += L.d_blk_stride * d.depth;
+    L.d_tail = q; q += 1024 + 32 + 8 * 32 + 8 + 8;
+    L.d_bias_t = q; q += d.NP;
+    L.d_be = q; q += (int64_t)d.n * E;
+    L.d_rb = q; q += (int64_t)d.n * d.Kp;
+    L.d_W0p = q; q += (int64_t)d.mid * d.K0;
+    L.d_total = q;
+    L.dbl = a.take(2 * q + 2);
+    if (a.o > mx) mx = a.o; }
+  L.total = mx;
+  return L;
+}
+
+bool train_ok(const dpot_config* c, const Dims& d) {
+  if (c->normalize) return false;
+  if (!use_tc16(d, DPOT_GEMM_AUTO)) return false;
+  if (d.depth < 1) return false;
+  if ((d.E / GROUPS) % 8 != 0 || d.E % GROUPS != 0) return false;
+  if (!dpot_out_tail_tc_supported(d.old, d.Co * d.To, d.Co) || !tk_tail_bwd_supported(d.old, d.Co * d.To)) return false;
+  if (!tk_patch_bwd_supported(d.mid, d.T, d.K0)) return false;
+  if (d.E % 32 != 0 || d.n % 32 != 0) return false;                 // fold GEMMs on the fp32 tensor-core engine (K % 32)
+  if ((2 * d.bs) % 8 != 0 || d.hid % 8 != 0 || d.NP % 8 != 0 || d.Kp % 8 != 0) return false;
+  if (d.C != d.Co) return false;
+  return true;
+}
+
+// split-fp16 matrix handle: `cols` columns, row = [hi cols halves | lo cols halves]
+dpot_gemm_args g16(const float* A16, int64_t a_cols, const float* W16, int64_t w_cols, float* C, int64_t ldc, int M, int N, int K) {
+  return gemm16_args(A16, a_cols, W16, w_cols, C, ldc, M, N, K, nullptr, DPOT_ACT_NONE);
+}
+void ksplit(dpot_gemm_args& g, int64_t chunk, int64_t slab) {
+  if (chunk > 0 && chunk < g.K) { g.k_split = (int)ceil_div(g.K, chunk); g.k_chunk = chunk; g.strideC_split = slab; }
+}
+
+// weight gradient dW[N, K] = g[Mtok, N]^T x[Mtok, K] (both stored token-major, split) -> `*ns` partial results in slabs
+int wgrad16(const float* g16p, int64_t g_cols, const float* x16p, int64_t x_cols, int N, int K, int Mtok, int batch, float* slabs,
+            int* ns, void* stream) {
+  dpot_gemm_args a = g16(g16p, g_cols, x16p, x_cols, slabs, K, N, K, Mtok);
+  a.a_trans = 1; a.w_trans = 1;
+  const int64_t tiles = ceil_div(N, 128) * ceil_div(K, 128) * batch;
+  if (batch > 1) { a.batch = batch; a.strideA = N; a.strideW = K; a.strideC = (int64_t)N * K; }
+  const int64_t ch = kchunk_for(Mtok, tiles);
+  ksplit(a, ch, (int64_t)batch * N * K);
+  *ns = a.k_split > 1 ? a.k_split : 1;
+  return dpot_gemm(&a, stream);
+}
+
+}  // namespace
+}  // namespace dpot
+
+using namespace dpot;
+
+extern "C" int dpot_train_supported(const dpot_config* cfg) {
+  Dims d;
+  if (make_dims(cfg, d) != 0) return 0;
+  return train_ok(cfg, d) ? 1 : 0;
+}
+extern "C" int64_t dpot_train_tape_floats(const dpot_config* cfg, int32_t B) {
+  Dims d;
+  if (make_dims(cfg, d) != 0 || B <= 0) return -1;
+  return tape_layout(d, B).total;
+}
+extern "C" int64_t dpot_train_scratch_floats(const dpot_config* cfg, int32_t B) {
+  Dims d;
+  if (make_dims(cfg, d) != 0 || B <= 0) return -1;
+  return scratch_layout(d, B).total;
+}
+extern "C" int64_t dpot_train_wprep_floats(const dpot_config* cfg) {
+  Dims d;
+  if (make_dims(cfg, d) != 0) return -1;
+  return prep_layout(d).total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm, float* packed, float* wprep, float* scratch,
+                                  void* stream) {
+  Dims d;
+  DPOT_CALL(make_dims(cfg, d));
+  DPOT_REQUIRE(train_ok(cfg, d), DPOT_E_UNSUPPORTED, "dpot_train_prepare: configuration not served by the fused training step");
+  DPOT_REQUIRE(prm && packed && wprep && scratch && prm->blocks, DPOT_E_BADARG, "dpot_train_prepare: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const Packed L = packed_layout(d);
+  const PrepL PL = prep_layout(d);
+  const ScratchL SL = scratch_layout(d, 1);
+  const int E = d.E;
+  DPOT_CALL(dpot_pack_patch(prm->pe0_w, prm->pe0_b, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h, d.T,
+                            packed + L.W0p, packed + L.rowbias0, stream));
+  // fold conv 1x1 + pos_embed + time aggregation with the contraction engine (the double-precision fold kernels of the
+  // inference packer take ~1 ms: fine once per checkpoint, not once per optimizer step)
+  float* wts = wprep + PL.wts; float* Wsum = wprep + PL.Wsum; float* bp = wprep + PL.bp;
+  float* wtsT = scratch + SL.wtsT; float* WsumT = scratch + SL.WsumT; float* bpT = scratch + SL.bpT; float* W2T = scratch + SL.W2T;
+  DPOT_CALL(tk_tagg_scale(prm->tagg_w, prm->temb, d.T, E, wts, wtsT, Wsum, WsumT, st));
+  DPOT_CALL(tk_transpose(prm->pe2_w, d.mid, W2T, E, E, d.mid, st));
+  DPOT_CUDA(cudaMemsetAsync(packed + L.WeffT, 0, sizeof(float) * (size_t)E * d.Kp, st));
+  for (int t = 0; t < d.T; ++t) {   // WeffT[j, t*mid + m] = sum_i wts[t,i,j] W2[i,m]
+    dpot_gemm_args g = gemm_args(wtsT + (int64_t)t * E * E, E, W2T, E, packed + L.WeffT + (int64_t)t * d.mid, d.Kp, E, d.mid, E,
+                                 nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+  DPOT_CALL(tk_tagg_bp(prm->pe2_b, prm->pos_embed, E, d.n, bp, bpT, st));
+  {   // bias_eff[p, j] = sum_i (b2[i] + pos[i,p]) Wsum[i,j]
+    dpot_gemm_args g = gemm_args(bpT, E, WsumT, E, packed + L.bias_eff, E, d.n, E, E, nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+  DPOT_CALL(dpot_pack_out(prm->out0_w, prm->out0_b, E, d.old, d.P, packed + L.WtT, packed + L.bias_t, stream));
+  DPOT_CALL(dpot_split_f16(packed + L.WeffT, d.Kp, E, d.Kp, nullptr, nullptr, 0, packed + L.WeffT16, 2 * d.Kp, d.Kp, stream));
+  DPOT_CALL(dpot_split_f16(packed + L.WtT, E, d.NP, E, nullptr, nullptr, 0, packed + L.WtT16, 2 * E, E, stream));
+  const int64_t kb = 2 * d.bs;
+  for (int i = 0; i < d.depth; ++i) {
+    float* base = packed + L.blocks + (int64_t)i * L.blk_stride;
+    const dpot_block_params& b = prm->blocks[i];
+    DPOT_CALL(dpot_pack_afno(b.w1, b.b1, d.nb, d.bs, base + L.Wc1, base + L.bc1, stream));
+    DPOT_CALL(dpot_pack_afno(b.w2, b.b2, d.nb, d.bs, base + L.Wc2, base + L.bc2, stream));
+    DPOT_CALL(dpot_split_f16(base + L.Wc1, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc1_16, 2 * kb, kb, stream));
+    DPOT_CALL(dpot_split_f16(base + L.Wc2, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc2_16, 2 * kb, kb, stream));
+    DPOT_CALL(dpot_split_f16(b.fc1_w, E, d.hid, E, nullptr, nullptr, 0, base + L.fc1_16, 2 * E, E, stream));
+    DPOT_CALL(dpot_split_f16(b.fc2_w, d.hid, E, d.hid, nullptr, nullptr, 0, base + L.fc2_16, 2 * d.hid, d.hid, stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int32_t B,
+                                  float* y, float* cls, float* tape, float* scratch, void* stream) {
+  Dims d;
+  DPOT_CALL(make_dims(cfg, d));
+  DPOT_REQUIRE(train_ok(cfg, d), DPOT_E_UNSUPPORTED, "dpot_train_forward: configuration not served by the fused training step");
+  DPOT_REQUIRE(prm && packed && x && y && tape && scratch && prm->blocks && B > 0, DPOT_E_BADARG, "dpot_train_forward: null pointer / bad B");
+  cudaStream_t st = as_stream(stream);
+  const Packed PL = packed_layout(d);
+  const TapeL TL = tape_layout(d, B);
+  const ScratchL SL = scratch_layout(d, B);
+  const int Mt = B * d.n, Ms = B * d.km1 * d.km2, act = cfg->act, R = cfg->img_size, E = d.E;
+  const int64_t kb = 2 * d.bs;
+  float* z1 = tape + TL.z1;
+  if (d.Kp != d.T * d.mid) DPOT_CUDA(cudaMemsetAsync(z1, 0, sizeof(float) * (size_t)Mt * d.Kp, st));
+  DPOT_CALL(dpot_patch_embed(x, 0, packed + PL.W0p, packed + PL.rowbias0, nullptr, nullptr, B, R, R, d.T, d.C, d.P, d.mid, act, z1,
+                             d.Kp, DPOT_FMT_HL16, stream));
+  auto blk = [&](int i) { return tape + TL.blocks + (int64_t)i * TL.blk_stride; };
+  {
+    dpot_gemm_args g = gemm16_args(z1, d.Kp, packed + PL.WeffT16, d.Kp, blk(0) + TL.lat, E, Mt, E, d.Kp, nullptr, DPOT_ACT_NONE);
+    g.rowbias = packed + PL.bias_eff; g.rowbias_period = d.n; g.ldrb = E;
+    g.out_stats = reinterpret_cast<double*>(blk(0) + TL.st1); g.stats_groups = GROUPS; g.stats_rows_per_sample = d.n;
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+  float* O2 = scratch + SL.O2;
+  for (int i = 0; i < d.depth; ++i) {
+    const dpot_block_params& bp = prm->blocks[i];
+    const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
+    float* tb = blk(i);
+    float* lat = tb + TL.lat;
+    double* st1 = reinterpret_cast<double*>(tb + TL.st1);
+    double* st2 = reinterpret_cast<double*>(tb + TL.st2);
+    DPOT_CALL(dpot_afno_fft_fwd16_gn(lat, st1, bp.norm1_w, bp.norm1_b, GROUPS, GN_EPS, B, d.h, E, d.nb, d.km1, d.km2, tb + TL.S, stream));
+    {
+      dpot_gemm_args g = gemm16_args(tb + TL.S, 2 * E, pk + PL.Wc1_16, kb, tb + TL.O1, 0, Ms, (int)kb, (int)kb, pk + PL.bc1, act);
+      g.batch = d.nb; g.strideA = kb; g.strideW = 2 * kb * kb; g.strideC = kb; g.strideBias = kb;
+      out16(g, 2 * E);
+      g.C_pre = tb + TL.O1pre; g.ld_pre = 2 * E; g.stride_pre = kb;
+      DPOT_CALL(dpot_gemm(&g, stream));
+      g = gemm16_args(tb + TL.O1, 2 * E, pk + PL.Wc2_16, kb, O2, 2 * E, Ms, (int)kb, (int)kb, pk + PL.bc2, DPOT_ACT_NONE);
+      g.batch = d.nb; g.strideA = kb; g.strideW = 2 * kb * kb; g.strideC = kb; g.strideBias = kb;
+      DPOT_CALL(dpot_gemm(&g, stream));
+    }
+    DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * GROUPS * B, st));
+    DPOT_CALL(dpot_afno_fft_inv_gn(O2, lat, st1, bp.norm1_w, bp.norm1_b, GROUPS, GN_EPS, B, d.h, E, d.nb, d.km1, d.km2, tb + TL.f, st2, stream));
+    DPOT_CALL(dpot_split_f16_gn(tb + TL.f, E, Mt, E, st2, bp.norm2_w, bp.norm2_b, GROUPS, GN_EPS, d.n, tb + TL.n2, 2 * E, E, stream));
+    {
+      dpot_gemm_args g = gemm16_args(tb + TL.n2, E, pk + PL.fc1_16, E, tb + TL.hid, 0, Mt, d.hid, E, bp.fc1_b, act);
+      out16(g, d.hid);
+      g.C_pre = tb + TL.hpre; g.ld_pre = d.hid;
+      DPOT_CALL(dpot_gemm(&g, stream));
+      const bool last = i + 1 == d.depth;
+      float* dst = last ? tape + TL.alat16 : blk(i + 1) + TL.lat;
+      g = gemm16_args(tb + TL.hid, d.hid, pk + PL.fc2_16, d.hid, dst, E, Mt, E, d.hid, bp.fc2_b, DPOT_ACT_NONE);
+      g.residual = lat; g.ldr = E;
+      if (!last) { g.out_stats = reinterpret_cast<double*>(blk(i + 1) + TL.st1); g.stats_groups = GROUPS; g.stats_rows_per_sample = d.n; }
+      else out16(g, E);
+      DPOT_CALL(dpot_gemm(&g, stream));
+    }
+  }
+  if (cls) {   // classification head; pre-activations kept for backward
+    DPOT_CALL(dpot_spatial_mean16(tape + TL.alat16, B, d.n, E, tape + TL.tok, stream));
+    dpot_gemm_args g = gemm_args(tape + TL.tok, E, prm->cls0_w, E, tape + TL.c1, E, B, E, E, prm->cls0_b, act, DPOT_GEMM_AUTO);
+    g.C_pre = tape + TL.c1pre;
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(tape + TL.c1, E, prm->cls2_w, E, tape + TL.c2, E, B, E, E, prm->cls2_b, act, DPOT_GEMM_AUTO);
+    g.C_pre = tape + TL.c2pre;
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm_args(tape + TL.c2, E, prm->cls4_w, E, cls, d.ncls, B, d.ncls, E, prm->cls4_b, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+    DPOT_CALL(dpot_gemm(&g, stream));
+  }
+  {   // output head: ConvTranspose GEMM (per-pixel [hi 32 | lo 32] records for the tcgen05 tail, fp32 pre-activation for backward)
+    float* Y1g = scratch + SL.Y1g;
+    dpot_gemm_args g = gemm16_args(tape + TL.alat16, E, packed + PL.WtT16, E, Y1g, d.NP, Mt, d.NP, E, packed + PL.bias_t, act);
+    g.c_fmt = DPOT_FMT_HL16G32; g.ldc = 2 * (int64_t)d.NP;
+    g.C_pre = tape + TL.Y1pre; g.ld_pre = d.NP;
+    DPOT_CALL(dpot_gemm(&g, stream));
+    DPOT_CALL(dpot_out_tail_tc(Y1g, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, d.Co * d.To, act,
+                               nullptr, nullptr, d.Co, y, nullptr, nullptr, d.T, 0, 0, 0, stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+namespace dpot {
+namespace {
+
+// classification head backward (M = B rows: CUDA-core kernels); gc = dcls * S.  Adds dtok / n into g (the gradient of the
+// last latent).  Scratch `cs` as laid out by scratch_layout (cls).
+int cls_backward(const dpot_config* cfg, const dpot_params* prm, const Dims& d, int B, const float* dcls, const float* tape,
+                 const TapeL& TL, float* cs, const float* scale, const dpot_params* gr, float* g, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const int E = d.E, act = cfg->act;
+  const float* inv = scale + 1;
+  Bump a;
+  float* gc = cs + a.take((int64_t)B * d.ncls);
+  float* dc2 = cs + a.take((int64_t)B * E); float* g2 = cs + a.take((int64_t)B * E);
+  float* dc1 = cs + a.take((int64_t)B * E); float* g1 = cs + a.take((int64_t)B * E);
+  float* dtok = cs + a.take((int64_t)B * E);
+  float* WT = cs + a.take((int64_t)E * E);
+  float* W4T = cs + a.take((int64_t)d.ncls * E);
+  DPOT_CALL(tk_scale_copy(dcls, (int64_t)B * d.ncls, scale, gc, st));
+  auto wgrad = [&](const float* X, int ldx, const float* Y, int ldy, int N, int K, float* dW) -> int {
+    dpot_wgrad_args w; memset(&w, 0, sizeof(w));
+    w.X = X; w.ldx = ldx; w.Y = Y; w.ldy = ldy; w.dW = dW; w.ldw = K; w.M = B; w.N = N; w.K = K; w.batch = 1;
+    DPOT_CALL(dpot_wgrad(&w, stream));
+    return tk_scale_copy(dW, (int64_t)N * K, inv, dW, st);
+  };
+  auto bgrad = [&](const float* X, int N, float* db) -> int {
+    DPOT_CALL(dpot_colsum(X, N, B, N, db, 0, stream));
+    return tk_scale_copy(db, N, inv, db, st);
+  };
+  // layer 4: cls = c2 W4^T + b4
+  DPOT_CALL(wgrad(gc, d.ncls, tape + TL.c2, E, d.ncls, E, const_cast<float*>(gr->cls4_w)));
+  DPOT_CALL(bgrad(gc, d.ncls, const_cast<float*>(gr->cls4_b)));
+  DPOT_CALL(tk_transpose(prm->cls4_w, E, W4T, d.ncls, d.ncls, E, st));          // [E, ncls]
+  dpot_gemm_args m = gemm_args(gc, d.ncls, W4T, d.ncls, dc2, E, B, E, d.ncls, nullptr, DPOT_ACT_NONE, DPOT_GEMM_SIMT);
+  DPOT_CALL(dpot_gemm(&m, stream));
+  DPOT_CALL(dpot_act_bwd(dc2, tape + TL.c2pre, act, (int64_t)B * E, g2, stream));
+  // layer 2
+  DPOT_CALL(wgrad(g2, E, tape + TL.c1, E, E, E, const_cast<float*>(gr->cls2_w)));
+  DPOT_CALL(bgrad(g2, E, const_cast<float*>(gr->cls2_b)));
+  DPOT_CALL(tk_transpose(prm->cls2_w, E, WT, E, E, E, st));
+  m = gemm_args(g2, E, WT, E, dc1, E, B, E, E, nullptr, DPOT_ACT_NONE, DPOT_GEMM_SIMT);
+  DPOT_CALL(dpot_gemm(&m, stream));
+  DPOT_CALL(dpot_act_bwd(dc1, tape + TL.c1pre, act, (int64_t)B * E, g1, stream));
+  // layer 0
+  DPOT_CALL(wgrad(g1, E, tape + TL.tok, E, E, E, const_cast<float*>(gr->cls0_w)));
+  DPOT_CALL(bgrad(g1, E, const_cast<float*>(gr->cls0_b)));
+  DPOT_CALL(tk_transpose(prm->cls0_w, E, WT, E, E, E, st));
+  m = gemm_args(g1, E, WT, E, dtok, E, B, E, E, nullptr, DPOT_ACT_NONE, DPOT_GEMM_SIMT);
+  DPOT_CALL(dpot_gemm(&m, stream));
+  return tk_add_mean_grad(dtok, B, d.n, E, g, st);
+}
+
+}  // namespace
+}  // namespace dpot
+
+extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
+                                   const float* x, int32_t B, const float* dy, const float* dcls, const float* tape,
+                                   float* scratch, const dpot_params* grads, float* dx, void* stream) {
+  Dims d;
+  DPOT_CALL(make_dims(cfg, d));
+  DPOT_REQUIRE(train_ok(cfg, d), DPOT_E_UNSUPPORTED, "dpot_train_backward: configuration not served by the fused training step");
+  DPOT_REQUIRE(prm && packed && wprep && x && dy && tape && scratch && grads && grads->blocks && prm->blocks && B > 0, DPOT_E_BADARG,
+               "dpot_train_backward: null pointer / bad B");
+  cudaStream_t st = as_stream(stream);
+  const Packed PL = packed_layout(d);
+  const PrepL WL = prep_layout(d);
+  const TapeL TL = tape_layout(d, B);
+  const ScratchL SL = scratch_layout(d, B);
+  const int Mt = B * d.n, Ms = B * d.km1 * d.km2, act = cfg->act, R = cfg->img_size, E = d.E, H = d.hid, NP = d.NP;
+  const int nout = d.Co * d.To;
+  const int64_t kb = 2 * d.bs;
+  auto G = [](const float* p) { return const_cast<float*>(p); };
+  auto blk = [&](int i) { return tape + TL.blocks + (int64_t)i * TL.blk_stride; };
+  float* scale = scratch + SL.scale;                 // [S, 1/S]
+  const float* inv = scale + 1;
+  double* dbl = reinterpret_cast<double*>(scratch + SL.dbl);
+  DPOT_CUDA(cudaMemsetAsync(dbl, 0, sizeof(double) * (size_t)SL.d_total, st));
+  DPOT_CALL(tk_grad_scale(dy, (int64_t)B * R * R * nout, reinterpret_cast<unsigned*>(scale + 8), scale, st));
+  float* slabs = scratch + SL.slabs;
+  int ns = 1;
+
+  // ---- output head (models/dpot.py:315-321)
+  float* g1t = scratch + SL.g1t;
+  {
+    double* acc = dbl + SL.d_tail;
+    DPOT_CALL(tk_tail_bwd(tape + TL.Y1pre, dy, scale, prm->out2_w, prm->out2_b, prm->out4_w, B, d.h, d.h, d.P, nout, act,
+                          reinterpret_cast<__half*>(g1t), acc, st));
+    DPOT_CALL(tk_finish_double(acc, 1024, inv, G(grads->out2_w), st));
+    DPOT_CALL(tk_finish_double(acc + 1024, 32, inv, G(grads->out2_b), st));
+    DPOT_CALL(tk_finish_double(acc + 1056, (int64_t)nout * 32, inv, G(grads->out4_w), st));
+    DPOT_CALL(tk_finish_double(acc + 1056 + nout * 32, nout, inv, G(grads->out4_b), st));
+    DPOT_CALL(tk_colsum(g1t, true, 2 * (int64_t)NP, NP, Mt, NP, dbl + SL.d_bias_t, st));
+    DPOT_CALL(wgrad16(g1t, NP, tape + TL.alat16, E, NP, E, Mt, 1, slabs, &ns, stream));
+    DPOT_CALL(tk_unpack_out_grad(slabs, ns, (int64_t)NP * E, dbl + SL.d_bias_t, E, d.old, d.P, inv, G(grads->out0_w), G(grads->out0_b), st));
+  }
+  float* g = scratch + SL.gA;          // dL/d(latent after the last block), fp32, scaled by S
+  float* g_other = scratch + SL.gB;
+  float* gs16 = scratch + SL.g16;      // the same, split
+  {
+    dpot_gemm_args a = g16(g1t, NP, packed + PL.WtT16, E, g, E, Mt, E, NP);
+    a.w_trans = 1;
+    DPOT_CALL(dpot_gemm(&a, stream));
+  }
+  if (dcls)
+    DPOT_CALL(cls_backward(cfg, prm, d, B, dcls, tape, TL, scratch + SL.cls, scale, grads, g, stream));
+  DPOT_CALL(tk_split_scaled(g, Mt, E, nullptr, reinterpret_cast<__half*>(gs16), 2 * (int64_t)E, E, st));
+
+  // ---- blocks, last to first (models/dpot.py:165-180)
+  for (int i = d.depth - 1; i >= 0; --i) {
+    const dpot_block_params& bp = prm->blocks[i];
+    const dpot_block_params& gb = grads->blocks[i];
+    const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
+    const float* tb = blk(i);
+    double* dblk = dbl + SL.d_blk + (int64_t)i * SL.d_blk_stride;
+    double* db2 = dblk; double* db1 = db2 + E; double* dbc2 = db1 + H; double* dbc1 = dbc2 + 2 * E;
+    float* g1h = scratch + SL.g1_16;
+    // channel MLP: lat_next = fc2(act(fc1(n2))) + lat
+    DPOT_CALL(tk_colsum(g, false, E, 0, Mt, E, db2, st));
+    DPOT_CALL(tk_finish_double(db2, E, inv, G(gb.fc2_b), st));
+    DPOT_CALL(wgrad16(gs16, E, tb + TL.hid, H, E, H, Mt, 1, slabs, &ns, stream));
+    DPOT_CALL(tk_slab_reduce(slabs, ns, (int64_t)E * H, (int64_t)E * H, inv, G(gb.fc2_w), st));
+    {   // g1 = (g W2) * act'(hpre), split
+      dpot_gemm_args a = g16(gs16, E, pk + PL.fc2_16, H, g1h, 0, Mt, H, E);
+      a.w_trans = 1; out16(a, H);
+      a.dact_src = tb + TL.hpre; a.ld_dact = H; a.dact = act;
+      DPOT_CALL(dpot_gemm(&a, stream));
+    }
+    DPOT_CALL(tk_colsum(g1h, true, 2 * (int64_t)H, H, Mt, H, db1, st));
+    DPOT_CALL(tk_finish_double(db1, H, inv, G(gb.fc1_b), st));
+    DPOT_CALL(wgrad16(g1h, H, tb + TL.n2, E, H, E, Mt, 1, slabs, &ns, stream));
+    DPOT_CALL(tk_slab_reduce(slabs, ns, (int64_t)E * H, (int64_t)E * H, inv, G(gb.fc1_w), st));
+    float* dn2 = scratch + SL.dn2;
+    {
+      dpot_gemm_args a = g16(g1h, H, pk + PL.fc1_16, E, dn2, E, Mt, E, H);
+      a.w_trans = 1;
+      DPOT_CALL(dpot_gemm(&a, stream));
+    }
+    // GroupNorm-2
+    float* df = scratch + SL.df;
+    DPOT_CALL(tk_gn_bwd(dn2, tb + TL.f, reinterpret_cast<const double*>(tb + TL.st2), bp.norm2_w, nullptr, B, d.n, E, GROUPS, GN_EPS,
+                        inv, scratch + SL.gn, df, nullptr, G(gb.norm2_w), G(gb.norm2_b), st));
+    // AFNO mixer: f = irfft2(O2) + n1, O2 = O1 Wc2 + bc2, O1 = act(S Wc1 + bc1), S = rfft2(n1)
+    float* dO2 = scratch + SL.dO2; float* dO1 = scratch + SL.dO1; float* dS = scratch + SL.dS;
+    DPOT_CALL(dpot_afno_fft_fwd16w(df, B, d.h, E, d.nb, d.km1, d.km2, dO2, 2.0f, stream));       // adjoint of the inverse transform
+    DPOT_CALL(tk_colsum(dO2, true, 4 * (int64_t)E, 2 * E, Ms, 2 * E, dbc2, st));
+    DPOT_CALL(wgrad16(dO2, 2 * E, tb + TL.O1, 2 * E, (int)kb, (int)kb, Ms, d.nb, slabs, &ns, stream));
+    DPOT_CALL(tk_unpack_afno_grad(slabs, ns, (int64_t)d.nb * kb * kb, dbc2, d.nb, d.bs, inv, G(gb.w2), G(gb.b2), st));
+    {
+      dpot_gemm_args a = g16(dO2, 2 * E, pk + PL.Wc2_16, kb, dO1, 0, Ms, (int)kb, (int)kb);
+      a.w_trans = 1; a.batch = d.nb; a.strideA = kb; a.strideW = 2 * kb * kb; a.strideC = kb;
+      out16(a, 2 * E);
+      a.dact_src = tb + TL.O1pre; a.ld_dact = 2 * E; a.stride_dact = kb; a.dact = act;
+      DPOT_CALL(dpot_gemm(&a, stream));
+    }
+    DPOT_CALL(tk_colsum(dO1, true, 4 * (int64_t)E, 2 * E, Ms, 2 * E, dbc1, st));
+    DPOT_CALL(wgrad16(dO1, 2 * E, tb + TL.S, 2 * E, (int)kb, (int)kb, Ms, d.nb, slabs, &ns, stream));
+    DPOT_CALL(tk_unpack_afno_grad(slabs, ns, (int64_t)d.nb * kb * kb, dbc1, d.nb, d.bs, inv, G(gb.w1), G(gb.b1), st));
+    {
+      dpot_gemm_args a = g16(dO1, 2 * E, pk + PL.Wc1_16, kb, dS, 2 * E, Ms, (int)kb, (int)kb);
+      a.w_trans = 1; a.batch = d.nb; a.strideA = kb; a.strideW = 2 * kb * kb; a.strideC = kb;
+      DPOT_CALL(dpot_gemm(&a, stream));
+    }
+    float* dn1 = scratch + SL.dn1;
+    DPOT_CALL(dpot_afno_fft_inv(dS, df, nullptr, nullptr, B, d.h, E, d.nb, d.km1, d.km2, dn1, nullptr, GROUPS, 0.5f, stream));   // adjoint of the forward transform + skip
+    // GroupNorm-1 + the residual path
+    DPOT_CALL(tk_gn_bwd(dn1, tb + TL.lat, reinterpret_cast<const double*>(tb + TL.st1), bp.norm1_w, g, B, d.n, E, GROUPS, GN_EPS, inv,
+                        scratch + SL.gn, g_other, reinterpret_cast<__half*>(gs16), G(gb.norm1_w), G(gb.norm1_b), st));
+    float* t = g; g = g_other; g_other = t;
+  }
+
+  // ---- front: lat0 = z1 WeffT^T + bias_eff  (conv 1x1 + pos_embed + time aggregation folded), z1 = act(conv0(x))
+  float* dWeffT = scratch + SL.dWeffT; float* dbe = scratch + SL.dbe;
+  DPOT_CALL(tk_colsum(g, false, (int64_t)d.n * E, 0, B, d.n * E, dbl + SL.d_be, st));
+  DPOT_CALL(tk_finish_double(dbl + SL.d_be, (int64_t)d.n * E, nullptr, dbe, st));          // stays scaled by S
+  DPOT_CALL(wgrad16(gs16, E, tape + TL.z1, d.Kp, E, d.Kp, Mt, 1, slabs, &ns, stream));
+  DPOT_CALL(tk_slab_reduce(slabs, ns, (int64_t)E * d.Kp, (int64_t)E * d.Kp, nullptr, dWeffT, st));
+  float* z1pre = scratch + SL.z1pre; float* gz = scratch + SL.gz;
+  if (d.Kp != d.T * d.mid) DPOT_CUDA(cudaMemsetAsync(z1pre, 0, sizeof(float) * (size_t)Mt * d.Kp, st));
+  DPOT_CALL(dpot_patch_embed(x, 0, packed + PL.W0p, packed + PL.rowbias0, nullptr, nullptr, B, R, R, d.T, d.C, d.P, d.mid, DPOT_ACT_NONE,
+                             z1pre, d.Kp, DPOT_FMT_F32, stream));
+  {
+    dpot_gemm_args a = g16(gs16, E, packed + PL.WeffT16, d.Kp, gz, d.Kp, Mt, d.Kp, E);
+    a.w_trans = 1;
+    a.dact_src = z1pre; a.ld_dact = d.Kp; a.dact = act;
+    DPOT_CALL(dpot_gemm(&a, stream));
+  }
+  DPOT_CALL(tk_colsum(gz, false, (int64_t)d.n * d.Kp, 0, B, d.n * d.Kp, dbl + SL.d_rb, st));
+  DPOT_CALL(tk_patch_bwd(gz, x, packed + PL.W0p, B, R, R, d.T, d.C, d.P, d.mid, d.Kp, inv, dbl + SL.d_W0p, dx, st));
+  DPOT_CALL(tk_unpack_patch_grad(dbl + SL.d_W0p, dbl + SL.d_rb, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h, d.T,
+                                 d.Kp, inv, G(grads->pe0_w), G(grads->pe0_b), st));
+  // fold backward
+  {
+    const float* wts = wprep + WL.wts; const float* Wsum = wprep + WL.Wsum; const float* bpm = wprep + WL.bp;
+    float* dWeffT_T = scratch + SL.dWeffT_T; float* dbeT = scratch + SL.dbeT; float* dWsum = scratch + SL.dWsum;
+    float* dwt = scratch + SL.dwt; float* dW2acc = scratch + SL.dW2acc; float* dbp = scratch + SL.dbp; float* dtemb = scratch + SL.dtemb;
+    DPOT_CALL(tk_transpose(dWeffT, d.Kp, dWeffT_T, E, E, d.Kp, st));                 // [Kp, E]
+    DPOT_CALL(tk_transpose(dbe, E, dbeT, d.n, d.n, E, st));                          // [E, n]
+    dpot_gemm_args m = gemm_args(bpm, d.n, dbeT, d.n, dWsum, E, E, E, d.n, nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);   // dWsum[i,j]
+    DPOT_CALL(dpot_gemm(&m, stream));
+    for (int t = 0; t < d.T; ++t) {
+      // dwt[t][i,j] = sum_m W2[i,m] dWeffT[j, t*mid+m] + dWsum[i,j]
+      m = gemm_args(prm->pe2_w, d.mid, dWeffT + (int64_t)t * d.mid, d.Kp, dwt + (int64_t)t * E * E, E, E, E, d.mid, nullptr,
+                    DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+      m.residual = dWsum; m.ldr = E;
+      DPOT_CALL(dpot_gemm(&m, stream));
+      // dW2[i,m] += sum_j wts[t][i,j] dWeffT[j, t*mid+m]
+      m = gemm_args(wts + (int64_t)t * E * E, E, dWeffT_T + (int64_t)t * d.mid * E, E, dW2acc, d.mid, E, d.mid, E, nullptr,
+                    DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+      if (t > 0) { m.residual = dW2acc; m.ldr = d.mid; }
+      DPOT_CALL(dpot_gemm(&m, stream));
+    }
+    DPOT_CALL(tk_scale_copy(dW2acc, (int64_t)E * d.mid, inv, G(grads->pe2_w), st));
+    m = gemm_args(Wsum, E, dbe, E, dbp, d.n, E, d.n, E, nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);       // dbp[i,p] = sum_j Wsum[i,j] dbe[p,j]
+    DPOT_CALL(dpot_gemm(&m, stream));
+    DPOT_CALL(tk_rowsum_scale(dbp, E, d.n, inv, G(grads->pe2_b), G(grads->pos_embed), st));
+    DPOT_CALL(tk_tagg_finish(dwt, prm->tagg_w, prm->temb, d.T, E, inv, G(grads->tagg_w), dtemb, st));
+    if (cfg->time_agg == 1 && grads->tagg_gamma)
+      DPOT_CALL(tk_tagg_gamma_grad(dtemb, prm->tagg_gamma, d.T, E, inv, G(grads->tagg_gamma), st));
+  }
+  return 0;
+}

@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import logging
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -328,6 +329,8 @@ class DPOTNet(nn.Module):
         # engine state (not part of the state dict)
         self.gemm_engine = GEMM_AUTO
         self._eng: Optional[_InferenceEngine] = None
+        self._train_eng = None
+        self.train_path = os.environ.get('DPOT_TRAIN_PATH', 'auto')   # 'auto' | 'generic' (per-operator autograd only)
 
     # -- reference helpers kept for API compatibility ------------------------------------------
     def _init_weights(self, m):  # defined but never applied in the reference (:329-337)
@@ -363,7 +366,11 @@ class DPOTNet(nn.Module):
         if T != self.in_timesteps or Cc != self.in_channels:
             raise ValueError(f"expected T={self.in_timesteps}, C={self.in_channels}; got T={T}, C={Cc}")
         if _grad_needed(x, *self.parameters()):
-            from ..autograd import dpot_forward_train
+            from ..train_engine import fused_train_forward
+            out = fused_train_forward(self, x)         # one-call training step (dpot_train_*) when the geometry is served
+            if out is not None:
+                return out
+            from ..autograd import dpot_forward_train  # generic per-operator path
             return dpot_forward_train(self, x)
         return self.engine().forward(x)
 
@@ -383,12 +390,14 @@ class DPOTNet(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._eng = None  # parameter storage may move (.to(device))
+        self._train_eng = None
         return super()._apply(fn, *a, **k)
 
     # the engine caches raw pointers: never pickle / deepcopy it
     def __getstate__(self):
         st = self.__dict__.copy()
         st['_eng'] = None
+        st['_train_eng'] = None
         return st
 
 
@@ -426,6 +435,15 @@ class _InferenceEngine:
         key = self._param_key()
         if key == self.key and self.packed is not None and self.packed.device == device:
             return
+        self.bind_params(device)
+        if self.packed is None or self.packed.device != device:
+            self.packed = torch.empty(self.packed_floats, device=device, dtype=torch.float32)
+        check(self.lib.dpot_pack_weights(C.byref(self.cfg), C.byref(self.prm), ptr(self.packed),
+                                         torch.cuda.current_stream().cuda_stream), "dpot_pack_weights")
+        self.key = key
+
+    def bind_params(self, device) -> None:
+        """Point the C parameter struct at the current parameter storage (+ the coordinate / time-embedding tables)."""
         net = self.net
         for p in net.parameters():
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
@@ -460,11 +478,6 @@ class _InferenceEngine:
         temb = net.time_agg_layer.time_embedding(T, device).contiguous()
         self.aux = (gx, gt, temb)
         prm.grid_x, prm.grid_y, prm.grid_t, prm.temb = ptr(gx), ptr(gx), ptr(gt), ptr(temb)
-        if self.packed is None or self.packed.device != device:
-            self.packed = torch.empty(self.packed_floats, device=device, dtype=torch.float32)
-        check(self.lib.dpot_pack_weights(C.byref(self.cfg), C.byref(prm), ptr(self.packed),
-                                         torch.cuda.current_stream().cuda_stream), "dpot_pack_weights")
-        self.key = key
 
     def workspace(self, B: int, device) -> torch.Tensor:
         ws = self.ws.get(B)

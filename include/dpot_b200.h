@@ -415,6 +415,11 @@ DPOT_API int dpot_lp_loss(const float* x, const float* y, const float* mask, int
 DPOT_API int dpot_lp_loss_bwd(const float* x, const float* y, const float* mask, const float* coef, const float* gscale,
                               int32_t B, int64_t nxy, int32_t T, int32_t C, float* dx, void* stream);
 
+/* fwd16 without GroupNorm and with the interior-column weight (weight 2 = the adjoint of the inverse transform, whose
+   result the backward pass feeds straight into the split-fp16 contractions) */
+DPOT_API int dpot_afno_fft_fwd16w(const float* a, int32_t B, int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2,
+                                  void* S16, float interior_weight, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-model inference forward: DPOTNet.forward under no_grad (models/dpot.py:364-403).
  * ---------------------------------------------------------------------------------------- */
@@ -459,6 +464,33 @@ DPOT_API int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm, c
 DPOT_API int dpot_rollout_step(const dpot_config* cfg, const dpot_params* prm, const float* packed, float* ring, int32_t t0,
                       int32_t B, float* y, float* cls, float* ws, int32_t engine, float* pred, int32_t pred_frames,
                       int32_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The training step: DPOTNet.forward with the activations backward needs kept on a caller-owned tape, and its
+ * autograd -- what `im, cls = model(xx)` ... `loss.backward()` run in train_temporal.py:206,227 -- with every dense
+ * contraction of forward and backward on the f16-split tcgen05 engine (data gradients read the weights in their
+ * forward layout, weight gradients read both token-major activations as stored; no transposed copies).
+ *   packed  : dpot_packed_floats(cfg) floats, filled by dpot_train_prepare (the fused-mixer slab is not written)
+ *   wprep   : dpot_train_wprep_floats(cfg) floats, fold intermediates kept for backward
+ *   tape    : dpot_train_tape_floats(cfg, B) floats per forward call, alive until its backward
+ *   scratch : dpot_train_scratch_floats(cfg, B) floats, reusable by every call on the same stream
+ *   grads   : a dpot_params whose pointers are the DESTINATIONS of the parameter gradients (same shapes as the
+ *             parameters; written, not accumulated; grid/temb/mu/sigma members ignored; the cls members are written
+ *             only when dcls != NULL; tagg_gamma only for 'exp_mlp').  dx: gradient w.r.t. x or NULL.
+ * dpot_train_supported: 1 when the configuration is served (normalize = False, out_layer_dim = 32, patch geometry of
+ * DPOT-Ti/S/M); other configurations train through the generic per-operator path of the Python binding.
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int     dpot_train_supported(const dpot_config* cfg);
+DPOT_API int64_t dpot_train_tape_floats(const dpot_config* cfg, int32_t B);
+DPOT_API int64_t dpot_train_scratch_floats(const dpot_config* cfg, int32_t B);
+DPOT_API int64_t dpot_train_wprep_floats(const dpot_config* cfg);
+DPOT_API int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm, float* packed, float* wprep, float* scratch,
+                                void* stream);
+DPOT_API int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int32_t B,
+                                float* y, float* cls, float* tape, float* scratch, void* stream);
+DPOT_API int dpot_train_backward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
+                                 const float* x, int32_t B, const float* dy, const float* dcls, const float* tape,
+                                 float* scratch, const dpot_params* grads, float* dx, void* stream);
 
 #ifdef __cplusplus
 }
