@@ -81,6 +81,7 @@ struct Tc16Params {
   int n_tiles, m_tiles, total_tiles, kblocks;
   int dbg;           // experiment mask (dpot_tc16_set_debug): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
   int batch;         // independent problems; total_tiles also spans the g.ksplit contraction chunks (bz = b + batch * chunk)
+  int w_bmul, a_bmul; // 0: the operand is shared by every problem of the batch (batch stride 0), else 1
 };
 
 // ACT_MODE: 0 = none, 1 = GELU (erf), 2 = runtime switch.  OUT16: store the result as DPOT_FMT_HL16.
@@ -147,6 +148,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         const int nt = rest % P.n_tiles; const int bz = rest / P.n_tiles;
         const int n0 = (nt * CG + (int)rank) * TN, m0 = mt * BA + (int)rank * rows_a;
         const int bb = bz % P.batch, k00 = (bz / P.batch) * (int)g.kchunk;     // problem of the batch, contraction chunk
+        const int bw = bb * P.w_bmul, ba = bb * P.a_bmul;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(EMPTY(s), ph ^ 1);
           const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
@@ -167,21 +169,21 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
             if (g.w_tr) {                       // stored [K, N]: dims (n, k, batch), two boxes of 64 channels per plane
 #pragma unroll
               for (int j = 0; j < TN / 64; ++j) {
-                ld(sb + OFF_W_HI + j * MN_BOX_BYTES, &mapWh, n0 + 64 * j, k0, bb);
-                ld(sb + OFF_W_LO + j * MN_BOX_BYTES, &mapWl, n0 + 64 * j, k0, bb);
+                ld(sb + OFF_W_HI + j * MN_BOX_BYTES, &mapWh, n0 + 64 * j, k0, bw);
+                ld(sb + OFF_W_LO + j * MN_BOX_BYTES, &mapWl, n0 + 64 * j, k0, bw);
               }
             } else {
-              ld(sb + OFF_W_HI, &mapWh, k0, n0, bb);                   // dims (k, n, batch)
-              ld(sb + OFF_W_LO, &mapWl, k0, n0, bb);
+              ld(sb + OFF_W_HI, &mapWh, k0, n0, bw);                   // dims (k, n, batch)
+              ld(sb + OFF_W_LO, &mapWl, k0, n0, bw);
             }
             if (g.a_tr) {                       // stored [K, M]: dims (m, k, batch), rows_a / 64 boxes per plane
               for (int j = 0; j < rows_a / 64; ++j) {
-                ld(sb + OFF_A + j * MN_BOX_BYTES, &mapAh, m0 + 64 * j, k0, bb);
-                ld(sb + OFF_A + a_plane + j * MN_BOX_BYTES, &mapAl, m0 + 64 * j, k0, bb);
+                ld(sb + OFF_A + j * MN_BOX_BYTES, &mapAh, m0 + 64 * j, k0, ba);
+                ld(sb + OFF_A + a_plane + j * MN_BOX_BYTES, &mapAl, m0 + 64 * j, k0, ba);
               }
             } else {
-              ld(sb + OFF_A, &mapAh, k0, bb, m0);                      // dims (k, batch, m)
-              ld(sb + OFF_A + a_plane, &mapAl, k0, bb, m0);
+              ld(sb + OFF_A, &mapAh, k0, ba, m0);                      // dims (k, batch, m)
+              ld(sb + OFF_A + a_plane, &mapAl, k0, ba, m0);
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -475,7 +477,7 @@ bool gemm_tc16_supports(const GemmDev& p, int batch) {
   if (p.lda % 8 || p.ldw % 8 || p.a_lo % 8 || p.w_lo % 8) return false;
   if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W)) % 16) return false;
   if (batch > 1) {
-    if (p.sA <= 0 || p.sW <= 0 || p.sA % 8 || p.sW % 8) return false;
+    if (p.sA < 0 || p.sW < 0 || p.sA % 8 || p.sW % 8) return false;      // stride 0: the operand is shared by the batch
   }
   return true;
 }
@@ -492,7 +494,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
   g_sm_count = sm_count_cur();
-  const bool bw_form = p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src;
+  const bool bw_form = p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src || (batch > 1 && (p.sA == 0 || p.sW == 0));
   if (!bw_form && gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
@@ -505,29 +507,34 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   P.kblocks = (int)ceil_div(p.ksplit > 1 ? p.kchunk : p.K, BKH);
   P.dbg = g_dbg;
   P.batch = batch;
+  P.w_bmul = (batch > 1 && p.sW == 0) ? 0 : 1;
+  P.a_bmul = (batch > 1 && p.sA == 0) ? 0 : 1;
+  const int batchW = P.w_bmul ? batch : 1, batchA = P.a_bmul ? batch : 1;
   if (p.ksplit <= 1) { P.g.kchunk = 0; P.g.sC2 = 0; P.g.ksplit = 1; }
 
   const __half* Ah = reinterpret_cast<const __half*>(p.A);
   const __half* Wh = reinterpret_cast<const __half*>(p.W);
   alignas(64) CUtensorMap mWh, mWl, mAh, mAl;
-  const uint64_t sWb = batch > 1 ? (uint64_t)p.sW * 2 : (uint64_t)p.ldw * 2 * (uint64_t)p.N;
+  const uint64_t sWh = (batch > 1 && p.sW > 0) ? (uint64_t)p.sW * 2 : 0;      // batch stride in bytes, 0 = derive a dummy
+  const uint64_t sAh = (batch > 1 && p.sA > 0) ? (uint64_t)p.sA * 2 : 0;
   if (p.w_tr) {   // stored [K, N] (row stride ldw): dims (n, k, batch), boxes of 64 channels x 64 k rows
-    const uint64_t sWt = batch > 1 ? (uint64_t)p.sW * 2 : (uint64_t)p.ldw * 2 * (uint64_t)p.K;
-    DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.ldw * 2, sWt, 64, BKH, 1));
-    DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.ldw * 2, sWt, 64, BKH, 1));
+    const uint64_t sWt = sWh ? sWh : (uint64_t)p.ldw * 2 * (uint64_t)p.K;
+    DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)batchW, (uint64_t)p.ldw * 2, sWt, 64, BKH, 1));
+    DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)batchW, (uint64_t)p.ldw * 2, sWt, 64, BKH, 1));
   } else {
-    DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
-    DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batch, (uint64_t)p.ldw * 2, sWb, BKH, TN, 1));
+    const uint64_t sWk = sWh ? sWh : (uint64_t)p.ldw * 2 * (uint64_t)p.N;
+    DPOT_CALL(tc_encode_map_f16(&mWh, Wh, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batchW, (uint64_t)p.ldw * 2, sWk, BKH, TN, 1));
+    DPOT_CALL(tc_encode_map_f16(&mWl, Wh + p.w_lo, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)batchW, (uint64_t)p.ldw * 2, sWk, BKH, TN, 1));
   }
-  const uint64_t sAb = batch > 1 ? (uint64_t)p.sA * 2 : (uint64_t)p.lda * 2;
   const uint32_t box_m = (uint32_t)(P.BA / CGn);
   if (p.a_tr) {   // stored [K, M] (row stride lda): dims (m, k, batch)
-    const uint64_t sAt = batch > 1 ? (uint64_t)p.sA * 2 : (uint64_t)p.lda * 2 * (uint64_t)p.K;
-    DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.lda * 2, sAt, 64, BKH, 1));
-    DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.lda * 2, sAt, 64, BKH, 1));
+    const uint64_t sAt = sAh ? sAh : (uint64_t)p.lda * 2 * (uint64_t)p.K;
+    DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)batchA, (uint64_t)p.lda * 2, sAt, 64, BKH, 1));
+    DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)batchA, (uint64_t)p.lda * 2, sAt, 64, BKH, 1));
   } else {
-    DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
-    DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batch, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
+    const uint64_t sAb = sAh ? sAh : (uint64_t)p.lda * 2;
+    DPOT_CALL(tc_encode_map_f16(&mAh, Ah, (uint64_t)p.K, (uint64_t)batchA, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
+    DPOT_CALL(tc_encode_map_f16(&mAl, Ah + p.a_lo, (uint64_t)p.K, (uint64_t)batchA, (uint64_t)p.M, sAb, (uint64_t)p.lda * 2, BKH, 1, box_m));
   }
 
   const int units = g_sm_count / CGn;

@@ -272,135 +272,159 @@ __global__ void out_bias_grad_kernel(const double* __restrict__ dbias_t, int old
 }
 
 // ------------------------------------------------------------------------------------------------ output tail backward
-// One thread per pixel (32 channels in registers), the two 32 x 32 weight products against broadcast shared-memory reads;
-// the parameter gradients (outer products summed over pixels) are taken from shared-memory copies of the block's 128
-// pixels by a second mapping (8 entries of dW2 per thread) and accumulated in registers across the tiles of a
-// persistent block, then added once per block with double atomics.
-constexpr int TB_PIX = 128, TB_OLD = 32, TB_NOUT_MAX = 8;
+// A tile of 128 pixels per pass of a persistent block; the two 32 x 32 products are register-tiled (4 pixels x 8
+// channels per thread) against transposed shared-memory copies ([channel][pixel]: one LDS.128 feeds 4 pixels), so the
+// inner loops run 32 FMAs per 3 shared loads.  The parameter gradients (outer products summed over pixels) are taken
+// from the same shared copies by a second mapping, accumulated in registers across the tiles of the block and written
+// as ONE partial result per block (summed in double by tail_finish_kernel).
+constexpr int TB_PIX = 128, TB_OLD = 32, TB_NOUT_MAX = 8, TB_LD = 132;
+constexpr int TB_ACC = 1024 + 32 + TB_NOUT_MAX * 32 + TB_NOUT_MAX;       // [dW2 | db2 | dW4 | db4] floats per block partial
 struct TailBwdArgs {
   const float* Y1pre; const float* dout; const float* scale; const float* w2; const float* b2; const float* w4;
-  __half* g1; double* acc;
+  __half* g1; float* part;
   int B, h, w, P, nout, act; int64_t ntiles;
 };
-__global__ void __launch_bounds__(TB_PIX) tail_bwd_kernel(const TailBwdArgs a) {
+__global__ void __launch_bounds__(TB_PIX, 3) tail_bwd_kernel(const TailBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
-  float* W2s = sm;                          // [32][32]  (n, k)
-  float* W4s = W2s + 32 * 32;               // [nout][32]
-  float* b2s = W4s + TB_NOUT_MAX * 32;      // [32]
-  float* y1s = b2s + 32;                    // [128][33]
-  float* y2s = y1s + TB_PIX * 33;           // [128][33]
-  float* g2s = y2s + TB_PIX * 33;           // [128][33]
-  float* g3s = g2s + TB_PIX * 33;           // [128][8]
-  const int tid = threadIdx.x;
-  const int PP = a.P * a.P, NP = PP * TB_OLD, nout = a.nout;
-  for (int i = tid; i < 32 * 32; i += TB_PIX) W2s[i] = a.w2[i];
-  for (int i = tid; i < nout * 32; i += TB_PIX) W4s[i] = a.w4[i];
+  float* Y1T = sm;                           // [32 k][TB_LD] act(y1pre), transposed
+  float* G2T = Y1T + 32 * TB_LD;             // [32 n][TB_LD] gradient w.r.t. pre2, transposed
+  float* Y2s = G2T + 32 * TB_LD;             // [128 px][32 n]
+  float* G3s = Y2s + TB_PIX * 32;            // [128 px][8]
+  float* W2s = G3s + TB_PIX * 8;             // [n][k]
+  float* W2Ts = W2s + 32 * 32;               // [k][n]
+  float* W4s = W2Ts + 32 * 32;               // [8 j][32 n] (rows >= nout zero)
+  float* b2s = W4s + TB_NOUT_MAX * 32;       // [32]
+  const int tid = threadIdx.x, tx = tid & 3, ty = tid >> 2;
+  const int PP = a.P * a.P, NP = PP * TB_OLD, nout = a.nout, act = a.act;
+  for (int i = tid; i < 32 * 32; i += TB_PIX) { const float v = a.w2[i]; W2s[i] = v; W2Ts[(i & 31) * 32 + (i >> 5)] = v; }
+  for (int i = tid; i < TB_NOUT_MAX * 32; i += TB_PIX) W4s[i] = i < nout * 32 ? a.w4[i] : 0.f;
   if (tid < 32) b2s[tid] = a.b2[tid];
   const float S = a.scale ? __ldg(a.scale) : 1.f;
-  // second mapping: dW2 entries (n2, k2..k2+7); dW4 entry (j4, n4) for tid < nout*32 (nout <= 4 -> one pass; else two)
-  const int n2 = tid >> 2, k2 = (tid & 3) * 8;
   float dW2r[8], db2r = 0.f, dW4r[2] = {0.f, 0.f}, db4r = 0.f;
 #pragma unroll
   for (int u = 0; u < 8; ++u) dW2r[u] = 0.f;
+  const int R = a.h * a.P, Wd = a.w * a.P;
+  const int64_t npix = (int64_t)a.B * a.h * a.w * PP;
   __syncthreads();
-  const int R = a.h * a.P;                  // field height
-  const int Wd = a.w * a.P;
   for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const int64_t pix = tile * TB_PIX + tid;                 // pixel = (tok, uv)
-    const int64_t tok = pix / PP; const int uv = (int)(pix % PP);
-    const int u_ = uv / a.P, v_ = uv % a.P;
-    const int q = (int)(tok % a.w); const int64_t r_ = tok / a.w;
-    const int p = (int)(r_ % a.h); const int b = (int)(r_ / a.h);
-    const bool live = b < a.B;
-    float y1[32], t2[32];
-    const float* yp = a.Y1pre + tok * NP + (int64_t)uv * 32;
-    if (live) {
+    const int64_t pix0 = tile * TB_PIX;
+    {   // ---- phase A: this thread's pixel -> act(y1pre) column of Y1T, scaled dout row of G3s
+      const int64_t pix = pix0 + tid;
+      const bool live = pix < npix;
+      const int64_t tok = pix / PP; const int uv = (int)(pix % PP);
+      const float* yp = a.Y1pre + tok * NP + (int64_t)uv * 32;
 #pragma unroll
       for (int k = 0; k < 32; k += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(yp + k));
-        y1[k] = v.x; y1[k + 1] = v.y; y1[k + 2] = v.z; y1[k + 3] = v.w;
+        float4 v = live ? __ldg(reinterpret_cast<const float4*>(yp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        Y1T[(k + 0) * TB_LD + tid] = act_apply(v.x, act);
+        Y1T[(k + 1) * TB_LD + tid] = act_apply(v.y, act);
+        Y1T[(k + 2) * TB_LD + tid] = act_apply(v.z, act);
+        Y1T[(k + 3) * TB_LD + tid] = act_apply(v.w, act);
       }
-    } else {
+      const int u_ = uv / a.P, v_ = uv % a.P;
+      const int q = (int)(tok % a.w); const int64_t r_ = tok / a.w;
+      const int p = (int)(r_ % a.h); const int64_t b = r_ / a.h;
+      const float* dp = a.dout + (((b * R + p * a.P + u_) * Wd) + q * a.P + v_) * nout;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) y1[k] = 0.f;
+      for (int j = 0; j < TB_NOUT_MAX; ++j) G3s[tid * 8 + j] = (live && j < nout) ? dp[j] * S : 0.f;
+    }
+    __syncthreads();
+    float acc[4][8];
+    // ---- phase B: pre2[px, n] = b2[n] + sum_k y1[px, k] W2[n, k]   (4 px x 8 n per thread)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = b2s[8 * tx + j];
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float4 y = *reinterpret_cast<const float4*>(Y1T + k * TB_LD + 4 * ty);
+      const float4 w0 = *reinterpret_cast<const float4*>(W2Ts + k * 32 + 8 * tx);
+      const float4 w1 = *reinterpret_cast<const float4*>(W2Ts + k * 32 + 8 * tx + 4);
+      const float yv[4] = {y.x, y.y, y.z, y.w};
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(yv[i], wv[j], acc[i][j]);
+    }
+    // y2 = act(pre2) -> Y2s; g2 = (W4^T g3) * act'(pre2) -> G2T
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int px = 4 * ty + i;
+      const float4 ga = *reinterpret_cast<const float4*>(G3s + px * 8);
+      const float4 gb = *reinterpret_cast<const float4*>(G3s + px * 8 + 4);
+      const float g3[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      float y2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = acc[i][j];
+        y2[j] = act_apply(pre, act);
+        float s = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < TB_NOUT_MAX; ++jj) s = fmaf(W4s[jj * 32 + 8 * tx + j], g3[jj], s);
+        acc[i][j] = s * act_grad_fast(pre, act);
+      }
+      *reinterpret_cast<float4*>(Y2s + px * 32 + 8 * tx) = make_float4(y2[0], y2[1], y2[2], y2[3]);
+      *reinterpret_cast<float4*>(Y2s + px * 32 + 8 * tx + 4) = make_float4(y2[4], y2[5], y2[6], y2[7]);
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { y1[k] = act_apply(y1[k], a.act); y1s[tid * 33 + k] = y1[k]; }
-    // pre2 = W2 y1 + b2
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(G2T + (8 * tx + j) * TB_LD + 4 * ty) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    __syncthreads();
+    // ---- phase C: g1[px, k] = (sum_n g2[px, n] W2[n, k]) * act'(y1pre[px, k]) -> split store
 #pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
     for (int n = 0; n < 32; ++n) {
-      float acc = b2s[n];
+      const float4 g = *reinterpret_cast<const float4*>(G2T + n * TB_LD + 4 * ty);
+      const float4 w0 = *reinterpret_cast<const float4*>(W2s + n * 32 + 8 * tx);
+      const float4 w1 = *reinterpret_cast<const float4*>(W2s + n * 32 + 8 * tx + 4);
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int k = 0; k < 32; k += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(W2s + n * 32 + k);
-        acc = fmaf(wv.x, y1[k], acc); acc = fmaf(wv.y, y1[k + 1], acc); acc = fmaf(wv.z, y1[k + 2], acc); acc = fmaf(wv.w, y1[k + 3], acc);
-      }
-      t2[n] = acc;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gv[i], wv[j], acc[i][j]);
     }
-    float g3[TB_NOUT_MAX];
-    {
-      const float* dp = a.dout + ((((int64_t)b * R + p * a.P + u_) * Wd) + q * a.P + v_) * nout;
 #pragma unroll
-      for (int j = 0; j < TB_NOUT_MAX; ++j) {
-        g3[j] = (live && j < nout) ? dp[j] * S : 0.f;
-        g3s[tid * 8 + j] = g3[j];
-      }
-    }
-    // y2 = act(pre2) -> smem; g2 = (W4^T g3) * act'(pre2)
-#pragma unroll
-    for (int n = 0; n < 32; ++n) {
-      const float pre = t2[n];
-      y2s[tid * 33 + n] = act_apply(pre, a.act);
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < TB_NOUT_MAX; ++j)
-        if (j < nout) acc = fmaf(W4s[j * 32 + n], g3[j], acc);
-      t2[n] = live ? acc * act_grad_fast(pre, a.act) : 0.f;
-      g2s[tid * 33 + n] = t2[n];
-    }
-    // g1 = (W2^T g2) * act'(y1pre)
-#pragma unroll
-    for (int k = 0; k < 32; ++k) y1[k] = 0.f;
-#pragma unroll
-    for (int n = 0; n < 32; ++n) {
-      const float gn = t2[n];
-#pragma unroll
-      for (int k = 0; k < 32; k += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(W2s + n * 32 + k);
-        y1[k] = fmaf(wv.x, gn, y1[k]); y1[k + 1] = fmaf(wv.y, gn, y1[k + 1]);
-        y1[k + 2] = fmaf(wv.z, gn, y1[k + 2]); y1[k + 3] = fmaf(wv.w, gn, y1[k + 3]);
-      }
-    }
-    if (live) {
-      __half* gp = a.g1 + tok * (2 * (int64_t)NP) + (int64_t)uv * 32;
-#pragma unroll
-      for (int k = 0; k < 32; k += 8) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(yp + k)), p1 = __ldg(reinterpret_cast<const float4*>(yp + k + 4));
+    for (int i = 0; i < 4; ++i) {
+      const int64_t pix = pix0 + 4 * ty + i;
+      if (pix < npix) {
+        const int64_t tok = pix / PP; const int uv = (int)(pix % PP);
+        const float* yp = a.Y1pre + tok * NP + (int64_t)uv * 32 + 8 * tx;
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(yp)), p1 = __ldg(reinterpret_cast<const float4*>(yp + 4));
         const float pre[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
         alignas(16) __half hi[8];
         alignas(16) __half lo[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) hl_split(y1[k + u] * act_grad_fast(pre[u], a.act), hi[u], lo[u]);
-        *reinterpret_cast<uint4*>(gp + k) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(gp + k + NP) = *reinterpret_cast<const uint4*>(lo);
+        for (int j = 0; j < 8; ++j) hl_split(acc[i][j] * act_grad_fast(pre[j], act), hi[j], lo[j]);
+        __half* gp = a.g1 + tok * (2 * (int64_t)NP) + (int64_t)uv * 32 + 8 * tx;
+        *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(gp + NP) = *reinterpret_cast<const uint4*>(lo);
       }
     }
-    __syncthreads();
-    // parameter gradients of this tile from the shared copies
-#pragma unroll 4
-    for (int pp = 0; pp < TB_PIX; ++pp) {
-      const float g2v = g2s[pp * 33 + n2];
+    // ---- phase D: parameter gradients of this tile.  dW2[n, k] for n = ty, k = tx + 4 kk
+#pragma unroll 2
+    for (int p4 = 0; p4 < TB_PIX; p4 += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(G2T + ty * TB_LD + p4);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) dW2r[u] = fmaf(g2v, y1s[pp * 33 + k2 + u], dW2r[u]);
+      for (int kk = 0; kk < 8; ++kk) {
+        const float4 y = *reinterpret_cast<const float4*>(Y1T + (tx + 4 * kk) * TB_LD + p4);
+        dW2r[kk] = fmaf(g.x, y.x, fmaf(g.y, y.y, fmaf(g.z, y.z, fmaf(g.w, y.w, dW2r[kk]))));
+      }
     }
     if (tid < 32) {
       float s = 0.f;
-      for (int pp = 0; pp < TB_PIX; ++pp) s += g2s[pp * 33 + tid];
+      for (int p4 = 0; p4 < TB_PIX; p4 += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(G2T + tid * TB_LD + p4);
+        s += (g.x + g.y) + (g.z + g.w);
+      }
       db2r += s;
     } else if (tid < 32 + TB_NOUT_MAX) {
-      const int j = tid - 32;
       float s = 0.f;
-      for (int pp = 0; pp < TB_PIX; ++pp) s += g3s[pp * 8 + j];
+      for (int pp = 0; pp < TB_PIX; ++pp) s += G3s[pp * 8 + (tid - 32)];
       db4r += s;
     }
 #pragma unroll
@@ -409,42 +433,62 @@ __global__ void __launch_bounds__(TB_PIX) tail_bwd_kernel(const TailBwdArgs a) {
       if (e < nout * 32) {
         const int j = e >> 5, n = e & 31;
         float s = 0.f;
-        for (int pp = 0; pp < TB_PIX; ++pp) s = fmaf(g3s[pp * 8 + j], y2s[pp * 33 + n], s);
+#pragma unroll 4
+        for (int pp = 0; pp < TB_PIX; ++pp) s = fmaf(G3s[pp * 8 + j], Y2s[pp * 32 + n], s);
         dW4r[half] += s;
       }
     }
     __syncthreads();
   }
-  double* acc = a.acc;
+  float* part = a.part + (int64_t)blockIdx.x * TB_ACC;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) atomicAdd(acc + n2 * 32 + k2 + u, (double)dW2r[u]);
-  if (tid < 32) atomicAdd(acc + 1024 + tid, (double)db2r);
-  else if (tid < 32 + TB_NOUT_MAX && tid - 32 < nout) atomicAdd(acc + 1024 + 32 + nout * 32 + (tid - 32), (double)db4r);
+  for (int kk = 0; kk < 8; ++kk) part[ty * 32 + tx + 4 * kk] = dW2r[kk];
+  if (tid < 32) part[1024 + tid] = db2r;
+  else if (tid < 32 + TB_NOUT_MAX) part[1024 + 32 + TB_NOUT_MAX * 32 + (tid - 32)] = db4r;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int e = tid + half * TB_PIX;
-    if (e < nout * 32) atomicAdd(acc + 1024 + 32 + e, (double)dW4r[half]);
+    if (e < TB_NOUT_MAX * 32) part[1024 + 32 + e] = e < nout * 32 ? dW4r[half] : 0.f;
   }
+}
+// sums the per-block partials and writes the four parameter gradients (scaled by inv_scale)
+__global__ void tail_finish_kernel(const float* __restrict__ part, int nblk, int nout, const float* __restrict__ inv_scale,
+                                   float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dW4, float* __restrict__ db4) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= TB_ACC) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)part[(int64_t)b * TB_ACC + e];
+  const float v = (float)(s * (double)inv_of(inv_scale));
+  if (e < 1024) dW2[e] = v;
+  else if (e < 1056) db2[e - 1024] = v;
+  else if (e < 1056 + TB_NOUT_MAX * 32) { if (e - 1056 < nout * 32) dW4[e - 1056] = v; }
+  else if (e - 1056 - TB_NOUT_MAX * 32 < nout) db4[e - 1056 - TB_NOUT_MAX * 32] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ PatchEmbed conv0 backward
+// One patch (b, p, q) per pass of a persistent block; thread k owns column k = (u, v, c) of the im2col matrix: its slice
+// of the weight gradient dW0p[:, k] lives in registers across the block's patches, the patch's pixels and the gradient
+// rows gz[t, :] are staged in shared memory.  MIDC / TC > 0: compile-time mid / T (DPOT's Co*P+3 = 35, T = 10: no
+// predicates, exact register arrays); 0: runtime values up to PB_MID / PB_T.  One partial dW0p per block.
 constexpr int PB_MID = 40, PB_T = 10, PB_NT = 256;
 struct PatchBwdArgs {
-  const float* gz; const float* x; const float* W0p; const float* inv_scale; double* dW0p; float* dx;
+  const float* gz; const float* x; const float* W0p; const float* inv_scale; float* dW0p; float* dx;   // dW0p: [gridDim.x][mid*K0] partials
   int B, X, Y, T, C, P, mid, Kp, K0, h, w;
 };
-__global__ void __launch_bounds__(PB_NT) patch_bwd_kernel(const PatchBwdArgs a) {
+template <int MIDC, int TC, bool DX>
+__global__ void __launch_bounds__(PB_NT, MIDC ? 2 : 1) patch_bwd_kernel(const PatchBwdArgs a) {
+  constexpr int MB = MIDC ? MIDC : PB_MID, TB = TC ? TC : PB_T;
   extern __shared__ __align__(16) float sm[];
   float* gzs = sm;                              // [T][mid]  (<= 400 floats)
   float* xs = sm + PB_T * PB_MID;               // patch tile [u][(v, t, c)] = P * (P*T*C) floats; reused for dx
-  const int tid = threadIdx.x, K0 = a.K0, T = a.T, mid = a.mid, C = a.C, P = a.P;
+  const int tid = threadIdx.x, K0 = a.K0, T = TC ? TC : a.T, mid = MIDC ? MIDC : a.mid, C = a.C, P = a.P;
   const int run = P * T * C;                    // contiguous floats of one patch row u
   const bool kon = tid < K0;
   const int c = tid % C, uv = tid / C, v = uv % P, u = uv / P;
-  float wcol[PB_MID], dW[PB_MID];
+  float wcol[DX ? MB : 1], dW[MB];
 #pragma unroll
-  for (int m = 0; m < PB_MID; ++m) {
-    wcol[m] = (kon && m < mid && a.dx) ? a.W0p[(int64_t)m * K0 + tid] : 0.f;
+  for (int m = 0; m < MB; ++m) {
+    if (DX) wcol[m] = (kon && m < mid) ? a.W0p[(int64_t)m * K0 + tid] : 0.f;
     dW[m] = 0.f;
   }
   const float inv = inv_of(a.inv_scale);
@@ -458,31 +502,31 @@ __global__ void __launch_bounds__(PB_NT) patch_bwd_kernel(const PatchBwdArgs a) 
       xs[i] = a.x[(((int64_t)b * a.X + p * P + uu) * a.Y + (int64_t)q * P) * T * C + rr];
     }
     __syncthreads();
-    float xk[PB_T], dxk[PB_T];
+    float xk[TB], dxk[DX ? TB : 1];
 #pragma unroll
-    for (int t = 0; t < PB_T; ++t) {
+    for (int t = 0; t < TB; ++t) {
       xk[t] = (kon && t < T) ? xs[u * run + (v * T + t) * C + c] : 0.f;
-      dxk[t] = 0.f;
+      if (DX) dxk[t] = 0.f;
     }
 #pragma unroll
-    for (int m = 0; m < PB_MID; ++m) {
-      if (m < mid) {
+    for (int t = 0; t < TB; ++t) {
+      if (TC || t < T) {
 #pragma unroll
-        for (int t = 0; t < PB_T; ++t) {
-          if (t < T) {
+        for (int m = 0; m < MB; ++m) {
+          if (MIDC || m < mid) {
             const float gv = gzs[t * mid + m];
             dW[m] = fmaf(gv, xk[t], dW[m]);
-            dxk[t] = fmaf(gv, wcol[m], dxk[t]);
+            if (DX) dxk[t] = fmaf(gv, wcol[m], dxk[t]);
           }
         }
       }
     }
-    if (a.dx) {
+    if (DX) {
       __syncthreads();
       if (kon) {
 #pragma unroll
-        for (int t = 0; t < PB_T; ++t)
-          if (t < T) xs[u * run + (v * T + t) * C + c] = dxk[t] * inv;
+        for (int t = 0; t < TB; ++t)
+          if (TC || t < T) xs[u * run + (v * T + t) * C + c] = dxk[t] * inv;
       }
       __syncthreads();
       for (int i = tid; i < P * run; i += PB_NT) {
@@ -493,96 +537,133 @@ __global__ void __launch_bounds__(PB_NT) patch_bwd_kernel(const PatchBwdArgs a) 
     __syncthreads();
   }
   if (kon) {
+    float* slab = a.dW0p + (int64_t)blockIdx.x * mid * K0;
 #pragma unroll
-    for (int m = 0; m < PB_MID; ++m)
-      if (m < mid) atomicAdd(a.dW0p + (int64_t)m * K0 + tid, (double)dW[m]);
+    for (int m = 0; m < MB; ++m)
+      if (MIDC || m < mid) slab[(int64_t)m * K0 + tid] = dW[m];
   }
 }
 
-// dpe0_w[m, c, u, v] / dpe0_b[m] from dW0p[m, (u,v,c)] and drb[(p,q), t*mid + m] (row pitch Kp): one block per m
-__global__ void __launch_bounds__(256) unpack_patch_grad_kernel(const double* __restrict__ dW0p, const double* __restrict__ drb,
-                                                                const float* __restrict__ gx, const float* __restrict__ gy,
-                                                                const float* __restrict__ gt, int mid, int C, int P, int h, int w,
-                                                                int T, int Kp, const float* __restrict__ inv_scale,
-                                                                float* __restrict__ dw0, float* __restrict__ db0) {
+// dpe0_w[m, c < C, u, v] = inv * sum over the per-block partials dW0p[s][m, (u,v,c)]
+__global__ void __launch_bounds__(256) patch_w_reduce_kernel(const float* __restrict__ dW0p, int nslab, int mid, int C, int PP,
+                                                             const float* __restrict__ inv_scale, float* __restrict__ dw0) {
+  const int K0 = PP * C;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= mid * K0) return;
+  const int m = idx / K0, i = idx % K0;
+  double acc = 0.0;
+  for (int sl = 0; sl < nslab; ++sl) acc += (double)dW0p[(int64_t)sl * mid * K0 + idx];
+  const int c = i % C, uv = i / C;
+  dw0[((int64_t)m * (C + 3) + c) * PP + uv] = (float)(acc * (double)inv_of(inv_scale));
+}
+// coordinate channels and bias of conv0 from drb[(p,q), t*mid + m] (row pitch Kp, summed over the batch):
+// grid (mid, 2P + 2): which < P: x-channel row u = which; < 2P: y-channel column v; == 2P: t-channel; 2P + 1: bias
+__global__ void __launch_bounds__(256) patch_coord_grad_kernel(const double* __restrict__ drb, const float* __restrict__ gx,
+                                                               const float* __restrict__ gy, const float* __restrict__ gt, int mid,
+                                                               int C, int P, int h, int w, int T, int Kp,
+                                                               const float* __restrict__ inv_scale, float* __restrict__ dw0,
+                                                               float* __restrict__ db0) {
   __shared__ double red[256];
-  __shared__ double sums[2 * 32 + 2];           // [u: x-channel | v: y-channel | t-channel | bias], P <= 32
-  const int m = blockIdx.x, tid = threadIdx.x;
-  const double inv = (double)inv_of(inv_scale);
-  const int PP = P * P, K0 = PP * C;
-  for (int i = tid; i < K0; i += blockDim.x) {
-    const int c = i % C, uv = i / C;
-    dw0[((int64_t)m * (C + 3) + c) * PP + uv] = (float)(dW0p[(int64_t)m * K0 + i] * inv);
+  const int m = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
+  const int PP = P * P, nitem = h * w * T;
+  double acc = 0.0;
+  for (int i = tid; i < nitem; i += blockDim.x) {
+    const int t = i % T; const int pq = i / T; const int q = pq % w, p = pq / w;
+    const double g = drb[(int64_t)pq * Kp + t * mid + m];
+    double f;
+    if (which < P) f = (double)gx[p * P + which];
+    else if (which < 2 * P) f = (double)gy[q * P + (which - P)];
+    else if (which == 2 * P) f = (double)gt[t];
+    else f = 1.0;
+    acc += g * f;
   }
-  const int nitem = h * w * T;
-  for (int which = 0; which < 2 * P + 2; ++which) {
-    double acc = 0.0;
-    for (int i = tid; i < nitem; i += blockDim.x) {
-      const int t = i % T; const int pq = i / T; const int q = pq % w, p = pq / w;
-      const double g = drb[(int64_t)pq * Kp + t * mid + m];
-      double f;
-      if (which < P) f = (double)gx[p * P + which];
-      else if (which < 2 * P) f = (double)gy[q * P + (which - P)];
-      else if (which == 2 * P) f = (double)gt[t];
-      else f = 1.0;
-      acc += g * f;
-    }
-    red[tid] = acc;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if (tid < s) red[tid] += red[tid + s];
-      __syncthreads();
-    }
-    if (tid == 0) sums[which] = red[0];
+  red[tid] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
     __syncthreads();
   }
-  for (int i = tid; i < PP; i += blockDim.x) {
-    const int u = i / P, v = i % P;
-    dw0[((int64_t)m * (C + 3) + C) * PP + i] = (float)(sums[u] * inv);
-    dw0[((int64_t)m * (C + 3) + C + 1) * PP + i] = (float)(sums[P + v] * inv);
-    dw0[((int64_t)m * (C + 3) + C + 2) * PP + i] = (float)(sums[2 * P] * inv);
-  }
-  if (tid == 0) db0[m] = (float)(sums[2 * P + 1] * inv);
+  const float val = (float)(red[0] * (double)inv_of(inv_scale));
+  float* wx = dw0 + ((int64_t)m * (C + 3) + C) * PP;
+  if (which < P) { if (tid < P) wx[which * P + tid] = val; }                       // x channel: row u, every v
+  else if (which < 2 * P) { if (tid < P) wx[PP + tid * P + (which - P)] = val; }   // y channel: column v, every u
+  else if (which == 2 * P) { if (tid < PP) wx[2 * PP + tid] = val; }               // t channel: every (u, v)
+  else if (tid == 0) db0[m] = val;
 }
 
 // ------------------------------------------------------------------------------------------------ time aggregation fold
-// wts[t,i,j] = w[t,i,j] * temb[t,i];  wtsT[t,j,i] the transpose.  grid (E/32, E/32, T), block (32, 8)
-__global__ void tagg_scale_kernel(const float* __restrict__ w, const float* __restrict__ temb, int E, float* __restrict__ wts,
-                                  float* __restrict__ wtsT) {
-  __shared__ float tile[32][33];
-  const int t = blockIdx.z, j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
-  const int64_t base = (int64_t)t * E * E;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int i = i0 + r, j = j0 + threadIdx.x;
-    float v = 0.f;
-    if (i < E && j < E) {
-      v = w[base + (int64_t)i * E + j] * temb[(int64_t)t * E + i];
-      wts[base + (int64_t)i * E + j] = v;
-    }
-    tile[r][threadIdx.x] = v;
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int j = j0 + r, i = i0 + threadIdx.x;
-    if (i < E && j < E) wtsT[base + (int64_t)j * E + i] = tile[threadIdx.x][r];
+// wts16[(t,i), j] = split(w[t,i,j] * temb[t,i])   (rows of [hi E | lo E] halves)
+__global__ void __launch_bounds__(256) tagg_scale16_kernel(const float* __restrict__ w, const float* __restrict__ temb, int64_t rows,
+                                                           int E8, __half* __restrict__ dst) {
+  const int64_t total = rows * E8;
+  const int E = E8 * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / E8;
+    const int c = (int)(i % E8) * 8;
+    const float te = __ldg(temb + r);
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(w + r * E + c));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(w + r * E + c + 4));
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    alignas(16) __half hi[8];
+    alignas(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) hl_split(v[u] * te, hi[u], lo[u]);
+    *reinterpret_cast<uint4*>(dst + r * 2 * E + c) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + r * 2 * E + c + E) = *reinterpret_cast<const uint4*>(lo);
   }
 }
-__global__ void sum_over_t_kernel(const float* __restrict__ a, const float* __restrict__ b, int T, int64_t per,
-                                  float* __restrict__ sa, float* __restrict__ sb) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per) return;
-  double x = 0.0, y = 0.0;
-  for (int t = 0; t < T; ++t) { x += (double)a[(int64_t)t * per + i]; y += (double)b[(int64_t)t * per + i]; }
-  sa[i] = (float)x; sb[i] = (float)y;
+// Wsum16[i, j] = split(sum_t temb[t,i] * w[t,i,j])
+__global__ void tagg_wsum16_kernel(const float* __restrict__ w, const float* __restrict__ temb, int T, int E, __half* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)E * E) return;
+  const int i = (int)(idx / E), j = (int)(idx % E);
+  double acc = 0.0;
+  for (int t = 0; t < T; ++t) acc += (double)(temb[(int64_t)t * E + i] * w[(int64_t)t * E * E + idx]);
+  __half hi, lo;
+  hl_split((float)acc, hi, lo);
+  dst[(int64_t)i * 2 * E + j] = hi;
+  dst[(int64_t)i * 2 * E + E + j] = lo;
 }
-__global__ void tagg_bp_kernel(const float* __restrict__ b2, const float* __restrict__ pos, int E, int n, float* __restrict__ bp,
-                               float* __restrict__ bpT) {
+// bp16[i, p] = split(b2[i] + pos[i, p])
+__global__ void tagg_bp16_kernel(const float* __restrict__ b2, const float* __restrict__ pos, int E, int n, __half* __restrict__ dst) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)E * n) return;
   const int i = (int)(idx / n), p = (int)(idx % n);
-  const float v = b2[i] + pos[idx];
-  bp[idx] = v;
-  bpT[(int64_t)p * E + i] = v;
+  __half hi, lo;
+  hl_split(b2[i] + pos[idx], hi, lo);
+  dst[(int64_t)i * 2 * n + p] = hi;
+  dst[(int64_t)i * 2 * n + n + p] = lo;
+}
+// dst16[r, c] = split(c < cols ? src[r*lds + c] : 0), c < colsp   (zero-padded split copy; rows of [hi colsp | lo colsp])
+__global__ void pad_split_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols, int colsp, __half* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * colsp) return;
+  const int64_t r = idx / colsp; const int c = (int)(idx % colsp);
+  __half hi, lo;
+  hl_split(c < cols ? src[r * lds + c] : 0.f, hi, lo);
+  dst[r * 2 * colsp + c] = hi;
+  dst[r * 2 * colsp + colsp + c] = lo;
+}
+// Gp16[t][j][m] = split(m < mid ? dWeffT[j, t*mid + m] : 0), m < midp
+__global__ void tagg_pad_g_kernel(const float* __restrict__ dWeffT, int E, int Kp, int T, int mid, int midp, __half* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)T * E * midp) return;
+  const int m = (int)(idx % midp); const int64_t r = idx / midp;     // r = t*E + j
+  const int j = (int)(r % E), t = (int)(r / E);
+  __half hi, lo;
+  hl_split(m < mid ? dWeffT[(int64_t)j * Kp + t * mid + m] : 0.f, hi, lo);
+  dst[r * 2 * midp + m] = hi;
+  dst[r * 2 * midp + midp + m] = lo;
+}
+// dW2[i, m] = inv * sum_t slabs[t][i][m], m < mid (slab rows of midp)
+__global__ void tagg_dw2_finish_kernel(const float* __restrict__ slabs, int T, int E, int mid, int midp, const float* __restrict__ inv_scale,
+                                       float* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * mid) return;
+  const int i = idx / mid, m = idx % mid;
+  double acc = 0.0;
+  for (int t = 0; t < T; ++t) acc += (double)slabs[((int64_t)t * E + i) * midp + m];
+  dst[idx] = (float)(acc * (double)inv_of(inv_scale));
 }
 // one warp per (t, i) row
 __global__ void __launch_bounds__(256) tagg_finish_kernel(const float* __restrict__ dwt, const float* __restrict__ w,
@@ -763,66 +844,96 @@ int tk_unpack_out_grad(const float* dWtT, int nslab, int64_t stride, const doubl
 }
 
 int tk_tail_bwd_supported(int old, int nout) { return old == TB_OLD && nout >= 1 && nout <= TB_NOUT_MAX; }
+int tk_tail_bwd_blocks(int B, int h, int w, int P) {
+  const int64_t ntiles = ceil_div((int64_t)B * h * w * P * P, TB_PIX);
+  return (int)std::min<int64_t>(ntiles, (int64_t)sm_count_cur() * 3);
+}
+int64_t tk_tail_bwd_part_floats(int nblk) { return (int64_t)nblk * TB_ACC; }
 int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const float* w2, const float* b2, const float* w4,
-                int B, int h, int w, int P, int nout, int act, __half* g1, double* acc, cudaStream_t st) {
+                int B, int h, int w, int P, int nout, int act, __half* g1, float* part, const float* inv_scale, float* dW2,
+                float* db2, float* dW4, float* db4, cudaStream_t st) {
   DPOT_REQUIRE(tk_tail_bwd_supported(TB_OLD, nout), DPOT_E_UNSUPPORTED, "tail_bwd: nout %d unsupported", nout);
   const int64_t npix = (int64_t)B * h * w * P * P;
   TailBwdArgs a;
-  a.Y1pre = Y1pre; a.dout = dout; a.scale = scale; a.w2 = w2; a.b2 = b2; a.w4 = w4; a.g1 = g1; a.acc = acc;
+  a.Y1pre = Y1pre; a.dout = dout; a.scale = scale; a.w2 = w2; a.b2 = b2; a.w4 = w4; a.g1 = g1; a.part = part;
   a.B = B; a.h = h; a.w = w; a.P = P; a.nout = nout; a.act = act; a.ntiles = ceil_div(npix, TB_PIX);
-  const size_t smem = sizeof(float) * (32 * 32 + TB_NOUT_MAX * 32 + 32 + 3 * TB_PIX * 33 + TB_PIX * 8);
+  const size_t smem = sizeof(float) * (2 * 32 * TB_LD + TB_PIX * 32 + TB_PIX * 8 + 2 * 32 * 32 + TB_NOUT_MAX * 32 + 32);
   static DevOnce attr;
   if (attr.need()) {
     DPOT_CUDA(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr.done();
   }
-  const int sms = sm_count_cur();
-  const unsigned grid = (unsigned)std::min<int64_t>(a.ntiles, (int64_t)sms * 3);
-  tail_bwd_kernel<<<grid, TB_PIX, smem, st>>>(a);
+  const int nblk = tk_tail_bwd_blocks(B, h, w, P);
+  tail_bwd_kernel<<<(unsigned)nblk, TB_PIX, smem, st>>>(a);
   DPOT_LAUNCH_CHECK("tail_bwd_kernel");
+  tail_finish_kernel<<<(unsigned)ceil_div(TB_ACC, 128), 128, 0, st>>>(part, nblk, nout, inv_scale, dW2, db2, dW4, db4);
+  DPOT_LAUNCH_CHECK("tail_finish_kernel");
   return 0;
 }
 
 int tk_patch_bwd_supported(int mid, int T, int K0) { return mid <= PB_MID && T <= PB_T && K0 <= PB_NT; }
+int tk_patch_bwd_slabs(int B, int X, int Y, int P) {
+  const int64_t npatch = (int64_t)B * (X / P) * (Y / P);
+  return (int)std::min<int64_t>(npatch, (int64_t)sm_count_cur() * 2);
+}
 int tk_patch_bwd(const float* gz, const float* x, const float* W0p, int B, int X, int Y, int T, int C, int P, int mid, int Kp,
-                 const float* inv_scale, double* dW0p, float* dx, cudaStream_t st) {
+                 const float* inv_scale, float* dW0p, float* dx, cudaStream_t st) {
   DPOT_REQUIRE(tk_patch_bwd_supported(mid, T, P * P * C), DPOT_E_UNSUPPORTED, "patch_bwd: geometry unsupported");
   PatchBwdArgs a;
   a.gz = gz; a.x = x; a.W0p = W0p; a.inv_scale = inv_scale; a.dW0p = dW0p; a.dx = dx;
   a.B = B; a.X = X; a.Y = Y; a.T = T; a.C = C; a.P = P; a.mid = mid; a.Kp = Kp; a.K0 = P * P * C; a.h = X / P; a.w = Y / P;
   const size_t smem = sizeof(float) * (PB_T * PB_MID + (size_t)P * P * T * C);
-  static DevOnce attr;
-  if (attr.need()) {
-    DPOT_CUDA(cudaFuncSetAttribute(patch_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr.done();
+  DPOT_REQUIRE(smem <= 48 * 1024, DPOT_E_UNSUPPORTED, "patch_bwd: patch tile too large");
+  const unsigned grid = (unsigned)tk_patch_bwd_slabs(B, X, Y, P);
+  if (mid == 35 && T == 10) {
+    if (dx) patch_bwd_kernel<35, 10, true><<<grid, PB_NT, smem, st>>>(a);
+    else patch_bwd_kernel<35, 10, false><<<grid, PB_NT, smem, st>>>(a);
+  } else {
+    if (dx) patch_bwd_kernel<0, 0, true><<<grid, PB_NT, smem, st>>>(a);
+    else patch_bwd_kernel<0, 0, false><<<grid, PB_NT, smem, st>>>(a);
   }
-  DPOT_REQUIRE(smem <= 64 * 1024, DPOT_E_UNSUPPORTED, "patch_bwd: patch tile too large");
-  const int64_t npatch = (int64_t)B * a.h * a.w;
-  const unsigned grid = (unsigned)std::min<int64_t>(npatch, (int64_t)sm_count_cur() * 4);
-  patch_bwd_kernel<<<grid, PB_NT, smem, st>>>(a);
   DPOT_LAUNCH_CHECK("patch_bwd_kernel");
   return 0;
 }
 
-int tk_unpack_patch_grad(const double* dW0p, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
+int tk_unpack_patch_grad(const float* dW0p, int nslab, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
                          int P, int h, int w, int T, int Kp, const float* inv_scale, float* dw0, float* db0, cudaStream_t st) {
-  DPOT_REQUIRE(P <= 32, DPOT_E_UNSUPPORTED, "unpack_patch_grad: patch_size > 32");
-  unpack_patch_grad_kernel<<<(unsigned)mid, 256, 0, st>>>(dW0p, drb, gx, gy, gt, mid, C, P, h, w, T, Kp, inv_scale, dw0, db0);
-  DPOT_LAUNCH_CHECK("unpack_patch_grad_kernel");
+  DPOT_REQUIRE(P <= 16, DPOT_E_UNSUPPORTED, "unpack_patch_grad: patch_size > 16");
+  patch_w_reduce_kernel<<<blocks_for((int64_t)mid * P * P * C, 256), 256, 0, st>>>(dW0p, nslab, mid, C, P * P, inv_scale, dw0);
+  DPOT_LAUNCH_CHECK("patch_w_reduce_kernel");
+  patch_coord_grad_kernel<<<dim3((unsigned)mid, (unsigned)(2 * P + 2)), 256, 0, st>>>(drb, gx, gy, gt, mid, C, P, h, w, T, Kp, inv_scale,
+                                                                                    dw0, db0);
+  DPOT_LAUNCH_CHECK("patch_coord_grad_kernel");
   return 0;
 }
 
-int tk_tagg_scale(const float* w, const float* temb, int T, int E, float* wts, float* wtsT, float* Wsum, float* WsumT, cudaStream_t st) {
-  tagg_scale_kernel<<<dim3((unsigned)ceil_div(E, 32), (unsigned)ceil_div(E, 32), (unsigned)T), dim3(32, 8), 0, st>>>(w, temb, E, wts, wtsT);
-  DPOT_LAUNCH_CHECK("tagg_scale_kernel");
-  const int64_t per = (int64_t)E * E;
-  sum_over_t_kernel<<<blocks_for(per, 256), 256, 0, st>>>(wts, wtsT, T, per, Wsum, WsumT);
-  DPOT_LAUNCH_CHECK("sum_over_t_kernel");
+int tk_tagg_scale16(const float* w, const float* temb, int T, int E, __half* wts16, __half* Wsum16, cudaStream_t st) {
+  DPOT_REQUIRE(E % 8 == 0, DPOT_E_BADARG, "tagg_scale16: E %% 8");
+  const int64_t rows = (int64_t)T * E, total = rows * (E / 8);
+  tagg_scale16_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16), 256, 0, st>>>(w, temb, rows, E / 8, wts16);
+  DPOT_LAUNCH_CHECK("tagg_scale16_kernel");
+  tagg_wsum16_kernel<<<blocks_for((int64_t)E * E, 256), 256, 0, st>>>(w, temb, T, E, Wsum16);
+  DPOT_LAUNCH_CHECK("tagg_wsum16_kernel");
   return 0;
 }
-int tk_tagg_bp(const float* b2, const float* pos, int E, int n, float* bp, float* bpT, cudaStream_t st) {
-  tagg_bp_kernel<<<blocks_for((int64_t)E * n, 256), 256, 0, st>>>(b2, pos, E, n, bp, bpT);
-  DPOT_LAUNCH_CHECK("tagg_bp_kernel");
+int tk_tagg_bp16(const float* b2, const float* pos, int E, int n, __half* bp16, cudaStream_t st) {
+  tagg_bp16_kernel<<<blocks_for((int64_t)E * n, 256), 256, 0, st>>>(b2, pos, E, n, bp16);
+  DPOT_LAUNCH_CHECK("tagg_bp16_kernel");
+  return 0;
+}
+int tk_pad_split(const float* src, int64_t lds, int64_t rows, int cols, int colsp, __half* dst, cudaStream_t st) {
+  pad_split_kernel<<<blocks_for(rows * colsp, 256), 256, 0, st>>>(src, lds, rows, cols, colsp, dst);
+  DPOT_LAUNCH_CHECK("pad_split_kernel");
+  return 0;
+}
+int tk_tagg_pad_g(const float* dWeffT, int E, int Kp, int T, int mid, int midp, __half* dst, cudaStream_t st) {
+  tagg_pad_g_kernel<<<blocks_for((int64_t)T * E * midp, 256), 256, 0, st>>>(dWeffT, E, Kp, T, mid, midp, dst);
+  DPOT_LAUNCH_CHECK("tagg_pad_g_kernel");
+  return 0;
+}
+int tk_tagg_dw2_finish(const float* slabs, int T, int E, int mid, int midp, const float* inv_scale, float* dst, cudaStream_t st) {
+  tagg_dw2_finish_kernel<<<blocks_for((int64_t)E * mid, 256), 256, 0, st>>>(slabs, T, E, mid, midp, inv_scale, dst);
+  DPOT_LAUNCH_CHECK("tagg_dw2_finish_kernel");
   return 0;
 }
 int tk_tagg_finish(const float* dwt, const float* w, const float* temb, int T, int E, const float* inv_scale, float* dw,

@@ -28,24 +28,34 @@ int tk_unpack_out_grad(const float* dWtT, int nslab, int64_t stride, const doubl
                        const float* inv_scale, float* dwt, float* db, cudaStream_t st);
 // Output-head tail backward (out_layer[1..4] of models/dpot.py:317-321, out_layer_dim = 32):
 //   from Y1pre[Mt, PP*32] (pre-activation of the ConvTranspose GEMM) and dout[B, X, Y, nout] * scale[0] ->
-//   g1 (gradient w.r.t. Y1pre) stored split [Mt, 2*NP]; dW2 / db2 / dW4 / db4 accumulated (double atomics) into acc:
-//   [32*32 | 32 | nout*32 | nout].
+//   g1 (gradient w.r.t. Y1pre) stored split [Mt, 2*NP]; dW2 / db2 / dW4 / db4 written (times inv_scale[0]).
+//   part: tk_tail_bwd_part_floats(tk_tail_bwd_blocks(...)) floats of scratch (one partial result per thread block).
 int tk_tail_bwd_supported(int old, int nout);
+int tk_tail_bwd_blocks(int B, int h, int w, int P);
+int64_t tk_tail_bwd_part_floats(int nblk);
 int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const float* w2, const float* b2, const float* w4,
-                int B, int h, int w, int P, int nout, int act, __half* g1, double* acc, cudaStream_t st);
+                int B, int h, int w, int P, int nout, int act, __half* g1, float* part, const float* inv_scale, float* dW2,
+                float* db2, float* dW4, float* db4, cudaStream_t st);
 // PatchEmbed conv0 backward (models/dpot.py:199-200): gz[(b,pq), t*mid + m] (row pitch Kp; act' already applied),
-// x[B,X,Y,T,C] -> dW0p (double atomics, [mid, P*P*C]); dx (may be NULL) = inv_scale * gz W0p scattered to the field layout.
+// x[B,X,Y,T,C] -> dW0p (one partial [mid, P*P*C] per thread block); dx (may be NULL) = inv_scale * gz W0p scattered to the field layout.
 int tk_patch_bwd_supported(int mid, int T, int K0);
+int tk_patch_bwd_slabs(int B, int X, int Y, int P);     // number of per-block partial results [mid, P*P*C] the kernel writes
 int tk_patch_bwd(const float* gz, const float* x, const float* W0p, int B, int X, int Y, int T, int C, int P, int mid, int Kp,
-                 const float* inv_scale, double* dW0p, float* dx, cudaStream_t st);
-// transpose of pack_patch: dW0p (double [mid, (u,v,c)]), drb (double [(p,q), Kp] = sum_b gz) -> dpe0_w[mid, C+3, P, P], dpe0_b[mid]
-int tk_unpack_patch_grad(const double* dW0p, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
+                 const float* inv_scale, float* dW0p, float* dx, cudaStream_t st);
+// transpose of pack_patch: dW0p (nslab float partials [mid, (u,v,c)]), drb (double [(p,q), Kp] = sum_b gz) -> dpe0_w[mid, C+3, P, P], dpe0_b[mid]
+int tk_unpack_patch_grad(const float* dW0p, int nslab, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
                          int P, int h, int w, int T, int Kp, const float* inv_scale, float* dw0, float* db0, cudaStream_t st);
 // time-aggregation fold helpers (models/dpot.py:228-232 folded with PatchEmbed conv 1x1 + pos_embed)
-//   wts[t,i,j] = w[t,i,j]*temb[t,i], wtsT[t,j,i] likewise transposed, Wsum = sum_t wts[t], WsumT = sum_t wtsT[t]
-int tk_tagg_scale(const float* w, const float* temb, int T, int E, float* wts, float* wtsT, float* Wsum, float* WsumT, cudaStream_t st);
-//   bpT[p, i] = b2[i] + pos[i, p]   and   bp[i, p] the same untransposed
-int tk_tagg_bp(const float* b2, const float* pos, int E, int n, float* bp, float* bpT, cudaStream_t st);
+//   wts16[(t,i), j] = split(w[t,i,j]*temb[t,i]) rows of [hi E | lo E];  Wsum16[i, j] = split(sum_t temb[t,i] w[t,i,j])
+int tk_tagg_scale16(const float* w, const float* temb, int T, int E, __half* wts16, __half* Wsum16, cudaStream_t st);
+//   bp16[i, p] = split(b2[i] + pos[i, p])
+int tk_tagg_bp16(const float* b2, const float* pos, int E, int n, __half* bp16, cudaStream_t st);
+//   zero-padded split copy: dst16[r, c < colsp] = split(c < cols ? src[r*lds + c] : 0)
+int tk_pad_split(const float* src, int64_t lds, int64_t rows, int cols, int colsp, __half* dst, cudaStream_t st);
+//   Gp16[t][j][m < midp] = split(m < mid ? dWeffT[j, t*mid + m] : 0)
+int tk_tagg_pad_g(const float* dWeffT, int E, int Kp, int T, int mid, int midp, __half* dst, cudaStream_t st);
+//   dW2[i, m < mid] = inv * sum_t slabs[t][i][m]   (slab rows of midp)
+int tk_tagg_dw2_finish(const float* slabs, int T, int E, int mid, int midp, const float* inv_scale, float* dst, cudaStream_t st);
 //   dw[t,i,j] = inv * dwt[t,i,j]*temb[t,i];  dtemb[t,i] = sum_j dwt[t,i,j]*w[t,i,j] (float scratch [T,E])
 int tk_tagg_finish(const float* dwt, const float* w, const float* temb, int T, int E, const float* inv_scale, float* dw,
                    float* dtemb, cudaStream_t st);

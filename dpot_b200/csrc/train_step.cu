@@ -57,12 +57,15 @@ TapeL tape_layout(const Dims& d, int B) {
   return L;
 }
 
-struct PrepL { int64_t wts, Wsum, bp, total; };              // fold intermediates the backward needs
+inline int midp_of(const Dims& d) { return (int)round_up(d.mid, 8); }
+struct PrepL { int64_t wts16, Wsum16, bp16, W2p16, W2T16, total; };   // split-fp16 fold operands (prepare), reused by backward
 PrepL prep_layout(const Dims& d) {
   PrepL L; Bump a;
-  L.wts = a.take((int64_t)d.T * d.E * d.E);
-  L.Wsum = a.take((int64_t)d.E * d.E);
-  L.bp = a.take((int64_t)d.E * d.n);
+  L.wts16 = a.take((int64_t)d.T * d.E * d.E);         // [(t,i), hi E | lo E]
+  L.Wsum16 = a.take((int64_t)d.E * d.E);
+  L.bp16 = a.take((int64_t)d.E * d.n);
+  L.W2p16 = a.take((int64_t)d.E * midp_of(d));        // conv 1x1 weight [E, mid] zero-padded to a multiple of 8 columns
+  L.W2T16 = a.take((int64_t)midp_of(d) * d.E);        // its transpose [mid, E]
   L.total = a.o;
   return L;
 }
@@ -77,14 +80,14 @@ int64_t nchunks(int64_t K, int64_t ch) { return ch > 0 ? ceil_div(K, ch) : 1; }
 
 struct ScratchL {
   // prepare
-  int64_t wtsT, WsumT, bpT, W2T;
+  int64_t W2T;
   // forward
   int64_t O2, Y1g;
   // backward
-  int64_t gA, gB, g16, g1_16, dn2, df, dO2, dO1, dS, dn1, slabs, g1t, z1pre, gz, dWeffT, dWeffT_T, dbe, dbeT, dWsum, dwt,
-      dW2acc, dbp, dtemb, gn, cls, dbl, scale;
+  int64_t gA, gB, g16, g1_16, dn2, df, dO2, dO1, dS, dn1, slabs, g1t, z1pre, gz, dWeffT, Gp16, dbe, dbe16, dWsum, dwt,
+      dW2s, dbp, dtemb, gn, cls, dbl, scale, pslabs, tparts;
   // double accumulators (offsets in DOUBLES from dbl): per block [db2 E | db1 hid | dbc2 2E | dbc1 2E], then the rest
-  int64_t d_blk, d_blk_stride, d_tail, d_bias_t, d_be, d_rb, d_W0p, d_total;
+  int64_t d_blk, d_blk_stride, d_tail, d_bias_t, d_be, d_rb, d_total;
   int64_t total;
 };
 ScratchL scratch_layout(const Dims& d, int B) {
@@ -92,7 +95,7 @@ ScratchL scratch_layout(const Dims& d, int B) {
   const int64_t Mt = (int64_t)B * d.n, Ms = (int64_t)B * d.km1 * d.km2, E = d.E;
   int64_t mx = 0;
   { Bump a;   // prepare
-    L.wtsT = a.take((int64_t)d.T * E * E); L.WsumT = a.take(E * E); L.bpT = a.take((int64_t)d.n * E); L.W2T = a.take((int64_t)d.mid * E);
+    L.W2T = a.take((int64_t)d.mid * E);
     mx = a.o; }
   { Bump a;   // forward
     L.O2 = a.take(Ms * 2 * E); L.Y1g = a.take(Mt * d.NP);
@@ -109,9 +112,12 @@ ScratchL scratch_layout(const Dims& d, int B) {
     if (ks * (int64_t)d.nb * 4 * d.bs * d.bs > sl) sl = ks * (int64_t)d.nb * 4 * d.bs * d.bs;
     L.slabs = a.take(sl);
     L.g1t = a.take(Mt * d.NP); L.z1pre = a.take(Mt * d.Kp); L.gz = a.take(Mt * d.Kp);
-    L.dWeffT = a.take(E * d.Kp); L.dWeffT_T = a.take(E * d.Kp); L.dbe = a.take((int64_t)d.n * E); L.dbeT = a.take((int64_t)d.n * E);
-    L.dWsum = a.take(E * E); L.dwt = a.take((int64_t)d.T * E * E); L.dW2acc = a.take(E * d.mid); L.dbp = a.take(E * d.n);
+    L.dWeffT = a.take(E * d.Kp); L.Gp16 = a.take((int64_t)d.T * E * midp_of(d)); L.dbe = a.take((int64_t)d.n * E);
+    L.dbe16 = a.take((int64_t)d.n * E);
+    L.dWsum = a.take(E * E); L.dwt = a.take((int64_t)d.T * E * E); L.dW2s = a.take((int64_t)d.T * E * midp_of(d)); L.dbp = a.take(E * d.n);
+    L.pslabs = a.take((int64_t)2 * 160 * d.mid * d.K0);         // per-block partials of the PatchEmbed weight gradient (<= 2 per SM)
     L.dtemb = a.take((int64_t)d.T * E);
+    L.tparts = a.take(tk_tail_bwd_part_floats(3 * 160));
     L.gn = a.take(3 * (int64_t)B * E + 2 * (int64_t)B * GROUPS);
     L.cls = a.take(8 * (int64_t)B * E + 3 * E * E + (int64_t)d.ncls * E + 4096);
     L.scale = a.take(64);
@@ -122,7 +128,6 @@ ScratchL scratch_layout(const Dims& d, int B) {
     L.d_bias_t = q; q += d.NP;
     L.d_be = q; q += (int64_t)d.n * E;
     L.d_rb = q; q += (int64_t)d.n * d.Kp;
-    L.d_W0p = q; q += (int64_t)d.mid * d.K0;
     L.d_total = q;
     L.dbl = a.take(2 * q + 2);
     if (a.o > mx) mx = a.o; }
@@ -137,7 +142,7 @@ bool train_ok(const dpot_config* c, const Dims& d) {
   if ((d.E / GROUPS) % 8 != 0 || d.E % GROUPS != 0) return false;
   if (!dpot_out_tail_tc_supported(d.old, d.Co * d.To, d.Co) || !tk_tail_bwd_supported(d.old, d.Co * d.To)) return false;
   if (!tk_patch_bwd_supported(d.mid, d.T, d.K0)) return false;
-  if (d.E % 32 != 0 || d.n % 32 != 0) return false;                 // fold GEMMs on the fp32 tensor-core engine (K % 32)
+  if (d.E % 8 != 0 || d.n % 8 != 0) return false;                   // fold contractions on the f16-split engine
   if ((2 * d.bs) % 8 != 0 || d.hid % 8 != 0 || d.NP % 8 != 0 || d.Kp % 8 != 0) return false;
   if (d.C != d.Co) return false;
   return true;
@@ -206,19 +211,24 @@ extern "C" int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm
                             packed + L.W0p, packed + L.rowbias0, stream));
   // fold conv 1x1 + pos_embed + time aggregation with the contraction engine (the double-precision fold kernels of the
   // inference packer take ~1 ms: fine once per checkpoint, not once per optimizer step)
-  float* wts = wprep + PL.wts; float* Wsum = wprep + PL.Wsum; float* bp = wprep + PL.bp;
-  float* wtsT = scratch + SL.wtsT; float* WsumT = scratch + SL.WsumT; float* bpT = scratch + SL.bpT; float* W2T = scratch + SL.W2T;
-  DPOT_CALL(tk_tagg_scale(prm->tagg_w, prm->temb, d.T, E, wts, wtsT, Wsum, WsumT, st));
+  float* wts16 = wprep + PL.wts16; float* Wsum16 = wprep + PL.Wsum16; float* bp16 = wprep + PL.bp16;
+  float* W2p16 = wprep + PL.W2p16; float* W2T16 = wprep + PL.W2T16;
+  float* W2T = scratch + SL.W2T;
+  const int midp = midp_of(d);
+  DPOT_CALL(tk_tagg_scale16(prm->tagg_w, prm->temb, d.T, E, reinterpret_cast<__half*>(wts16), reinterpret_cast<__half*>(Wsum16), st));
+  DPOT_CALL(tk_tagg_bp16(prm->pe2_b, prm->pos_embed, E, d.n, reinterpret_cast<__half*>(bp16), st));
+  DPOT_CALL(tk_pad_split(prm->pe2_w, d.mid, E, d.mid, midp, reinterpret_cast<__half*>(W2p16), st));
   DPOT_CALL(tk_transpose(prm->pe2_w, d.mid, W2T, E, E, d.mid, st));
+  DPOT_CALL(dpot_split_f16(W2T, E, d.mid, E, nullptr, nullptr, 0, W2T16, 2 * E, E, stream));
   DPOT_CUDA(cudaMemsetAsync(packed + L.WeffT, 0, sizeof(float) * (size_t)E * d.Kp, st));
-  for (int t = 0; t < d.T; ++t) {   // WeffT[j, t*mid + m] = sum_i wts[t,i,j] W2[i,m]
-    dpot_gemm_args g = gemm_args(wtsT + (int64_t)t * E * E, E, W2T, E, packed + L.WeffT + (int64_t)t * d.mid, d.Kp, E, d.mid, E,
-                                 nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+  {   // WeffT[j, t*mid + m] = sum_i wts[t,i,j] W2[i,m]: T problems side by side, wts[t] read transposed, W2^T shared
+    dpot_gemm_args g = gemm16_args(wts16, E, W2T16, E, packed + L.WeffT, d.Kp, E, d.mid, E, nullptr, DPOT_ACT_NONE);
+    g.a_trans = 1; g.batch = d.T; g.strideA = 2 * (int64_t)E * E; g.strideW = 0; g.strideC = d.mid;
     DPOT_CALL(dpot_gemm(&g, stream));
   }
-  DPOT_CALL(tk_tagg_bp(prm->pe2_b, prm->pos_embed, E, d.n, bp, bpT, st));
   {   // bias_eff[p, j] = sum_i (b2[i] + pos[i,p]) Wsum[i,j]
-    dpot_gemm_args g = gemm_args(bpT, E, WsumT, E, packed + L.bias_eff, E, d.n, E, E, nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
+    dpot_gemm_args g = gemm16_args(bp16, d.n, Wsum16, E, packed + L.bias_eff, E, d.n, E, E, nullptr, DPOT_ACT_NONE);
+    g.a_trans = 1; g.w_trans = 1;
     DPOT_CALL(dpot_gemm(&g, stream));
   }
   DPOT_CALL(dpot_pack_out(prm->out0_w, prm->out0_b, E, d.old, d.P, packed + L.WtT, packed + L.bias_t, stream));
@@ -405,13 +415,9 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
   // ---- output head (models/dpot.py:315-321)
   float* g1t = scratch + SL.g1t;
   {
-    double* acc = dbl + SL.d_tail;
     DPOT_CALL(tk_tail_bwd(tape + TL.Y1pre, dy, scale, prm->out2_w, prm->out2_b, prm->out4_w, B, d.h, d.h, d.P, nout, act,
-                          reinterpret_cast<__half*>(g1t), acc, st));
-    DPOT_CALL(tk_finish_double(acc, 1024, inv, G(grads->out2_w), st));
-    DPOT_CALL(tk_finish_double(acc + 1024, 32, inv, G(grads->out2_b), st));
-    DPOT_CALL(tk_finish_double(acc + 1056, (int64_t)nout * 32, inv, G(grads->out4_w), st));
-    DPOT_CALL(tk_finish_double(acc + 1056 + nout * 32, nout, inv, G(grads->out4_b), st));
+                          reinterpret_cast<__half*>(g1t), scratch + SL.tparts, inv, G(grads->out2_w), G(grads->out2_b),
+                          G(grads->out4_w), G(grads->out4_b), st));
     DPOT_CALL(tk_colsum(g1t, true, 2 * (int64_t)NP, NP, Mt, NP, dbl + SL.d_bias_t, st));
     DPOT_CALL(wgrad16(g1t, NP, tape + TL.alat16, E, NP, E, Mt, 1, slabs, &ns, stream));
     DPOT_CALL(tk_unpack_out_grad(slabs, ns, (int64_t)NP * E, dbl + SL.d_bias_t, E, d.old, d.P, inv, G(grads->out0_w), G(grads->out0_b), st));
@@ -508,33 +514,39 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     DPOT_CALL(dpot_gemm(&a, stream));
   }
   DPOT_CALL(tk_colsum(gz, false, (int64_t)d.n * d.Kp, 0, B, d.n * d.Kp, dbl + SL.d_rb, st));
-  DPOT_CALL(tk_patch_bwd(gz, x, packed + PL.W0p, B, R, R, d.T, d.C, d.P, d.mid, d.Kp, inv, dbl + SL.d_W0p, dx, st));
-  DPOT_CALL(tk_unpack_patch_grad(dbl + SL.d_W0p, dbl + SL.d_rb, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h, d.T,
+  DPOT_CALL(tk_patch_bwd(gz, x, packed + PL.W0p, B, R, R, d.T, d.C, d.P, d.mid, d.Kp, inv, scratch + SL.pslabs, dx, st));
+  DPOT_CALL(tk_unpack_patch_grad(scratch + SL.pslabs, tk_patch_bwd_slabs(B, R, R, d.P), dbl + SL.d_rb, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h, d.T,
                                  d.Kp, inv, G(grads->pe0_w), G(grads->pe0_b), st));
-  // fold backward
+  // fold backward: every contraction on the f16-split engine (WeffT = sum_i wts W2, bias_eff = bp^T Wsum, Wsum = sum_t wts)
   {
-    const float* wts = wprep + WL.wts; const float* Wsum = wprep + WL.Wsum; const float* bpm = wprep + WL.bp;
-    float* dWeffT_T = scratch + SL.dWeffT_T; float* dbeT = scratch + SL.dbeT; float* dWsum = scratch + SL.dWsum;
-    float* dwt = scratch + SL.dwt; float* dW2acc = scratch + SL.dW2acc; float* dbp = scratch + SL.dbp; float* dtemb = scratch + SL.dtemb;
-    DPOT_CALL(tk_transpose(dWeffT, d.Kp, dWeffT_T, E, E, d.Kp, st));                 // [Kp, E]
-    DPOT_CALL(tk_transpose(dbe, E, dbeT, d.n, d.n, E, st));                          // [E, n]
-    dpot_gemm_args m = gemm_args(bpm, d.n, dbeT, d.n, dWsum, E, E, E, d.n, nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);   // dWsum[i,j]
-    DPOT_CALL(dpot_gemm(&m, stream));
-    for (int t = 0; t < d.T; ++t) {
-      // dwt[t][i,j] = sum_m W2[i,m] dWeffT[j, t*mid+m] + dWsum[i,j]
-      m = gemm_args(prm->pe2_w, d.mid, dWeffT + (int64_t)t * d.mid, d.Kp, dwt + (int64_t)t * E * E, E, E, E, d.mid, nullptr,
-                    DPOT_ACT_NONE, DPOT_GEMM_AUTO);
-      m.residual = dWsum; m.ldr = E;
-      DPOT_CALL(dpot_gemm(&m, stream));
-      // dW2[i,m] += sum_j wts[t][i,j] dWeffT[j, t*mid+m]
-      m = gemm_args(wts + (int64_t)t * E * E, E, dWeffT_T + (int64_t)t * d.mid * E, E, dW2acc, d.mid, E, d.mid, E, nullptr,
-                    DPOT_ACT_NONE, DPOT_GEMM_AUTO);
-      if (t > 0) { m.residual = dW2acc; m.ldr = d.mid; }
+    const float* wts16 = wprep + WL.wts16; const float* Wsum16 = wprep + WL.Wsum16; const float* bp16 = wprep + WL.bp16;
+    const float* W2p16 = wprep + WL.W2p16;
+    float* Gp16 = scratch + SL.Gp16; float* dbe16 = scratch + SL.dbe16; float* dWsum = scratch + SL.dWsum;
+    float* dwt = scratch + SL.dwt; float* dW2s = scratch + SL.dW2s; float* dbp = scratch + SL.dbp; float* dtemb = scratch + SL.dtemb;
+    const int midp = midp_of(d);
+    DPOT_CALL(tk_tagg_pad_g(dWeffT, E, d.Kp, d.T, d.mid, midp, reinterpret_cast<__half*>(Gp16), st));   // Gp[t][j][m]
+    DPOT_CALL(dpot_split_f16(dbe, E, d.n, E, nullptr, nullptr, 0, dbe16, 2 * E, E, stream));
+    {   // dWsum[i,j] = sum_p bp[i,p] dbe[p,j]
+      dpot_gemm_args m = g16(bp16, d.n, dbe16, E, dWsum, E, E, E, d.n);
+      m.w_trans = 1;
       DPOT_CALL(dpot_gemm(&m, stream));
     }
-    DPOT_CALL(tk_scale_copy(dW2acc, (int64_t)E * d.mid, inv, G(grads->pe2_w), st));
-    m = gemm_args(Wsum, E, dbe, E, dbp, d.n, E, d.n, E, nullptr, DPOT_ACT_NONE, DPOT_GEMM_AUTO);       // dbp[i,p] = sum_j Wsum[i,j] dbe[p,j]
-    DPOT_CALL(dpot_gemm(&m, stream));
+    {   // dwt[t][i,j] = sum_m W2[i,m] Gp[t][j][m] + dWsum[i,j]     (W2 shared by the T problems)
+      dpot_gemm_args m = g16(W2p16, midp, Gp16, midp, dwt, E, E, E, midp);
+      m.batch = d.T; m.strideA = 0; m.strideW = 2 * (int64_t)E * midp; m.strideC = (int64_t)E * E;
+      m.residual = dWsum; m.ldr = E;
+      DPOT_CALL(dpot_gemm(&m, stream));
+    }
+    {   // dW2 partials [t][i, m] = sum_j wts[t][i,j] Gp[t][j][m]
+      dpot_gemm_args m = g16(wts16, E, Gp16, midp, dW2s, midp, E, midp, E);
+      m.w_trans = 1; m.batch = d.T; m.strideA = 2 * (int64_t)E * E; m.strideW = 2 * (int64_t)E * midp; m.strideC = (int64_t)E * midp;
+      DPOT_CALL(dpot_gemm(&m, stream));
+    }
+    DPOT_CALL(tk_tagg_dw2_finish(dW2s, d.T, E, d.mid, midp, inv, G(grads->pe2_w), st));
+    {   // dbp[i,p] = sum_j Wsum[i,j] dbe[p,j]
+      dpot_gemm_args m = g16(Wsum16, E, dbe16, E, dbp, d.n, E, d.n, E);
+      DPOT_CALL(dpot_gemm(&m, stream));
+    }
     DPOT_CALL(tk_rowsum_scale(dbp, E, d.n, inv, G(grads->pe2_b), G(grads->pos_embed), st));
     DPOT_CALL(tk_tagg_finish(dwt, prm->tagg_w, prm->temb, d.T, E, inv, G(grads->tagg_w), dtemb, st));
     if (cfg->time_agg == 1 && grads->tagg_gamma)

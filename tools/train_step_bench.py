@@ -1,36 +1,55 @@
-"""Training-step timing of DPOT-S through the drop-in API (train_temporal.py:201-230 with T_ar = 1, noise off):
-forward (autograd path) + SimpleLpLoss + backward + clip_grad_norm_ + Adam.step, CUDA events, synthetic data."""
-import os, sys, time
+"""Training-step timing through the drop-in API (train_temporal.py:201-230, T_ar = 1, noise off): forward + SimpleLpLoss +
+backward + clip + Adam.step on one GPU, CUDA events, synthetic data.
+
+    python tools/train_step_bench.py [S|M|Ti] [batch] [path: auto|generic|both] [steps]
+
+Prints one JSON line: ms per step for the one-call training step (dpot_train_*) and/or the per-operator path."""
+import json
+import os
+import sys
+
 import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import dpot_oracle as O      # synthetic weights only
+from dpot_b200 import _lib, zoo
 from dpot_b200.models.dpot import DPOTNet
+from dpot_b200.train import ar_train_step
 from dpot_b200.utils.optimizer import Adam
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-cfg = O.zoo_cfg("S")
-m = DPOTNet(**cfg)
-m.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_params(cfg, seed=0).items()})
-m = m.cuda().train()
-opt = Adam(m.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=1e-6)
-x = torch.randn(B, 128, 128, 10, 4, device="cuda")
-y = torch.randn(B, 128, 128, 1, 4, device="cuda")
-def step():
-    im, _ = m(x)
-    diff = (im - y).reshape(B, -1, 4)
-    loss = (diff.norm(dim=1) / y.reshape(B, -1, 4).norm(dim=1)).mean(dim=1).sum()      # SimpleLpLoss, utils/criterion.py:38-59
-    opt.zero_grad()
-    loss.backward()
-    torch.nn.utils.clip_grad_norm_(m.parameters(), 10000.0)
-    opt.step()
-    return loss
-for _ in range(3):
-    step()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 10
-e0.record()
-for _ in range(n):
-    l = step()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / n
-print(f"DPOT-S train step B={B}: {ms:.2f} ms/step = {B / ms * 1e3:.0f} field-steps/s (fwd+bwd+clip+Adam), loss {float(l):.4f}")
+
+name = sys.argv[1] if len(sys.argv) > 1 else "S"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+which = sys.argv[3] if len(sys.argv) > 3 else "both"
+n = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+cfg = zoo.zoo_cfg(name)
+dev = torch.device("cuda")
+x = torch.randn(B, 128, 128, 10, 4, device=dev)
+y = torch.randn(B, 128, 128, 1, 4, device=dev)
+msk = torch.ones(B, 128, 128, 1, 4, device=dev)
+out = {"model": name, "batch": B, "steps": n}
+for path in (["auto", "generic"] if which == "both" else [which]):
+    m = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).train()
+    m.train_path = path
+    opt = Adam(m.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=1e-6)
+    it = {"i": 0}
+
+    def step():
+        it["i"] += 1
+        return ar_train_step(m, opt, x, y, msk, T_bundle=1, noise_scale=0.0, grad_clip=1e4, step=it["i"])
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.load().dpot_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    out[path] = {"ms_per_step": ms, "field_steps_per_s": B / ms * 1e3, "loss": float(loss),
+                 "launches_per_step": (_lib.load().dpot_launch_count() - l0) / n,
+                 "fused": bool(m._train_eng is not None and m._train_eng.supported)}
+    del m, opt
+    torch.cuda.empty_cache()
+print(json.dumps(out))
