@@ -45,6 +45,7 @@ class GemmArgs(C.Structure):
         ("a_trans", C.c_int32), ("w_trans", C.c_int32),
         ("k_split", C.c_int32), ("k_chunk", C.c_int64), ("strideC_split", C.c_int64),
         ("ld_pre", C.c_int64), ("stride_pre", C.c_int64), ("ld_dact", C.c_int64), ("stride_dact", C.c_int64),
+        ("out_colsum", C.c_void_p),
     ]
 
 
@@ -156,7 +157,7 @@ SIGNATURES = {
     "dpot_out_tail_tc": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p,
                                    _i32, _i32, _i32, _i32, _p]),
     "dpot_out_tail_tc_supported": (C.c_int, [_i32, _i32, _i32]),
-    "dpot_afno_fft_fwd16w": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p]),
+    "dpot_afno_fft_fwd16w": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _p]),
     "dpot_train_supported": (C.c_int, [C.POINTER(Config)]),
     "dpot_train_tape_floats": (C.c_int64, [C.POINTER(Config), _i32]),
     "dpot_train_scratch_floats": (C.c_int64, [C.POINTER(Config), _i32]),

@@ -54,7 +54,8 @@ struct Cfg {
 template <int H, bool OUT16, bool GN, int SPEC = 0>
 __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restrict__ a, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int E_rt, int bs_rt, int km1_rt,
-                                                          int km2_rt, float* __restrict__ S, float wint, const GnRef gn) {
+                                                          int km2_rt, float* __restrict__ S, float wint, const GnRef gn,
+                                                          double* __restrict__ csum = nullptr) {
   constexpr int CH = Cfg<H>::CH, NTASK = Cfg<H>::NTASK, HC = (H >= 2) ? H / 2 : 1, n = H * H;
   const int E = SPEC ? FftSpec<SPEC>::E : E_rt, bs = SPEC ? FftSpec<SPEC>::bs : bs_rt;
   const int km1 = SPEC ? H : km1_rt, km2 = SPEC ? H / 2 + 1 : km2_rt;
@@ -102,7 +103,9 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
   if (!live) return;
   const float norm = 1.0f / (float)H;  // ortho: 1/sqrt(H*W), H == W
   const int kap = ch / bs, j = ch % bs;
+  float sum_re = 0.f, sum_im = 0.f;      // column sums of this channel's stored modes (csum != NULL: bias gradient)
   auto store = [&](int k1, int k2, float re, float im) {
+    sum_re += re; sum_im += im;
     if (OUT16) {
       __half* dst = reinterpret_cast<__half*>(S) + (((int64_t)b * km1 + k1) * km2 + k2) * (4 * E) + (int64_t)kap * 2 * bs + j;
       __half hi, lo;
@@ -142,6 +145,10 @@ __global__ void __launch_bounds__(NT) afno_fft_fwd_kernel(const float* __restric
         }
       }
     }
+  }
+  if (csum) {
+    atomicAdd(csum + (int64_t)kap * 2 * bs + j, (double)sum_re);
+    atomicAdd(csum + (int64_t)kap * 2 * bs + bs + j, (double)sum_im);
   }
 }
 
@@ -276,13 +283,13 @@ __global__ void __launch_bounds__(NT, H <= 16 ? 3 : 1) afno_fft_inv_kernel(const
 
 template <int H, bool OUT16 = false, bool GN = false, int SPEC = 0>
 int launch_fwd(const float* a, const float* scale, const float* shift, int B, int E, int nb, int km1, int km2,
-               float* S, float wint, cudaStream_t st, const GnRef gn = GnRef()) {
+               float* S, float wint, cudaStream_t st, const GnRef gn = GnRef(), double* csum = nullptr) {
   constexpr int CH = Cfg<H>::CH, KH = Cfg<H>::KH;
   const size_t smem = (size_t)H * (H >= 2 ? H / 2 : 1) * CH * 8;
   (void)KH;
   DPOT_CUDA(cudaFuncSetAttribute(afno_fft_fwd_kernel<H, OUT16, GN, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(E, CH), (unsigned)B);
-  DPOT_CUDA(launch_pdl(afno_fft_fwd_kernel<H, OUT16, GN, SPEC>, grid, dim3(NT), smem, st, a, scale, shift, E, E / nb, km1, km2, S, wint, gn));
+  DPOT_CUDA(launch_pdl(afno_fft_fwd_kernel<H, OUT16, GN, SPEC>, grid, dim3(NT), smem, st, a, scale, shift, E, E / nb, km1, km2, S, wint, gn, csum));
   DPOT_LAUNCH_CHECK("afno_fft_fwd_kernel");
   return 0;
 }
@@ -349,17 +356,17 @@ extern "C" int dpot_afno_fft_fwd16(const float* a, const float* scale, const flo
 // fwd16 without GroupNorm and with the interior-column weight: the adjoint of the inverse transform (weight 2) that the
 // backward pass feeds straight into the f16-split contractions
 extern "C" int dpot_afno_fft_fwd16w(const float* a, int32_t B, int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2,
-                                    void* S16, float interior_weight, void* stream) {
+                                    void* S16, float interior_weight, double* colsum, void* stream) {
   DPOT_REQUIRE(a && S16, DPOT_E_BADARG, "dpot_afno_fft_fwd16w: null pointer");
   DPOT_CALL(check_common(B, h, E, nb, km1, km2));
   cudaStream_t st = as_stream(stream);
   float* S = reinterpret_cast<float*>(S16);
   switch (h) {
-    case 2: return launch_fwd<2, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
-    case 4: return launch_fwd<4, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
-    case 8: return launch_fwd<8, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
-    case 16: return launch_fwd<16, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
-    default: return launch_fwd<32, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st);
+    case 2: return launch_fwd<2, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st, GnRef(), colsum);
+    case 4: return launch_fwd<4, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st, GnRef(), colsum);
+    case 8: return launch_fwd<8, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st, GnRef(), colsum);
+    case 16: return launch_fwd<16, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st, GnRef(), colsum);
+    default: return launch_fwd<32, true>(a, nullptr, nullptr, B, E, nb, km1, km2, S, interior_weight, st, GnRef(), colsum);
   }
 }
 

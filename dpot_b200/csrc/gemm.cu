@@ -34,6 +34,8 @@ extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   p.a_fmt = a->a_fmt; p.w_fmt = a->w_fmt; p.c_fmt = a->c_fmt; p.a_lo = a->a_lo_off; p.w_lo = a->w_lo_off; p.c_lo = a->c_lo_off;
   p.a_tr = a->a_trans; p.w_tr = a->w_trans; p.ksplit = a->k_split > 1 ? a->k_split : 1; p.kchunk = a->k_chunk; p.sC2 = a->strideC_split;
   p.ldpre = a->ld_pre; p.sPre = a->stride_pre; p.lddact = a->ld_dact; p.sDact = a->stride_dact;
+  p.out_colsum = a->out_colsum;
+  DPOT_REQUIRE(!a->out_colsum || (a->a_fmt == DPOT_FMT_HL16 && a->k_split <= 1), DPOT_E_BADARG, "dpot_gemm: out_colsum needs the TC16 engine without k_split");
   const bool bw_form = a->a_trans || a->w_trans || a->k_split > 1;
   DPOT_REQUIRE(!bw_form || a->a_fmt == DPOT_FMT_HL16, DPOT_E_BADARG, "dpot_gemm: a_trans / w_trans / k_split need split-fp16 operands");
   if (a->k_split > 1)

@@ -25,6 +25,7 @@ struct GemmDev {
   // backward-pass forms of the f16-split engine (dpot_gemm_args ABI 2): transposed operand storage, contraction split
   int a_tr, w_tr, ksplit; int64_t kchunk, sC2;
   int64_t ldpre, sPre, lddact, sDact;                           // C_pre / dact_src geometry on the f16-split engine
+  double* out_colsum;                                           // f16-split engine: column sums of the stored result
 };
 
 // split fp16 storage (include/dpot_b200.h, DPOT_FMT_HL16): x ~= hi + lo / 2048

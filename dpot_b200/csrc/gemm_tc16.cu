@@ -253,6 +253,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       const float bias_n = (g.bias && nok) ? g.bias[(int64_t)bb * g.sBias + n] : 0.f;
       // fused GroupNorm statistics: a tile of <= 128 tokens touches at most two samples (slot 0 / slot 1)
       float st1a = 0.f, st2a = 0.f, st1b = 0.f, st2b = 0.f;
+      float csum = 0.f;                                 // column sum of this lane's channel over the warp's token groups
       const int smp0 = g.out_stats ? (mt * BA) / g.st_rps : 0;
       const int m_next = (smp0 + 1) * g.st_rps;       // first token of the next sample
       // side inputs (row-periodic bias, residual) of a group are fetched one group ahead: their global-load
@@ -329,10 +330,14 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         }
         if (SIDE == 2 && dact_on) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) t[u] *= act_grad(rs[u], g.dact);
+          for (int u = 0; u < 8; ++u) t[u] *= act_grad_fast(rs[u], g.dact);
         } else if (SIDE >= 2) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) t[u] += rs[u];
+        }
+        if (g.out_colsum) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) csum += u < cnt ? t[u] : 0.f;
         }
         if (OUT16) {
           const bool grp = g.c_fmt == DPOT_FMT_HL16G32;            // [hi 32 | lo 32] record per 32-column group
@@ -376,6 +381,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * buf); else mbar_arrive(TEMPTY(buf));
       }
+      if (g.out_colsum && nok) atomicAdd(g.out_colsum + (int64_t)bb * g.N + n, (double)csum);
       if (!OUT16 && g.out_stats) {   // host guarantees: the warp's 32 channels lie in one group
 #pragma unroll
         for (int slot = 0; slot < 2; ++slot) {
@@ -494,7 +500,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
   g_sm_count = sm_count_cur();
-  const bool bw_form = p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src || (batch > 1 && (p.sA == 0 || p.sW == 0));
+  const bool bw_form = p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src || p.out_colsum || (batch > 1 && (p.sA == 0 || p.sW == 0));
   if (!bw_form && gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused

@@ -10,16 +10,6 @@ namespace {
 
 __device__ __forceinline__ float inv_of(const float* inv_scale) { return inv_scale ? __ldg(inv_scale) : 1.0f; }
 
-// d act(x)/dx with the branch-free erf of common.cuh (GELU: Phi(x) + x phi(x); abs error ~1e-7)
-__device__ __forceinline__ float act_grad_fast(float x, int act) {
-  if (act == DPOT_ACT_GELU) {
-    const float cdf = 0.5f * (1.0f + erf_select(x * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-    return fmaf(x, pdf, cdf);
-  }
-  return act_grad(x, act);
-}
-
 // ------------------------------------------------------------------------------------------------ gradient scale
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ bits) {
   float m = 0.f;
@@ -147,39 +137,51 @@ __global__ void __launch_bounds__(128) gn_bwd_group2_kernel(const float* __restr
   }
 }
 
+constexpr int GNA_ROWS = 16;
+// thread: 4 channels x GNA_ROWS consecutive rows of one sample (coefficients fetched once); grid (E/4/128, rows/GNA_ROWS)
 template <bool OUT16>
-__global__ void __launch_bounds__(256) gn_bwd_apply2_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(128) gn_bwd_apply2_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ coefA, const float* __restrict__ coefBC,
-                                                            const float* __restrict__ add, int64_t total4, int n, int E, int gs,
+                                                            const float* __restrict__ add, int64_t rows, int n, int E, int gs,
                                                             int groups, float* __restrict__ dx, __half* __restrict__ dx16,
-                                                            int64_t ld16, int64_t lo16) {
-  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const int64_t i = i4 * 4;
-  const int64_t row = i / E; const int c = (int)(i % E);
-  const int b = (int)(row / n), g = c / gs;
-  const float4 gv = __ldcs(reinterpret_cast<const float4*>(dy + i));
-  const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + i));
+                                                            int64_t ld16, int64_t lo16, double* __restrict__ colsum) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= E) return;
+  const int64_t r0 = (int64_t)blockIdx.y * GNA_ROWS;
+  const int b = (int)(r0 / n), g = c / gs;
   const float4 ca = __ldg(reinterpret_cast<const float4*>(coefA + (int64_t)b * E + c));
   const float2 bc = __ldg(reinterpret_cast<const float2*>(coefBC + 2 * ((int64_t)b * groups + g)));
-  float4 o;
-  o.x = fmaf(ca.x, gv.x, fmaf(bc.x, xv.x, bc.y));
-  o.y = fmaf(ca.y, gv.y, fmaf(bc.x, xv.y, bc.y));
-  o.z = fmaf(ca.z, gv.z, fmaf(bc.x, xv.z, bc.y));
-  o.w = fmaf(ca.w, gv.w, fmaf(bc.x, xv.w, bc.y));
-  if (add) {
-    const float4 av = __ldcs(reinterpret_cast<const float4*>(add + i));
-    o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
-  }
-  *reinterpret_cast<float4*>(dx + i) = o;
-  if (OUT16) {
-    const float v[4] = {o.x, o.y, o.z, o.w};
-    alignas(8) __half hi[4];
-    alignas(8) __half lo[4];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const int64_t rend = r0 + GNA_ROWS < rows ? r0 + GNA_ROWS : rows;
+#pragma unroll 4
+  for (int64_t r = r0; r < rend; ++r) {
+    const int64_t i = r * E + c;
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(dy + i));
+    const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + i));
+    float4 o;
+    o.x = fmaf(ca.x, gv.x, fmaf(bc.x, xv.x, bc.y));
+    o.y = fmaf(ca.y, gv.y, fmaf(bc.x, xv.y, bc.y));
+    o.z = fmaf(ca.z, gv.z, fmaf(bc.x, xv.z, bc.y));
+    o.w = fmaf(ca.w, gv.w, fmaf(bc.x, xv.w, bc.y));
+    if (add) {
+      const float4 av = __ldcs(reinterpret_cast<const float4*>(add + i));
+      o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
+    }
+    *reinterpret_cast<float4*>(dx + i) = o;
+    s0 += o.x; s1 += o.y; s2 += o.z; s3 += o.w;
+    if (OUT16) {
+      const float v[4] = {o.x, o.y, o.z, o.w};
+      alignas(8) __half hi[4];
+      alignas(8) __half lo[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) hl_split(v[u], hi[u], lo[u]);
-    *reinterpret_cast<uint2*>(dx16 + row * ld16 + c) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(dx16 + row * ld16 + c + lo16) = *reinterpret_cast<const uint2*>(lo);
+      for (int u = 0; u < 4; ++u) hl_split(v[u], hi[u], lo[u]);
+      *reinterpret_cast<uint2*>(dx16 + r * ld16 + c) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(dx16 + r * ld16 + c + lo16) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+  if (colsum) {
+    atomicAdd(colsum + c, (double)s0); atomicAdd(colsum + c + 1, (double)s1);
+    atomicAdd(colsum + c + 2, (double)s2); atomicAdd(colsum + c + 3, (double)s3);
   }
 }
 
@@ -278,7 +280,7 @@ __global__ void out_bias_grad_kernel(const double* __restrict__ dbias_t, int old
 // from the same shared copies by a second mapping, accumulated in registers across the tiles of the block and written
 // as ONE partial result per block (summed in double by tail_finish_kernel).
 constexpr int TB_PIX = 128, TB_OLD = 32, TB_NOUT_MAX = 8, TB_LD = 132;
-constexpr int TB_ACC = 1024 + 32 + TB_NOUT_MAX * 32 + TB_NOUT_MAX;       // [dW2 | db2 | dW4 | db4] floats per block partial
+constexpr int TB_ACC = 1024 + 32 + TB_NOUT_MAX * 32 + TB_NOUT_MAX + 32;  // [dW2 | db2 | dW4 | db4 | db0] floats per block partial
 struct TailBwdArgs {
   const float* Y1pre; const float* dout; const float* scale; const float* w2; const float* b2; const float* w4;
   __half* g1; float* part;
@@ -300,9 +302,9 @@ __global__ void __launch_bounds__(TB_PIX, 3) tail_bwd_kernel(const TailBwdArgs a
   for (int i = tid; i < TB_NOUT_MAX * 32; i += TB_PIX) W4s[i] = i < nout * 32 ? a.w4[i] : 0.f;
   if (tid < 32) b2s[tid] = a.b2[tid];
   const float S = a.scale ? __ldg(a.scale) : 1.f;
-  float dW2r[8], db2r = 0.f, dW4r[2] = {0.f, 0.f}, db4r = 0.f;
+  float dW2r[8], db2r = 0.f, dW4r[2] = {0.f, 0.f}, db4r = 0.f, db0r[8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) dW2r[u] = 0.f;
+  for (int u = 0; u < 8; ++u) { dW2r[u] = 0.f; db0r[u] = 0.f; }
   const int R = a.h * a.P, Wd = a.w * a.P;
   const int64_t npix = (int64_t)a.B * a.h * a.w * PP;
   __syncthreads();
@@ -399,7 +401,11 @@ __global__ void __launch_bounds__(TB_PIX, 3) tail_bwd_kernel(const TailBwdArgs a
         alignas(16) __half hi[8];
         alignas(16) __half lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hl_split(acc[i][j] * act_grad_fast(pre[j], act), hi[j], lo[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float gv = acc[i][j] * act_grad_fast(pre[j], act);
+          db0r[j] += gv;                         // bias gradient of the ConvTranspose: sum over pixels per channel
+          hl_split(gv, hi[j], lo[j]);
+        }
         __half* gp = a.g1 + tok * (2 * (int64_t)NP) + (int64_t)uv * 32 + 8 * tx;
         *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(hi);
         *reinterpret_cast<uint4*>(gp + NP) = *reinterpret_cast<const uint4*>(lo);
@@ -441,6 +447,12 @@ __global__ void __launch_bounds__(TB_PIX, 3) tail_bwd_kernel(const TailBwdArgs a
     __syncthreads();
   }
   float* part = a.part + (int64_t)blockIdx.x * TB_ACC;
+  if (tid < 32) G3s[tid] = 0.f;                // (the tile loop ended on a barrier: G3s is free)
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(G3s + 8 * tx + j, db0r[j]);
+  __syncthreads();
+  if (tid < 32) part[1024 + 32 + TB_NOUT_MAX * 32 + TB_NOUT_MAX + tid] = G3s[tid];
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) part[ty * 32 + tx + 4 * kk] = dW2r[kk];
   if (tid < 32) part[1024 + tid] = db2r;
@@ -453,7 +465,8 @@ __global__ void __launch_bounds__(TB_PIX, 3) tail_bwd_kernel(const TailBwdArgs a
 }
 // sums the per-block partials and writes the four parameter gradients (scaled by inv_scale)
 __global__ void tail_finish_kernel(const float* __restrict__ part, int nblk, int nout, const float* __restrict__ inv_scale,
-                                   float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dW4, float* __restrict__ db4) {
+                                   float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dW4, float* __restrict__ db4,
+                                   float* __restrict__ db0) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= TB_ACC) return;
   double s = 0.0;
@@ -462,7 +475,8 @@ __global__ void tail_finish_kernel(const float* __restrict__ part, int nblk, int
   if (e < 1024) dW2[e] = v;
   else if (e < 1056) db2[e - 1024] = v;
   else if (e < 1056 + TB_NOUT_MAX * 32) { if (e - 1056 < nout * 32) dW4[e - 1056] = v; }
-  else if (e - 1056 - TB_NOUT_MAX * 32 < nout) db4[e - 1056 - TB_NOUT_MAX * 32] = v;
+  else if (e < 1056 + TB_NOUT_MAX * 32 + TB_NOUT_MAX) { if (e - 1056 - TB_NOUT_MAX * 32 < nout) db4[e - 1056 - TB_NOUT_MAX * 32] = v; }
+  else db0[e - 1056 - TB_NOUT_MAX * 32 - TB_NOUT_MAX] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ PatchEmbed conv0 backward
@@ -782,7 +796,7 @@ int tk_colsum(const void* X, bool f16, int64_t ld, int64_t lo_off, int M, int N,
 
 int tk_gn_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* add, int B, int n, int E,
               int groups, float eps, const float* inv_scale, float* scratch, float* dx, __half* dx16, float* dgamma,
-              float* dbeta, cudaStream_t st) {
+              float* dbeta, double* colsum, cudaStream_t st) {
   DPOT_REQUIRE(E % groups == 0 && (E / groups) % 4 == 0 && E % 2 == 0, DPOT_E_BADARG, "gn_bwd: group size must be a multiple of 4");
   float* A1 = scratch; float* A2 = A1 + (int64_t)B * E; float* coefA = A2 + (int64_t)B * E; float* coefBC = coefA + (int64_t)B * E;
   gn_bwd_reduce2_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B), 256, 0, st>>>(dy, x, n, E, A1, A2);
@@ -791,13 +805,15 @@ int tk_gn_bwd(const float* dy, const float* x, const double* stats, const float*
   gn_bwd_group2_kernel<<<(unsigned)(gblocks + ceil_div(E, 128)), 128, 0, st>>>(A1, A2, stats, gamma, B, n, E, groups, eps, gblocks,
                                                                               inv_scale, coefA, coefBC, dgamma, dbeta);
   DPOT_LAUNCH_CHECK("gn_bwd_group2_kernel");
-  const int64_t total4 = (int64_t)B * n * E / 4;
+  DPOT_REQUIRE(n % GNA_ROWS == 0, DPOT_E_BADARG, "gn_bwd: latent cells per sample must be a multiple of %d", GNA_ROWS);
+  const int64_t rows = (int64_t)B * n;
+  dim3 grid((unsigned)ceil_div(E / 4, 128), (unsigned)(rows / GNA_ROWS));
   if (dx16)
-    gn_bwd_apply2_kernel<true><<<blocks_for(total4, 256), 256, 0, st>>>(dy, x, coefA, coefBC, add, total4, n, E, E / groups, groups, dx,
-                                                                       dx16, 2 * (int64_t)E, E);
+    gn_bwd_apply2_kernel<true><<<grid, 128, 0, st>>>(dy, x, coefA, coefBC, add, rows, n, E, E / groups, groups, dx, dx16,
+                                                    2 * (int64_t)E, E, colsum);
   else
-    gn_bwd_apply2_kernel<false><<<blocks_for(total4, 256), 256, 0, st>>>(dy, x, coefA, coefBC, add, total4, n, E, E / groups, groups,
-                                                                        dx, nullptr, 0, 0);
+    gn_bwd_apply2_kernel<false><<<grid, 128, 0, st>>>(dy, x, coefA, coefBC, add, rows, n, E, E / groups, groups, dx, nullptr, 0, 0,
+                                                     colsum);
   DPOT_LAUNCH_CHECK("gn_bwd_apply2_kernel");
   return 0;
 }
@@ -838,8 +854,10 @@ int tk_unpack_out_grad(const float* dWtT, int nslab, int64_t stride, const doubl
   unpack_out_grad_kernel<<<dim3((unsigned)ceil_div(E, 32), (unsigned)ceil_div(PP, 32), (unsigned)old), dim3(32, 8), 0, st>>>(
       dWtT, nslab, stride, E, old, PP, inv_scale, dwt);
   DPOT_LAUNCH_CHECK("unpack_out_grad_kernel");
-  out_bias_grad_kernel<<<(unsigned)ceil_div(old, 64), 64, 0, st>>>(dbias_t, old, PP, inv_scale, db);
-  DPOT_LAUNCH_CHECK("out_bias_grad_kernel");
+  if (dbias_t) {
+    out_bias_grad_kernel<<<(unsigned)ceil_div(old, 64), 64, 0, st>>>(dbias_t, old, PP, inv_scale, db);
+    DPOT_LAUNCH_CHECK("out_bias_grad_kernel");
+  }
   return 0;
 }
 
@@ -851,7 +869,7 @@ int tk_tail_bwd_blocks(int B, int h, int w, int P) {
 int64_t tk_tail_bwd_part_floats(int nblk) { return (int64_t)nblk * TB_ACC; }
 int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const float* w2, const float* b2, const float* w4,
                 int B, int h, int w, int P, int nout, int act, __half* g1, float* part, const float* inv_scale, float* dW2,
-                float* db2, float* dW4, float* db4, cudaStream_t st) {
+                float* db2, float* dW4, float* db4, float* db0, cudaStream_t st) {
   DPOT_REQUIRE(tk_tail_bwd_supported(TB_OLD, nout), DPOT_E_UNSUPPORTED, "tail_bwd: nout %d unsupported", nout);
   const int64_t npix = (int64_t)B * h * w * P * P;
   TailBwdArgs a;
@@ -866,7 +884,7 @@ int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const
   const int nblk = tk_tail_bwd_blocks(B, h, w, P);
   tail_bwd_kernel<<<(unsigned)nblk, TB_PIX, smem, st>>>(a);
   DPOT_LAUNCH_CHECK("tail_bwd_kernel");
-  tail_finish_kernel<<<(unsigned)ceil_div(TB_ACC, 128), 128, 0, st>>>(part, nblk, nout, inv_scale, dW2, db2, dW4, db4);
+  tail_finish_kernel<<<(unsigned)ceil_div(TB_ACC, 128), 128, 0, st>>>(part, nblk, nout, inv_scale, dW2, db2, dW4, db4, db0);
   DPOT_LAUNCH_CHECK("tail_finish_kernel");
   return 0;
 }

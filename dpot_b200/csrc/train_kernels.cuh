@@ -13,9 +13,10 @@ int tk_colsum(const void* X, bool f16, int64_t ld, int64_t lo_off, int M, int N,
 // GroupNorm backward (torch.nn.GroupNorm(8, E) on token-major x[B*n, E]); stats = forward (sum, sumsq) doubles.
 //   dx = rstd * (gamma*dy - mean_g(gamma*dy) - xhat * mean_g(gamma*dy*xhat)) (+ add);  dx16 != NULL: also stored split.
 //   dgamma / dbeta (written, scaled by inv_scale[0] when given).  scratch: 3*B*E + 2*B*groups floats.
+//   colsum (may be NULL): double [E], colsum[c] += sum over rows of dx (the bias gradient of the layer below).
 int tk_gn_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* add, int B, int n, int E,
               int groups, float eps, const float* inv_scale, float* scratch, float* dx, __half* dx16, float* dgamma,
-              float* dbeta, cudaStream_t st);
+              float* dbeta, double* colsum, cudaStream_t st);
 // dst[i] = inv_scale * sum_s slabs[s * stride + i]
 int tk_slab_reduce(const float* slabs, int nslab, int64_t stride, int64_t count, const float* inv_scale, float* dst, cudaStream_t st);
 // dst[i] = inv_scale * src[i]  (double -> float)
@@ -28,14 +29,15 @@ int tk_unpack_out_grad(const float* dWtT, int nslab, int64_t stride, const doubl
                        const float* inv_scale, float* dwt, float* db, cudaStream_t st);
 // Output-head tail backward (out_layer[1..4] of models/dpot.py:317-321, out_layer_dim = 32):
 //   from Y1pre[Mt, PP*32] (pre-activation of the ConvTranspose GEMM) and dout[B, X, Y, nout] * scale[0] ->
-//   g1 (gradient w.r.t. Y1pre) stored split [Mt, 2*NP]; dW2 / db2 / dW4 / db4 written (times inv_scale[0]).
+//   g1 (gradient w.r.t. Y1pre) stored split [Mt, 2*NP]; dW2 / db2 / dW4 / db4 and db0 (the ConvTranspose bias gradient:
+//   sum of g1 over pixels per channel) written (times inv_scale[0]).
 //   part: tk_tail_bwd_part_floats(tk_tail_bwd_blocks(...)) floats of scratch (one partial result per thread block).
 int tk_tail_bwd_supported(int old, int nout);
 int tk_tail_bwd_blocks(int B, int h, int w, int P);
 int64_t tk_tail_bwd_part_floats(int nblk);
 int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const float* w2, const float* b2, const float* w4,
                 int B, int h, int w, int P, int nout, int act, __half* g1, float* part, const float* inv_scale, float* dW2,
-                float* db2, float* dW4, float* db4, cudaStream_t st);
+                float* db2, float* dW4, float* db4, float* db0, cudaStream_t st);
 // PatchEmbed conv0 backward (models/dpot.py:199-200): gz[(b,pq), t*mid + m] (row pitch Kp; act' already applied),
 // x[B,X,Y,T,C] -> dW0p (one partial [mid, P*P*C] per thread block); dx (may be NULL) = inv_scale * gz W0p scattered to the field layout.
 int tk_patch_bwd_supported(int mid, int T, int K0);

@@ -417,10 +417,9 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
   {
     DPOT_CALL(tk_tail_bwd(tape + TL.Y1pre, dy, scale, prm->out2_w, prm->out2_b, prm->out4_w, B, d.h, d.h, d.P, nout, act,
                           reinterpret_cast<__half*>(g1t), scratch + SL.tparts, inv, G(grads->out2_w), G(grads->out2_b),
-                          G(grads->out4_w), G(grads->out4_b), st));
-    DPOT_CALL(tk_colsum(g1t, true, 2 * (int64_t)NP, NP, Mt, NP, dbl + SL.d_bias_t, st));
+                          G(grads->out4_w), G(grads->out4_b), G(grads->out0_b), st));
     DPOT_CALL(wgrad16(g1t, NP, tape + TL.alat16, E, NP, E, Mt, 1, slabs, &ns, stream));
-    DPOT_CALL(tk_unpack_out_grad(slabs, ns, (int64_t)NP * E, dbl + SL.d_bias_t, E, d.old, d.P, inv, G(grads->out0_w), G(grads->out0_b), st));
+    DPOT_CALL(tk_unpack_out_grad(slabs, ns, (int64_t)NP * E, nullptr, E, d.old, d.P, inv, G(grads->out0_w), G(grads->out0_b), st));
   }
   float* g = scratch + SL.gA;          // dL/d(latent after the last block), fp32, scaled by S
   float* g_other = scratch + SL.gB;
@@ -428,10 +427,13 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
   {
     dpot_gemm_args a = g16(g1t, NP, packed + PL.WtT16, E, g, E, Mt, E, NP);
     a.w_trans = 1;
+    if (!dcls) a.out_colsum = dbl + SL.d_blk + (int64_t)(d.depth - 1) * SL.d_blk_stride;   // = db2 of the last block
     DPOT_CALL(dpot_gemm(&a, stream));
   }
-  if (dcls)
+  if (dcls) {
     DPOT_CALL(cls_backward(cfg, prm, d, B, dcls, tape, TL, scratch + SL.cls, scale, grads, g, stream));
+    DPOT_CALL(tk_colsum(g, false, E, 0, Mt, E, dbl + SL.d_blk + (int64_t)(d.depth - 1) * SL.d_blk_stride, st));
+  }
   DPOT_CALL(tk_split_scaled(g, Mt, E, nullptr, reinterpret_cast<__half*>(gs16), 2 * (int64_t)E, E, st));
 
   // ---- blocks, last to first (models/dpot.py:165-180)
@@ -444,17 +446,16 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     double* db2 = dblk; double* db1 = db2 + E; double* dbc2 = db1 + H; double* dbc1 = dbc2 + 2 * E;
     float* g1h = scratch + SL.g1_16;
     // channel MLP: lat_next = fc2(act(fc1(n2))) + lat
-    DPOT_CALL(tk_colsum(g, false, E, 0, Mt, E, db2, st));
-    DPOT_CALL(tk_finish_double(db2, E, inv, G(gb.fc2_b), st));
+    DPOT_CALL(tk_finish_double(db2, E, inv, G(gb.fc2_b), st));      // accumulated by the producer of g (epilogue / GroupNorm-1 backward)
     DPOT_CALL(wgrad16(gs16, E, tb + TL.hid, H, E, H, Mt, 1, slabs, &ns, stream));
     DPOT_CALL(tk_slab_reduce(slabs, ns, (int64_t)E * H, (int64_t)E * H, inv, G(gb.fc2_w), st));
     {   // g1 = (g W2) * act'(hpre), split
       dpot_gemm_args a = g16(gs16, E, pk + PL.fc2_16, H, g1h, 0, Mt, H, E);
       a.w_trans = 1; out16(a, H);
       a.dact_src = tb + TL.hpre; a.ld_dact = H; a.dact = act;
+      a.out_colsum = db1;
       DPOT_CALL(dpot_gemm(&a, stream));
     }
-    DPOT_CALL(tk_colsum(g1h, true, 2 * (int64_t)H, H, Mt, H, db1, st));
     DPOT_CALL(tk_finish_double(db1, H, inv, G(gb.fc1_b), st));
     DPOT_CALL(wgrad16(g1h, H, tb + TL.n2, E, H, E, Mt, 1, slabs, &ns, stream));
     DPOT_CALL(tk_slab_reduce(slabs, ns, (int64_t)E * H, (int64_t)E * H, inv, G(gb.fc1_w), st));
@@ -467,11 +468,10 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     // GroupNorm-2
     float* df = scratch + SL.df;
     DPOT_CALL(tk_gn_bwd(dn2, tb + TL.f, reinterpret_cast<const double*>(tb + TL.st2), bp.norm2_w, nullptr, B, d.n, E, GROUPS, GN_EPS,
-                        inv, scratch + SL.gn, df, nullptr, G(gb.norm2_w), G(gb.norm2_b), st));
+                        inv, scratch + SL.gn, df, nullptr, G(gb.norm2_w), G(gb.norm2_b), nullptr, st));
     // AFNO mixer: f = irfft2(O2) + n1, O2 = O1 Wc2 + bc2, O1 = act(S Wc1 + bc1), S = rfft2(n1)
     float* dO2 = scratch + SL.dO2; float* dO1 = scratch + SL.dO1; float* dS = scratch + SL.dS;
-    DPOT_CALL(dpot_afno_fft_fwd16w(df, B, d.h, E, d.nb, d.km1, d.km2, dO2, 2.0f, stream));       // adjoint of the inverse transform
-    DPOT_CALL(tk_colsum(dO2, true, 4 * (int64_t)E, 2 * E, Ms, 2 * E, dbc2, st));
+    DPOT_CALL(dpot_afno_fft_fwd16w(df, B, d.h, E, d.nb, d.km1, d.km2, dO2, 2.0f, dbc2, stream));   // adjoint of the inverse transform (+ bias gradient)
     DPOT_CALL(wgrad16(dO2, 2 * E, tb + TL.O1, 2 * E, (int)kb, (int)kb, Ms, d.nb, slabs, &ns, stream));
     DPOT_CALL(tk_unpack_afno_grad(slabs, ns, (int64_t)d.nb * kb * kb, dbc2, d.nb, d.bs, inv, G(gb.w2), G(gb.b2), st));
     {
@@ -479,9 +479,9 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
       a.w_trans = 1; a.batch = d.nb; a.strideA = kb; a.strideW = 2 * kb * kb; a.strideC = kb;
       out16(a, 2 * E);
       a.dact_src = tb + TL.O1pre; a.ld_dact = 2 * E; a.stride_dact = kb; a.dact = act;
+      a.out_colsum = dbc1;
       DPOT_CALL(dpot_gemm(&a, stream));
     }
-    DPOT_CALL(tk_colsum(dO1, true, 4 * (int64_t)E, 2 * E, Ms, 2 * E, dbc1, st));
     DPOT_CALL(wgrad16(dO1, 2 * E, tb + TL.S, 2 * E, (int)kb, (int)kb, Ms, d.nb, slabs, &ns, stream));
     DPOT_CALL(tk_unpack_afno_grad(slabs, ns, (int64_t)d.nb * kb * kb, dbc1, d.nb, d.bs, inv, G(gb.w1), G(gb.b1), st));
     {
@@ -493,7 +493,8 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     DPOT_CALL(dpot_afno_fft_inv(dS, df, nullptr, nullptr, B, d.h, E, d.nb, d.km1, d.km2, dn1, nullptr, GROUPS, 0.5f, stream));   // adjoint of the forward transform + skip
     // GroupNorm-1 + the residual path
     DPOT_CALL(tk_gn_bwd(dn1, tb + TL.lat, reinterpret_cast<const double*>(tb + TL.st1), bp.norm1_w, g, B, d.n, E, GROUPS, GN_EPS, inv,
-                        scratch + SL.gn, g_other, reinterpret_cast<__half*>(gs16), G(gb.norm1_w), G(gb.norm1_b), st));
+                        scratch + SL.gn, g_other, reinterpret_cast<__half*>(gs16), G(gb.norm1_w), G(gb.norm1_b),
+                        i > 0 ? dbl + SL.d_blk + (int64_t)(i - 1) * SL.d_blk_stride : nullptr, st));   // db2 of the block below
     float* t = g; g = g_other; g_other = t;
   }
 

@@ -149,6 +149,9 @@ typedef struct dpot_gemm_args {
   int32_t a_trans, w_trans;
   int32_t k_split; int64_t k_chunk; int64_t strideC_split;
   int64_t ld_pre, stride_pre, ld_dact, stride_dact;
+  /* TC16 engine: out_colsum[b * N + n] += sum_m C[m, n] of problem b (double accumulation of the stored values; NOT
+     zeroed by the call) -- the bias gradient of the layer whose data gradient this contraction produces. */
+  double* out_colsum;
 } dpot_gemm_args;
 
 DPOT_API int dpot_gemm(const dpot_gemm_args* args, void* stream);
@@ -416,9 +419,10 @@ DPOT_API int dpot_lp_loss_bwd(const float* x, const float* y, const float* mask,
                               int32_t B, int64_t nxy, int32_t T, int32_t C, float* dx, void* stream);
 
 /* fwd16 without GroupNorm and with the interior-column weight (weight 2 = the adjoint of the inverse transform, whose
-   result the backward pass feeds straight into the split-fp16 contractions) */
+   result the backward pass feeds straight into the split-fp16 contractions).  colsum (may be NULL): double [2E],
+   colsum[c] += sum over the stored rows of column c (the bias gradient of the spectral layer; not zeroed). */
 DPOT_API int dpot_afno_fft_fwd16w(const float* a, int32_t B, int32_t h, int32_t E, int32_t nb, int32_t km1, int32_t km2,
-                                  void* S16, float interior_weight, void* stream);
+                                  void* S16, float interior_weight, double* colsum, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-model inference forward: DPOTNet.forward under no_grad (models/dpot.py:364-403).
