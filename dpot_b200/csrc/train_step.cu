@@ -388,7 +388,7 @@ int cls_backward(const dpot_config* cfg, const dpot_params* prm, const Dims& d, 
 
 extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
                                    const float* x, int32_t B, const float* dy, const float* dcls, const float* tape,
-                                   float* scratch, const dpot_params* grads, float* dx, void* stream) {
+                                   float* scratch, const dpot_params* grads, float* dx, void* const* events, void* stream) {
   Dims d;
   DPOT_CALL(make_dims(cfg, d));
   DPOT_REQUIRE(train_ok(cfg, d), DPOT_E_UNSUPPORTED, "dpot_train_backward: configuration not served by the fused training step");
@@ -421,6 +421,7 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     DPOT_CALL(wgrad16(g1t, NP, tape + TL.alat16, E, NP, E, Mt, 1, slabs, &ns, stream));
     DPOT_CALL(tk_unpack_out_grad(slabs, ns, (int64_t)NP * E, nullptr, E, d.old, d.P, inv, G(grads->out0_w), G(grads->out0_b), st));
   }
+  if (events) DPOT_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[0]), st));   // out_layer gradients are final
   float* g = scratch + SL.gA;          // dL/d(latent after the last block), fp32, scaled by S
   float* g_other = scratch + SL.gB;
   float* gs16 = scratch + SL.g16;      // the same, split
@@ -496,6 +497,7 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
                         scratch + SL.gn, g_other, reinterpret_cast<__half*>(gs16), G(gb.norm1_w), G(gb.norm1_b),
                         i > 0 ? dbl + SL.d_blk + (int64_t)(i - 1) * SL.d_blk_stride : nullptr, st));   // db2 of the block below
     float* t = g; g = g_other; g_other = t;
+    if (events) DPOT_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[1 + (d.depth - 1 - i)]), st));   // block i's gradients are final
   }
 
   // ---- front: lat0 = z1 WeffT^T + bias_eff  (conv 1x1 + pos_embed + time aggregation folded), z1 = act(conv0(x))
@@ -553,5 +555,6 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     if (cfg->time_agg == 1 && grads->tagg_gamma)
       DPOT_CALL(tk_tagg_gamma_grad(dtemb, prm->tagg_gamma, d.T, E, inv, G(grads->tagg_gamma), st));
   }
+  if (events) DPOT_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[1 + d.depth]), st));
   return 0;
 }

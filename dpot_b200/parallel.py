@@ -220,3 +220,87 @@ class OverlappedGradArena:
         for h in self.hooks:
             h.remove()
         self.hooks = []
+
+
+class FusedGradExchange:
+    """The DDP gradient average (train_temporal_parallel.py:185,244) for the one-call training step (train_engine.py):
+    dpot_train_backward writes every parameter gradient straight into ONE flat arena laid out in the order groups of
+    gradients become final (out_layer | block depth-1 | ... | block 0 | front) and records a CUDA event per group; as
+    soon as the call has been enqueued, each group's all-reduce(AVG) is queued on a communication stream behind its
+    event, so the exchange of the last layers travels over NVLink while backward still computes the first ones.  No
+    packing copy: .grad of every parameter is a view of the arena.  finish() (after loss.backward(), before clip /
+    optimizer.step()) makes the compute stream wait for the exchange.
+
+    With several forward calls per optimizer step (T_ar > 1: autograd accumulates the calls' gradients in place into the
+    arena views) the exchange cannot start before the last accumulation: finish() then runs one all-reduce of the arena.
+    """
+
+    def __init__(self, model, group_mb: float = 24.0):
+        from .train_engine import _TrainEngine
+        if model._train_eng is None:
+            model._train_eng = _TrainEngine(model)
+        self.eng = model._train_eng
+        self.eng.exchange = self
+        self.buf: Optional[torch.Tensor] = None
+        self.events = None
+        self.comm = None
+        self.handles = []
+        self.calls = 0
+        self.overlapped = False
+        # merge consecutive completion groups into messages of >= group_mb (launch latency vs overlap)
+        self.msgs, lo, last = [], None, 0
+        for gi, (a, b) in enumerate(self.eng.buckets):
+            if lo is None:
+                lo = a
+            if (b - lo) * 4 >= group_mb * 2 ** 20 or gi == len(self.eng.buckets) - 1:
+                self.msgs.append((gi, lo, b))          # (event index that completes the message, float range)
+                lo = None
+
+    def _world(self) -> int:
+        return dist.get_world_size() if dist.is_initialized() else 1
+
+    def begin(self, eng, dev):
+        """Called by FusedTrainFn.backward: (flat gradient buffer, events) for this call, or (None, None)."""
+        self.calls += 1
+        if self.calls > 1:
+            return None, None                          # a later call of the same step: plain buffer, autograd accumulates
+        if self.buf is None or self.buf.device != dev:
+            self.buf = torch.empty(eng.total, device=dev, dtype=torch.float32)
+            self.events = [torch.cuda.Event() for _ in eng.buckets]
+            for e in self.events:
+                e.record()                             # torch creates the cudaEvent lazily: force it
+            self.comm = torch.cuda.Stream(device=dev)
+        self.overlapped = eng.n_forward == 1 and self._world() > 1
+        return self.buf, (self.events if self.overlapped else None)
+
+    def enqueued(self, eng, flat, events) -> None:
+        """dpot_train_backward has been enqueued: queue every message's all-reduce behind its completion event."""
+        op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        with torch.cuda.stream(self.comm):
+            for gi, lo, hi in self.msgs:
+                self.comm.wait_event(events[gi])
+                self.handles.append(dist.all_reduce(flat[lo:hi], op=op, async_op=True))
+
+    @torch.no_grad()
+    def finish(self) -> int:
+        """Returns the number of fp32 elements exchanged."""
+        world = self._world()
+        n = 0
+        if self.calls and world > 1:
+            if self.overlapped:
+                for h in self.handles:
+                    h.wait()                           # the current stream waits for the message
+            else:
+                if dist.get_backend() == "nccl":
+                    dist.all_reduce(self.buf, op=dist.ReduceOp.AVG)
+                else:
+                    dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            if dist.get_backend() != "nccl":
+                self.buf.div_(world)
+            n = self.buf.numel()
+        self.handles, self.calls, self.overlapped = [], 0, False
+        self.eng.n_forward = 0
+        return n
+
+    def close(self) -> None:
+        self.eng.exchange = None

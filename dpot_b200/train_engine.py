@@ -51,11 +51,26 @@ class _TrainEngine:
         self.table = _param_table(net)
         named = {id(p) for p in net.parameters()}
         self.complete = named == {id(p) for _, _, p in self.table}   # no parameter outside the C structs (normalize=False)
-        self.offsets, o = [], 0
-        for _, _, p in self.table:
-            self.offsets.append(o)
-            o += (p.numel() + 63) // 64 * 64
+        # flat gradient layout in the order groups become final during backward (dpot_train_backward `events`):
+        # out_layer | block depth-1 | ... | block 0 | front (pos_embed, PatchEmbed, time aggregation) + cls head
+        def group(entry):
+            f, bi, _ = entry
+            if bi is not None:
+                return 1 + (net.depth - 1 - bi)
+            return 0 if f.startswith("out") else net.depth + 1
+        order = sorted(range(len(self.table)), key=lambda i: (group(self.table[i]), i))
+        self.offsets, o = [0] * len(self.table), 0
+        self.buckets = []                             # (lo, hi) float ranges, one per event
+        for gi in range(net.depth + 2):
+            lo = o
+            for i in order:
+                if group(self.table[i]) == gi:
+                    self.offsets[i] = o
+                    o += (self.table[i][2].numel() + 63) // 64 * 64
+            self.buckets.append((lo, o))
         self.total = o
+        self.exchange = None                          # FusedGradExchange (parallel.py) when training data-parallel
+        self.n_forward = 0                            # forwards since the last optimizer step (T_ar > 1: several backward calls)
         self.packed = self.wprep = None
         self.key = None
         self.scratch: Dict[int, torch.Tensor] = {}
@@ -79,6 +94,7 @@ class _TrainEngine:
         check(self.lib.dpot_train_prepare(C.byref(self.cfg), C.byref(self.binder.prm), ptr(self.packed), ptr(self.wprep),
                                           ptr(self.get_scratch(1, dev)), self._stream()), "dpot_train_prepare")
         self.key = key
+        self.n_forward = 0                            # new weights = new optimizer step
 
     def get_scratch(self, B: int, dev) -> torch.Tensor:
         big = max(self.scratch) if self.scratch else 0
@@ -123,6 +139,7 @@ class FusedTrainFn(Function):
             cls = torch.empty((B, net.n_cls), device=dev, dtype=torch.float32)
             check(lib.dpot_train_forward(C.byref(eng.cfg), C.byref(eng.binder.prm), ptr(eng.packed), ptr(x), B, ptr(y), ptr(cls),
                                          ptr(tape), ptr(eng.get_scratch(B, dev)), eng._stream()), "dpot_train_forward")
+        eng.n_forward += 1
         ctx.eng = eng
         ctx.save_for_backward(x, tape)
         ctx.need_dx = x.requires_grad
@@ -143,13 +160,21 @@ class FusedTrainFn(Function):
                 dy = torch.zeros((B, eng.net.img_size, eng.net.img_size, eng.net.out_timesteps, eng.net.out_channels), device=dev)
             dy = dy.contiguous().float()
             dcls = dcls.contiguous().float() if dcls is not None else None
-            flat = eng.grad_buffer(eng.total, dev) if eng.grad_buffer is not None else torch.empty(eng.total, device=dev)
+            ex = eng.exchange
+            flat, events = (ex.begin(eng, dev) if ex is not None else (None, None))
+            if flat is None:
+                flat = eng.grad_buffer(eng.total, dev) if eng.grad_buffer is not None else torch.empty(eng.total, device=dev)
             g, keep, views = eng.grads_struct(flat, dcls is not None)
             dx = torch.empty_like(x) if ctx.need_dx else None
+            ev = None
+            if events is not None:
+                ev = (C.c_void_p * len(events))(*[e.cuda_event for e in events])
             check(lib.dpot_train_backward(C.byref(eng.cfg), C.byref(eng.binder.prm), ptr(eng.packed), ptr(eng.wprep), ptr(x), B,
                                           ptr(dy), ptr(dcls), ptr(tape), ptr(eng.get_scratch(B, dev)), C.byref(g), ptr(dx),
-                                          eng._stream()), "dpot_train_backward")
+                                          ev, eng._stream()), "dpot_train_backward")
             del keep
+            if events is not None:
+                ex.enqueued(eng, flat, events)
         by_id = {id(p): v for (_, _, p), v in zip(eng.table, views)}
         return (None, dx) + tuple(by_id.get(id(p)) if p.requires_grad else None for p in eng.net.parameters())
 

@@ -481,6 +481,9 @@ DPOT_API int dpot_rollout_step(const dpot_config* cfg, const dpot_params* prm, c
  *   grads   : a dpot_params whose pointers are the DESTINATIONS of the parameter gradients (same shapes as the
  *             parameters; written, not accumulated; grid/temb/mu/sigma members ignored; the cls members are written
  *             only when dcls != NULL; tagg_gamma only for 'exp_mlp').  dx: gradient w.r.t. x or NULL.
+ *   events  : NULL, or depth + 2 cudaEvent_t recorded on `stream` as groups of gradients become final -- [0] the
+ *             out_layer parameters, [1 + j] block depth-1-j, [depth + 1] everything -- so that a data-parallel caller can
+ *             start exchanging a group (train_temporal_parallel.py:185,244) while the rest of backward still runs.
  * dpot_train_supported: 1 when the configuration is served (normalize = False, out_layer_dim = 32, patch geometry of
  * DPOT-Ti/S/M); other configurations train through the generic per-operator path of the Python binding.
  * ---------------------------------------------------------------------------------------- */
@@ -494,7 +497,7 @@ DPOT_API int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, 
                                 float* y, float* cls, float* tape, float* scratch, void* stream);
 DPOT_API int dpot_train_backward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
                                  const float* x, int32_t B, const float* dy, const float* dcls, const float* tape,
-                                 float* scratch, const dpot_params* grads, float* dx, void* stream);
+                                 float* scratch, const dpot_params* grads, float* dx, void* const* events, void* stream);
 
 #ifdef __cplusplus
 }

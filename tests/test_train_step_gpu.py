@@ -92,3 +92,32 @@ def test_fused_training_step_matches_per_operator_path():
         assert (p1.grad is None) == (p2.grad is None), k
         if p1.grad is not None:
             assert O.rel_l2(p1.grad.cpu().numpy(), p2.grad.cpu().numpy()) < 5e-5, k
+
+
+def test_gradients_written_into_the_exchange_arena():
+    """FusedGradExchange (parallel.py): with a single process the exchange is the identity, the gradients must be the
+    same numbers, live in the arena (no packing copy) and a second step must reuse it."""
+    from dpot_b200.parallel import FusedGradExchange
+    z = np.load(os.path.join(G, "train_grads_fused2.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    params = O.make_params(cfg, seed=0)
+    x = torch.from_numpy(O.make_input(cfg, 2, seed=5)).cuda()
+    ref = build_model(cfg, params).train()
+    im, _ = ref(x)
+    im.square().sum().backward()
+    m = build_model(cfg, params).train()
+    ex = FusedGradExchange(m)
+    for _ in range(2):
+        for p in m.parameters():
+            p.grad = None
+        im, _ = m(x)
+        im.square().sum().backward()
+        n = ex.finish()
+        lo, hi = ex.buf.data_ptr(), ex.buf.data_ptr() + 4 * ex.buf.numel()
+        for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            assert (p.grad is None) == (q.grad is None), k
+            if p.grad is not None:
+                assert lo <= p.grad.data_ptr() < hi, k
+                # (double atomics accumulate the GroupNorm statistics / bias gradients: last-bit differences between runs)
+                assert O.rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 1e-6, k
+    ex.close()

@@ -21,7 +21,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dpot_b200 import zoo
 from dpot_b200.models.dpot import DPOTNet
-from dpot_b200.parallel import GradArena, OverlappedGradArena, init_from_env
+from dpot_b200.parallel import FusedGradExchange, GradArena, OverlappedGradArena, init_from_env
 from dpot_b200.train import ar_train_step
 from dpot_b200.utils.optimizer import Adam
 
@@ -67,12 +67,17 @@ def step_with(arena):
     return ar_train_step(model, opt, xx, yy, msk, T_bundle=1, noise_scale=0.0, grad_clip=1e4, arena=arena, step=state["i"])
 
 
+out["fused_training_step"] = bool(model._train_eng is not None and model._train_eng.supported) if hasattr(model, "_train_eng") else False
 out["ms_step_no_exchange"] = timed(lambda: step_with(None))
+out["fused_training_step"] = bool(model._train_eng is not None and model._train_eng.supported)
 flat = GradArena(model.parameters())
 out["ms_step_flat_allreduce"] = timed(lambda: step_with(flat))
-over = OverlappedGradArena(model.parameters(), bucket_mb=32.0)
+if out["fused_training_step"]:
+    over = FusedGradExchange(model)
+    out["messages"] = len(over.msgs)
+else:
+    over = OverlappedGradArena(model.parameters(), bucket_mb=32.0)
 out["ms_step_overlapped"] = timed(lambda: step_with(over))
-out["buckets"] = len(over.buckets)
 # the exchange alone
 buf = over.buf if over.buf is not None else torch.zeros(nparam, device=dev)
 if world > 1:
@@ -94,7 +99,12 @@ if world > 1:
     Y = torch.randn((world * Bc, 128, 128, 1, 4), generator=gx).to(dev)
     M = torch.ones((world * Bc, 128, 128, 1, 4), device=dev)
     from dpot_b200.train import LpLossFn
-    arena = OverlappedGradArena(model2.parameters(), bucket_mb=32.0)
+    im0, _ = model2(X[:1].contiguous())        # builds the training engine
+    del im0
+    fusedx = model2._train_eng is not None and model2._train_eng.supported
+    arena = FusedGradExchange(model2) if fusedx else OverlappedGradArena(model2.parameters(), bucket_mb=32.0)
+    if fusedx:
+        model2._train_eng.n_forward = 0
     sl = slice(rank * Bc, (rank + 1) * Bc)
     im, _ = model2(X[sl].contiguous())
     LpLossFn.apply(im, Y[sl].contiguous(), M[sl].contiguous()).backward()
