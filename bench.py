@@ -219,6 +219,69 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------ training step
+TRAIN_BATCH = 16
+
+
+def train_leg(dev, world, rank, timed_fn):
+    """The training step of train_temporal.py:201-230 (T_ar = 1, noise off) on DPOT-S, 16 samples per GPU: forward +
+    SimpleLpLoss + backward + (gradient all-reduce when world > 1) + clip_grad_norm_ + Adam, through the drop-in API
+    (DPOTNet / Adam / ar_train_step).  Device-timed, max over ranks.  Also the fused clip + Adam kernel alone against its
+    28 B / parameter HBM floor."""
+    import torch
+    from dpot_b200 import _lib, zoo
+    from dpot_b200.models.dpot import DPOTNet
+    from dpot_b200.parallel import FusedGradExchange
+    from dpot_b200.train import ar_train_step
+    from dpot_b200.utils.clip import clip_grad_norm_
+    from dpot_b200.utils.optimizer import Adam
+    lib = _lib.load()
+    cfg = zoo.zoo_cfg(MODEL)
+    m = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).train()
+    opt = Adam(m.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=1e-6)
+    g = torch.Generator(device="cpu").manual_seed(77 + rank)
+    xs = [torch.randn((TRAIN_BATCH, 128, 128, 10, 4), generator=g).to(dev) for _ in range(4)]
+    ys = [torch.randn((TRAIN_BATCH, 128, 128, 1, 4), generator=g).to(dev) for _ in range(4)]
+    msk = torch.ones((TRAIN_BATCH, 128, 128, 1, 4), device=dev)
+    ar_train_step(m, opt, xs[0], ys[0], msk, grad_clip=1e4, step=0)          # builds the training engine
+    fused = bool(m._train_eng is not None and m._train_eng.supported)
+    ex = FusedGradExchange(m) if (world > 1 and fused) else None
+    n, l0 = 8, [0]
+
+    def step(s):
+        ar_train_step(m, opt, xs[s % 4], ys[s % 4], msk, T_bundle=1, noise_scale=0.0, grad_clip=1e4, arena=ex, step=s + 1)
+
+    for s in range(3):
+        step(s)
+    torch.cuda.synchronize()
+    l0 = lib.dpot_launch_count()
+    ms = timed_fn(step, n) / n
+    launches = (lib.dpot_launch_count() - l0) / n
+    nparam = sum(p.numel() for p in m.parameters())
+    # the optimizer step alone (gradients in place from the last step)
+    for _ in range(2):
+        clip_grad_norm_(m.parameters(), 1e4, optimizer=opt); opt.step()
+    ms_opt = timed_fn(lambda s: (clip_grad_norm_(m.parameters(), 1e4, optimizer=opt), opt.step()), 10) / 10
+    if ex is not None:
+        ex.close()
+    fl = zoo.forward_flops(cfg)
+    pk = peaks()
+    exec_gf = 3.0 * fl["executed"] / 1e9            # forward + data gradient + weight gradient
+    fs = TRAIN_BATCH * world / (ms * 1e-3)
+    return {"workload": f"DPOT-{MODEL} training step, {TRAIN_BATCH} samples / GPU, T_ar = 1 (forward + SimpleLpLoss + backward + "
+                        f"{'gradient all-reduce + ' if world > 1 else ''}clip_grad_norm_ + Adam), fp32",
+            "ms_per_step": ms, "field_steps_per_s": fs, "one_call_training_step": fused,
+            "gpu_launches_per_step": launches,
+            "executed_gflop_per_field_step": exec_gf,
+            "executed_tflops_per_gpu": exec_gf * fs / world / 1e3,
+            "frac_executed_of_fp32_faithful_sustained_peak": exec_gf * fs / world / 1e3 / (pk["bf16_sus"] / 3.0),
+            "optimizer": {"kernel": "gradient norm + clip folded into the fused multi-tensor Adam", "params": nparam,
+                          "ms": ms_opt, "algorithmic_bytes": 28 * nparam,
+                          "achieved_GBs": 28 * nparam / (ms_opt * 1e-3) / 1e9, "frac_of_hbm_peak": 28 * nparam / (ms_opt * 1e-3) / 1e9 / pk["hbm"],
+                          "note": "p, m, v read + written, g read twice (norm, update) = 28 B / parameter"},
+            "note": "executed FLOPs = 3 x the forward's (every contraction has a data-gradient and a weight-gradient twin)"}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -322,6 +385,7 @@ def run_ours(args):
     for s in range(3):
         eng_nocls.run(devbuf[s % NBUF])
     ms_nocls = timed(lambda s: eng_nocls.run(devbuf[s % NBUF]), args.steps)
+    train = None if args.no_train else train_leg(dev, world, rank, timed)
 
     fs_per_step = BATCH * N_AR * world
     value = fs_per_step * args.steps / (ms * 1e-3)
@@ -422,6 +486,7 @@ def run_ours(args):
                                        "all host threads), rank 0"},
             "gpu_eager_baseline": eager,
             "parity_in_run": parity,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -439,6 +504,7 @@ def main():
     ap.add_argument("--ws-mode", type=int, default=None, help="dpot_tc16_set_ws: 0 = no weight-stationary plan, 2 = without early start")
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels of the forward chain")
     ap.add_argument("--engine", type=int, default=None, help="force GEMM engine: 1 = SIMT fp32, 2 = tcgen05")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block of the JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

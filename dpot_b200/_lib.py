@@ -104,6 +104,7 @@ SIGNATURES = {
     "dpot_out_tail_set_engine": (None, [_i32]),
     "dpot_patch_embed_set_engine": (None, [_i32]),
     "dpot_tc16_set_debug": (None, [_i32]),
+    "dpot_tc16_set_precision": (C.c_int, [_i32]),
     "dpot_tc16_set_ws": (None, [_i32]),
     "dpot_set_pdl": (None, [_i32]),
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),

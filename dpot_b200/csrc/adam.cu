@@ -28,7 +28,7 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
   p = p - step_size * (m / denom);                   // addcdiv_(m, denom, -step_size)    :50-52
 }
 
-constexpr int MT_MAX = 32;
+constexpr int MT_MAX = 56;     // 56 x 68 B of tables = 3.9 KB of kernel parameters (limit 4 KB)
 struct MultiArgs {
   float* p[MT_MAX]; const float* g[MT_MAX]; float* m[MT_MAX]; float* v[MT_MAX]; float* vmax[MT_MAX];
   int64_t n[MT_MAX];
@@ -56,6 +56,30 @@ __global__ void __launch_bounds__(ADAM_NT) adam_multi_kernel(const MultiArgs a, 
   const float ss = a.step_size[ti], sb = a.sqrt_bc2[ti];
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vm)) % 16 == 0);
+  if (vec && !vm && base + ADAM_PER_BLOCK <= n) {
+    // full block, no amsgrad: all 16 loads of the thread are issued before the first use (bytes in flight, HBM-bound)
+    float4 P[4], Gv[4], M[4], V[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int64_t i = base + ((int64_t)it * ADAM_NT + threadIdx.x) * 4;
+      P[it] = *reinterpret_cast<const float4*>(p + i);
+      Gv[it] = __ldcs(reinterpret_cast<const float4*>(g + i));
+      M[it] = *reinterpret_cast<const float4*>(m + i);
+      V[it] = *reinterpret_cast<const float4*>(v + i);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int64_t i = base + ((int64_t)it * ADAM_NT + threadIdx.x) * 4;
+      adam_elem(P[it].x, Gv[it].x, M[it].x, V[it].x, nullptr, c, ss, 0.f, sb);
+      adam_elem(P[it].y, Gv[it].y, M[it].y, V[it].y, nullptr, c, ss, 0.f, sb);
+      adam_elem(P[it].z, Gv[it].z, M[it].z, V[it].z, nullptr, c, ss, 0.f, sb);
+      adam_elem(P[it].w, Gv[it].w, M[it].w, V[it].w, nullptr, c, ss, 0.f, sb);
+      *reinterpret_cast<float4*>(p + i) = P[it];
+      *reinterpret_cast<float4*>(m + i) = M[it];
+      *reinterpret_cast<float4*>(v + i) = V[it];
+    }
+    return;
+  }
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int64_t i = base + ((int64_t)it * ADAM_NT + threadIdx.x) * 4;

@@ -82,6 +82,7 @@ struct Tc16Params {
   int dbg;           // experiment mask (dpot_tc16_set_debug): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work
   int batch;         // independent problems; total_tiles also spans the g.ksplit contraction chunks (bz = b + batch * chunk)
   int w_bmul, a_bmul; // 0: the operand is shared by every problem of the batch (batch stride 0), else 1
+  int single;        // 1: half-precision operand mode -- only the hi planes are loaded and multiplied (1 MMA per product)
 };
 
 // ACT_MODE: 0 = none, 1 = GELU (erf), 2 = runtime switch.  OUT16: store the result as DPOT_FMT_HL16.
@@ -135,7 +136,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
   const int rows_a = BA / CG;                                  // token rows this CTA stages (a multiple of 8)
   const uint32_t a_bytes = (uint32_t)rows_a * 128u;
   const uint32_t a_plane = CG == 2 ? ((a_bytes + 1023u) & ~1023u) : a_bytes;   // lo plane on a swizzle-atom boundary
-  const uint32_t stage_tx = 2u * W_BYTES + 2u * a_bytes;       // bytes this CTA loads per stage
+  const uint32_t stage_tx = P.single ? W_BYTES + a_bytes : 2u * W_BYTES + 2u * a_bytes;       // bytes this CTA loads per stage
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0) {
@@ -170,20 +171,20 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
 #pragma unroll
               for (int j = 0; j < TN / 64; ++j) {
                 ld(sb + OFF_W_HI + j * MN_BOX_BYTES, &mapWh, n0 + 64 * j, k0, bw);
-                ld(sb + OFF_W_LO + j * MN_BOX_BYTES, &mapWl, n0 + 64 * j, k0, bw);
+                if (!P.single) ld(sb + OFF_W_LO + j * MN_BOX_BYTES, &mapWl, n0 + 64 * j, k0, bw);
               }
             } else {
               ld(sb + OFF_W_HI, &mapWh, k0, n0, bw);                   // dims (k, n, batch)
-              ld(sb + OFF_W_LO, &mapWl, k0, n0, bw);
+              if (!P.single) ld(sb + OFF_W_LO, &mapWl, k0, n0, bw);
             }
             if (g.a_tr) {                       // stored [K, M]: dims (m, k, batch), rows_a / 64 boxes per plane
               for (int j = 0; j < rows_a / 64; ++j) {
                 ld(sb + OFF_A + j * MN_BOX_BYTES, &mapAh, m0 + 64 * j, k0, ba);
-                ld(sb + OFF_A + a_plane + j * MN_BOX_BYTES, &mapAl, m0 + 64 * j, k0, ba);
+                if (!P.single) ld(sb + OFF_A + a_plane + j * MN_BOX_BYTES, &mapAl, m0 + 64 * j, k0, ba);
               }
             } else {
               ld(sb + OFF_A, &mapAh, k0, ba, m0);                      // dims (k, batch, m)
-              ld(sb + OFF_A + a_plane, &mapAl, k0, ba, m0);
+              if (!P.single) ld(sb + OFF_A + a_plane, &mapAl, k0, ba, m0);
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -220,8 +221,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
               // the pair's token operand: first BA/2 rows from the leader's shared memory, the rest from the peer's
               const uint64_t a_lo = g.a_tr ? make_smem_desc_mn(sb + OFF_A + a_plane + k4 * a_kstep) : make_smem_desc(sb + OFF_A + a_plane + k4 * a_kstep);
               umma_f16_2cta(d1, w_hi, a_hi, idesc_ba, acc);
-              umma_f16_2cta(d2, w_hi, a_lo, idesc_ba, acc);
-              umma_f16_2cta(d2, w_lo, a_hi, idesc_ba, 1u);
+              if (!P.single) {
+                umma_f16_2cta(d2, w_hi, a_lo, idesc_ba, acc);
+                umma_f16_2cta(d2, w_lo, a_hi, idesc_ba, 1u);
+              }
+            } else if (P.single) {
+              umma_f16(d1, w_hi, a_hi, idesc_ba, acc);
             } else {
               umma_f16(d1, w_hi, a_hi, idesc_2ba, acc);
               umma_f16(d2, w_lo, a_hi, idesc_ba, 1u);
@@ -292,7 +297,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         const int c0 = gi * 8;
         uint32_t r1[8], r2[8];
         tmem_ld8(t_row + (uint32_t)c0, r1);
-        tmem_ld8(t_row + (uint32_t)(BA + c0), r2);
+        if (P.single) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) r2[u] = 0u;
+        } else {
+          tmem_ld8(t_row + (uint32_t)(BA + c0), r2);
+        }
         float rb[8], rs[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -417,6 +427,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
 
 int g_sm_count = 0;
 int g_dbg = 0;
+int g_single = 0;        // dpot_tc16_set_precision: 1 = half-precision operand mode (hi planes only)
 int g_pair_mode = -1;    // -1: auto (cost model below), 0: never, 1: pairs whenever legal (dpot_tc16_set_pair)
 
 bool stats_any_ba(const GemmDev& p) { return p.st_rps % 8 == 0 && p.st_rps >= TA; }
@@ -500,7 +511,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
   g_sm_count = sm_count_cur();
-  const bool bw_form = p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src || p.out_colsum || (batch > 1 && (p.sA == 0 || p.sW == 0));
+  const bool bw_form = g_single || p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src || p.out_colsum || (batch > 1 && (p.sA == 0 || p.sW == 0));
   if (!bw_form && gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
@@ -513,6 +524,7 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   P.kblocks = (int)ceil_div(p.ksplit > 1 ? p.kchunk : p.K, BKH);
   P.dbg = g_dbg;
   P.batch = batch;
+  P.single = g_single;
   P.w_bmul = (batch > 1 && p.sW == 0) ? 0 : 1;
   P.a_bmul = (batch > 1 && p.sA == 0) ? 0 : 1;
   const int batchW = P.w_bmul ? batch : 1, batchA = P.a_bmul ? batch : 1;
@@ -593,3 +605,4 @@ extern "C" int dpot_tc16_available(void) { return dpot::tc_device_ok() ? 1 : 0; 
 // experiment / test knob: -1 auto, 0 single-CTA tiles only, 1 CTA pairs whenever legal
 extern "C" void dpot_tc16_set_pair(int32_t mode) { dpot::g_pair_mode = mode; }
 extern "C" void dpot_tc16_set_debug(int32_t mask) { dpot::g_dbg = mask; }
+extern "C" int dpot_tc16_set_precision(int32_t mode) { const int prev = dpot::g_single; if (mode >= 0) dpot::g_single = mode ? 1 : 0; return prev; }

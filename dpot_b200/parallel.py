@@ -235,8 +235,14 @@ class FusedGradExchange:
     arena views) the exchange cannot start before the last accumulation: finish() then runs one all-reduce of the arena.
     """
 
-    def __init__(self, model, group_mb: float = 24.0):
+    def __init__(self, model, overlap: bool = False, group_mb: float = 24.0):
+        """overlap=False (default): one all-reduce of the arena after backward.  Measured on 8 x B200 (profiles/r02p_*):
+        queuing the messages behind backward's completion events does NOT pay -- the contraction kernels are persistent,
+        one CTA per SM with a static tile partition, so every SM NCCL occupies delays a whole share of tiles (DPOT-M,
+        16 / GPU: 15.6 ms overlapped vs 15.1 ms sequential vs 13.6 ms without exchange); the exchange itself runs at
+        ~620 GB/s bus bandwidth (1.37 ms for 489 MB)."""
         from .train_engine import _TrainEngine
+        self.overlap = overlap
         if model._train_eng is None:
             model._train_eng = _TrainEngine(model)
         self.eng = model._train_eng
@@ -270,7 +276,7 @@ class FusedGradExchange:
             for e in self.events:
                 e.record()                             # torch creates the cudaEvent lazily: force it
             self.comm = torch.cuda.Stream(device=dev)
-        self.overlapped = eng.n_forward == 1 and self._world() > 1
+        self.overlapped = self.overlap and eng.n_forward == 1 and self._world() > 1
         return self.buf, (self.events if self.overlapped else None)
 
     def enqueued(self, eng, flat, events) -> None:

@@ -171,6 +171,12 @@ DPOT_API void dpot_tc16_set_pair(int32_t mode);
 DPOT_API void dpot_set_pdl(int32_t on);
 /* weight-stationary plan for short-K batched problems (K <= 256; the AFNO block MLP): -1 = auto, 0 = never */
 DPOT_API void dpot_tc16_set_ws(int32_t mode);
+/* Operand precision of the f16-split engine: 0 (default) = fp32-faithful, three MMAs per product on the hi / lo planes;
+   1 = HALF-PRECISION OPERAND MODE -- only the hi planes (fp16, 11-bit significand: finer than bf16's 8, same tensor-core
+   rate) are loaded and multiplied, one MMA per product, fp32 accumulation, fp32 master weights and epilogues unchanged.
+   This is the library's 16-bit mixed-precision mode (the reference's bf16 autocast configs, configs/pretrain_medium.yaml);
+   results differ from fp32 at the 1e-3 level.  Returns the previous mode; mode < 0 only queries. */
+DPOT_API int dpot_tc16_set_precision(int32_t mode);
 /* pipeline-isolation experiments (results are garbage when non-zero): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue */
 DPOT_API void dpot_tc16_set_debug(int32_t mask);
 

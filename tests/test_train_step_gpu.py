@@ -121,3 +121,35 @@ def test_gradients_written_into_the_exchange_arena():
                 # (double atomics accumulate the GroupNorm statistics / bias gradients: last-bit differences between runs)
                 assert O.rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 1e-6, k
     ex.close()
+
+
+def test_half_precision_operand_mode():
+    """dpot_b200.set_precision("half"): fp16 operands (hi planes only), one MMA per product, fp32 accumulate -- the
+    16-bit mixed-precision mode for the reference's bf16 configs (configs/pretrain_medium.yaml).  A contraction must
+    equal the fp64 product of the fp16-rounded operands; the training step must stay within 1e-2 of the fp32 gradients
+    (tolerance of a 16-bit mode: measured ~1e-3)."""
+    import dpot_b200
+    from dpot_b200 import ops
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((512, 320)).astype(np.float32)
+    W = (rng.standard_normal((256, 320)) / 18).astype(np.float32)
+    z = np.load(os.path.join(G, "train_grads_fused2.npz"))
+    m32, x32, l32 = _run(z, "auto")
+    prev = dpot_b200.set_precision("half")
+    try:
+        out = ops.gemm16(ops.split_f16(torch.from_numpy(A).cuda()), ops.split_f16(torch.from_numpy(W).cuda()))
+        ref = A.astype(np.float16).astype(np.float64) @ W.astype(np.float16).astype(np.float64).T
+        assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
+        assert O.rel_l2(out.cpu().numpy(), A.astype(np.float64) @ W.astype(np.float64).T) > 1e-5     # it really is 16-bit
+        m16, x16, l16 = _run(z, "auto")
+    finally:
+        dpot_b200.set_precision(prev)
+    assert float(l16) == pytest.approx(float(l32), rel=2e-3)
+    worst = 0.0
+    for (k, p), (_, q) in zip(m16.named_parameters(), m32.named_parameters()):
+        if q.grad is None:
+            continue
+        e = O.rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy())
+        worst = max(worst, e)
+        assert e < 1e-2, (k, e)
+    print("half-precision operand mode: worst parameter-gradient rel-L2 vs fp32 =", worst)

@@ -73,7 +73,10 @@ out["fused_training_step"] = bool(model._train_eng is not None and model._train_
 flat = GradArena(model.parameters())
 out["ms_step_flat_allreduce"] = timed(lambda: step_with(flat))
 if out["fused_training_step"]:
-    over = FusedGradExchange(model)
+    seq = FusedGradExchange(model, overlap=False)
+    out["ms_step_arena_sequential"] = timed(lambda: step_with(seq))
+    seq.close()
+    over = FusedGradExchange(model, overlap=True)
     out["messages"] = len(over.msgs)
 else:
     over = OverlappedGradArena(model.parameters(), bucket_mb=32.0)

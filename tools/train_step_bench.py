@@ -1,7 +1,7 @@
 """Training-step timing through the drop-in API (train_temporal.py:201-230, T_ar = 1, noise off): forward + SimpleLpLoss +
 backward + clip + Adam.step on one GPU, CUDA events, synthetic data.
 
-    python tools/train_step_bench.py [S|M|Ti] [batch] [path: auto|generic|both] [steps]
+    python tools/train_step_bench.py [S|M|Ti] [batch] [path: auto|generic|both] [steps] [fp32|half]
 
 Prints one JSON line: ms per step for the one-call training step (dpot_train_*) and/or the per-operator path."""
 import json
@@ -20,12 +20,15 @@ name = sys.argv[1] if len(sys.argv) > 1 else "S"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 which = sys.argv[3] if len(sys.argv) > 3 else "both"
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+precision = sys.argv[5] if len(sys.argv) > 5 else "fp32"
+import dpot_b200
+dpot_b200.set_precision(precision)
 cfg = zoo.zoo_cfg(name)
 dev = torch.device("cuda")
 x = torch.randn(B, 128, 128, 10, 4, device=dev)
 y = torch.randn(B, 128, 128, 1, 4, device=dev)
 msk = torch.ones(B, 128, 128, 1, 4, device=dev)
-out = {"model": name, "batch": B, "steps": n}
+out = {"model": name, "batch": B, "steps": n, "precision": precision}
 for path in (["auto", "generic"] if which == "both" else [which]):
     m = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).train()
     m.train_path = path
