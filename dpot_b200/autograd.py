@@ -448,3 +448,87 @@ def _forward_train(net, x):
     if net.normalize:                                                      # models/dpot.py:400-401
         out = out * sigma + mu
     return out, cls_pred
+
+
+# ------------------------------------------------------------------------------------------------ standalone modules
+# The reference exports AFNO2D / Block / Mlp / PatchEmbed / TimeAggregator as ordinary differentiable nn.Modules
+# (models/dpot.py:29-234).  Under grad their forwards run on the same per-operator Functions as the generic training
+# path above; layout changes (NCHW <-> token-major) and parameter re-shapes are differentiable torch views.
+def _afno_tokens(flt, a, B, h, skip):
+    """AFNO2D on token-major a[B*h*h, E] (models/dpot.py:51-110): irfft2(MLP(rfft2(a))) + skip."""
+    km1, km2 = min(flt.modes, h), min(flt.modes, h // 2 + 1)
+    act = ACT_IDS[flt.act_name]
+    Wc1, bc1 = PackAfnoFn.apply(flt.w1, flt.b1)
+    Wc2, bc2 = PackAfnoFn.apply(flt.w2, flt.b2)
+    S = SpectralFn.apply(a, B, h, flt.num_blocks, km1, km2)
+    O1 = BlockDiagLinearFn.apply(S, Wc1, bc1, act)
+    O2 = BlockDiagLinearFn.apply(O1, Wc2, bc2, ACT_NONE)
+    return SpectralInvFn.apply(O2, skip, B, h, flt.num_blocks, km1, km2)
+
+
+def afno2d_train(flt, x):
+    with torch.cuda.device(x.device):
+        a = x.permute(0, 2, 3, 1) if flt.channel_first else x
+        B, H, W, Cc = a.shape
+        a = a.reshape(B * H * W, Cc).contiguous().float()
+        f = _afno_tokens(flt, a, B, H, a).reshape(B, H, W, Cc)
+        return f.permute(0, 3, 1, 2) if flt.channel_first else f
+
+
+def block_train(blk, x):
+    """Block.forward (models/dpot.py:165-180) on x[B, E, H, W]."""
+    with torch.cuda.device(x.device):
+        B, E, H, W = x.shape
+        n = H * W
+        act = ACT_IDS[blk.act_name] if hasattr(blk, "act_name") else ACT_IDS[blk.filter.act_name]
+        a = x.permute(0, 2, 3, 1).reshape(B * n, E).contiguous().float()
+        n1 = GroupNormFn.apply(a, blk.norm1.weight, blk.norm1.bias, B, n, blk.norm1.eps)
+        f = _afno_tokens(blk.filter, n1, B, H, n1)
+        res = a
+        if blk.double_skip:                       # :171-173
+            f = f + a
+            res = f
+        n2 = GroupNormFn.apply(f, blk.norm2.weight, blk.norm2.bias, B, n, blk.norm2.eps)
+        fc1, fc2 = blk.mlp[0], blk.mlp[2]
+        hid = fc1.out_channels
+        hdn = LinearFn.apply(n2, fc1.weight.reshape(hid, E), fc1.bias, None, None, act)
+        out = LinearFn.apply(hdn, fc2.weight.reshape(E, hid), fc2.bias, None, res, ACT_NONE)
+        return out.reshape(B, H, W, E).permute(0, 3, 1, 2)
+
+
+def mlp_train(mod, x):
+    with torch.cuda.device(x.device):
+        lead = x.shape[:-1]
+        a = x.reshape(-1, x.shape[-1]).contiguous().float()
+        hdn = LinearFn.apply(a, mod.fc1.weight, mod.fc1.bias, None, None, ACT_IDS[mod.act_name])
+        return LinearFn.apply(hdn, mod.fc2.weight, mod.fc2.bias, None, None, ACT_NONE).reshape(*lead, -1)
+
+
+def patch_embed_train(pe, x):
+    """PatchEmbed.forward (models/dpot.py:203-209) on NCHW frames."""
+    with torch.cuda.device(x.device):
+        B, Cc, H, W = x.shape
+        P = pe.patch_size[0]
+        c0, c2 = pe.proj[0], pe.proj[2]
+        mid = c0.out_channels
+        h, w = H // P, W // P
+        xf = x.permute(0, 2, 3, 1).reshape(B, H, W, 1, Cc).contiguous().float()
+        W0p = c0.weight.permute(0, 2, 3, 1).reshape(mid, P * P * Cc)
+        rb = c0.bias.reshape(1, mid).expand(h * w, mid)
+        z1 = PatchGemmFn.apply(xf, W0p, rb, P, ACT_IDS[pe.act_name])
+        out = LinearFn.apply(z1, c2.weight.reshape(c2.out_channels, mid), c2.bias, None, None, ACT_NONE)
+        return out.reshape(B, h, w, -1).permute(0, 3, 1, 2)
+
+
+def time_agg_train(ta, x):
+    """TimeAggregator.forward (models/dpot.py:226-234): out[..., j] = sum_{t,i} w[t,i,j] x[..., t, i] temb[t,i]."""
+    with torch.cuda.device(x.device):
+        lead, T, E = x.shape[:-2], x.shape[-2], x.shape[-1]
+        if ta.type == 'exp_mlp':
+            t = torch.linspace(0, 1, T).unsqueeze(-1).to(x.device)
+            temb = torch.cos(t * ta.gamma)
+        else:
+            temb = torch.ones((T, E), device=x.device)
+        Wt = (ta.w * temb.unsqueeze(-1)).reshape(T * E, E).t()
+        a = x.reshape(-1, T * E).contiguous().float()
+        return LinearFn.apply(a, Wt, None, None, None, ACT_NONE).reshape(*lead, E)

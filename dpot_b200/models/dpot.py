@@ -95,7 +95,8 @@ class AFNO2D(nn.Module):
     def forward(self, x, spatial_size=None):
         _require_cuda(x, "AFNO2D.forward")
         if _grad_needed(x, self.w1, self.b1, self.w2, self.b2):
-            raise NotImplementedError("dpot_b200: standalone AFNO2D.forward is inference-only; train through DPOTNet")
+            from ..autograd import afno2d_train
+            return afno2d_train(self, x)
         if self.channel_first:
             B, Cc, H, W = x.shape
             a = x.permute(0, 2, 3, 1)
@@ -126,7 +127,8 @@ class Mlp(nn.Module):
     def forward(self, x):
         _require_cuda(x, "Mlp.forward")
         if _grad_needed(x, *self.parameters()):
-            raise NotImplementedError("dpot_b200: Mlp.forward is inference-only")
+            from ..autograd import mlp_train
+            return mlp_train(self, x)
         lead = x.shape[:-1]
         a = x.reshape(-1, x.shape[-1]).contiguous().float()
         hdn = ops.gemm(a, self.fc1.weight.detach(), bias=self.fc1.bias.detach(), act=self.act_name)
@@ -180,7 +182,8 @@ class Block(nn.Module):
     def forward(self, x):
         _require_cuda(x, "Block.forward")
         if _grad_needed(x, *self.parameters()):
-            raise NotImplementedError("dpot_b200: standalone Block.forward is inference-only; train through DPOTNet")
+            from ..autograd import block_train
+            return block_train(self, x)
         B, E, H, W = x.shape
         if H != W or H not in _SUPPORTED_LATENT:
             raise RuntimeError(f"Block: latent grid {H}x{W} unsupported (square power of two in [2,32])")
@@ -210,7 +213,8 @@ class PatchEmbed(nn.Module):
     def forward(self, x):
         _require_cuda(x, "PatchEmbed.forward")
         if _grad_needed(x, *self.parameters()):
-            raise NotImplementedError("dpot_b200: standalone PatchEmbed.forward is inference-only")
+            from ..autograd import patch_embed_train
+            return patch_embed_train(self, x)
         B, Cc, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
@@ -253,7 +257,8 @@ class TimeAggregator(nn.Module):
     def forward(self, x):
         _require_cuda(x, "TimeAggregator.forward")
         if _grad_needed(x, *self.parameters()):
-            raise NotImplementedError("dpot_b200: standalone TimeAggregator.forward is inference-only")
+            from ..autograd import time_agg_train
+            return time_agg_train(self, x)
         lead, T, E = x.shape[:-2], x.shape[-2], x.shape[-1]
         temb = self.time_embedding(T, x.device)
         # out[..., j] = sum_{t,i} w[t,i,j] x[..., t, i] temb[t,i]  ==  A[M, T*E] @ Wt[E, T*E]^T

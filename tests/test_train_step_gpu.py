@@ -153,3 +153,79 @@ def test_half_precision_operand_mode():
         worst = max(worst, e)
         assert e < 1e-2, (k, e)
     print("half-precision operand mode: worst parameter-gradient rel-L2 vs fp32 =", worst)
+
+
+def test_standalone_modules_are_differentiable():
+    """AFNO2D / Block / Mlp / PatchEmbed / TimeAggregator are ordinary differentiable nn.Modules in the reference
+    (models/dpot.py:29-234).  Gradients of each against torch autograd over a plain-torch restatement of the same lines
+    (fp64 on the GPU)."""
+    import torch.nn.functional as F
+    from dpot_b200.models.dpot import AFNO2D, Block, PatchEmbed, TimeAggregator
+    torch.manual_seed(0)
+    dev = "cuda"
+
+    def afno_ref(x, w1, b1, w2, b2, nb, modes):            # models/dpot.py:51-110, channel-last x[B,H,W,C]
+        B, H, W, Cc = x.shape
+        bias = x
+        xf = torch.fft.rfft2(x, dim=(1, 2), norm="ortho").reshape(B, H, W // 2 + 1, nb, Cc // nb)
+        km = modes
+        o1r = torch.zeros_like(xf.real); o1i = torch.zeros_like(xf.real)
+        s = (slice(None), slice(0, km), slice(0, km))
+        ein = lambda a, w: torch.einsum('...bi,bio->...bo', a, w)
+        o1r[s] = F.gelu(ein(xf[s].real, w1[0]) - ein(xf[s].imag, w1[1]) + b1[0])
+        o1i[s] = F.gelu(ein(xf[s].imag, w1[0]) + ein(xf[s].real, w1[1]) + b1[1])
+        o2r = torch.zeros_like(o1r); o2i = torch.zeros_like(o1r)
+        o2r[s] = ein(o1r[s], w2[0]) - ein(o1i[s], w2[1]) + b2[0]
+        o2i[s] = ein(o1i[s], w2[0]) + ein(o1r[s], w2[1]) + b2[1]
+        y = torch.fft.irfft2(torch.complex(o2r, o2i).reshape(B, H, W // 2 + 1, Cc), s=(H, W), dim=(1, 2), norm="ortho")
+        return y + bias
+
+    def check(mod, x, ref_fn, tol=2e-5):
+        x1 = x.clone().requires_grad_(True)
+        y = mod(x1)
+        gy = torch.randn_like(y)
+        (y * gy).sum().backward()
+        p64 = [p.detach().double().requires_grad_(True) for p in mod.parameters()]
+        x2 = x.detach().double().requires_grad_(True)
+        y2 = ref_fn(x2, *p64)
+        assert O.rel_l2(y.detach().cpu().numpy(), y2.detach().cpu().numpy()) < 1e-5
+        (y2 * gy.double()).sum().backward()
+        assert O.rel_l2(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) < tol, "dx"
+        for (k, p), q in zip(mod.named_parameters(), p64):
+            assert p.grad is not None, k
+            assert O.rel_l2(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < tol, k
+
+    nb, E, H = 4, 64, 8
+    flt = AFNO2D(width=E, num_blocks=nb, channel_first=False, modes=5, act='gelu').to(dev)
+    with torch.no_grad():
+        for p in flt.parameters():
+            p.copy_(torch.randn_like(p) * 0.2)
+    check(flt, torch.randn(2, H, H, E, device=dev), lambda x, w1, b1, w2, b2: afno_ref(x, w1, b1, w2, b2, nb, 5))
+
+    blk = Block(width=E, n_blocks=nb, mlp_ratio=2, modes=32, double_skip=False).to(dev)
+    with torch.no_grad():
+        for k, p in blk.named_parameters():
+            if "filter" in k:
+                p.copy_(torch.randn_like(p) * 0.2)
+
+    def block_ref(x, n1w, n1b, w1, b1, w2, b2, n2w, n2b, f1w, f1b, f2w, f2b):      # models/dpot.py:165-180
+        r = x
+        y = F.group_norm(x, 8, n1w, n1b, 1e-5)
+        y = afno_ref(y.permute(0, 2, 3, 1), w1, b1, w2, b2, nb, 32).permute(0, 3, 1, 2)
+        y = F.group_norm(y, 8, n2w, n2b, 1e-5)
+        y = F.conv2d(F.gelu(F.conv2d(y, f1w, f1b)), f2w, f2b)
+        return y + r
+    check(blk, torch.randn(2, E, H, H, device=dev), block_ref)
+
+    pe = PatchEmbed(img_size=32, patch_size=4, in_chans=6, embed_dim=15, out_dim=32).to(dev)
+    check(pe, torch.randn(3, 6, 32, 32, device=dev),
+          lambda x, w0, b0, w2, b2: F.conv2d(F.gelu(F.conv2d(x, w0, b0, stride=4)), w2, b2))
+
+    ta = TimeAggregator(3, 5, 32, "exp_mlp").to(dev)
+    with torch.no_grad():
+        ta.gamma.copy_(torch.rand_like(ta.gamma) * 3)
+
+    def ta_ref(x, w, gamma):                                # models/dpot.py:228-232
+        t = torch.linspace(0, 1, x.shape[-2], device=x.device, dtype=x.dtype).unsqueeze(-1)
+        return torch.einsum('tij,...ti->...j', w, x * torch.cos(t @ gamma))
+    check(ta, torch.randn(2, 8, 8, 5, 32, device=dev), ta_ref)
