@@ -53,6 +53,23 @@ static int run_tail(const float* Y, const float* w2, const float* b2, const dpot
   return dpot_out_tail(Y, w2, b2, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act, mu_c, sg_c, d.Co, y, stream);
 }
 
+// The classification head (a spatial mean + three M = B skinny contractions, ~60 us of latency-bound work) depends only on
+// the last latent, like the output head: it runs on a library-owned side stream between a fork event (after the last
+// block) and a join event (end of the forward) -- also under stream capture, where the events become graph edges.
+// One side stream per device: concurrent forwards from SEVERAL host threads on one device are not supported with it.
+int g_cls_overlap = 0;   // measured (r02t): the side stream takes SMs from the persistent contraction kernels of the output head: -3 %
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+  static SideStream tab[64];
+  SideStream& s = tab[cur_dev()];
+  if (!s.st) {
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+
 // ---- the f16-split tensor-core pipeline (DPOT_GEMM_TC16) ---------------------------------------
 // Every activation that feeds a dense contraction is written by its producer as split fp16
 // (DPOT_FMT_HL16, 4 bytes per element like fp32): conv0 epilogue -> z1, forward FFT -> S, GEMM
@@ -129,16 +146,28 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
     float* tmp = lat; lat = lat_next; lat_next = tmp;
   }
 
-  if (cls) {   // classification head (M = B rows: skinny CUDA-core GEMMs)
-    if (d.depth > 0) DPOT_CALL(dpot_spatial_mean16(ws + WL.n2, B, d.n, d.E, ws + WL.tok, stream));
-    else DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, stream));
+  SideStream* side = (cls && g_cls_overlap && d.depth > 0) ? side_stream() : nullptr;
+  if (cls) {   // classification head (M = B rows: skinny CUDA-core GEMMs), on the side stream when available
+    void* cs = stream;
+    if (side) {
+      DPOT_CUDA(cudaEventRecord(side->fork, st));
+      DPOT_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+      cs = side->st;
+    }
+    if (d.depth > 0) DPOT_CALL(dpot_spatial_mean16(ws + WL.n2, B, d.n, d.E, ws + WL.tok, cs));
+    else DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, cs));
     dpot_gemm_args g = gemm_args(ws + WL.tok, d.E, prm->cls0_w, d.E, ws + WL.c1, d.E, B, d.E, d.E, prm->cls0_b, act, DPOT_GEMM_AUTO);
-    DPOT_CALL(dpot_gemm(&g, stream));
+    DPOT_CALL(dpot_gemm(&g, cs));
     g = gemm_args(ws + WL.c1, d.E, prm->cls2_w, d.E, ws + WL.c2, d.E, B, d.E, d.E, prm->cls2_b, act, DPOT_GEMM_AUTO);
-    DPOT_CALL(dpot_gemm(&g, stream));
+    DPOT_CALL(dpot_gemm(&g, cs));
     g = gemm_args(ws + WL.c2, d.E, prm->cls4_w, d.E, cls, d.ncls, B, d.ncls, d.E, prm->cls4_b, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
-    DPOT_CALL(dpot_gemm(&g, stream));
+    DPOT_CALL(dpot_gemm(&g, cs));
+    if (side) DPOT_CUDA(cudaEventRecord(side->join, side->st));
   }
+  auto join_side = [&]() -> int {
+    if (side) DPOT_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    return 0;
+  };
 
   // output head: ConvTranspose as a GEMM on the split latent (written split by the last fc2 unless the cls head
   // needed it in fp32), then the fused per-pixel tail
@@ -166,7 +195,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       DPOT_CALL(dpot_out_tail_tc(ws + WL.Y1, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, nout, act,
                                  mu_c, sg_c, d.Co, y, ro ? ro->ring : nullptr, ro ? ro->pred : nullptr, d.T, ro ? ro->slot0 : 0,
                                  ro ? ro->Ttot : 0, ro ? ro->step : 0, stream));
-      return 0;
+      return join_side();
     }
     if (fused_tail) {
       DPOT_CALL(run_tail(ws + WL.Y1, prm->out2_w, prm->out2_b, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));
@@ -176,7 +205,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       DPOT_CALL(run_tail(ws + WL.Y2, nullptr, nullptr, prm, B, d, nout, act, mu_c, sg_c, y, ro, stream));
     }
   }
-  return 0;
+  return join_side();
 }
 
 }  // namespace dpot
@@ -373,3 +402,6 @@ static int forward_impl(const dpot_config* cfg, const dpot_params* prm, const fl
   }
   return 0;
 }
+
+// 1: the classification head of dpot_forward* runs on a library-owned side stream, concurrently with the output head (default 0)
+extern "C" void dpot_set_cls_overlap(int32_t on) { dpot::g_cls_overlap = on ? 1 : 0; }

@@ -198,6 +198,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
       const uint32_t idesc_2ba = make_idesc16((uint32_t)(2 * BA), 128u, wmn, amn);   // CG 1: [hi ; lo] token rows in one MMA
       const uint32_t idesc_ba = make_idesc16((uint32_t)BA, 128u * CG, wmn, amn);
       const uint32_t w_kstep = g.w_tr ? 2048u : 32u, a_kstep = g.a_tr ? 2048u : 32u;
+      // descriptor = constant high part (layout, LBO / SBO) | start address: one OR per operand inside the loop
+      const uint64_t w_hi_bits = (g.w_tr ? make_smem_desc_mn(0u) : make_smem_desc(0u));
+      const uint64_t a_hi_bits = (g.a_tr ? make_smem_desc_mn(0u) : make_smem_desc(0u));
+      auto DW = [&](uint32_t addr) -> uint64_t { return w_hi_bits | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+      auto DA = [&](uint32_t addr) -> uint64_t { return a_hi_bits | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+      const bool single = P.single != 0;
       int s = 0; uint32_t ph = 0; uint32_t tc = 0;
       for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++tc) {
         const uint32_t buf = tc & 1u, bph = (tc >> 1) & 1u;
@@ -209,27 +215,31 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
           mbar_wait(FULL(s), ph);
           tc_fence_after();
           const uint32_t sb = smem0 + (uint32_t)s * STAGE_BYTES;
+          if (P.dbg & 2) {                      // experiment: the load pipeline alone
+          } else if (single) {                  // half-precision operand mode: hi x hi only
 #pragma unroll
-          for (int k4 = 0; k4 < BKH / 16; ++k4) {
-            const uint64_t w_hi = g.w_tr ? make_smem_desc_mn(sb + OFF_W_HI + k4 * w_kstep) : make_smem_desc(sb + OFF_W_HI + k4 * w_kstep);
-            const uint64_t w_lo = g.w_tr ? make_smem_desc_mn(sb + OFF_W_LO + k4 * w_kstep) : make_smem_desc(sb + OFF_W_LO + k4 * w_kstep);
-            // CG 1: rows [0,BA) = hi, [BA,2BA) = lo
-            const uint64_t a_hi = g.a_tr ? make_smem_desc_mn(sb + OFF_A + k4 * a_kstep) : make_smem_desc(sb + OFF_A + k4 * a_kstep);
-            const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
-            if (P.dbg & 2) {                    // experiment: the load pipeline alone
-            } else if (CG == 2) {
-              // the pair's token operand: first BA/2 rows from the leader's shared memory, the rest from the peer's
-              const uint64_t a_lo = g.a_tr ? make_smem_desc_mn(sb + OFF_A + a_plane + k4 * a_kstep) : make_smem_desc(sb + OFF_A + a_plane + k4 * a_kstep);
-              umma_f16_2cta(d1, w_hi, a_hi, idesc_ba, acc);
-              if (!P.single) {
+            for (int k4 = 0; k4 < BKH / 16; ++k4) {
+              const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
+              if (CG == 2) umma_f16_2cta(d1, DW(sb + OFF_W_HI + k4 * w_kstep), DA(sb + OFF_A + k4 * a_kstep), idesc_ba, acc);
+              else umma_f16(d1, DW(sb + OFF_W_HI + k4 * w_kstep), DA(sb + OFF_A + k4 * a_kstep), idesc_ba, acc);
+            }
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < BKH / 16; ++k4) {
+              const uint64_t w_hi = DW(sb + OFF_W_HI + k4 * w_kstep);
+              const uint64_t w_lo = DW(sb + OFF_W_LO + k4 * w_kstep);
+              const uint64_t a_hi = DA(sb + OFF_A + k4 * a_kstep);      // CG 1: rows [0,BA) = hi, [BA,2BA) = lo
+              const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
+              if (CG == 2) {
+                // the pair's token operand: first BA/2 rows from the leader's shared memory, the rest from the peer's
+                const uint64_t a_lo = DA(sb + OFF_A + a_plane + k4 * a_kstep);
+                umma_f16_2cta(d1, w_hi, a_hi, idesc_ba, acc);
                 umma_f16_2cta(d2, w_hi, a_lo, idesc_ba, acc);
                 umma_f16_2cta(d2, w_lo, a_hi, idesc_ba, 1u);
+              } else {
+                umma_f16(d1, w_hi, a_hi, idesc_2ba, acc);
+                umma_f16(d2, w_lo, a_hi, idesc_ba, 1u);
               }
-            } else if (P.single) {
-              umma_f16(d1, w_hi, a_hi, idesc_ba, acc);
-            } else {
-              umma_f16(d1, w_hi, a_hi, idesc_2ba, acc);
-              umma_f16(d2, w_lo, a_hi, idesc_ba, 1u);
             }
           }
           if (CG == 2) umma_commit_2cta(EMPTY(s)); else umma_commit(EMPTY(s));
@@ -245,6 +255,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
     const int ngroups = BA / 8;
     __half* const Ch_base = reinterpret_cast<__half*>(g.C);
     const uint32_t tempty_leader = CG == 2 ? mapa_rank(TEMPTY(0), 0) : TEMPTY(0);
+    const bool epi_single = P.single != 0;
     uint32_t tc = 0;
     for (int tile = tile0; tile < P.total_tiles; tile += tile_step, ++tc) {
       const int mt = tile % P.m_tiles; const int rest = tile / P.m_tiles;
@@ -297,12 +308,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         const int c0 = gi * 8;
         uint32_t r1[8], r2[8];
         tmem_ld8(t_row + (uint32_t)c0, r1);
-        if (P.single) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) r2[u] = 0u;
-        } else {
-          tmem_ld8(t_row + (uint32_t)(BA + c0), r2);
-        }
+        tmem_ld8(t_row + (uint32_t)(BA + c0), r2);          // (half-precision operand mode: stale columns, ignored below)
         float rb[8], rs[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -316,7 +322,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constan
         if (cnt <= 0 || !nok) return;
         float t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = fmaf(__uint_as_float(r2[u]), HL_INV, __uint_as_float(r1[u])) + bias_n + rb[u];
+        for (int u = 0; u < 8; ++u)
+          t[u] = (epi_single ? __uint_as_float(r1[u]) : fmaf(__uint_as_float(r2[u]), HL_INV, __uint_as_float(r1[u]))) + bias_n + rb[u];
         if (g.C_pre) {                                   // training: keep the pre-activation (fp32) for the backward pass
           float* __restrict__ pp = g.C_pre + (int64_t)bb * g.sPre + (int64_t)m0 * g.ldpre + n;
 #pragma unroll

@@ -464,6 +464,11 @@ DPOT_API int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm, f
 DPOT_API int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                  int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
 
+/* 1: the classification head of dpot_forward* / dpot_rollout_step runs on a library-owned side stream (one per device)
+   concurrently with the output head, joined before the call's work on `stream` ends; 0 (default): everything on `stream`.
+   Measured slower on B200 (the side stream takes SMs from the persistent contraction kernels); kept as a knob. */
+DPOT_API void dpot_set_cls_overlap(int32_t on);
+
 /* dpot_forward on a time-ring input window (see dpot_ring_insert): logical frame t of x is slot (t + t0) % T */
 DPOT_API int dpot_forward_ring(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                       int32_t t0, int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
