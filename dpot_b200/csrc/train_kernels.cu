@@ -57,19 +57,21 @@ __global__ void __launch_bounds__(128) colsum2_kernel(const void* __restrict__ X
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm backward
-// per (sample, channel): A1 = sum_pos dy, A2 = sum_pos dy * x (raw x; the centring happens in the group kernel)
+// per (sample, channel) and position half z: A1[z] = sum_pos dy, A2[z] = sum_pos dy * x (raw x; the centring happens in
+// the group kernel, which adds the two halves).  grid (E/64, B, 2): 3.5 waves of blocks on 148 SMs instead of 1.7.
 __global__ void __launch_bounds__(256) gn_bwd_reduce2_kernel(const float* __restrict__ dy, const float* __restrict__ x, int n, int E,
-                                                             float* __restrict__ A1, float* __restrict__ A2) {
+                                                             int B, float* __restrict__ A1, float* __restrict__ A2) {
   __shared__ float2 r1[8][32], r2[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int b = blockIdx.y, c = blockIdx.x * 64 + lane * 2;
+  const int b = blockIdx.y, c = blockIdx.x * 64 + lane * 2, z = blockIdx.z;
+  const int p0 = z * (n / 2), p1 = z ? n : n / 2;
   float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
   if (c < E) {
     const int64_t base = (int64_t)b * n * E + c;
 #pragma unroll 4
-    for (int pos = w; pos < n; pos += 8) {
-      const float2 g = *reinterpret_cast<const float2*>(dy + base + (int64_t)pos * E);
-      const float2 xv = *reinterpret_cast<const float2*>(x + base + (int64_t)pos * E);
+    for (int pos = p0 + w; pos < p1; pos += 8) {
+      const float2 g = __ldcs(reinterpret_cast<const float2*>(dy + base + (int64_t)pos * E));
+      const float2 xv = __ldcs(reinterpret_cast<const float2*>(x + base + (int64_t)pos * E));
       s1.x += g.x; s1.y += g.y;
       s2.x = fmaf(g.x, xv.x, s2.x); s2.y = fmaf(g.y, xv.y, s2.y);
     }
@@ -80,8 +82,9 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce2_kernel(const float* __rest
     float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { t1.x += r1[k][lane].x; t1.y += r1[k][lane].y; t2.x += r2[k][lane].x; t2.y += r2[k][lane].y; }
-    *reinterpret_cast<float2*>(A1 + (int64_t)b * E + c) = t1;
-    *reinterpret_cast<float2*>(A2 + (int64_t)b * E + c) = t2;
+    const int64_t o = ((int64_t)z * B + b) * E + c;
+    *reinterpret_cast<float2*>(A1 + o) = t1;
+    *reinterpret_cast<float2*>(A2 + o) = t2;
   }
 }
 
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(128) gn_bwd_group2_kernel(const float* __restr
                                                             float* __restrict__ dbeta) {
   const int gs = E / groups;
   const double cnt = (double)gs * n;
+  const int64_t half = (int64_t)B * E;            // A1 / A2 hold two position halves
   if ((int)blockIdx.x < gblocks) {
     const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (wid >= B * groups) return;
@@ -106,10 +110,11 @@ __global__ void __launch_bounds__(128) gn_bwd_group2_kernel(const float* __restr
     const double rstd = 1.0 / sqrt(var + (double)eps);
     double g1 = 0.0, g2 = 0.0;
     for (int c = g * gs + lane; c < (g + 1) * gs; c += 32) {
-      const double gm = (double)gamma[c], a1 = (double)A1[(int64_t)b * E + c], a2 = (double)A2[(int64_t)b * E + c];
+      const int64_t o = (int64_t)b * E + c;
+      const double gm = (double)gamma[c], a1 = (double)A1[o] + (double)A1[half + o], a2 = (double)A2[o] + (double)A2[half + o];
       g1 += gm * a1;
       g2 += gm * (a2 - mean * a1) * rstd;            // sum gamma * dy * xhat
-      coefA[(int64_t)b * E + c] = (float)(rstd * gm);
+      coefA[o] = (float)(rstd * gm);
     }
     g1 = warp_sum(g1); g2 = warp_sum(g2);
     if (lane == 0) {
@@ -117,19 +122,26 @@ __global__ void __launch_bounds__(128) gn_bwd_group2_kernel(const float* __restr
       coefBC[2 * wid + 1] = (float)((rstd * rstd * g2 * mean - rstd * g1) / cnt);
     }
   } else {
+    // dgamma / dbeta: the (sample, group) mean and rstd once per block in shared memory (fp64 sqrt / divide are slow)
+    extern __shared__ float ms[];                  // [B*groups][2] = (mean, rstd)
+    for (int i = threadIdx.x; i < B * groups; i += blockDim.x) {
+      const double mean = stats[2 * (int64_t)i] / cnt;
+      double var = stats[2 * (int64_t)i + 1] / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      ms[2 * i] = (float)mean;
+      ms[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
     const int c = ((int)blockIdx.x - gblocks) * blockDim.x + threadIdx.x;
     if (c >= E) return;
     const int g = c / gs;
     double d1 = 0.0, d2 = 0.0;
     for (int b = 0; b < B; ++b) {
-      const double* st = stats + ((int64_t)b * groups + g) * 2;
-      const double mean = st[0] / cnt;
-      double var = st[1] / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double rstd = 1.0 / sqrt(var + (double)eps);
-      const double a1 = (double)A1[(int64_t)b * E + c], a2 = (double)A2[(int64_t)b * E + c];
-      d1 += a1;
-      d2 += (a2 - mean * a1) * rstd;
+      const int64_t o = (int64_t)b * E + c;
+      const float a1 = A1[o] + A1[half + o], a2 = A2[o] + A2[half + o];
+      const float mean = ms[2 * (b * groups + g)], rstd = ms[2 * (b * groups + g) + 1];
+      d1 += (double)a1;
+      d2 += (double)(fmaf(-mean, a1, a2) * rstd);
     }
     const double inv = (double)inv_of(inv_scale);
     dbeta[c] = (float)(d1 * inv);
@@ -219,29 +231,41 @@ __global__ void scale_copy_kernel(const float* __restrict__ src, int64_t count, 
 }
 
 // dWc[nb, 2bs(out), 2bs(in)] partials -> dw[2, nb, bs(in), bs(out)], dbc -> db[2, nb, bs]   (transpose of pack_afno_kernel)
-__global__ void unpack_afno_grad2_kernel(const float* __restrict__ dWc, int nslab, int64_t stride, const double* __restrict__ dbc,
+// 32 x 32 (out, in) tiles through shared memory: reads run along `in`, writes along `out`.  grid (bs/32, bs/32, nb), block (32, 16)
+__global__ void __launch_bounds__(512) unpack_afno_grad2_kernel(const float* __restrict__ dWc, int nslab, int64_t stride, const double* __restrict__ dbc,
                                          int nb, int bs, const float* __restrict__ inv_scale, float* __restrict__ dw,
                                          float* __restrict__ db) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per = (int64_t)nb * bs * bs;
+  __shared__ float re[32][33], im[32][33];
+  const int o0 = blockIdx.x * 32, k0 = blockIdx.y * 32, kap = blockIdx.z;
+  const int64_t L = 2 * bs, per = (int64_t)nb * bs * bs;
   const float inv = inv_of(inv_scale);
-  if (i < per) {
-    const int o = (int)(i % bs), ki = (int)((i / bs) % bs), kap = (int)(i / ((int64_t)bs * bs));
-    const int64_t L = 2 * bs;
-    float re = 0.f, im = 0.f;
-    for (int s = 0; s < nslab; ++s) {
-      const float* Wk = dWc + (int64_t)s * stride + (int64_t)kap * 4 * bs * bs;
-      // Wc[n=o][k=ki] = wr, Wc[o][ki+bs] = -wi, Wc[o+bs][ki] = wi, Wc[o+bs][ki+bs] = wr
-      re += Wk[(int64_t)o * L + ki] + Wk[(int64_t)(o + bs) * L + ki + bs];
-      im += -Wk[(int64_t)o * L + ki + bs] + Wk[(int64_t)(o + bs) * L + ki];
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int o = o0 + i, ki = k0 + threadIdx.x;
+    float r = 0.f, m = 0.f;
+    if (o < bs && ki < bs) {
+      for (int s = 0; s < nslab; ++s) {
+        const float* Wk = dWc + (int64_t)s * stride + (int64_t)kap * 4 * bs * bs;
+        // Wc[n=o][k=ki] = wr, Wc[o][ki+bs] = -wi, Wc[o+bs][ki] = wi, Wc[o+bs][ki+bs] = wr
+        r += Wk[(int64_t)o * L + ki] + Wk[(int64_t)(o + bs) * L + ki + bs];
+        m += -Wk[(int64_t)o * L + ki + bs] + Wk[(int64_t)(o + bs) * L + ki];
+      }
     }
-    dw[i] = re * inv;
-    dw[per + i] = im * inv;
+    re[i][threadIdx.x] = r; im[i][threadIdx.x] = m;
   }
-  if (i < (int64_t)nb * bs) {
-    const int o = (int)(i % bs), kap = (int)(i / bs);
-    db[i] = (float)(dbc[(int64_t)kap * 2 * bs + o] * (double)inv);
-    db[(int64_t)nb * bs + i] = (float)(dbc[(int64_t)kap * 2 * bs + bs + o] * (double)inv);
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ki = k0 + i, o = o0 + threadIdx.x;
+    if (o < bs && ki < bs) {
+      const int64_t d = ((int64_t)kap * bs + ki) * bs + o;
+      dw[d] = re[threadIdx.x][i] * inv;
+      dw[per + d] = im[threadIdx.x][i] * inv;
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int o = threadIdx.y * 32 + threadIdx.x; o < bs; o += 32 * blockDim.y) {
+      db[(int64_t)kap * bs + o] = (float)(dbc[(int64_t)kap * 2 * bs + o] * (double)inv);
+      db[(int64_t)nb * bs + (int64_t)kap * bs + o] = (float)(dbc[(int64_t)kap * 2 * bs + bs + o] * (double)inv);
+    }
   }
 }
 
@@ -769,6 +793,72 @@ __global__ void __launch_bounds__(256) split_scaled_kernel(const float* __restri
   }
 }
 
+// AFNO2D w[2,nb,bs,bs] ("bio": in,out), b[2,nb,bs] -> the real block form of pack_afno_kernel (norm_misc.cu) stored
+// directly as split fp16: Wc16[kap][n][hi 2bs | lo 2bs], bc[nb, 2bs] fp32
+__global__ void pack_afno16_kernel(const float* __restrict__ w, const float* __restrict__ b, int nb, int bs,
+                                   __half* __restrict__ Wc16, float* __restrict__ bc) {
+  const int64_t total = (int64_t)nb * 4 * bs * bs;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const int k = (int)(i % (2 * bs));
+    const int64_t row = i / (2 * bs);                       // kap * 2bs + nn
+    const int nn = (int)(row % (2 * bs));
+    const int kap = (int)(row / (2 * bs));
+    const int ki = k % bs, no = nn % bs;
+    const float wr = w[(((int64_t)0 * nb + kap) * bs + ki) * bs + no];
+    const float wi = w[(((int64_t)1 * nb + kap) * bs + ki) * bs + no];
+    float v;
+    if (nn < bs) v = (k < bs) ? wr : -wi;
+    else         v = (k < bs) ? wi : wr;
+    __half hi, lo;
+    hl_split(v, hi, lo);
+    Wc16[row * 4 * bs + k] = hi;
+    Wc16[row * 4 * bs + 2 * bs + k] = lo;
+  }
+  if (i < (int64_t)nb * 2 * bs) {
+    const int nn = (int)(i % (2 * bs));
+    const int kap = (int)(i / (2 * bs));
+    bc[i] = b[(((int64_t)(nn / bs)) * nb + kap) * bs + nn % bs];
+  }
+}
+// pack_patch (norm_misc.cu) with the coordinate sums separated: one block per conv0 output channel m
+//   rowbias0[(p,q,t), m] = b0[m] + sum_u gx[pP+u] sx[u] + sum_v gy[qP+v] sy[v] + gt[t] st,  sx[u] = sum_v wx[u,v], ...
+__global__ void __launch_bounds__(256) pack_patch_fast_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
+                                                              const float* __restrict__ gx, const float* __restrict__ gy,
+                                                              const float* __restrict__ gt, int mid, int C, int P, int h, int w,
+                                                              int T, float* __restrict__ W0p, float* __restrict__ rowbias0) {
+  __shared__ double sx[32], sy[32], st_;
+  __shared__ double ax[64], ay[64];                      // per latent row p / column q sums (h, w <= 64)
+  const int m = blockIdx.x, tid = threadIdx.x, PP = P * P, K = PP * C;
+  for (int k = tid; k < K; k += blockDim.x) {
+    const int c = k % C, uv = k / C;
+    W0p[(int64_t)m * K + k] = w0[((int64_t)m * (C + 3) + c) * PP + uv];
+  }
+  const float* wx = w0 + ((int64_t)m * (C + 3) + C) * PP;
+  const float* wy = wx + PP;
+  const float* wt = wy + PP;
+  if (tid < P) {
+    double a = 0.0, bsum = 0.0;
+    for (int v = 0; v < P; ++v) { a += (double)wx[tid * P + v]; bsum += (double)wy[v * P + tid]; }
+    sx[tid] = a; sy[tid] = bsum;
+  }
+  if (tid == 0) {
+    double a = 0.0;
+    for (int i = 0; i < PP; ++i) a += (double)wt[i];
+    st_ = a;
+  }
+  __syncthreads();
+  if (tid < h) { double a = 0.0; for (int u = 0; u < P; ++u) a += (double)gx[tid * P + u] * sx[u]; ax[tid] = a; }
+  if (tid >= 64 && tid - 64 < w) { const int q = tid - 64; double a = 0.0; for (int v = 0; v < P; ++v) a += (double)gy[q * P + v] * sy[v]; ay[q] = a; }
+  __syncthreads();
+  const double bias = (double)b0[m];
+  for (int i = tid; i < h * w * T; i += blockDim.x) {
+    const int t = i % T; const int pq = i / T; const int q = pq % w, p = pq / w;
+    // same summation order per term as the reference fold is not required: every term is accumulated in double
+    rowbias0[(int64_t)i * mid + m] = (float)(bias + ax[p] + ay[q] + (double)gt[t] * st_);
+  }
+}
+
 inline unsigned blocks_for(int64_t total, int per) { return (unsigned)ceil_div(total, per); }
 
 }  // namespace
@@ -798,12 +888,13 @@ int tk_gn_bwd(const float* dy, const float* x, const double* stats, const float*
               int groups, float eps, const float* inv_scale, float* scratch, float* dx, __half* dx16, float* dgamma,
               float* dbeta, double* colsum, cudaStream_t st) {
   DPOT_REQUIRE(E % groups == 0 && (E / groups) % 4 == 0 && E % 2 == 0, DPOT_E_BADARG, "gn_bwd: group size must be a multiple of 4");
-  float* A1 = scratch; float* A2 = A1 + (int64_t)B * E; float* coefA = A2 + (int64_t)B * E; float* coefBC = coefA + (int64_t)B * E;
-  gn_bwd_reduce2_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B), 256, 0, st>>>(dy, x, n, E, A1, A2);
+  float* A1 = scratch; float* A2 = A1 + 2 * (int64_t)B * E; float* coefA = A2 + 2 * (int64_t)B * E; float* coefBC = coefA + (int64_t)B * E;
+  DPOT_REQUIRE(n % 2 == 0 && B * groups * 2 * sizeof(float) <= 40 * 1024, DPOT_E_BADARG, "gn_bwd: odd n or too many (sample, group) pairs");
+  gn_bwd_reduce2_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B, 2), 256, 0, st>>>(dy, x, n, E, B, A1, A2);
   DPOT_LAUNCH_CHECK("gn_bwd_reduce2_kernel");
   const int gblocks = (int)ceil_div(B * groups, 4);
-  gn_bwd_group2_kernel<<<(unsigned)(gblocks + ceil_div(E, 128)), 128, 0, st>>>(A1, A2, stats, gamma, B, n, E, groups, eps, gblocks,
-                                                                              inv_scale, coefA, coefBC, dgamma, dbeta);
+  gn_bwd_group2_kernel<<<(unsigned)(gblocks + ceil_div(E, 128)), 128, sizeof(float) * 2 * B * groups, st>>>(
+      A1, A2, stats, gamma, B, n, E, groups, eps, gblocks, inv_scale, coefA, coefBC, dgamma, dbeta);
   DPOT_LAUNCH_CHECK("gn_bwd_group2_kernel");
   DPOT_REQUIRE(n % GNA_ROWS == 0, DPOT_E_BADARG, "gn_bwd: latent cells per sample must be a multiple of %d", GNA_ROWS);
   const int64_t rows = (int64_t)B * n;
@@ -841,8 +932,8 @@ int tk_scale_copy(const float* src, int64_t count, const float* inv_scale, float
 
 int tk_unpack_afno_grad(const float* dWc, int nslab, int64_t stride, const double* dbc, int nb, int bs, const float* inv_scale,
                         float* dw, float* db, cudaStream_t st) {
-  const int64_t per = (int64_t)nb * bs * bs;
-  unpack_afno_grad2_kernel<<<blocks_for(per, 256), 256, 0, st>>>(dWc, nslab, stride, dbc, nb, bs, inv_scale, dw, db);
+  unpack_afno_grad2_kernel<<<dim3((unsigned)ceil_div(bs, 32), (unsigned)ceil_div(bs, 32), (unsigned)nb), dim3(32, 16), 0, st>>>(
+      dWc, nslab, stride, dbc, nb, bs, inv_scale, dw, db);
   DPOT_LAUNCH_CHECK("unpack_afno_grad2_kernel");
   return 0;
 }
@@ -925,6 +1016,19 @@ int tk_unpack_patch_grad(const float* dW0p, int nslab, const double* drb, const 
   return 0;
 }
 
+int tk_pack_afno16(const float* w, const float* b, int nb, int bs, __half* Wc16, float* bc, cudaStream_t st) {
+  const int64_t total = (int64_t)nb * 4 * bs * bs;
+  pack_afno16_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, b, nb, bs, Wc16, bc);
+  DPOT_LAUNCH_CHECK("pack_afno16_kernel");
+  return 0;
+}
+int tk_pack_patch(const float* w0, const float* b0, const float* gx, const float* gy, const float* gt, int mid, int C, int P, int h,
+                  int w, int T, float* W0p, float* rowbias0, cudaStream_t st) {
+  if (P > 32 || h > 64 || w > 64) return dpot_pack_patch(w0, b0, gx, gy, gt, mid, C, P, h, w, T, W0p, rowbias0, st);
+  pack_patch_fast_kernel<<<(unsigned)mid, 256, 0, st>>>(w0, b0, gx, gy, gt, mid, C, P, h, w, T, W0p, rowbias0);
+  DPOT_LAUNCH_CHECK("pack_patch_fast_kernel");
+  return 0;
+}
 int tk_tagg_scale16(const float* w, const float* temb, int T, int E, __half* wts16, __half* Wsum16, cudaStream_t st) {
   DPOT_REQUIRE(E % 8 == 0, DPOT_E_BADARG, "tagg_scale16: E %% 8");
   const int64_t rows = (int64_t)T * E, total = rows * (E / 8);

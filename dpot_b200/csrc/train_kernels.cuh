@@ -12,7 +12,7 @@ int tk_grad_scale(const float* dy, int64_t n, unsigned* bits, float* scale, cuda
 int tk_colsum(const void* X, bool f16, int64_t ld, int64_t lo_off, int M, int N, double* out, cudaStream_t st);
 // GroupNorm backward (torch.nn.GroupNorm(8, E) on token-major x[B*n, E]); stats = forward (sum, sumsq) doubles.
 //   dx = rstd * (gamma*dy - mean_g(gamma*dy) - xhat * mean_g(gamma*dy*xhat)) (+ add);  dx16 != NULL: also stored split.
-//   dgamma / dbeta (written, scaled by inv_scale[0] when given).  scratch: 3*B*E + 2*B*groups floats.
+//   dgamma / dbeta (written, scaled by inv_scale[0] when given).  scratch: 5*B*E + 2*B*groups floats.
 //   colsum (may be NULL): double [E], colsum[c] += sum over rows of dx (the bias gradient of the layer below).
 int tk_gn_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* add, int B, int n, int E,
               int groups, float eps, const float* inv_scale, float* scratch, float* dx, __half* dx16, float* dgamma,
@@ -47,6 +47,11 @@ int tk_patch_bwd(const float* gz, const float* x, const float* W0p, int B, int X
 // transpose of pack_patch: dW0p (nslab float partials [mid, (u,v,c)]), drb (double [(p,q), Kp] = sum_b gz) -> dpe0_w[mid, C+3, P, P], dpe0_b[mid]
 int tk_unpack_patch_grad(const float* dW0p, int nslab, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
                          int P, int h, int w, int T, int Kp, const float* inv_scale, float* dw0, float* db0, cudaStream_t st);
+// weight packing of the per-step prepare: AFNO real block form written directly as split fp16; PatchEmbed conv0 im2col
+// weight + coordinate-channel bias table with the coordinate sums separated (same results as dpot_pack_afno / dpot_pack_patch)
+int tk_pack_afno16(const float* w, const float* b, int nb, int bs, __half* Wc16, float* bc, cudaStream_t st);
+int tk_pack_patch(const float* w0, const float* b0, const float* gx, const float* gy, const float* gt, int mid, int C, int P, int h,
+                  int w, int T, float* W0p, float* rowbias0, cudaStream_t st);
 // time-aggregation fold helpers (models/dpot.py:228-232 folded with PatchEmbed conv 1x1 + pos_embed)
 //   wts16[(t,i), j] = split(w[t,i,j]*temb[t,i]) rows of [hi E | lo E];  Wsum16[i, j] = split(sum_t temb[t,i] w[t,i,j])
 int tk_tagg_scale16(const float* w, const float* temb, int T, int E, __half* wts16, __half* Wsum16, cudaStream_t st);

@@ -118,7 +118,7 @@ ScratchL scratch_layout(const Dims& d, int B) {
     L.pslabs = a.take((int64_t)2 * 160 * d.mid * d.K0);         // per-block partials of the PatchEmbed weight gradient (<= 2 per SM)
     L.dtemb = a.take((int64_t)d.T * E);
     L.tparts = a.take(tk_tail_bwd_part_floats(3 * 160));
-    L.gn = a.take(3 * (int64_t)B * E + 2 * (int64_t)B * GROUPS);
+    L.gn = a.take(5 * (int64_t)B * E + 2 * (int64_t)B * GROUPS);
     L.cls = a.take(8 * (int64_t)B * E + 3 * E * E + (int64_t)d.ncls * E + 4096);
     L.scale = a.take(64);
     // doubles
@@ -207,8 +207,8 @@ extern "C" int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm
   const PrepL PL = prep_layout(d);
   const ScratchL SL = scratch_layout(d, 1);
   const int E = d.E;
-  DPOT_CALL(dpot_pack_patch(prm->pe0_w, prm->pe0_b, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h, d.T,
-                            packed + L.W0p, packed + L.rowbias0, stream));
+  DPOT_CALL(tk_pack_patch(prm->pe0_w, prm->pe0_b, prm->grid_x, prm->grid_y, prm->grid_t, d.mid, d.C, d.P, d.h, d.h, d.T,
+                          packed + L.W0p, packed + L.rowbias0, st));
   // fold conv 1x1 + pos_embed + time aggregation with the contraction engine (the double-precision fold kernels of the
   // inference packer take ~1 ms: fine once per checkpoint, not once per optimizer step)
   float* wts16 = wprep + PL.wts16; float* Wsum16 = wprep + PL.Wsum16; float* bp16 = wprep + PL.bp16;
@@ -238,10 +238,8 @@ extern "C" int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm
   for (int i = 0; i < d.depth; ++i) {
     float* base = packed + L.blocks + (int64_t)i * L.blk_stride;
     const dpot_block_params& b = prm->blocks[i];
-    DPOT_CALL(dpot_pack_afno(b.w1, b.b1, d.nb, d.bs, base + L.Wc1, base + L.bc1, stream));
-    DPOT_CALL(dpot_pack_afno(b.w2, b.b2, d.nb, d.bs, base + L.Wc2, base + L.bc2, stream));
-    DPOT_CALL(dpot_split_f16(base + L.Wc1, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc1_16, 2 * kb, kb, stream));
-    DPOT_CALL(dpot_split_f16(base + L.Wc2, kb, (int64_t)d.nb * kb, (int)kb, nullptr, nullptr, 0, base + L.Wc2_16, 2 * kb, kb, stream));
+    DPOT_CALL(tk_pack_afno16(b.w1, b.b1, d.nb, d.bs, reinterpret_cast<__half*>(base + L.Wc1_16), base + L.bc1, st));
+    DPOT_CALL(tk_pack_afno16(b.w2, b.b2, d.nb, d.bs, reinterpret_cast<__half*>(base + L.Wc2_16), base + L.bc2, st));
     DPOT_CALL(dpot_split_f16(b.fc1_w, E, d.hid, E, nullptr, nullptr, 0, base + L.fc1_16, 2 * E, E, stream));
     DPOT_CALL(dpot_split_f16(b.fc2_w, d.hid, E, d.hid, nullptr, nullptr, 0, base + L.fc2_16, 2 * d.hid, d.hid, stream));
   }
