@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDe
   const bool live = n0 < p.N;
   const float* __restrict__ wrow = p.W + (int64_t)(live ? n0 : 0) * p.ldw;
   const bool vec = (p.ldw % 4 == 0) && (reinterpret_cast<uintptr_t>(p.W) % 16 == 0);
+  const bool fastA = !p.a_scale && p.a_mode == DPOT_A_PLAIN && p.a_fmt == DPOT_FMT_F32 && (p.lda % 4 == 0) &&
+                     (reinterpret_cast<uintptr_t>(p.A) % 16 == 0);
   auto load_w = [&](int kc, float4 (&w)[SK_V]) {
 #pragma unroll
     for (int v = 0; v < SK_V; ++v) {
@@ -209,9 +211,18 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDe
     for (int kc = 0; kc < p.K; kc += SK_KC) {
       if (kc + SK_KC < p.K) load_w(kc + SK_KC, wn);          // next slice in flight while this one is consumed
       __syncthreads();
-      for (int e = threadIdx.x; e < MT * SK_KC; e += SK_WARPS * 32) {
-        const int i = e / SK_KC, k = e - i * SK_KC;
-        A_s[e] = (mb + i < p.M && kc + k < p.K) ? gemm_load_a(p, p.A, mb + i, kc + k) : 0.f;
+      if (fastA && kc + SK_KC <= p.K) {       // plain contiguous rows: 16-byte copies (the staging was most of this kernel's time)
+        for (int e = threadIdx.x; e < MT * (SK_KC / 4); e += SK_WARPS * 32) {
+          const int i = e / (SK_KC / 4), k4 = e - i * (SK_KC / 4);
+          const float4 v = (mb + i < p.M) ? __ldg(reinterpret_cast<const float4*>(p.A + (int64_t)(mb + i) * p.lda + kc) + k4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(A_s)[e] = v;
+        }
+      } else {
+        for (int e = threadIdx.x; e < MT * SK_KC; e += SK_WARPS * 32) {
+          const int i = e / SK_KC, k = e - i * SK_KC;
+          A_s[e] = (mb + i < p.M && kc + k < p.K) ? gemm_load_a(p, p.A, mb + i, kc + k) : 0.f;
+        }
       }
       __syncthreads();
 #pragma unroll
