@@ -261,7 +261,24 @@ def train_leg(dev, world, rank, timed_fn):
     # the optimizer step alone (gradients in place from the last step)
     for _ in range(2):
         clip_grad_norm_(m.parameters(), 1e4, optimizer=opt); opt.step()
-    ms_opt = timed_fn(lambda s: (clip_grad_norm_(m.parameters(), 1e4, optimizer=opt), opt.step()), 10) / 10
+    # the optimizer kernels alone: captured once, replayed (the eager loop below is bound by ~110 python-side tensor visits
+    # per step, which a real step hides behind backward's kernels)
+    ms_opt_eager = timed_fn(lambda s: (clip_grad_norm_(m.parameters(), 1e4, optimizer=opt), opt.step()), 10) / 10
+    ms_opt = ms_opt_eager
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                clip_grad_norm_(m.parameters(), 1e4, optimizer=opt)
+                opt.step()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(2):
+            gr.replay()
+        ms_opt = timed_fn(lambda s: gr.replay(), 20) / 20
+    except Exception as e:                                   # capture not possible: keep the eager number
+        sys.stderr.write(f"bench.py: optimizer graph capture failed ({e}); reporting the eager loop\n")
     if ex is not None:
         ex.close()
     fl = zoo.forward_flops(cfg)
@@ -276,7 +293,7 @@ def train_leg(dev, world, rank, timed_fn):
             "executed_tflops_per_gpu": exec_gf * fs / world / 1e3,
             "frac_executed_of_fp32_faithful_sustained_peak": exec_gf * fs / world / 1e3 / (pk["bf16_sus"] / 3.0),
             "optimizer": {"kernel": "gradient norm + clip folded into the fused multi-tensor Adam", "params": nparam,
-                          "ms": ms_opt, "algorithmic_bytes": 28 * nparam,
+                          "ms": ms_opt, "ms_eager_python_loop": ms_opt_eager, "algorithmic_bytes": 28 * nparam,
                           "achieved_GBs": 28 * nparam / (ms_opt * 1e-3) / 1e9, "frac_of_hbm_peak": 28 * nparam / (ms_opt * 1e-3) / 1e9 / pk["hbm"],
                           "note": "p, m, v read + written, g read twice (norm, update) = 28 B / parameter"},
             "note": "executed FLOPs = 3 x the forward's (every contraction has a data-gradient and a weight-gradient twin)"}
