@@ -108,6 +108,7 @@ SIGNATURES = {
     "dpot_tc16_set_ws": (None, [_i32]),
     "dpot_set_pdl": (None, [_i32]),
     "dpot_set_cls_overlap": (None, [_i32]),
+    "dpot_set_sm_budget": (C.c_int, [_i32]),
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_gn_finalize": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p]),
     "dpot_afno_fft_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p]),

@@ -8,6 +8,7 @@ namespace dpot {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 int g_pdl = 0;
+int g_sm_budget = 0;     // dpot_set_sm_budget: > 0 caps the SM count the persistent kernels size their grids for
 int sm_count_cur() {
   static int cache[64] = {0};
   const int d = cur_dev();
@@ -16,7 +17,9 @@ int sm_count_cur() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
     cache[d] = n;
   }
-  return cache[d];
+  int n = cache[d];
+  if (g_sm_budget > 0 && g_sm_budget < n) n = g_sm_budget & ~1;    // even: CTA pairs
+  return n < 2 ? 2 : n;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -48,3 +51,12 @@ extern "C" int dpot_device_supported(void) {
 }
 
 extern "C" void dpot_set_pdl(int32_t on) { dpot::g_pdl = on ? 1 : 0; }
+
+// SM budget of the persistent kernels (contractions, fused mixer, tail / PatchEmbed backward): n > 0 makes them size
+// their grids for n SMs instead of the whole device, leaving the rest to kernels that run CONCURRENTLY on other streams
+// (NCCL's all-reduce during backward).  0 = the whole device (default).  Returns the previous value; n < 0 only queries.
+extern "C" int dpot_set_sm_budget(int32_t n) {
+  const int prev = dpot::g_sm_budget;
+  if (n >= 0) dpot::g_sm_budget = n;
+  return prev;
+}

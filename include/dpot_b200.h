@@ -464,6 +464,12 @@ DPOT_API int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm, f
 DPOT_API int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                  int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
 
+/* SM budget of the persistent kernels (contractions, fused mixer, tail / PatchEmbed backward): n > 0 sizes their grids
+   for n SMs instead of the whole device, leaving the rest to kernels that run CONCURRENTLY on other streams (NCCL's
+   all-reduce during backward: a persistent grid with a static tile partition is delayed by a whole share of tiles for
+   every SM it has to share).  0 = the whole device (default).  Returns the previous value; n < 0 only queries. */
+DPOT_API int dpot_set_sm_budget(int32_t n);
+
 /* 1: the classification head of dpot_forward* / dpot_rollout_step runs on a library-owned side stream (one per device)
    concurrently with the output head, joined before the call's work on `stream` ends; 0 (default): everything on `stream`.
    Measured slower on B200 (the side stream takes SMs from the persistent contraction kernels); kept as a knob. */

@@ -25,6 +25,9 @@ from dpot_b200.parallel import FusedGradExchange, GradArena, OverlappedGradArena
 from dpot_b200.train import ar_train_step
 from dpot_b200.utils.optimizer import Adam
 
+from dpot_b200 import _lib
+QUICK = os.environ.get("DDP_QUICK", "0") == "1"          # only the no-exchange / sequential / overlapped step times
+BUDGET = int(os.environ.get("DPOT_SM_BUDGET", "0"))       # SM budget of the persistent kernels while overlapping
 name = sys.argv[1] if len(sys.argv) > 1 else "S"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 T_ar = int(sys.argv[3]) if len(sys.argv) > 3 else 1
@@ -70,20 +73,24 @@ def step_with(arena):
 out["fused_training_step"] = bool(model._train_eng is not None and model._train_eng.supported) if hasattr(model, "_train_eng") else False
 out["ms_step_no_exchange"] = timed(lambda: step_with(None))
 out["fused_training_step"] = bool(model._train_eng is not None and model._train_eng.supported)
-flat = GradArena(model.parameters())
-out["ms_step_flat_allreduce"] = timed(lambda: step_with(flat))
+if not QUICK:
+    flat = GradArena(model.parameters())
+    out["ms_step_flat_allreduce"] = timed(lambda: step_with(flat))
 if out["fused_training_step"]:
     seq = FusedGradExchange(model, overlap=False)
     out["ms_step_arena_sequential"] = timed(lambda: step_with(seq))
     seq.close()
     over = FusedGradExchange(model, overlap=True)
+    out["sm_budget"], out["nccl_max_ctas"] = BUDGET, os.environ.get("NCCL_MAX_CTAS", "")
+    _lib.load().dpot_set_sm_budget(BUDGET)
     out["messages"] = len(over.msgs)
 else:
     over = OverlappedGradArena(model.parameters(), bucket_mb=32.0)
 out["ms_step_overlapped"] = timed(lambda: step_with(over))
+_lib.load().dpot_set_sm_budget(0)
 # the exchange alone
 buf = over.buf if over.buf is not None else torch.zeros(nparam, device=dev)
-if world > 1:
+if world > 1 and not QUICK:
     ms_ar = timed(lambda: dist.all_reduce(buf, op=dist.ReduceOp.AVG), n=20, warm=5)
     nbytes = buf.numel() * 4
     out["allreduce_ms"] = ms_ar
@@ -94,7 +101,7 @@ over.close()
 out["field_steps_per_s_overlapped"] = world * B * T_ar / (out["ms_step_overlapped"] * 1e-3)
 
 # ---- gradient equality: N ranks x B samples averaged == one rank on the concatenated batch, divided by N
-if world > 1:
+if world > 1 and not QUICK:
     Bc = 2
     model2 = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).train()
     gx = torch.Generator(device="cpu").manual_seed(7)
