@@ -91,6 +91,8 @@ struct AfArgs {
   int B, E, nb, act, groups;
   float* dbg;              // test hook: units x (X operand | O1 operand) images, 2 * AF_OPER bytes per unit, or nullptr
   long long* trace;        // profiling hook: clock64() of CTA 0 / thread 0 at the phase boundaries, 8 per unit, or nullptr
+  // GroupNorm-2 applied in the kernel (the unit owns whole groups): n2 = split fp16 of GN2(f), rows [hi E | lo E]; or nullptr
+  __half* n2; const float* gamma2; const float* beta2; float eps2;
 };
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
@@ -460,12 +462,50 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
             s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
           }
         }
+        if (P.stats2 || P.n2) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
         if (P.stats2) {        // the warp's 32 channels lie in one group (host guarantees (E / groups) % 32 == 0)
-          s1 = warp_sum(s1); s2 = warp_sum(s2);
           if (lane == 0) {
             double* dst = P.stats2 + ((int64_t)b * P.groups + (kap * AF_BS + q4 * 32) / (E / P.groups)) * 2;
             atomicAdd(dst, (double)s1);
             atomicAdd(dst + 1, (double)s2);
+          }
+        }
+        if (P.n2) {
+          // GroupNorm-2 + fp16 split of the channel-MLP input in the same launch: a unit covers whole groups (group size
+          // 32 / 64 / 128 channels of its 128), so its statistics are complete once the 16 warps have met; every thread
+          // then re-reads the f values it has just written (its own stores: L1 / L2 hits) and writes them normalised.
+          float* red = reinterpret_cast<float*>(S + 131072);       // the 16 KB of the operand tile beyond Z
+          if (lane == 0) { red[2 * warp] = s1; red[2 * warp + 1] = s2; }
+          named_bar_sync(1, AF_CTHREADS);
+          const int gs = E / P.groups, qpg = gs >> 5, q0 = (q4 / qpg) * qpg;
+          double t1 = 0.0, t2 = 0.0;
+          for (int qq = q0; qq < q0 + qpg; ++qq)
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) { t1 += (double)red[2 * (ss * 4 + qq)]; t2 += (double)red[2 * (ss * 4 + qq) + 1]; }
+          const double inv_cnt = 1.0 / ((double)gs * 256.0);
+          const double mean = t1 * inv_cnt;
+          const double var = fma(-mean, mean, t2 * inv_cnt);
+          const float vv = fmaxf((float)var, 0.f) + P.eps2;
+          float rstd = rsqrtf(vv);
+          rstd = rstd * fmaf(-0.5f * vv * rstd, rstd, 1.5f);
+          const int ch = kap * AF_BS + j;
+          const float sc2 = rstd * __ldg(P.gamma2 + ch), sh2 = fmaf(-(float)mean, sc2, __ldg(P.beta2 + ch));
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t) {
+            const int pr = sl + 4 * t;
+            const float* fp = f_u + (int64_t)(2 * pr) * 16 * E + j;
+            __half* np_ = P.n2 + ((int64_t)b * 256 + (2 * pr) * 16) * (2 * (int64_t)E) + ch;
+            float v0[16], v1[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { v0[q] = fp[(int64_t)q * E]; v1[q] = fp[(int64_t)(16 + q) * E]; }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              __half hi, lo;
+              hl_split(fmaf(v0[q], sc2, sh2), hi, lo);
+              np_[(int64_t)q * 2 * E] = hi; np_[(int64_t)q * 2 * E + E] = lo;
+              hl_split(fmaf(v1[q], sc2, sh2), hi, lo);
+              np_[(int64_t)(16 + q) * 2 * E] = hi; np_[(int64_t)(16 + q) * 2 * E + E] = lo;
+            }
           }
         }
       }
@@ -575,16 +615,30 @@ extern "C" int dpot_afno_fused_pack(const float* w1, const float* b1, const floa
   return 0;
 }
 
+extern "C" int dpot_afno_fused_gn2(const float* lat, const double* stats1, const float* gamma1, const float* beta1,
+                                   int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
+                                   int32_t act, float* f, double* stats2, float* dbg, void* n2_16, const float* gamma2,
+                                   const float* beta2, float eps2, void* stream);
 extern "C" int dpot_afno_fused(const float* lat, const double* stats1, const float* gamma1, const float* beta1,
                                int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
                                int32_t act, float* f, double* stats2, float* dbg, void* stream) {
+  return dpot_afno_fused_gn2(lat, stats1, gamma1, beta1, groups, eps, B, h, E, nb, packed, act, f, stats2, dbg, nullptr, nullptr,
+                             nullptr, 0.f, stream);
+}
+extern "C" int dpot_afno_fused_gn2(const float* lat, const double* stats1, const float* gamma1, const float* beta1,
+                                   int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
+                                   int32_t act, float* f, double* stats2, float* dbg, void* n2_16, const float* gamma2,
+                                   const float* beta2, float eps2, void* stream) {
   DPOT_REQUIRE(lat && stats1 && gamma1 && beta1 && packed && f, DPOT_E_BADARG, "dpot_afno_fused: null pointer");
   DPOT_REQUIRE(lat != f, DPOT_E_BADARG, "dpot_afno_fused: in-place operation is not supported (the skip term re-reads the input)");
   DPOT_REQUIRE(B > 0 && dpot_afno_fused_supported(h, E, nb, h, h / 2 + 1, groups), DPOT_E_UNSUPPORTED,
                "dpot_afno_fused: geometry h=%d E=%d nb=%d groups=%d is not served by the fused mixer", h, E, nb, groups);
   DPOT_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 16 == 0, DPOT_E_ALIGN, "dpot_afno_fused: packed must be 16-byte aligned");
+  DPOT_REQUIRE(!n2_16 || (gamma2 && beta2 && AF_BS % (E / groups) == 0 && (E / groups) % 32 == 0), DPOT_E_BADARG,
+               "dpot_afno_fused_gn2: GroupNorm-2 in the kernel needs gamma2 / beta2 and a group size of 32, 64 or 128 channels");
   AfArgs P;
   P.lat = lat; P.f = f; P.packed = packed; P.stats2 = stats2; P.dbg = dbg; P.trace = g_fused_trace;
+  P.n2 = reinterpret_cast<__half*>(n2_16); P.gamma2 = gamma2; P.beta2 = beta2; P.eps2 = eps2;
   P.gn = make_gn_ref(stats1, gamma1, beta1, groups, eps, E, (int64_t)h * h);
   P.B = B; P.E = E; P.nb = nb; P.act = act; P.groups = groups;
   const int units = B * nb, sms = sm_count_cur();

@@ -57,6 +57,9 @@ static int run_tail(const float* Y, const float* w2, const float* b2, const dpot
 // the last latent, like the output head: it runs on a library-owned side stream between a fork event (after the last
 // block) and a join event (end of the forward) -- also under stream capture, where the events become graph edges.
 // One side stream per device: concurrent forwards from SEVERAL host threads on one device are not supported with it.
+int g_fused_gn2 = 0;     // dpot_afno_set_fused_gn2: GroupNorm-2 + split inside the fused mixer.  Measured neutral (the in-kernel
+                         // pass costs the 11 us the separate 12 us kernel took: it sits on the unit's serial path) -> off
+constexpr int AF_UNIT_CH = 128;
 int g_cls_overlap = 0;   // measured (r02t): the side stream takes SMs from the persistent contraction kernels of the output head: -3 %
 struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 static SideStream* side_stream() {
@@ -103,12 +106,20 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
     const dpot_block_params& bp = prm->blocks[i];
     const float* pk = packed + PL.blocks + (int64_t)i * PL.blk_stride;
     // GroupNorm by reference: the consumers derive their affines from the raw statistics (no finalize launches)
+    bool fused_gn2 = false;
     const bool gnref = (d.E / groups) % 8 == 0 && (reinterpret_cast<uintptr_t>(bp.norm2_w) | reinterpret_cast<uintptr_t>(bp.norm2_b)) % 16 == 0;
     if (fused_geometry(d) && dpot_afno_fused_supported(d.h, d.E, d.nb, d.km1, d.km2, groups)) {
-      // the whole mixer in one launch: spectrum and hidden layer stay on chip
-      DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
-      DPOT_CALL(dpot_afno_fused(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, pk + PL.Wfus, act,
-                                ws + WL.f, st2, nullptr, stream));
+      // the whole mixer in one launch: spectrum and hidden layer stay on chip; with whole GroupNorm groups inside a work
+      // unit the kernel also applies GroupNorm-2 and writes the channel MLP's split-fp16 operand itself
+      fused_gn2 = gnref && g_fused_gn2 && AF_UNIT_CH % (d.E / groups) == 0 && (d.E / groups) % 32 == 0;
+      if (fused_gn2) {
+        DPOT_CALL(dpot_afno_fused_gn2(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, pk + PL.Wfus, act,
+                                      ws + WL.f, nullptr, nullptr, ws + WL.n2, bp.norm2_w, bp.norm2_b, 1e-5f, stream));
+      } else {
+        DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
+        DPOT_CALL(dpot_afno_fused(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, pk + PL.Wfus, act,
+                                  ws + WL.f, st2, nullptr, stream));
+      }
     } else {
     DPOT_CALL(dpot_afno_fft_fwd16_gn(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, d.km1, d.km2,
                                      ws + WL.S, stream));
@@ -127,7 +138,8 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
                                    ws + WL.f, st2, stream));
     }
     // GroupNorm-2 apply fused with the fp16 split of the channel-MLP input
-    if (gnref) {
+    if (fused_gn2) {
+    } else if (gnref) {
       DPOT_CALL(dpot_split_f16_gn(ws + WL.f, d.E, Mt, d.E, st2, bp.norm2_w, bp.norm2_b, groups, 1e-5f, d.n, ws + WL.n2, 2 * d.E, d.E, stream));
     } else {
       DPOT_CALL(dpot_gn_finalize(st2, bp.norm2_w, bp.norm2_b, B, d.n, d.E, groups, 1e-5f, ws + WL.sc2, ws + WL.sh2, stream));
@@ -405,3 +417,4 @@ static int forward_impl(const dpot_config* cfg, const dpot_params* prm, const fl
 
 // 1: the classification head of dpot_forward* runs on a library-owned side stream, concurrently with the output head (default 0)
 extern "C" void dpot_set_cls_overlap(int32_t on) { dpot::g_cls_overlap = on ? 1 : 0; }
+extern "C" void dpot_afno_set_fused_gn2(int32_t on) { dpot::g_fused_gn2 = on ? 1 : 0; }

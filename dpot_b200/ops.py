@@ -360,7 +360,7 @@ def afno_fft_inv(O2, a, scale, shift, B, h, nb, km1, km2, want_stats=True, group
 
 @_on_device
 def afno_fused(lat: torch.Tensor, stats1: torch.Tensor, gamma1, beta1, w1, b1, w2, b2, B: int, h: int, act="gelu",
-               eps: float = 1e-5, groups: int = GROUPS, want_stats: bool = True, debug: bool = False):
+               eps: float = 1e-5, groups: int = GROUPS, want_stats: bool = True, debug: bool = False, gn2=None):
     """dpot_afno_fused: the whole AFNO2D mixer of one block (GroupNorm-1 by reference -> rfft2 -> complex block MLP ->
     irfft2 -> + skip) in one kernel.  lat[B*h*h, E]; stats1[B, groups, 2] (double); w1/w2 (2, nb, bs, bs), b1/b2 (2, nb, bs).
     Returns (f, stats2[, dbg]) -- dbg = per-unit images of the X and O1 operand tiles (test hook)."""
@@ -376,6 +376,12 @@ def afno_fused(lat: torch.Tensor, stats1: torch.Tensor, gamma1, beta1, w1, b1, w
     f = torch.empty_like(lat)
     stats2 = torch.zeros((B, groups, 2), device=lat.device, dtype=torch.float64) if want_stats else None
     dbg = torch.zeros((B * nb, 2 * 147456 // 4), device=lat.device, dtype=torch.float32) if debug else None
+    if gn2 is not None:      # (gamma2, beta2): GroupNorm-2 applied in the kernel -> also returns n2 as split fp16 [M, 2E]
+        n2 = torch.empty((lat.shape[0], 2 * E), device=lat.device, dtype=torch.float16)
+        check(lib.dpot_afno_fused_gn2(ptr(lat), ptr(stats1), ptr(gamma1), ptr(beta1), groups, eps, B, h, E, nb, ptr(packed),
+                                      act_id(act), ptr(f), ptr(stats2), ptr(dbg), ptr(n2), ptr(gn2[0]), ptr(gn2[1]), eps,
+                                      _stream()), "dpot_afno_fused_gn2")
+        return f, stats2, n2
     check(lib.dpot_afno_fused(ptr(lat), ptr(stats1), ptr(gamma1), ptr(beta1), groups, eps, B, h, E, nb, ptr(packed),
                               act_id(act), ptr(f), ptr(stats2), ptr(dbg), _stream()), "dpot_afno_fused")
     return (f, stats2, dbg) if debug else (f, stats2)

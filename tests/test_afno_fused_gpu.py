@@ -158,3 +158,38 @@ def test_fused_mixer_equals_four_kernel_path_in_the_model():
     assert O.rel_l2(outs[0][0], yo) < 1e-5 and O.rel_l2(outs[0][1], co) < 1e-5
     assert O.rel_l2(outs[0][0], outs[1][0]) < 2e-6
     assert outs[0][2] < outs[1][2]          # fewer launches: 4 kernels -> 1 per block
+
+
+@pytest.mark.parametrize("B,nb", [(3, 8), (2, 4)])
+def test_fused_mixer_applies_groupnorm2_itself(B, nb):
+    """dpot_afno_fused_gn2: the unit (sample, channel block) covers whole GroupNorm groups (128 channels at E = 1024,
+    64 at E = 512), so the kernel normalises f itself and writes the channel MLP's split-fp16 operand: against
+    GroupNorm-2 of the fp64 reference f, and against the separate pass it replaces."""
+    from dpot_b200 import ops
+    if not _supported(16, 128 * nb, nb):
+        pytest.skip("fused AFNO mixer not available on this device")
+    lat, w, gamma, beta = _make(B, nb, seed=21 + nb)
+    E = 128 * nb
+    rng = np.random.default_rng(5)
+    g2 = (1.0 + 0.1 * rng.standard_normal(E)).astype(np.float32)
+    b2 = (0.1 * rng.standard_normal(E)).astype(np.float32)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    lt = dev(lat)
+    st1 = ops.gn_stats(lt, B, 256)
+    g2d, b2d = dev(g2), dev(b2)
+    f, st2, n2 = ops.afno_fused(lt, st1, dev(gamma), dev(beta), dev(w["w1"]), dev(w["b1"]), dev(w["w2"]), dev(w["b2"]), B, 16,
+                                gn2=(g2d, b2d))
+    _, _, f_ref, _ = _reference(lat, w, gamma, beta, B, nb)
+    fr = f_ref.reshape(B, 256, 8, E // 8)
+    mean = fr.mean(axis=(1, 3), keepdims=True)
+    var = fr.var(axis=(1, 3), keepdims=True)
+    want = ((fr - mean) / np.sqrt(var + 1e-5)).reshape(B * 256, E) * g2.astype(np.float64) + b2.astype(np.float64)
+    got = ops.unsplit_f16(n2).cpu().numpy()
+    assert O.rel_l2(got, want) < 3e-6
+    # the statistics the kernel still reports, and the separate GroupNorm-2 + split pass on the same f
+    sep = torch.empty_like(n2)
+    from dpot_b200 import _lib
+    from dpot_b200._lib import check, ptr
+    check(_lib.load().dpot_split_f16_gn(ptr(f), E, B * 256, E, ptr(st2), ptr(g2d), ptr(b2d), 8, 1e-5, 256, ptr(sep),
+                                        2 * E, E, torch.cuda.current_stream().cuda_stream), "dpot_split_f16_gn")
+    assert O.rel_l2(got, ops.unsplit_f16(sep).cpu().numpy()) < 1e-6
