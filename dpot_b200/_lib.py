@@ -163,6 +163,7 @@ SIGNATURES = {
                                    _i32, _i32, _i32, _i32, _p]),
     "dpot_out_tail_tc_supported": (C.c_int, [_i32, _i32, _i32]),
     "dpot_afno_fft_fwd16w": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _p]),
+    "dpot_assemble_batch": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dpot_train_supported": (C.c_int, [C.POINTER(Config)]),
     "dpot_train_tape_floats": (C.c_int64, [C.POINTER(Config), _i32]),
     "dpot_train_scratch_floats": (C.c_int64, [C.POINTER(Config), _i32]),

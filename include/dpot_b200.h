@@ -498,6 +498,17 @@ DPOT_API int dpot_rollout_step(const dpot_config* cfg, const dpot_params* prm, c
                       int32_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GPU-side batch assembly of the data path, utils/griddataset.py:88-100 (pad_data: bilinear resize of every
+ * (t, c) plane to res x res, torch align_corners=False rule; channels padded with 1.0), :152-157 (training window: T_in
+ * frames from t_start[b], the next T_ar as targets) and the masks (:156 ones; mask_mode = 1: get_target_mask :102-116 with
+ * pred_channels).  raw[B, H0, W0, T0, C0] (device; same-shaped samples), t_start[B] (device int32, t_start + T_in + T_ar
+ * <= T0) -> xx[B, res, res, T_in, C], yy[B, res, res, T_ar, C], msk[B, res, res, 1, C] (may be NULL).
+ * ---------------------------------------------------------------------------------------- */
+DPOT_API int dpot_assemble_batch(const float* raw, const int32_t* t_start, int32_t B, int32_t H0, int32_t W0, int32_t T0,
+                                 int32_t C0, int32_t res, int32_t T_in, int32_t T_ar, int32_t C, int32_t mask_mode,
+                                 int32_t pred_channels, float* xx, float* yy, float* msk, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The training step: DPOTNet.forward with the activations backward needs kept on a caller-owned tape, and its
  * autograd -- what `im, cls = model(xx)` ... `loss.backward()` run in train_temporal.py:206,227 -- with every dense
  * contraction of forward and backward on the f16-split tcgen05 engine (data gradients read the weights in their

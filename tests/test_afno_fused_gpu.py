@@ -193,3 +193,33 @@ def test_fused_mixer_applies_groupnorm2_itself(B, nb):
     check(_lib.load().dpot_split_f16_gn(ptr(f), E, B * 256, E, ptr(st2), ptr(g2d), ptr(b2d), 8, 1e-5, 256, ptr(sep),
                                         2 * E, E, torch.cuda.current_stream().cuda_stream), "dpot_split_f16_gn")
     assert O.rel_l2(got, ops.unsplit_f16(sep).cpu().numpy()) < 1e-6
+
+
+def test_model_forward_with_groupnorm2_inside_the_mixer():
+    """dpot_afno_set_fused_gn2(1): the forward without the separate GroupNorm-2 + split launches gives the same output."""
+    from dpot_b200 import _lib
+    from dpot_b200.models.dpot import DPOTNet
+    lib = _lib.load()
+    if not _supported(16, 1024, 8):
+        pytest.skip("fused AFNO mixer not available on this device")
+    cfg = O.zoo_cfg("S", depth=2)
+    params = O.make_params(cfg, seed=0)
+    x = torch.from_numpy(O.make_input(cfg, 3, seed=1)).cuda()
+    outs = []
+    for on in (0, 1):
+        lib.dpot_afno_set_fused_gn2(on)
+        try:
+            m = DPOTNet(**cfg)
+            m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()})
+            m = m.cuda().eval()
+            l0 = lib.dpot_launch_count()
+            with torch.no_grad():
+                y, cls = m(x)
+            torch.cuda.synchronize()
+            outs.append((y.cpu().numpy(), cls.cpu().numpy(), lib.dpot_launch_count() - l0))
+        finally:
+            lib.dpot_afno_set_fused_gn2(0)
+    yo, _ = O.dpot_forward(x.cpu().numpy(), params, cfg)
+    assert O.rel_l2(outs[1][0], yo) < 1e-5
+    assert O.rel_l2(outs[0][0], outs[1][0]) < 2e-6 and O.rel_l2(outs[0][1], outs[1][1]) < 2e-6
+    assert outs[1][2] == outs[0][2] - cfg["depth"]          # one launch fewer per block
