@@ -229,3 +229,40 @@ def test_standalone_modules_are_differentiable():
         t = torch.linspace(0, 1, x.shape[-2], device=x.device, dtype=x.dtype).unsqueeze(-1)
         return torch.einsum('tij,...ti->...j', w, x * torch.cos(t @ gamma))
     check(ta, torch.randn(2, 8, 8, 5, 32, device=dev), ta_ref)
+
+
+def test_evaluation_loop_matches_the_reference_loop():
+    """dpot_b200.evaluate.evaluate_loaders against evaluate.py:182-222 restated verbatim with torch ops on the same model
+    (two loaders, different trajectory lengths / batch sizes, a masked channel, T_bundle = 1)."""
+    from dpot_b200.evaluate import evaluate_loaders
+    cfg = O.zoo_cfg("Ti", depth=2)
+    m = build_model(cfg, O.make_params(cfg, seed=0))
+    g = torch.Generator().manual_seed(5)
+    loaders, ntests = [], []
+    for B, T_ar, nb in ((3, 4, 2), (2, 3, 1)):
+        batches = []
+        for _ in range(nb):
+            xx = torch.randn((B, 128, 128, 10, 4), generator=g)
+            yy = torch.randn((B, 128, 128, T_ar, 4), generator=g)
+            msk = torch.ones((B, 128, 128, 1, 4))
+            msk[0, ..., 3] = 0.0
+            batches.append((xx, yy, msk, torch.zeros(B, 1, dtype=torch.long)))
+        loaders.append(batches)
+        ntests.append(B * nb)
+    fulls, steps = evaluate_loaders(m, loaders, ntests, T_bundle=1)
+    with torch.no_grad():                                   # evaluate.py:182-217
+        for lid, loader in enumerate(loaders):
+            test_l2_full, test_l2_step = 0, 0
+            for xx, yy, msk, _ in loader:
+                loss = 0
+                xx, yy, msk = xx.cuda(), yy.cuda(), msk.cuda()
+                for t in range(0, yy.shape[-2], 1):
+                    y = yy[..., t:t + 1, :]
+                    im, _ = m(xx)
+                    loss += _simple_lp_loss(im, y, msk)
+                    pred = im if t == 0 else torch.cat((pred, im), -2)
+                    xx = torch.cat((xx[..., 1:, :], im), dim=-2)
+                test_l2_step += loss.item()
+                test_l2_full += _simple_lp_loss(pred, yy, msk)
+            assert steps[lid] == pytest.approx(test_l2_step / ntests[lid] / (yy.shape[-2] / 1), rel=2e-5)
+            assert fulls[lid] == pytest.approx(float(test_l2_full) / ntests[lid], rel=2e-5)
