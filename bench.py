@@ -319,8 +319,6 @@ def run_ours(args):
     lib = _lib.load()
     if args.pdl:
         lib.dpot_set_pdl(1)
-    if args.ws_mode is not None:
-        lib.dpot_tc16_set_ws(args.ws_mode)
 
     cfg = zoo.zoo_cfg(MODEL)
     model = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).eval()
@@ -518,7 +516,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the rollout kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--ws-mode", type=int, default=None, help="dpot_tc16_set_ws: 0 = no weight-stationary plan, 2 = without early start")
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between the kernels of the forward chain")
     ap.add_argument("--engine", type=int, default=None, help="force GEMM engine: 1 = SIMT fp32, 2 = tcgen05")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block of the JSON line")

@@ -105,7 +105,6 @@ SIGNATURES = {
     "dpot_patch_embed_set_engine": (None, [_i32]),
     "dpot_tc16_set_debug": (None, [_i32]),
     "dpot_tc16_set_precision": (C.c_int, [_i32]),
-    "dpot_tc16_set_ws": (None, [_i32]),
     "dpot_set_pdl": (None, [_i32]),
     "dpot_set_cls_overlap": (None, [_i32]),
     "dpot_set_sm_budget": (C.c_int, [_i32]),

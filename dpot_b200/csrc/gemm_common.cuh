@@ -98,8 +98,6 @@ bool gemm_tc_fuses_stats(const GemmDev& p);   // can the TC epilogue accumulate 
 int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st);
 bool gemm_tc16_supports(const GemmDev& p, int batch);
 bool gemm_tc16_fuses_stats(const GemmDev& p);
-bool gemm_tc16_ws_takes(const GemmDev& p, int batch, int sms);       // weight-stationary short-K variant (gemm_tc16_ws.cu)
-int gemm_tc16_ws_launch(const GemmDev& p, int batch, int sms, cudaStream_t st);
 bool tc_device_ok();
 int tc_encode_map_f16(void* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                       uint32_t b0, uint32_t b1, uint32_t b2);

@@ -518,8 +518,6 @@ int gemm_tc16_launch(const GemmDev& p, int batch, cudaStream_t st) {
   Tc16Params P;
   P.g = p;
   g_sm_count = sm_count_cur();
-  const bool bw_form = g_single || p.a_tr || p.w_tr || p.ksplit > 1 || p.C_pre || p.dact_src || p.out_colsum || (batch > 1 && (p.sA == 0 || p.sW == 0));
-  if (!bw_form && gemm_tc16_ws_takes(p, batch, g_sm_count)) return gemm_tc16_ws_launch(p, batch, g_sm_count, st);   // short-K batched: weight-stationary
   GemmDev q = p;
   if (!p.out_stats) { q.st_groups = 0; q.st_rps = 0; }   // the tile plan only honours the statistics geometry when they are fused
   const Plan pl = make_plan(q, batch * p.ksplit);

@@ -20,9 +20,6 @@ namespace {
 
 int g_patch_engine = 0;    // 0 auto, 1 fp32 CUDA cores only, 2 warp-MMA only, 3 tcgen05 only (dpot_patch_embed_set_engine; tests)
 }
-int patch_embed_tc_launch(const float* x, int t0, const float* W0p, const float* rowbias0, const float* a_scale, const float* a_shift,
-                          int B, int X, int Y, int T, int C, int P, int mid, int act, void* z1, int Kp, int out_fmt, cudaStream_t st,
-                          bool* served);
 namespace {
 
 struct PatchArgs {
@@ -444,14 +441,7 @@ extern "C" int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, co
   const bool o16 = out_fmt == DPOT_FMT_HL16;
   cudaStream_t st = as_stream(stream);
 
-  // ---- tcgen05 path (patch_embed_tc.cu): P*C = 32, mid <= 48.  Correct but measured SLOWER than the warp-MMA kernel
-  // (85 vs 48 us on DPOT-S B=32: one CTA per SM and a four-role hand-off per 10 KB slab), so only on request (engine 3).
-  if (g_patch_engine == 3) {
-    bool served = false;
-    DPOT_CALL(patch_embed_tc_launch(x, t0, W0p, rowbias0, a_scale, a_shift, B, X, Y, T, C, P, mid, act, z1, Kp, out_fmt, st, &served));
-    if (served) return 0;
-    DPOT_REQUIRE(g_patch_engine != 3, DPOT_E_UNSUPPORTED, "dpot_patch_embed: the tcgen05 engine does not take this geometry");
-  }
+  DPOT_REQUIRE(g_patch_engine != 3, DPOT_E_UNSUPPORTED, "dpot_patch_embed: engine 3 (the tcgen05 PatchEmbed) was removed: measured slower than the warp-MMA kernel (DESIGN 4.3)");
   // ---- tensor-core path (mma.sync on split fp16): needs float4-able runs and 16-deep k-steps per image row
   const int nt8 = (int)ceil_div(mid, 8);
   if (g_patch_engine != 1 && vec4 && C == 4 && a.PC % 16 == 0 && a.PC <= 64 && nt8 <= 9) {

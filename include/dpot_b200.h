@@ -169,8 +169,6 @@ DPOT_API int dpot_tc16_available(void);
 DPOT_API void dpot_tc16_set_pair(int32_t mode);
 /* programmatic dependent launch between the kernels of the forward chain: 0 = plain stream order (default), 1 = on */
 DPOT_API void dpot_set_pdl(int32_t on);
-/* weight-stationary plan for short-K batched problems (K <= 256; the AFNO block MLP): -1 = auto, 0 = never */
-DPOT_API void dpot_tc16_set_ws(int32_t mode);
 /* Operand precision of the f16-split engine: 0 (default) = fp32-faithful, three MMAs per product on the hi / lo planes;
    1 = HALF-PRECISION OPERAND MODE -- only the hi planes (fp16, 11-bit significand: finer than bf16's 8, same tensor-core
    rate) are loaded and multiplied, one MMA per product, fp32 accumulation, fp32 master weights and epilogues unchanged.
@@ -380,7 +378,7 @@ DPOT_API int dpot_patch_embed(const float* x, int32_t t0, const float* W0p, cons
                      const float* a_shift, int32_t B, int32_t X, int32_t Y, int32_t T, int32_t C, int32_t P,
                      int32_t mid, int32_t act, void* z1, int32_t Kp, int32_t out_fmt, void* stream);
 /* engine knob (tests): 0 = auto (warp-MMA on split fp16 when the geometry allows, else CUDA cores), 1 = fp32 CUDA cores,
-   2 = warp-MMA only, 3 = tcgen05 only (P*C = 32, mid <= 48; measured slower than warp-MMA, kept as a tested alternative) */
+   2 = warp-MMA only.  (Engine 3, a tcgen05 PatchEmbed, was measured slower and removed: DESIGN 4.3.) */
 DPOT_API void dpot_patch_embed_set_engine(int32_t engine);
 
 /* ------------------------------------------------------------------------------------------

@@ -424,7 +424,7 @@ def test_tc16_fused_groupnorm_statistics(M, N, K, rps, pair):
     assert np.abs(st[..., 1] / s2 - 1).max() < 1e-5
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("geo", [(2, 64, 8, 10, 4, 35, 3), (3, 32, 4, 6, 4, 19, 0), (1, 128, 8, 10, 4, 35, 7), (2, 32, 8, 5, 4, 11, 2),
                                  (2, 48, 8, 10, 4, 27, 9)])
 def test_patch_embed_engines(geo, engine):
@@ -433,8 +433,6 @@ def test_patch_embed_engines(geo, engine):
     from dpot_b200 import _lib, ops
     lib = _lib.load()
     B, R, P, T, Cc, mid, t0 = geo
-    if engine == 3 and P * Cc != 32:
-        pytest.skip("the tcgen05 PatchEmbed serves P*C = 32")
     h = R // P
     rng = np.random.default_rng(sum(geo))
     x = rng.standard_normal((B, R, R, T, Cc)).astype(np.float32)
@@ -594,9 +592,10 @@ def test_rollout_cuda_graph_replay_matches_eager():
 
 @pytest.mark.parametrize("M,N,K,nb,act,out16", [(4608, 256, 256, 8, "gelu", True), (4608, 256, 256, 8, None, False),
                                                  (5000, 128, 192, 4, "tanh", False), (5000, 512, 128, 1, "gelu", True)])
-def test_tc16_weight_stationary_plan(M, N, K, nb, act, out16):
-    """Weight-stationary short-K plan (gemm_tc16_ws.cu: resident weight tile, 64-token tiles, four TMEM buffers) against
-    float64 and against the generic plan, incl. a ragged last token tile and K of 2 / 3 k-blocks."""
+def test_tc16_short_k_batched_problems(M, N, K, nb, act, out16):
+    """Short-K batched problems (the AFNO block MLP shapes; a ragged last token tile, K of 2 / 3 k-blocks) on the generic
+    plan of the f16-split engine against float64.  (A weight-stationary plan for these shapes was built in round 1, measured
+    within 3 % of the generic plan and removed in round 2.)"""
     from dpot_b200 import _lib, ops
     lib = _lib.load()
     if not lib.dpot_tc16_available():
@@ -614,19 +613,11 @@ def test_tc16_weight_stationary_plan(M, N, K, nb, act, out16):
     ref = np.concatenate([O.activation(A[:, i * K:(i + 1) * K].astype(np.float64) @ W[i].T.astype(np.float64) + b[i], act or "none")
                           if act else A[:, i * K:(i + 1) * K].astype(np.float64) @ W[i].T.astype(np.float64) + b[i]
                           for i in range(nb)], axis=1)
-    outs = []
-    for ws in (-1, 0):
-        lib.dpot_tc16_set_ws(ws)
-        try:
-            l0 = lib.dpot_launch_count()
-            out = ops.gemm16(A16, W16, bias=bias, act=act, out16=out16, nb=nb)
-            assert lib.dpot_launch_count() == l0 + 1
-        finally:
-            lib.dpot_tc16_set_ws(-1)
-        out = ops.unsplit_f16(out) if out16 else out
-        outs.append(out.cpu().numpy())
-        assert O.rel_l2(outs[-1], ref) < 2e-6, (ws,)
-    assert O.rel_l2(outs[0], outs[1]) < 1e-6
+    l0 = lib.dpot_launch_count()
+    out = ops.gemm16(A16, W16, bias=bias, act=act, out16=out16, nb=nb)
+    assert lib.dpot_launch_count() == l0 + 1
+    out = ops.unsplit_f16(out) if out16 else out
+    assert O.rel_l2(out.cpu().numpy(), ref) < 2e-6
 
 
 @pytest.mark.parametrize("name,kw,B", [
