@@ -223,6 +223,10 @@ class ClockSampler:
 TRAIN_BATCH = 16
 
 
+def fs_per_step_fn(world):
+    return BATCH * N_AR * world
+
+
 def train_leg(dev, world, rank, timed_fn):
     """The training step of train_temporal.py:201-230 (T_ar = 1, noise off) on DPOT-S, 16 samples per GPU: forward +
     SimpleLpLoss + backward + (gradient all-reduce when world > 1) + clip_grad_norm_ + Adam, through the drop-in API
@@ -400,6 +404,23 @@ def run_ours(args):
     for s in range(3):
         eng_nocls.run(devbuf[s % NBUF])
     ms_nocls = timed(lambda s: eng_nocls.run(devbuf[s % NBUF]), args.steps)
+    # 16-bit mixed-precision mode of the contraction engine (fp16 operands, one MMA per product; the reference's bf16
+    # autocast configs): the same rollout, reported NEXT TO the fp32-faithful headline, never instead of it
+    import dpot_b200
+    ref32 = eng.run(devbuf[0]).clone()
+    dpot_b200.set_precision("half")
+    try:
+        eng_h = RolloutEngine(model, BATCH, N_AR, device=dev, use_graph=not args.no_graph, want_cls=True)
+        for s in range(3):
+            eng_h.run(devbuf[s % NBUF])
+        ms_half = timed(lambda s: eng_h.run(devbuf[s % NBUF]), args.steps)
+        out16 = eng_h.run(devbuf[0]).clone()
+        half = {"value": fs_per_step_fn(world) * args.steps / (ms_half * 1e-3), "unit": "field-steps/s",
+                "rel_l2_vs_fp32_path_full_rollout": float((out16 - ref32).norm() / ref32.norm()),
+                "note": "dpot_b200.set_precision('half'): fp16 operands (hi planes), fp32 accumulate / epilogues / residual stream; "
+                        "the fused AFNO mixer stays fp32-faithful"}
+    finally:
+        dpot_b200.set_precision("fp32")
     train = None if args.no_train else train_leg(dev, world, rank, timed)
 
     fs_per_step = BATCH * N_AR * world
@@ -502,6 +523,7 @@ def run_ours(args):
             "gpu_eager_baseline": eager,
             "parity_in_run": parity,
             "train": train,
+            "half_precision_mode": half,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
