@@ -168,7 +168,7 @@ SIGNATURES = {
     "dpot_train_scratch_floats": (C.c_int64, [C.POINTER(Config), _i32]),
     "dpot_train_wprep_floats": (C.c_int64, [C.POINTER(Config)]),
     "dpot_train_prepare": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _p, _p]),
-    "dpot_train_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "dpot_train_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "dpot_train_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Params), _p, _p, _p, _i32, _p, _p, _p, _p,
                                       C.POINTER(Params), _p, _p, _p]),
     "dpot_out_tail_ring": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p,

@@ -859,6 +859,37 @@ __global__ void __launch_bounds__(256) pack_patch_fast_kernel(const float* __res
   }
 }
 
+// generic output-head tail (out_layer_dim != 32): dL/d(out field) -> per-pixel rows with the nout channels zero-padded to
+// NPAD = 8 (the contraction engine's minimum K), scaled by S and stored split: g3[tok, hi (uv, 8) | lo (uv, 8)]
+__global__ void unshuffle_pad_split_kernel(const float* __restrict__ dout, const float* __restrict__ scale, int B, int h, int w, int P,
+                                           int nout, __half* __restrict__ g3) {
+  const int PP = P * P;
+  const int64_t total = (int64_t)B * h * w * PP * 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int64_t tok = pix / PP; const int uv = (int)(pix % PP);
+  const int u_ = uv / P, v_ = uv % P;
+  const int q = (int)(tok % w); const int64_t r_ = tok / w;
+  const int p = (int)(r_ % h); const int64_t b = r_ / h;
+  float v = 0.f;
+  if (j < nout) v = dout[(((b * h * P + p * P + u_) * (int64_t)(w * P)) + q * P + v_) * nout + j] * (scale ? __ldg(scale) : 1.f);
+  __half hi, lo;
+  hl_split(v, hi, lo);
+  g3[tok * (2 * (int64_t)PP * 8) + uv * 8 + j] = hi;
+  g3[tok * (2 * (int64_t)PP * 8) + (int64_t)PP * 8 + uv * 8 + j] = lo;
+}
+// dst[i] = inv * sum_b src[b * n + i], i < keep  (column sums taken per (u, v) problem of a batched contraction)
+__global__ void sum_batches_kernel(const double* __restrict__ src, int nbat, int n, int keep, const float* __restrict__ inv_scale,
+                                   float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= keep) return;
+  double a = 0.0;
+  for (int b = 0; b < nbat; ++b) a += src[(int64_t)b * n + i];
+  dst[i] = (float)(a * (double)inv_of(inv_scale));
+}
+
 inline unsigned blocks_for(int64_t total, int per) { return (unsigned)ceil_div(total, per); }
 
 }  // namespace
@@ -1016,6 +1047,18 @@ int tk_unpack_patch_grad(const float* dW0p, int nslab, const double* drb, const 
   return 0;
 }
 
+int tk_unshuffle_pad_split(const float* dout, const float* scale, int B, int h, int w, int P, int nout, __half* g3, cudaStream_t st) {
+  DPOT_REQUIRE(nout >= 1 && nout <= 8, DPOT_E_UNSUPPORTED, "unshuffle_pad_split: nout %d > 8", nout);
+  const int64_t total = (int64_t)B * h * w * P * P * 8;
+  unshuffle_pad_split_kernel<<<blocks_for(total, 256), 256, 0, st>>>(dout, scale, B, h, w, P, nout, g3);
+  DPOT_LAUNCH_CHECK("unshuffle_pad_split_kernel");
+  return 0;
+}
+int tk_sum_batches(const double* src, int nbat, int n, int keep, const float* inv_scale, float* dst, cudaStream_t st) {
+  sum_batches_kernel<<<(unsigned)ceil_div(keep, 128), 128, 0, st>>>(src, nbat, n, keep, inv_scale, dst);
+  DPOT_LAUNCH_CHECK("sum_batches_kernel");
+  return 0;
+}
 int tk_pack_afno16(const float* w, const float* b, int nb, int bs, __half* Wc16, float* bc, cudaStream_t st) {
   const int64_t total = (int64_t)nb * 4 * bs * bs;
   pack_afno16_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, b, nb, bs, Wc16, bc);

@@ -47,6 +47,10 @@ int tk_patch_bwd(const float* gz, const float* x, const float* W0p, int B, int X
 // transpose of pack_patch: dW0p (nslab float partials [mid, (u,v,c)]), drb (double [(p,q), Kp] = sum_b gz) -> dpe0_w[mid, C+3, P, P], dpe0_b[mid]
 int tk_unpack_patch_grad(const float* dW0p, int nslab, const double* drb, const float* gx, const float* gy, const float* gt, int mid, int C,
                          int P, int h, int w, int T, int Kp, const float* inv_scale, float* dw0, float* db0, cudaStream_t st);
+// generic output-head tail (out_layer_dim != 32): dL/d(out field) -> g3[tok, hi (uv, 8) | lo (uv, 8)], nout channels zero-padded
+// to 8, scaled by scale[0], split; and dst[i < keep] = inv * sum_b src[b*n + i] (column sums taken per (u, v) problem)
+int tk_unshuffle_pad_split(const float* dout, const float* scale, int B, int h, int w, int P, int nout, __half* g3, cudaStream_t st);
+int tk_sum_batches(const double* src, int nbat, int n, int keep, const float* inv_scale, float* dst, cudaStream_t st);
 // weight packing of the per-step prepare: AFNO real block form written directly as split fp16; PatchEmbed conv0 im2col
 // weight + coordinate-channel bias table with the coordinate sums separated (same results as dpot_pack_afno / dpot_pack_patch)
 int tk_pack_afno16(const float* w, const float* b, int nb, int bs, __half* Wc16, float* bc, cudaStream_t st);

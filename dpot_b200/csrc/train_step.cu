@@ -25,7 +25,7 @@ struct Bump {   // bump allocator over a float arena (sizes in floats, 256-byte 
 };
 
 struct TapeL {
-  int64_t z1, blocks, blk_stride, alat16, Y1pre, tok, c1pre, c2pre, c1, c2, total;
+  int64_t z1, blocks, blk_stride, alat16, Y1pre, tok, c1pre, c2pre, c1, c2, Y1_16, Y2pre, Y2_16, total;   // Y1_16.. : generic tail only
   // offsets inside a block slab
   int64_t lat, st1, st2, S, O1pre, O1, f, n2, hpre, hid;
 };
@@ -53,12 +53,16 @@ TapeL tape_layout(const Dims& d, int B) {
   L.c2pre = a.take((int64_t)B * d.E);
   L.c1 = a.take((int64_t)B * d.E);
   L.c2 = a.take((int64_t)B * d.E);
+  const bool gen_tail = d.old != 32;
+  L.Y1_16 = a.take(gen_tail ? Mt * d.NP : 0);
+  L.Y2pre = a.take(gen_tail ? Mt * d.NP : 0);
+  L.Y2_16 = a.take(gen_tail ? Mt * d.NP : 0);
   L.total = a.o;
   return L;
 }
 
 inline int midp_of(const Dims& d) { return (int)round_up(d.mid, 8); }
-struct PrepL { int64_t wts16, Wsum16, bp16, W2p16, W2T16, total; };   // split-fp16 fold operands (prepare), reused by backward
+struct PrepL { int64_t wts16, Wsum16, bp16, W2p16, W2T16, o2_16, o4_16, o4p16, total; };   // split-fp16 fold operands (prepare), reused by backward
 PrepL prep_layout(const Dims& d) {
   PrepL L; Bump a;
   L.wts16 = a.take((int64_t)d.T * d.E * d.E);         // [(t,i), hi E | lo E]
@@ -66,6 +70,9 @@ PrepL prep_layout(const Dims& d) {
   L.bp16 = a.take((int64_t)d.E * d.n);
   L.W2p16 = a.take((int64_t)d.E * midp_of(d));        // conv 1x1 weight [E, mid] zero-padded to a multiple of 8 columns
   L.W2T16 = a.take((int64_t)midp_of(d) * d.E);        // its transpose [mid, E]
+  L.o2_16 = a.take((int64_t)d.old * d.old);          // generic tail: out_layer[2] / [4] weights split, [4] also zero-padded to 8 rows
+  L.o4_16 = a.take((int64_t)8 * d.old);
+  L.o4p16 = a.take((int64_t)8 * d.old);
   L.total = a.o;
   return L;
 }
@@ -85,9 +92,9 @@ struct ScratchL {
   int64_t O2, Y1g;
   // backward
   int64_t gA, gB, g16, g1_16, dn2, df, dO2, dO1, dS, dn1, slabs, g1t, z1pre, gz, dWeffT, Gp16, dbe, dbe16, dWsum, dwt,
-      dW2s, dbp, dtemb, gn, cls, dbl, scale, pslabs, tparts;
+      dW2s, dbp, dtemb, gn, cls, dbl, scale, pslabs, tparts, g3_16, g2_16, Y3;
   // double accumulators (offsets in DOUBLES from dbl): per block [db2 E | db1 hid | dbc2 2E | dbc1 2E], then the rest
-  int64_t d_blk, d_blk_stride, d_tail, d_bias_t, d_be, d_rb, d_total;
+  int64_t d_blk, d_blk_stride, d_tail, d_bias_t, d_be, d_rb, d_gt, d_total;
   int64_t total;
 };
 ScratchL scratch_layout(const Dims& d, int B) {
@@ -98,7 +105,7 @@ ScratchL scratch_layout(const Dims& d, int B) {
     L.W2T = a.take((int64_t)d.mid * E);
     mx = a.o; }
   { Bump a;   // forward
-    L.O2 = a.take(Ms * 2 * E); L.Y1g = a.take(Mt * d.NP);
+    L.O2 = a.take(Ms * 2 * E); L.Y1g = a.take(Mt * d.NP); L.Y3 = a.take(Mt * d.P * d.P * 8);
     if (a.o > mx) mx = a.o; }
   { Bump a;   // backward
     const int64_t W = E > d.hid ? E : d.hid;
@@ -118,6 +125,8 @@ ScratchL scratch_layout(const Dims& d, int B) {
     L.pslabs = a.take((int64_t)2 * 160 * d.mid * d.K0);         // per-block partials of the PatchEmbed weight gradient (<= 2 per SM)
     L.dtemb = a.take((int64_t)d.T * E);
     L.tparts = a.take(tk_tail_bwd_part_floats(3 * 160));
+    L.g3_16 = a.take(d.old != 32 ? Mt * d.P * d.P * 8 : 0);
+    L.g2_16 = a.take(d.old != 32 ? Mt * d.NP : 0);
     L.gn = a.take(5 * (int64_t)B * E + 2 * (int64_t)B * GROUPS);
     L.cls = a.take(8 * (int64_t)B * E + 3 * E * E + (int64_t)d.ncls * E + 4096);
     L.scale = a.take(64);
@@ -128,6 +137,7 @@ ScratchL scratch_layout(const Dims& d, int B) {
     L.d_bias_t = q; q += d.NP;
     L.d_be = q; q += (int64_t)d.n * E;
     L.d_rb = q; q += (int64_t)d.n * d.Kp;
+    L.d_gt = q; q += (int64_t)2 * d.NP + (int64_t)d.P * d.P * 8;     // generic tail: per-(u,v) column sums of g2, g1, g3
     L.d_total = q;
     L.dbl = a.take(2 * q + 2);
     if (a.o > mx) mx = a.o; }
@@ -140,7 +150,8 @@ bool train_ok(const dpot_config* c, const Dims& d) {
   if (!use_tc16(d, DPOT_GEMM_AUTO)) return false;
   if (d.depth < 1) return false;
   if ((d.E / GROUPS) % 8 != 0 || d.E % GROUPS != 0) return false;
-  if (!dpot_out_tail_tc_supported(d.old, d.Co * d.To, d.Co) || !tk_tail_bwd_supported(d.old, d.Co * d.To)) return false;
+  const bool fast_tail = dpot_out_tail_tc_supported(d.old, d.Co * d.To, d.Co) && tk_tail_bwd_supported(d.old, d.Co * d.To);
+  if (!fast_tail && !(d.old % 8 == 0 && d.old >= 8 && d.Co * d.To <= 8)) return false;   // else: the generic tail on batched contractions
   if (!tk_patch_bwd_supported(d.mid, d.T, d.K0)) return false;
   if (d.E % 8 != 0 || d.n % 8 != 0) return false;                   // fold contractions on the f16-split engine
   if ((2 * d.bs) % 8 != 0 || d.hid % 8 != 0 || d.NP % 8 != 0 || d.Kp % 8 != 0) return false;
@@ -234,7 +245,13 @@ extern "C" int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm
   DPOT_CALL(dpot_pack_out(prm->out0_w, prm->out0_b, E, d.old, d.P, packed + L.WtT, packed + L.bias_t, stream));
   DPOT_CALL(dpot_split_f16(packed + L.WeffT, d.Kp, E, d.Kp, nullptr, nullptr, 0, packed + L.WeffT16, 2 * d.Kp, d.Kp, stream));
   DPOT_CALL(dpot_split_f16(packed + L.WtT, E, d.NP, E, nullptr, nullptr, 0, packed + L.WtT16, 2 * E, E, stream));
-  const int64_t kb = 2 * d.bs;
+  if (d.old != 32) {   // generic tail: the 1x1 conv weights of out_layer[2] / [4] as split operands ([4] also zero-padded to 8 rows)
+    const int nout = d.Co * d.To;
+    DPOT_CALL(dpot_split_f16(prm->out2_w, d.old, d.old, d.old, nullptr, nullptr, 0, wprep + PL.o2_16, 2 * d.old, d.old, stream));
+    DPOT_CUDA(cudaMemsetAsync(wprep + PL.o4p16, 0, sizeof(float) * 8 * (size_t)d.old, st));
+    DPOT_CALL(dpot_split_f16(prm->out4_w, d.old, nout, d.old, nullptr, nullptr, 0, wprep + PL.o4_16, 2 * d.old, d.old, stream));
+    DPOT_CALL(dpot_split_f16(prm->out4_w, d.old, nout, d.old, nullptr, nullptr, 0, wprep + PL.o4p16, 2 * d.old, d.old, stream));
+  }
   for (int i = 0; i < d.depth; ++i) {
     float* base = packed + L.blocks + (int64_t)i * L.blk_stride;
     const dpot_block_params& b = prm->blocks[i];
@@ -247,12 +264,12 @@ extern "C" int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-extern "C" int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int32_t B,
-                                  float* y, float* cls, float* tape, float* scratch, void* stream) {
+extern "C" int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
+                                  const float* x, int32_t B, float* y, float* cls, float* tape, float* scratch, void* stream) {
   Dims d;
   DPOT_CALL(make_dims(cfg, d));
   DPOT_REQUIRE(train_ok(cfg, d), DPOT_E_UNSUPPORTED, "dpot_train_forward: configuration not served by the fused training step");
-  DPOT_REQUIRE(prm && packed && x && y && tape && scratch && prm->blocks && B > 0, DPOT_E_BADARG, "dpot_train_forward: null pointer / bad B");
+  DPOT_REQUIRE(prm && packed && wprep && x && y && tape && scratch && prm->blocks && B > 0, DPOT_E_BADARG, "dpot_train_forward: null pointer / bad B");
   cudaStream_t st = as_stream(stream);
   const Packed PL = packed_layout(d);
   const TapeL TL = tape_layout(d, B);
@@ -317,7 +334,8 @@ extern "C" int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm
     g = gemm_args(tape + TL.c2, E, prm->cls4_w, E, cls, d.ncls, B, d.ncls, E, prm->cls4_b, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
     DPOT_CALL(dpot_gemm(&g, stream));
   }
-  {   // output head: ConvTranspose GEMM (per-pixel [hi 32 | lo 32] records for the tcgen05 tail, fp32 pre-activation for backward)
+  const bool fast_tail = dpot_out_tail_tc_supported(d.old, d.Co * d.To, d.Co) && tk_tail_bwd_supported(d.old, d.Co * d.To);
+  if (fast_tail) {   // output head: ConvTranspose GEMM (per-pixel [hi 32 | lo 32] records for the tcgen05 tail, fp32 pre-activation for backward)
     float* Y1g = scratch + SL.Y1g;
     dpot_gemm_args g = gemm16_args(tape + TL.alat16, E, packed + PL.WtT16, E, Y1g, d.NP, Mt, d.NP, E, packed + PL.bias_t, act);
     g.c_fmt = DPOT_FMT_HL16G32; g.ldc = 2 * (int64_t)d.NP;
@@ -325,6 +343,26 @@ extern "C" int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm
     DPOT_CALL(dpot_gemm(&g, stream));
     DPOT_CALL(dpot_out_tail_tc(Y1g, prm->out2_w, prm->out2_b, prm->out4_w, prm->out4_b, B, d.h, d.h, d.P, d.old, d.Co * d.To, act,
                                nullptr, nullptr, d.Co, y, nullptr, nullptr, d.T, 0, 0, 0, stream));
+  } else {
+    // generic tail (out_layer_dim = 128 of DPOT-L/H): the per-pixel layers are contractions batched over the P*P
+    // intra-patch positions (u, v) -- pixel (tok, uv) is row tok of problem uv, column offset uv*old -- with the 1x1
+    // conv weights shared by the batch; every result is kept split + its pre-activation for backward
+    const PrepL WP = prep_layout(d);
+    const int PP = d.P * d.P, old = d.old, nout = d.Co * d.To;
+    dpot_gemm_args g = gemm16_args(tape + TL.alat16, E, packed + PL.WtT16, E, tape + TL.Y1_16, 0, Mt, d.NP, E, packed + PL.bias_t, act);
+    out16(g, d.NP);
+    g.C_pre = tape + TL.Y1pre; g.ld_pre = d.NP;
+    DPOT_CALL(dpot_gemm(&g, stream));
+    g = gemm16_args(tape + TL.Y1_16, d.NP, wprep + WP.o2_16, old, tape + TL.Y2_16, 0, Mt, old, old, prm->out2_b, act);
+    g.batch = PP; g.strideA = old; g.strideW = 0; g.strideC = old; g.strideBias = 0;
+    out16(g, d.NP);
+    g.C_pre = tape + TL.Y2pre; g.ld_pre = d.NP; g.stride_pre = old;
+    DPOT_CALL(dpot_gemm(&g, stream));
+    float* Y3 = scratch + SL.Y3;                                  // rows (tok, uv) x nout
+    g = gemm16_args(tape + TL.Y2_16, d.NP, wprep + WP.o4_16, old, Y3, (int64_t)PP * nout, Mt, nout, old, prm->out4_b, DPOT_ACT_NONE);
+    g.batch = PP; g.strideA = old; g.strideW = 0; g.strideC = nout; g.strideBias = 0;
+    DPOT_CALL(dpot_gemm(&g, stream));
+    DPOT_CALL(dpot_pixel_shuffle(Y3, y, B, d.h, d.h, d.P, nout, 1, stream));
   }
   return 0;
 }
@@ -412,10 +450,44 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
 
   // ---- output head (models/dpot.py:315-321)
   float* g1t = scratch + SL.g1t;
-  {
+  const bool fast_tail = dpot_out_tail_tc_supported(d.old, nout, d.Co) && tk_tail_bwd_supported(d.old, nout);
+  if (fast_tail) {
     DPOT_CALL(tk_tail_bwd(tape + TL.Y1pre, dy, scale, prm->out2_w, prm->out2_b, prm->out4_w, B, d.h, d.h, d.P, nout, act,
                           reinterpret_cast<__half*>(g1t), scratch + SL.tparts, inv, G(grads->out2_w), G(grads->out2_b),
                           G(grads->out4_w), G(grads->out4_b), G(grads->out0_b), st));
+  } else {
+    // generic tail: the same chain as contractions batched over the P*P intra-patch positions (see dpot_train_forward)
+    const int PP = d.P * d.P, old = d.old;
+    float* g3 = scratch + SL.g3_16; float* g2 = scratch + SL.g2_16;
+    double* cs_g2 = dbl + SL.d_gt; double* cs_g1 = cs_g2 + NP; double* cs_g3 = cs_g1 + NP;
+    DPOT_CALL(tk_unshuffle_pad_split(dy, scale, B, d.h, d.h, d.P, nout, reinterpret_cast<__half*>(g3), st));   // [tok, (uv, 8)] split, x S
+    // out_layer[4]: y3 = y2 W4^T + b4
+    DPOT_CALL(tk_colsum(g3, true, 2 * (int64_t)PP * 8, (int64_t)PP * 8, Mt, PP * 8, cs_g3, st));
+    DPOT_CALL(tk_sum_batches(cs_g3, PP, 8, nout, inv, G(grads->out4_b), st));
+    DPOT_CALL(wgrad16(g3, (int64_t)PP * 8, tape + TL.Y2_16, NP, 8, old, Mt, PP, slabs, &ns, stream));            // [ks][uv][8, old]
+    DPOT_CALL(tk_slab_reduce(slabs, ns * PP, (int64_t)8 * old, (int64_t)nout * old, inv, G(grads->out4_w), st));
+    {   // g2 = (g3 W4) * act'(Y2pre), split; column sums per (u, v) -> db2
+      dpot_gemm_args a = g16(g3, (int64_t)PP * 8, wprep + WL.o4p16, old, g2, 0, Mt, old, 8);
+      a.w_trans = 1; a.batch = PP; a.strideA = 8; a.strideW = 0; a.strideC = old;
+      out16(a, NP);
+      a.dact_src = tape + TL.Y2pre; a.ld_dact = NP; a.stride_dact = old; a.dact = act;
+      a.out_colsum = cs_g2;
+      DPOT_CALL(dpot_gemm(&a, stream));
+    }
+    DPOT_CALL(tk_sum_batches(cs_g2, PP, old, old, inv, G(grads->out2_b), st));
+    DPOT_CALL(wgrad16(g2, NP, tape + TL.Y1_16, NP, old, old, Mt, PP, slabs, &ns, stream));                         // [ks][uv][old, old]
+    DPOT_CALL(tk_slab_reduce(slabs, ns * PP, (int64_t)old * old, (int64_t)old * old, inv, G(grads->out2_w), st));
+    {   // g1 = (g2 W2) * act'(Y1pre), split; column sums -> the ConvTranspose bias gradient
+      dpot_gemm_args a = g16(g2, NP, wprep + WL.o2_16, old, g1t, 0, Mt, old, old);
+      a.w_trans = 1; a.batch = PP; a.strideA = old; a.strideW = 0; a.strideC = old;
+      out16(a, NP);
+      a.dact_src = tape + TL.Y1pre; a.ld_dact = NP; a.stride_dact = old; a.dact = act;
+      a.out_colsum = cs_g1;
+      DPOT_CALL(dpot_gemm(&a, stream));
+    }
+    DPOT_CALL(tk_sum_batches(cs_g1, PP, old, old, inv, G(grads->out0_b), st));
+  }
+  {
     DPOT_CALL(wgrad16(g1t, NP, tape + TL.alat16, E, NP, E, Mt, 1, slabs, &ns, stream));
     DPOT_CALL(tk_unpack_out_grad(slabs, ns, (int64_t)NP * E, nullptr, E, d.old, d.P, inv, G(grads->out0_w), G(grads->out0_b), st));
   }

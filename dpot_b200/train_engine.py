@@ -137,7 +137,7 @@ class FusedTrainFn(Function):
             tape = torch.empty(lib.dpot_train_tape_floats(C.byref(eng.cfg), B), device=dev, dtype=torch.float32)
             y = torch.empty((B, net.img_size, net.img_size, net.out_timesteps, net.out_channels), device=dev, dtype=torch.float32)
             cls = torch.empty((B, net.n_cls), device=dev, dtype=torch.float32)
-            check(lib.dpot_train_forward(C.byref(eng.cfg), C.byref(eng.binder.prm), ptr(eng.packed), ptr(x), B, ptr(y), ptr(cls),
+            check(lib.dpot_train_forward(C.byref(eng.cfg), C.byref(eng.binder.prm), ptr(eng.packed), ptr(eng.wprep), ptr(x), B, ptr(y), ptr(cls),
                                          ptr(tape), ptr(eng.get_scratch(B, dev)), eng._stream()), "dpot_train_forward")
         eng.n_forward += 1
         ctx.eng = eng

@@ -521,8 +521,9 @@ DPOT_API int dpot_assemble_batch(const float* raw, const int32_t* t_start, int32
  *   events  : NULL, or depth + 2 cudaEvent_t recorded on `stream` as groups of gradients become final -- [0] the
  *             out_layer parameters, [1 + j] block depth-1-j, [depth + 1] everything -- so that a data-parallel caller can
  *             start exchanging a group (train_temporal_parallel.py:185,244) while the rest of backward still runs.
- * dpot_train_supported: 1 when the configuration is served (normalize = False, out_layer_dim = 32, patch geometry of
- * DPOT-Ti/S/M); other configurations train through the generic per-operator path of the Python binding.
+ * dpot_train_supported: 1 when the configuration is served (normalize = False; patch size 8 geometry of DPOT-Ti/S/M/H;
+ * out_layer_dim = 32 on the fused tail kernels, other multiples of 8 -- DPOT-H's 128 -- on contractions batched over the
+ * intra-patch positions); other configurations train through the generic per-operator path of the Python binding.
  * ---------------------------------------------------------------------------------------- */
 DPOT_API int     dpot_train_supported(const dpot_config* cfg);
 DPOT_API int64_t dpot_train_tape_floats(const dpot_config* cfg, int32_t B);
@@ -530,8 +531,8 @@ DPOT_API int64_t dpot_train_scratch_floats(const dpot_config* cfg, int32_t B);
 DPOT_API int64_t dpot_train_wprep_floats(const dpot_config* cfg);
 DPOT_API int dpot_train_prepare(const dpot_config* cfg, const dpot_params* prm, float* packed, float* wprep, float* scratch,
                                 void* stream);
-DPOT_API int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x, int32_t B,
-                                float* y, float* cls, float* tape, float* scratch, void* stream);
+DPOT_API int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
+                                const float* x, int32_t B, float* y, float* cls, float* tape, float* scratch, void* stream);
 DPOT_API int dpot_train_backward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* wprep,
                                  const float* x, int32_t B, const float* dy, const float* dcls, const float* tape,
                                  float* scratch, const dpot_params* grads, float* dx, void* const* events, void* stream);
