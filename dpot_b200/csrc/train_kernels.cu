@@ -512,6 +512,7 @@ constexpr int PB_MID = 40, PB_T = 10, PB_NT = 256;
 struct PatchBwdArgs {
   const float* gz; const float* x; const float* W0p; const float* inv_scale; float* dW0p; float* dx;   // dW0p: [gridDim.x][mid*K0] partials
   int B, X, Y, T, C, P, mid, Kp, K0, h, w;
+  int koff, moff, mcnt, dx_accum;   // this launch: im2col columns [koff, koff + 256), conv0 channels [moff, moff + mcnt)
 };
 template <int MIDC, int TC, bool DX>
 __global__ void __launch_bounds__(PB_NT, MIDC ? 2 : 1) patch_bwd_kernel(const PatchBwdArgs a) {
@@ -519,14 +520,16 @@ __global__ void __launch_bounds__(PB_NT, MIDC ? 2 : 1) patch_bwd_kernel(const Pa
   extern __shared__ __align__(16) float sm[];
   float* gzs = sm;                              // [T][mid]  (<= 400 floats)
   float* xs = sm + PB_T * PB_MID;               // patch tile [u][(v, t, c)] = P * (P*T*C) floats; reused for dx
-  const int tid = threadIdx.x, K0 = a.K0, T = TC ? TC : a.T, mid = MIDC ? MIDC : a.mid, C = a.C, P = a.P;
+  const int tid = threadIdx.x, K0 = a.K0, T = TC ? TC : a.T, mid = MIDC ? MIDC : a.mcnt, C = a.C, P = a.P;
+  const int midt = a.mid, moff = a.moff;        // gz rows hold all midt channels; this launch handles [moff, moff + mid)
   const int run = P * T * C;                    // contiguous floats of one patch row u
-  const bool kon = tid < K0;
-  const int c = tid % C, uv = tid / C, v = uv % P, u = uv / P;
+  const int k = a.koff + tid;
+  const bool kon = k < K0;
+  const int c = k % C, uv = k / C, v = uv % P, u = uv / P;
   float wcol[DX ? MB : 1], dW[MB];
 #pragma unroll
   for (int m = 0; m < MB; ++m) {
-    if (DX) wcol[m] = (kon && m < mid) ? a.W0p[(int64_t)m * K0 + tid] : 0.f;
+    if (DX) wcol[m] = (kon && m < mid) ? a.W0p[(int64_t)(moff + m) * K0 + k] : 0.f;
     dW[m] = 0.f;
   }
   const float inv = inv_of(a.inv_scale);
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(PB_NT, MIDC ? 2 : 1) patch_bwd_kernel(const Pa
   for (int64_t pt = blockIdx.x; pt < npatch; pt += gridDim.x) {
     const int q = (int)(pt % a.w); const int64_t r_ = pt / a.w;
     const int p = (int)(r_ % a.h); const int b = (int)(r_ / a.h);
-    for (int i = tid; i < T * mid; i += PB_NT) gzs[i] = a.gz[pt * a.Kp + i];
+    for (int i = tid; i < T * mid; i += PB_NT) gzs[i] = a.gz[pt * a.Kp + (i / mid) * midt + moff + (i % mid)];
     for (int i = tid; i < P * run; i += PB_NT) {
       const int uu = i / run, rr = i % run;
       xs[i] = a.x[(((int64_t)b * a.X + p * P + uu) * a.Y + (int64_t)q * P) * T * C + rr];
@@ -560,25 +563,36 @@ __global__ void __launch_bounds__(PB_NT, MIDC ? 2 : 1) patch_bwd_kernel(const Pa
       }
     }
     if (DX) {
-      __syncthreads();
-      if (kon) {
+      if (K0 <= PB_NT && !a.dx_accum) {
+        // the launch covers every column of the patch: stage dx in the (dead) pixel tile, store whole image-row runs
+        __syncthreads();
+        if (kon) {
+#pragma unroll
+          for (int t = 0; t < TB; ++t)
+            if (TC || t < T) xs[u * run + (v * T + t) * C + c] = dxk[t] * inv;
+        }
+        __syncthreads();
+        for (int i = tid; i < P * run; i += PB_NT) {
+          const int uu = i / run, rr = i % run;
+          a.dx[(((int64_t)b * a.X + p * P + uu) * a.Y + (int64_t)q * P) * T * C + rr] = xs[i];
+        }
+      } else if (kon) {
+        // column / channel chunks (patch 16): each launch owns its columns; a later channel chunk adds to the first one's
 #pragma unroll
         for (int t = 0; t < TB; ++t)
-          if (TC || t < T) xs[u * run + (v * T + t) * C + c] = dxk[t] * inv;
-      }
-      __syncthreads();
-      for (int i = tid; i < P * run; i += PB_NT) {
-        const int uu = i / run, rr = i % run;
-        a.dx[(((int64_t)b * a.X + p * P + uu) * a.Y + (int64_t)q * P) * T * C + rr] = xs[i];
+          if (TC || t < T) {
+            float* dp = a.dx + (((int64_t)b * a.X + p * P + u) * a.Y + (int64_t)q * P + v) * T * C + t * C + c;
+            *dp = a.dx_accum ? *dp + dxk[t] * inv : dxk[t] * inv;
+          }
       }
     }
     __syncthreads();
   }
   if (kon) {
-    float* slab = a.dW0p + (int64_t)blockIdx.x * mid * K0;
+    float* slab = a.dW0p + (int64_t)blockIdx.x * midt * K0;
 #pragma unroll
     for (int m = 0; m < MB; ++m)
-      if (MIDC || m < mid) slab[(int64_t)m * K0 + tid] = dW[m];
+      if (MIDC || m < mid) slab[(int64_t)(moff + m) * K0 + k] = dW[m];
   }
 }
 
@@ -1011,7 +1025,7 @@ int tk_tail_bwd(const float* Y1pre, const float* dout, const float* scale, const
   return 0;
 }
 
-int tk_patch_bwd_supported(int mid, int T, int K0) { return mid <= PB_MID && T <= PB_T && K0 <= PB_NT; }
+int tk_patch_bwd_supported(int mid, int T, int K0) { return mid <= 4 * PB_MID && T <= PB_T && K0 <= 8 * PB_NT; }
 int tk_patch_bwd_slabs(int B, int X, int Y, int P) {
   const int64_t npatch = (int64_t)B * (X / P) * (Y / P);
   return (int)std::min<int64_t>(npatch, (int64_t)sm_count_cur() * 2);
@@ -1025,14 +1039,21 @@ int tk_patch_bwd(const float* gz, const float* x, const float* W0p, int B, int X
   const size_t smem = sizeof(float) * (PB_T * PB_MID + (size_t)P * P * T * C);
   DPOT_REQUIRE(smem <= 48 * 1024, DPOT_E_UNSUPPORTED, "patch_bwd: patch tile too large");
   const unsigned grid = (unsigned)tk_patch_bwd_slabs(B, X, Y, P);
-  if (mid == 35 && T == 10) {
+  if (mid == 35 && T == 10 && a.K0 <= PB_NT) {          // DPOT-Ti/S/M/H at patch 8: one launch, compile-time loops
+    a.koff = 0; a.moff = 0; a.mcnt = mid; a.dx_accum = 0;
     if (dx) patch_bwd_kernel<35, 10, true><<<grid, PB_NT, smem, st>>>(a);
     else patch_bwd_kernel<35, 10, false><<<grid, PB_NT, smem, st>>>(a);
-  } else {
-    if (dx) patch_bwd_kernel<0, 0, true><<<grid, PB_NT, smem, st>>>(a);
-    else patch_bwd_kernel<0, 0, false><<<grid, PB_NT, smem, st>>>(a);
+    DPOT_LAUNCH_CHECK("patch_bwd_kernel");
+    return 0;
   }
-  DPOT_LAUNCH_CHECK("patch_bwd_kernel");
+  // other geometries (DPOT-L: patch 16 -> 1024 columns, 67 channels): chunks of 256 columns x <= 40 channels per launch
+  for (int koff = 0; koff < a.K0; koff += PB_NT)
+    for (int moff = 0; moff < mid; moff += PB_MID) {
+      a.koff = koff; a.moff = moff; a.mcnt = std::min(PB_MID, mid - moff); a.dx_accum = moff > 0 ? 1 : 0;
+      if (dx) patch_bwd_kernel<0, 0, true><<<grid, PB_NT, smem, st>>>(a);
+      else patch_bwd_kernel<0, 0, false><<<grid, PB_NT, smem, st>>>(a);
+      DPOT_LAUNCH_CHECK("patch_bwd_kernel");
+    }
   return 0;
 }
 

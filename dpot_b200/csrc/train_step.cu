@@ -117,6 +117,8 @@ ScratchL scratch_layout(const Dims& d, int B) {
     if (kt * (int64_t)d.NP * E > sl) sl = kt * (int64_t)d.NP * E;
     if (kt * E * d.Kp > sl) sl = kt * E * d.Kp;
     if (ks * (int64_t)d.nb * 4 * d.bs * d.bs > sl) sl = ks * (int64_t)d.nb * 4 * d.bs * d.bs;
+    if (ceil_div(d.NP, 1024) * Mt * E > sl) sl = ceil_div(d.NP, 1024) * Mt * E;
+    if (ceil_div(d.hid, 1024) * Mt * E > sl) sl = ceil_div(d.hid, 1024) * Mt * E;        // split-K partials of the head's data gradient
     L.slabs = a.take(sl);
     L.g1t = a.take(Mt * d.NP); L.z1pre = a.take(Mt * d.Kp); L.gz = a.take(Mt * d.Kp);
     L.dWeffT = a.take(E * d.Kp); L.Gp16 = a.take((int64_t)d.T * E * midp_of(d)); L.dbe = a.take((int64_t)d.n * E);
@@ -496,14 +498,23 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
   float* g_other = scratch + SL.gB;
   float* gs16 = scratch + SL.g16;      // the same, split
   {
+    // dL/d(latent) = g1 WtT: the contraction runs over the P*P*out_layer_dim head columns -- 2048 for the 32-wide head,
+    // 8192 / 32768 for DPOT-H / L.  A tensor-core accumulation chain is kept <= 1024 deep (measured 1e-5 /
+    // 3.9e-5 on these two before the split), so long ones are cut into chunks summed in fp32
     dpot_gemm_args a = g16(g1t, NP, packed + PL.WtT16, E, g, E, Mt, E, NP);
     a.w_trans = 1;
-    if (!dcls) a.out_colsum = dbl + SL.d_blk + (int64_t)(d.depth - 1) * SL.d_blk_stride;   // = db2 of the last block
+    const bool split_k = NP > 2048;
+    if (split_k) {
+      a.C = slabs;
+      ksplit(a, 1024, (int64_t)Mt * E);
+    } else if (!dcls) {
+      a.out_colsum = dbl + SL.d_blk + (int64_t)(d.depth - 1) * SL.d_blk_stride;   // = db2 of the last block
+    }
     DPOT_CALL(dpot_gemm(&a, stream));
-  }
-  if (dcls) {
-    DPOT_CALL(cls_backward(cfg, prm, d, B, dcls, tape, TL, scratch + SL.cls, scale, grads, g, stream));
-    DPOT_CALL(tk_colsum(g, false, E, 0, Mt, E, dbl + SL.d_blk + (int64_t)(d.depth - 1) * SL.d_blk_stride, st));
+    if (split_k) DPOT_CALL(tk_slab_reduce(slabs, a.k_split, (int64_t)Mt * E, (int64_t)Mt * E, nullptr, g, st));
+    if (dcls) DPOT_CALL(cls_backward(cfg, prm, d, B, dcls, tape, TL, scratch + SL.cls, scale, grads, g, stream));
+    if (dcls || split_k)
+      DPOT_CALL(tk_colsum(g, false, E, 0, Mt, E, dbl + SL.d_blk + (int64_t)(d.depth - 1) * SL.d_blk_stride, st));
   }
   DPOT_CALL(tk_split_scaled(g, Mt, E, nullptr, reinterpret_cast<__half*>(gs16), 2 * (int64_t)E, E, st));
 
@@ -534,7 +545,12 @@ extern "C" int dpot_train_backward(const dpot_config* cfg, const dpot_params* pr
     {
       dpot_gemm_args a = g16(g1h, H, pk + PL.fc1_16, E, dn2, E, Mt, E, H);
       a.w_trans = 1;
+      if (H > 2048) {        // mlp_ratio 4 (DPOT-M/L/H): keep the accumulation chain <= 1024 deep (see the head's data gradient)
+        a.C = slabs;
+        ksplit(a, 1024, (int64_t)Mt * E);
+      }
       DPOT_CALL(dpot_gemm(&a, stream));
+      if (a.k_split > 1) DPOT_CALL(tk_slab_reduce(slabs, a.k_split, (int64_t)Mt * E, (int64_t)Mt * E, nullptr, dn2, st));
     }
     // GroupNorm-2
     float* df = scratch + SL.df;

@@ -2,7 +2,7 @@
 autograd: loss, dL/dx and every parameter gradient of a 2-step autoregressive training loss (train_temporal.py:201-227)
 on two geometries -- the DPOT-S width (fixture train_grads_swidth.npz) and a truncated-mode / 2-frame-bundle / SiLU /
 time_agg='mlp' / cls-in-the-loss variant (train_grads_fused2.npz) and an out_layer_dim = 128 head as DPOT-L/H have it
-(train_grads_fused3.npz: the generic tail on batched contractions) -- and against the per-operator path of autograd.py.
+(train_grads_fused3.npz: the generic tail on batched contractions; train_grads_fused4.npz: patch 16, block size 96 -- DPOT-L) -- and against the per-operator path of autograd.py.
 Fixtures: tests/golden/make_golden_r2.py (imports the unmodified reference in the build container)."""
 import json
 import os
@@ -72,7 +72,7 @@ def _check_against_fixture(z, m, x_in, loss, tol):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("fixture", ["train_grads_swidth.npz", "train_grads_fused2.npz", "train_grads_fused3.npz"])
+@pytest.mark.parametrize("fixture", ["train_grads_swidth.npz", "train_grads_fused2.npz", "train_grads_fused3.npz", "train_grads_fused4.npz"])
 def test_fused_training_step_matches_reference_autograd(fixture):
     from dpot_b200.train_engine import _TrainEngine
     z = np.load(os.path.join(G, fixture))

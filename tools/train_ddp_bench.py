@@ -32,14 +32,16 @@ name = sys.argv[1] if len(sys.argv) > 1 else "S"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 T_ar = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 rank, world, dev = init_from_env()
-cfg = zoo.zoo_cfg(name)
+SHAPES = {"L": dict(img_size=256, patch_size=16, modes=64)}          # BASELINE.json config 4
+cfg = zoo.zoo_cfg(name, **SHAPES.get(name, {}))
+R = cfg["img_size"]
 model = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).train()
 opt = Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.9), weight_decay=1e-6)
 opt.grad_scale = 1.0
 g = torch.Generator(device="cpu").manual_seed(100 + rank)
-xx = torch.randn((B, 128, 128, 10, 4), generator=g).to(dev)
-yy = torch.randn((B, 128, 128, T_ar, 4), generator=g).to(dev)
-msk = torch.ones((B, 128, 128, 1, 4), device=dev)
+xx = torch.randn((B, R, R, 10, 4), generator=g).to(dev)
+yy = torch.randn((B, R, R, T_ar, 4), generator=g).to(dev)
+msk = torch.ones((B, R, R, 1, 4), device=dev)
 nparam = sum(p.numel() for p in model.parameters())
 
 
@@ -105,9 +107,9 @@ if world > 1 and not QUICK:
     Bc = 2
     model2 = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0).to(dev).train()
     gx = torch.Generator(device="cpu").manual_seed(7)
-    X = torch.randn((world * Bc, 128, 128, 10, 4), generator=gx).to(dev)
-    Y = torch.randn((world * Bc, 128, 128, 1, 4), generator=gx).to(dev)
-    M = torch.ones((world * Bc, 128, 128, 1, 4), device=dev)
+    X = torch.randn((world * Bc, R, R, 10, 4), generator=gx).to(dev)
+    Y = torch.randn((world * Bc, R, R, 1, 4), generator=gx).to(dev)
+    M = torch.ones((world * Bc, R, R, 1, 4), device=dev)
     from dpot_b200.train import LpLossFn
     im0, _ = model2(X[:1].contiguous())        # builds the training engine
     del im0
