@@ -235,18 +235,22 @@ class FusedGradExchange:
     arena views) the exchange cannot start before the last accumulation: finish() then runs one all-reduce of the arena.
     """
 
-    def __init__(self, model, overlap: bool = False, group_mb: float = 24.0):
+    def __init__(self, model, overlap: Optional[bool] = None, group_mb: float = 24.0):
         """overlap=False (default): one all-reduce of the arena after backward.  Measured on 8 x B200 (profiles/r02p_*):
         queuing the messages behind backward's completion events does NOT pay -- the contraction kernels are persistent,
         one CTA per SM with a static tile partition, so every SM NCCL occupies delays a whole share of tiles (DPOT-M,
         16 / GPU: 15.6 ms overlapped vs 15.1 ms sequential vs 13.6 ms without exchange); the exchange itself runs at
-        ~620 GB/s bus bandwidth (1.37 ms for 489 MB)."""
+        ~620 GB/s bus bandwidth (1.37 ms for 489 MB).  For the two large models the overlap DOES pay (profiles/r02ah_*, 8 per
+        GPU: DPOT-L 38.3 -> 36.8 ms, DPOT-H 59.8 -> 57.1 ms), so overlap=None (default) turns it on above 1 GB of gradients."""
         from .train_engine import _TrainEngine
         self.overlap = overlap
+        self._auto = overlap is None
         if model._train_eng is None:
             model._train_eng = _TrainEngine(model)
         self.eng = model._train_eng
         self.eng.exchange = self
+        if self._auto:
+            self.overlap = self.eng.total * 4 > 1e9
         self.buf: Optional[torch.Tensor] = None
         self.events = None
         self.comm = None
