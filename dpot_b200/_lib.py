@@ -22,6 +22,9 @@ A_PLAIN, A_PATCH = 0, 1
 c_f32p = C.c_void_p  # device pointers travel as integers
 
 
+ABI_VERSION = 2          # DPOT_ABI_VERSION of include/dpot_b200.h this binding was written against
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", c_f32p), ("lda", C.c_int64), ("W", c_f32p), ("ldw", C.c_int64), ("C", c_f32p), ("ldc", C.c_int64),
@@ -201,7 +204,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.dpot_abi_version() != 2:
+        if lib.dpot_abi_version() != ABI_VERSION:
             raise DpotLibraryError("libdpot_b200.so ABI version mismatch")
         _lib = lib
     return _lib

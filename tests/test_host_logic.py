@@ -24,7 +24,15 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dpot_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.dpot_abi_version() == 2
+    assert lib.dpot_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define DPOT_ABI_VERSION (\d+)", hdr).group(1))
+
+
+def test_graft_entry_build_passes():
+    """The driver's build check: __graft_entry__.build() compiles, loads and verifies the library (it once asserted a stale
+    ABI version)."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
 
 
 def test_ctypes_struct_sizes_match_header():
