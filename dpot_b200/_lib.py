@@ -110,6 +110,7 @@ SIGNATURES = {
     "dpot_tc16_set_precision": (C.c_int, [_i32]),
     "dpot_set_pdl": (None, [_i32]),
     "dpot_set_cls_overlap": (None, [_i32]),
+    "dpot_set_cls_engine": (None, [_i32]),
     "dpot_set_sm_budget": (C.c_int, [_i32]),
     "dpot_gn_stats": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "dpot_gn_finalize": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p, _p, _p]),
@@ -142,6 +143,7 @@ SIGNATURES = {
     "dpot_out_tail": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p]),
     "dpot_spatial_mean": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "dpot_spatial_mean16": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "dpot_spatial_mean16s": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "dpot_input_stats": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p, _p, _p, _p]),
     "dpot_window_advance": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "dpot_ring_insert": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -60,6 +60,7 @@ static int run_tail(const float* Y, const float* w2, const float* b2, const dpot
 int g_fused_gn2 = 0;     // dpot_afno_set_fused_gn2: GroupNorm-2 + split inside the fused mixer.  Measured neutral (the in-kernel
                          // pass costs the 11 us the separate 12 us kernel took: it sits on the unit's serial path) -> off
 constexpr int AF_UNIT_CH = 128;
+int g_cls_tc = 1;        // dpot_set_cls_engine: 1 = the cls head on the f16-split engine, 0 = CUDA-core skinny contractions
 int g_cls_overlap = 0;   // measured (r02t): the side stream takes SMs from the persistent contraction kernels of the output head: -3 %
 struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 static SideStream* side_stream() {
@@ -166,6 +167,18 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       DPOT_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
       cs = side->st;
     }
+    if (d.depth > 0 && g_cls_tc) {
+      // mean -> split token; three contractions on the f16-split engine with split intermediates
+      DPOT_CALL(dpot_spatial_mean16s(ws + WL.n2, B, d.n, d.E, nullptr, ws + WL.tok, cs));
+      dpot_gemm_args g = gemm16_args(ws + WL.tok, d.E, packed + PL.cls0_16, d.E, ws + WL.c1, 0, B, d.E, d.E, prm->cls0_b, act);
+      out16(g, d.E);
+      DPOT_CALL(dpot_gemm(&g, cs));
+      g = gemm16_args(ws + WL.c1, d.E, packed + PL.cls2_16, d.E, ws + WL.c2, 0, B, d.E, d.E, prm->cls2_b, act);
+      out16(g, d.E);
+      DPOT_CALL(dpot_gemm(&g, cs));
+      g = gemm16_args(ws + WL.c2, d.E, packed + PL.cls4_16, d.E, cls, d.ncls, B, d.ncls, d.E, prm->cls4_b, DPOT_ACT_NONE);
+      DPOT_CALL(dpot_gemm(&g, cs));
+    } else {
     if (d.depth > 0) DPOT_CALL(dpot_spatial_mean16(ws + WL.n2, B, d.n, d.E, ws + WL.tok, cs));
     else DPOT_CALL(dpot_spatial_mean(lat, B, d.n, d.E, ws + WL.tok, cs));
     dpot_gemm_args g = gemm_args(ws + WL.tok, d.E, prm->cls0_w, d.E, ws + WL.c1, d.E, B, d.E, d.E, prm->cls0_b, act, DPOT_GEMM_AUTO);
@@ -174,6 +187,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
     DPOT_CALL(dpot_gemm(&g, cs));
     g = gemm_args(ws + WL.c2, d.E, prm->cls4_w, d.E, cls, d.ncls, B, d.ncls, d.E, prm->cls4_b, DPOT_ACT_NONE, DPOT_GEMM_AUTO);
     DPOT_CALL(dpot_gemm(&g, cs));
+    }
     if (side) DPOT_CUDA(cudaEventRecord(side->join, side->st));
   }
   auto join_side = [&]() -> int {
@@ -255,6 +269,11 @@ extern "C" int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm,
   if (use_tc16(d, DPOT_GEMM_AUTO)) {   // split-fp16 copies of every GEMM weight
     DPOT_CALL(dpot_split_f16(packed + L.WeffT, d.Kp, d.E, d.Kp, nullptr, nullptr, 0, packed + L.WeffT16, 2 * d.Kp, d.Kp, stream));
     DPOT_CALL(dpot_split_f16(packed + L.WtT, d.E, d.NP, d.E, nullptr, nullptr, 0, packed + L.WtT16, 2 * d.E, d.E, stream));
+    if (prm->cls0_w && prm->cls2_w && prm->cls4_w) {   // the cls head on the same engine (M = B rows: 8 tiles, latency ~1/2 of the CUDA-core form)
+      DPOT_CALL(dpot_split_f16(prm->cls0_w, d.E, d.E, d.E, nullptr, nullptr, 0, packed + L.cls0_16, 2 * d.E, d.E, stream));
+      DPOT_CALL(dpot_split_f16(prm->cls2_w, d.E, d.E, d.E, nullptr, nullptr, 0, packed + L.cls2_16, 2 * d.E, d.E, stream));
+      DPOT_CALL(dpot_split_f16(prm->cls4_w, d.E, d.ncls, d.E, nullptr, nullptr, 0, packed + L.cls4_16, 2 * d.E, d.E, stream));
+    }
     for (int i = 0; i < d.depth; ++i) {
       float* base = packed + L.blocks + (int64_t)i * L.blk_stride;
       const dpot_block_params& b = prm->blocks[i];
@@ -418,3 +437,4 @@ static int forward_impl(const dpot_config* cfg, const dpot_params* prm, const fl
 // 1: the classification head of dpot_forward* runs on a library-owned side stream, concurrently with the output head (default 0)
 extern "C" void dpot_set_cls_overlap(int32_t on) { dpot::g_cls_overlap = on ? 1 : 0; }
 extern "C" void dpot_afno_set_fused_gn2(int32_t on) { dpot::g_fused_gn2 = on ? 1 : 0; }
+extern "C" void dpot_set_cls_engine(int32_t tc) { dpot::g_cls_tc = tc ? 1 : 0; }

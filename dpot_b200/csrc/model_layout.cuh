@@ -44,6 +44,7 @@ struct Packed {
   // split-fp16 (DPOT_FMT_HL16) copies for the f16-split tensor-core engine; same float counts as the fp32 originals
   int64_t WeffT16, WtT16, Wc1_16, Wc2_16, fc1_16, fc2_16;   // the last four are offsets inside a block slab
   int64_t Wfus;                                             // fused AFNO mixer arena inside a block slab (afno_fused.cu)
+  int64_t cls0_16, cls2_16, cls4_16;                        // split-fp16 copies of the cls head weights
 };
 static inline Packed packed_layout(const Dims& d) {
   Packed L; int64_t o = 0;
@@ -67,6 +68,9 @@ static inline Packed packed_layout(const Dims& d) {
   L.bias_t = o; o += slot(d.NP);
   L.WeffT16 = o; o += slot((int64_t)d.E * d.Kp);
   L.WtT16 = o; o += slot((int64_t)d.NP * d.E);
+  L.cls0_16 = o; o += slot((int64_t)d.E * d.E);
+  L.cls2_16 = o; o += slot((int64_t)d.E * d.E);
+  L.cls4_16 = o; o += slot((int64_t)d.ncls * d.E);
   L.total = o;
   return L;
 }

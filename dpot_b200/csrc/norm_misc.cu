@@ -1,6 +1,7 @@
 // GroupNorm statistics, weight packing / folding, output-head tail, rollout window advance.
 // All of these are HBM/L2-bound streaming kernels: coalesced along the channel axis.
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include <cuda_fp16.h>
 
 namespace dpot {
@@ -261,7 +262,8 @@ __global__ void spatial_mean_kernel(const float* __restrict__ a, int n, int E, f
 }
 
 // split-fp16 rows [hi E | lo E]: 64 channels x 4 row slices per CTA, fp32 partial sums (<= n/4 terms) combined in double
-__global__ void __launch_bounds__(256) spatial_mean16_kernel(const __half* __restrict__ a, int n, int E, float* __restrict__ tok) {
+__global__ void __launch_bounds__(256) spatial_mean16_kernel(const __half* __restrict__ a, int n, int E, float* __restrict__ tok,
+                                                             __half* __restrict__ tok16) {
   __shared__ float red[2][4][64];
   const int c = threadIdx.x & 63, sl = threadIdx.x >> 6;
   const int e = blockIdx.x * 64 + c, b = blockIdx.y;
@@ -278,7 +280,14 @@ __global__ void __launch_bounds__(256) spatial_mean16_kernel(const __half* __res
   if (sl == 0 && e < E) {
     double hi = 0.0, lo = 0.0;
     for (int k = 0; k < 4; ++k) { hi += (double)red[0][k][c]; lo += (double)red[1][k][c]; }
-    tok[(int64_t)b * E + e] = (float)((hi + lo * (1.0 / 2048.0)) / (double)n);
+    const float m = (float)((hi + lo * (1.0 / 2048.0)) / (double)n);
+    if (tok) tok[(int64_t)b * E + e] = m;
+    if (tok16) {                      // the cls head's first contraction reads the token split (rows [hi E | lo E])
+      __half h, l;
+      hl_split(m, h, l);
+      tok16[(int64_t)b * 2 * E + e] = h;
+      tok16[(int64_t)b * 2 * E + E + e] = l;
+    }
   }
 }
 
@@ -531,9 +540,12 @@ extern "C" int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E
 }
 
 extern "C" int dpot_spatial_mean16(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* stream) {
-  DPOT_REQUIRE(a16 && tok && B > 0 && n > 0 && E > 0, DPOT_E_BADARG, "dpot_spatial_mean16: bad args");
+  return dpot_spatial_mean16s(a16, B, n, E, tok, nullptr, stream);
+}
+extern "C" int dpot_spatial_mean16s(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* tok16, void* stream) {
+  DPOT_REQUIRE(a16 && (tok || tok16) && B > 0 && n > 0 && E > 0, DPOT_E_BADARG, "dpot_spatial_mean16: bad args");
   spatial_mean16_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(a16), n, E, tok);
+      reinterpret_cast<const __half*>(a16), n, E, tok, reinterpret_cast<__half*>(tok16));
   DPOT_LAUNCH_CHECK("spatial_mean16_kernel");
   return 0;
 }

@@ -349,6 +349,9 @@ DPOT_API int dpot_spatial_mean(const float* a, int32_t B, int32_t n, int32_t E, 
 /* the same on a split-fp16 latent (DPOT_FMT_HL16 rows [hi E | lo E], as the last block's fc2 writes it for the output
    GEMM): the cls head then costs no extra fp32 copy of the latent. */
 DPOT_API int dpot_spatial_mean16(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* stream);
+/* the same, also (or only: tok = NULL) storing the token split, tok16[B, hi E | lo E]: the operand of the cls head's first
+   contraction on the f16-split engine */
+DPOT_API int dpot_spatial_mean16s(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* tok16, void* stream);
 /* per (sample, channel) mean and unbiased std + 1e-6 over (X,Y,T)  (models/dpot.py:367);
    writes musig[B, 2C] = [mu | sigma] and the im2col prologue tables a_scale/a_shift[B, P*P*C]. */
 DPOT_API int dpot_input_stats(const float* x, int32_t B, int64_t per_sample, int32_t C, int32_t PP,
@@ -472,6 +475,10 @@ DPOT_API int dpot_pack_weights(const dpot_config* cfg, const dpot_params* prm, f
 /* x[B,X,Y,T,C] -> y[B,X,Y,To,Co], cls[B,n_cls] (cls may be NULL) */
 DPOT_API int dpot_forward(const dpot_config* cfg, const dpot_params* prm, const float* packed, const float* x,
                  int32_t B, float* y, float* cls, float* workspace, int32_t engine, void* stream);
+
+/* knob (tests / A-B measurements): the classification head of the f16-split inference pipeline on 1 = the f16-split
+   tensor-core engine (default), 0 = the CUDA-core skinny contractions */
+DPOT_API void dpot_set_cls_engine(int32_t tc);
 
 /* SM budget of the persistent kernels (contractions, fused mixer, tail / PatchEmbed backward): n > 0 sizes their grids
    for n SMs instead of the whole device, leaving the rest to kernels that run CONCURRENTLY on other streams (NCCL's
