@@ -21,3 +21,10 @@ def set_precision(mode: str = "fp32") -> str:
         raise ValueError("precision must be 'fp32' or 'half'")
     prev = _lib.load().dpot_tc16_set_precision(1 if mode == "half" else 0)
     return "half" if prev else "fp32"
+
+
+def set_chain(k_chain: int = 2048) -> int:
+    """Longest tensor-core accumulation chain of one launch of the f16-split engine (dpot_tc16_set_chain): deeper forward
+    contractions (the channel MLP's fc2 of DPOT-M / L / H) run as chained launches over K-ranges.  0 = never chain
+    (one launch whatever the depth: 1.2e-9 * K relative error).  Returns the previous limit."""
+    return int(_lib.load().dpot_tc16_set_chain(int(k_chain)))

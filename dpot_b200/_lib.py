@@ -108,6 +108,8 @@ SIGNATURES = {
     "dpot_patch_embed_set_engine": (None, [_i32]),
     "dpot_tc16_set_debug": (None, [_i32]),
     "dpot_tc16_set_precision": (C.c_int, [_i32]),
+    "dpot_tc16_set_chain": (C.c_int, [_i32]),
+    "dpot_gemm_chained": (C.c_int, [C.POINTER(GemmArgs), _i32, _p, _i64, _p]),
     "dpot_set_pdl": (None, [_i32]),
     "dpot_set_cls_overlap": (None, [_i32]),
     "dpot_set_cls_engine": (None, [_i32]),

@@ -154,7 +154,8 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       g.residual = lat; g.ldr = d.E;
       if (i + 1 < d.depth) { g.out_stats = st1; g.stats_groups = groups; g.stats_rows_per_sample = d.n; }
       else { g.C = ws + WL.n2; out16(g, d.E); }   // last block: the latent is only read by the output GEMM (and the cls mean) -> split fp16
-      DPOT_CALL(dpot_gemm(&g, stream));
+      // hid > 2048 (DPOT-M / L / H): accumulation chains of <= dpot_tc16_set_chain halves (gemm.cu), partial sums in lat_next
+      DPOT_CALL(dpot_gemm_chained(&g, dpot_tc16_set_chain(-1), lat_next, d.E, stream));
     }
     float* tmp = lat; lat = lat_next; lat_next = tmp;
   }

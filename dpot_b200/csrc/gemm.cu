@@ -4,8 +4,68 @@
 
 using namespace dpot;
 
+namespace dpot {
+int g_chain_max = 2048;   // dpot_tc16_set_chain: longest accumulation chain of one launch of the f16-split engine (0 = unlimited)
+}
+
+static int gemm_one(const dpot_gemm_args* a, void* stream);
+
+// A tcgen05 fp32 accumulator truncates (round toward zero) on every accumulation step, so the error of a contraction
+// grows LINEARLY with its depth: measured 1.2e-9 * K relative L2 on this engine (tools/numerics_longk.py: K = 8192 ->
+// 9.7e-6, cuBLAS fp32 1.6e-6).  The channel MLP's fc2 of DPOT-M / L / H is 4096 / 6144 / 8192 deep and 12 / 24 / 27
+// blocks stack it, which put the full-depth forwards of L and H at 1.4e-5 (tests/test_full_depth_gpu.py).  Chained
+// form: the contraction runs as ceil(K / k_chain) launches over K-ranges; every launch but the last stores its fp32
+// partial sum (bias and row bias included) in `scratch`, the next one reads it back as a per-row bias -- an fp32
+// round-to-nearest add in the epilogue -- and the last launch applies the activation / scale / residual / statistics
+// / output format of the original call.  The error becomes that of one k_chain-deep chain (2048: 2.5e-6).
+static bool chain_form_ok(const dpot_gemm_args* a) {
+  return a->a_fmt == DPOT_FMT_HL16 && a->w_fmt == DPOT_FMT_HL16 && a->batch == 1 && !a->a_trans && !a->w_trans && a->k_split <= 1 &&
+         a->a_mode == DPOT_A_PLAIN && !a->C_pre && !a->dact_src && !a->a_scale;
+}
+
+extern "C" int dpot_gemm_chained(const dpot_gemm_args* a, int32_t k_chain, float* scratch, int64_t ld_scratch, void* stream) {
+  DPOT_REQUIRE(a != nullptr, DPOT_E_BADARG, "dpot_gemm_chained: null args");
+  if (k_chain <= 0 || a->K <= k_chain) return gemm_one(a, stream);
+  DPOT_REQUIRE(chain_form_ok(a), DPOT_E_BADARG,
+               "dpot_gemm_chained: needs the plain forward form of the f16-split engine (batch 1, no transposes / k_split / C_pre / dact)");
+  DPOT_REQUIRE(scratch && ld_scratch >= a->N && reinterpret_cast<uintptr_t>(scratch) % 16 == 0, DPOT_E_BADARG,
+               "dpot_gemm_chained: scratch [M, ld_scratch >= N] fp32, 16-byte aligned");
+  const int nch = (a->K + k_chain - 1) / k_chain;
+  const int64_t chunk = ((a->K + nch - 1) / nch + 63) / 64 * 64;       // equal chains, whole 64-half k-blocks
+  for (int64_t k0 = 0; k0 < a->K; k0 += chunk) {
+    dpot_gemm_args c = *a;
+    const bool first = k0 == 0, last = k0 + chunk >= a->K;
+    // A / W point to halves on this engine: a K-range is a column offset in both planes (lo plane = + *_lo_off)
+    c.A = reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(a->A) + k0);
+    c.W = reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(a->W) + k0);
+    c.K = (int32_t)(last ? a->K - k0 : chunk);
+    if (!first) { c.bias = nullptr; c.rowbias = scratch; c.rowbias_period = a->M; c.ldrb = ld_scratch; }
+    if (!last) {
+      c.C = scratch; c.ldc = ld_scratch; c.c_fmt = DPOT_FMT_F32; c.c_lo_off = 0; c.c_group = 0; c.c_group_stride = 0; c.c_mode = DPOT_A_PLAIN;
+      c.act = DPOT_ACT_NONE; c.residual = nullptr; c.c_scale = c.c_shift = nullptr; c.out_stats = nullptr; c.out_colsum = nullptr;
+    }
+    DPOT_CALL(gemm_one(&c, stream));
+  }
+  return 0;
+}
+
+extern "C" int dpot_tc16_set_chain(int32_t k_chain) {
+  const int prev = dpot::g_chain_max;
+  if (k_chain >= 0) dpot::g_chain_max = k_chain;
+  return prev;
+}
+
+// Entry point: long contractions whose result is plain fp32 chain in place (the partial sums live in C itself).
 extern "C" int dpot_gemm(const dpot_gemm_args* a, void* stream) {
   DPOT_REQUIRE(a != nullptr, DPOT_E_BADARG, "dpot_gemm: null args");
+  const int kc = dpot::g_chain_max;
+  if (kc > 0 && a->K > kc && a->A && a->W && a->C && chain_form_ok(a) && a->c_fmt == DPOT_FMT_F32 && a->c_group == 0 &&
+      a->c_mode == DPOT_A_PLAIN && a->ldc >= a->N && reinterpret_cast<uintptr_t>(a->C) % 16 == 0)
+    return dpot_gemm_chained(a, kc, a->C, a->ldc, stream);
+  return gemm_one(a, stream);
+}
+
+static int gemm_one(const dpot_gemm_args* a, void* stream) {
   DPOT_REQUIRE(a->A && a->W && a->C, DPOT_E_BADARG, "dpot_gemm: null A/W/C");
   DPOT_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, DPOT_E_BADARG, "dpot_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   DPOT_REQUIRE(a->batch >= 1, DPOT_E_BADARG, "dpot_gemm: batch must be >= 1");

@@ -322,7 +322,9 @@ extern "C" int dpot_train_forward(const dpot_config* cfg, const dpot_params* prm
       g.residual = lat; g.ldr = E;
       if (!last) { g.out_stats = reinterpret_cast<double*>(blk(i + 1) + TL.st1); g.stats_groups = GROUPS; g.stats_rows_per_sample = d.n; }
       else out16(g, E);
-      DPOT_CALL(dpot_gemm(&g, stream));
+      // long contraction (hid > 2048: DPOT-M / L / H): accumulation chains of <= dpot_tc16_set_chain halves, partial sums in
+      // the result itself or, for the split result of the last block, in a backward-phase scratch slot (free until then)
+      DPOT_CALL(dpot_gemm_chained(&g, dpot_tc16_set_chain(-1), last ? scratch + SL.dn2 : dst, E, stream));
     }
   }
   if (cls) {   // classification head; pre-activations kept for backward

@@ -146,7 +146,13 @@ def gemm16(A16: torch.Tensor, W16: torch.Tensor, *, bias=None, act=None, residua
         groups, rps = stats
         st = torch.empty((M // rps, groups, 2), device=A16.device, dtype=torch.float64)
         g.out_stats, g.stats_groups, g.stats_rows_per_sample = ptr(st), groups, rps
-    check(_lib.load().dpot_gemm(C.byref(g), _stream()), "dpot_gemm(tc16)")
+    lib = _lib.load()
+    kc = lib.dpot_tc16_set_chain(-1)
+    if out16 and nb == 1 and 0 < kc < K:    # split result: the chained partial sums need an fp32 buffer of their own
+        scratch = torch.empty((M, Nt), device=A16.device, dtype=torch.float32)
+        check(lib.dpot_gemm_chained(C.byref(g), kc, ptr(scratch), Nt, _stream()), "dpot_gemm_chained(tc16)")
+    else:
+        check(lib.dpot_gemm(C.byref(g), _stream()), "dpot_gemm(tc16)")
     return out if st is None else (out, st)
 
 

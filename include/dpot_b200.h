@@ -175,6 +175,16 @@ DPOT_API void dpot_set_pdl(int32_t on);
    This is the library's 16-bit mixed-precision mode (the reference's bf16 autocast configs, configs/pretrain_medium.yaml);
    results differ from fp32 at the 1e-3 level.  Returns the previous mode; mode < 0 only queries. */
 DPOT_API int dpot_tc16_set_precision(int32_t mode);
+/* Accumulation-chain limit of the f16-split engine.  A tcgen05 fp32 accumulator truncates on every step, so the error
+   of one launch grows linearly with the contraction depth (1.2e-9 * K rel-L2, measured).  dpot_gemm therefore runs a
+   plain forward-form contraction (batch 1, fp32 result) deeper than k_chain halves as ceil(K / k_chain) launches over
+   K-ranges whose fp32 partial sums pass through the result buffer (round-to-nearest adds in the epilogue); the last
+   launch applies the epilogue of the call.  Default 2048; 0 = never chain; negative = query.  Returns the previous
+   value.  Serves the channel MLP's fc2 (models/dpot.py:160) of DPOT-M / L / H (4096 / 6144 / 8192 deep). */
+DPOT_API int dpot_tc16_set_chain(int32_t k_chain);
+/* dpot_gemm with an explicit chain limit and partial-sum buffer scratch[M, ld_scratch] (fp32, may be args->C when the
+   result is plain fp32): for results stored in another format (split fp16).  K <= k_chain or k_chain <= 0: plain dpot_gemm. */
+DPOT_API int dpot_gemm_chained(const dpot_gemm_args* args, int32_t k_chain, float* scratch, int64_t ld_scratch, void* stream);
 /* pipeline-isolation experiments (results are garbage when non-zero): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue */
 DPOT_API void dpot_tc16_set_debug(int32_t mask);
 

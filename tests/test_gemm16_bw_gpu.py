@@ -93,3 +93,36 @@ def test_forward_with_preactivation_and_split_result():
     refp = x.astype(np.float64) @ W.astype(np.float64).T + b
     assert O.rel_l2(pre.cpu().numpy(), refp) < TOL
     assert O.rel_l2(ops.unsplit_f16(out16).cpu().numpy(), O.activation(refp, "gelu")) < TOL
+
+
+@pytest.mark.parametrize("K", [4096, 6144, 8192, 2112])
+def test_long_contraction_runs_as_chained_launches(K):
+    """fc2 of DPOT-M / L / H (models/dpot.py:160) is 4096 / 6144 / 8192 deep.  One tcgen05 accumulation chain of that
+    length is 1.2e-9 * K off (truncating accumulator); dpot_gemm chains <= 2048-deep launches through the result buffer.
+    Checked against fp64: plain fp32 result with bias + residual + GroupNorm statistics (chained in place), activation
+    result (partial sums must enter the activation), split-fp16 result (dpot_gemm_chained with scratch), and the
+    unchained launch for contrast."""
+    import dpot_b200
+    from dpot_b200 import ops
+    M, N, rps = 1024, 512, 256
+    A = np.maximum(_rand((M, K), 3), 0) + 0.1 * _rand((M, K), 4)
+    W, b, R = _rand((N, K), 5, K ** -0.5), _rand((N,), 6), _rand((M, N), 7)
+    pre = A.astype(np.float64) @ W.astype(np.float64).T + b
+    A16, W16 = ops.split_f16(_dev(A)), ops.split_f16(_dev(W))
+    rel = lambda x, ref: float(np.linalg.norm(x.double().cpu().numpy() - ref) / np.linalg.norm(ref))
+    assert dpot_b200.set_chain(2048) == 2048      # the default
+    out, st = ops.gemm16(A16, W16, bias=_dev(b), residual=_dev(R), stats=(8, rps))
+    e_plain = rel(out, pre + R)
+    ref_st = (pre + R).reshape(M // rps, rps, 8, N // 8)
+    e_st = max(rel(st[..., 0], ref_st.sum((1, 3))), rel(st[..., 1], (ref_st ** 2).sum((1, 3))))
+    e_act = rel(ops.gemm16(A16, W16, bias=_dev(b), act="gelu", residual=_dev(R)), O.activation(pre, "gelu") + R)
+    e_16 = rel(ops.unsplit_f16(ops.gemm16(A16, W16, bias=_dev(b), residual=_dev(R), out16=True)), pre + R)
+    try:
+        dpot_b200.set_chain(0)
+        e_one = rel(ops.gemm16(A16, W16, bias=_dev(b), residual=_dev(R)), pre + R)
+    finally:
+        dpot_b200.set_chain(2048)
+    print(f"K={K}: chained {e_plain:.2e} (stats {e_st:.2e}, gelu {e_act:.2e}, split result {e_16:.2e}); one launch {e_one:.2e}")
+    assert max(e_plain, e_act, e_16) < TOL and e_st < 2e-6      # statistics: fp32 partial sums per warp, double across tiles
+    if K >= 4096:
+        assert e_one > 1.5 * e_plain      # the reason the chained form exists
