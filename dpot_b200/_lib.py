@@ -152,6 +152,7 @@ SIGNATURES = {
     "dpot_patch_embed": (C.c_int, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
     "dpot_adam_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _d, _i32, _i32, _d, _p]),
     "dpot_adam_step_multi": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _p, _i32, _d, _p]),
+    "dpot_lamb_step_multi": (C.c_int, [_p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _d, _p, _i32, _i32, _p, _p, _p]),
     "dpot_adam_step_multi_clip": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _d, _d, _d, _d, _d, _p, _i32, _d, _p, _d, _p]),
     "dpot_grad_sqnorm": (C.c_int, [_p, _p, _i32, _p, _p]),
     "dpot_chan_sumsq": (C.c_int, [_p, _i32, _i64, _i32, _p, _p]),

@@ -513,3 +513,25 @@ def adam_step_multi(params, grads, ms, vs, vmaxs, steps, *, lr, beta1, beta2, ep
     check(_lib.load().dpot_adam_step_multi_clip(pa, ga, ma, va, xa, na, n, lr, beta1, beta2, eps, weight_decay, sa,
                                                 1 if decoupled else 0, grad_scale, ptr(grad_sqnorm), float(max_norm),
                                                 _stream()), "dpot_adam_step_multi")
+
+
+@_on_device
+def lamb_step_multi(params, grads, ms, vs, steps, *, lr, beta1, beta2, eps, weight_decay, clamp_value, debias, adam,
+                    norms: torch.Tensor, info: torch.Tensor):
+    """Lamb.step (utils/optimizer.py:421-499) over a list of tensors: dpot_lamb_step_multi.  norms [2n] double and
+    info [3n] float (weight_norm, adam_norm, trust_ratio per tensor) are caller-owned device buffers."""
+    n = len(params)
+    if n == 0:
+        return
+    _need_cuda(*params, *grads, *ms, *vs, info)
+    assert norms.is_cuda and norms.dtype == torch.float64 and norms.numel() >= 2 * n and info.numel() >= 3 * n
+    VP = C.c_void_p * n
+    pa = VP(*[p.data_ptr() for p in params])
+    ga = VP(*[g.data_ptr() for g in grads])
+    ma = VP(*[m.data_ptr() for m in ms])
+    va = VP(*[v.data_ptr() for v in vs])
+    na = (C.c_int64 * n)(*[p.numel() for p in params])
+    sa = (C.c_int32 * n)(*steps)
+    check(_lib.load().dpot_lamb_step_multi(pa, ga, ma, va, na, n, lr, beta1, beta2, eps, weight_decay, float(clamp_value), sa,
+                                           1 if debias else 0, 1 if adam else 0, ptr(norms), ptr(info), _stream()),
+          "dpot_lamb_step_multi")

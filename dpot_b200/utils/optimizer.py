@@ -8,8 +8,9 @@ kernel of libdpot_b200.so per 32 tensors instead of ~8 elementwise kernels per t
 The reference's ``grad * grad.conj()`` only differs from ``grad**2`` for complex parameters;
 no parameter of the reference is complex (models/dpot.py:45-48), complex tensors raise here.
 
-``Lamb`` (utils/optimizer.py:359-499) is off the hot path (no config selects it); it is kept as a
-small plain-torch optimizer so that ``from utils.optimizer import Adam, Lamb`` keeps working.
+``Lamb`` (utils/optimizer.py:359-499, the ``--opt lamb`` branch of the scripts) keeps the reference's
+constructor and state layout too; its step is the fused two-stage multi-tensor kernel pair of
+csrc/lamb.cu (moments + per-tensor norms, then the trust-ratio update) without host synchronisation.
 """
 from __future__ import annotations
 
@@ -109,44 +110,67 @@ class AdamW(_FusedAdamBase):
 
 
 class Lamb(Optimizer):
-    """Layer-wise adaptive moments (reference utils/optimizer.py:359-499).  Plain torch: not on the
-    hot path (no shipped config uses --opt lamb)."""
+    """Layer-wise adaptive moments, reference utils/optimizer.py:359-499 (`--opt lamb`, evaluate.py:135-136 constructs it
+    with adam=True).  Same constructor, param_groups and per-parameter state (`step`, `exp_avg`, `exp_avg_sq`,
+    `weight_norm`, `adam_norm`, `trust_ratio`) as the reference; the step itself is dpot_lamb_step_multi: two launches
+    per 56 tensors, no host synchronisation (the reference synchronises twice per parameter: `weight_norm == 0` and the
+    tensor-valued alpha of the final add_).  weight_norm / adam_norm / trust_ratio are 0-dim device tensors (views of
+    one buffer per group), as the reference's are whenever both norms are non-zero."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0, clamp_value=10, adam=False,
                  debias=False):
-        if lr <= 0.0 or eps < 0.0 or weight_decay < 0 or clamp_value < 0.0:
-            raise ValueError("Invalid Lamb hyper-parameter")
-        if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
-            raise ValueError("Invalid beta parameter: {}".format(betas))
+        if lr <= 0.0:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if eps < 0.0:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if weight_decay < 0:
+            raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
+        if clamp_value < 0.0:
+            raise ValueError("Invalid clamp value: {}".format(clamp_value))
         self.clamp_value, self.adam, self.debias = clamp_value, adam, debias
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
     def step(self, closure=None):
-        loss = closure() if closure is not None else None
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         for group in self.param_groups:
-            b1, b2 = group['betas']
+            ps, gs, ms, vs, steps = [], [], [], [], []
             for p in group['params']:
                 if p.grad is None:
                     continue
+                if p.grad.is_sparse:
+                    raise RuntimeError('Lamb does not support sparse gradients, please consider SparseAdam instead')
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise RuntimeError('dpot_b200 Lamb: parameters must be float32 CUDA tensors (no CPU fallback)')
+                if not (p.is_contiguous() and p.grad.is_contiguous()):
+                    raise RuntimeError('dpot_b200 Lamb: parameters and gradients must be contiguous')
                 st = self.state[p]
-                if not st:
+                if len(st) == 0:
                     st['step'] = 0
-                    st['exp_avg'] = torch.zeros_like(p)
-                    st['exp_avg_sq'] = torch.zeros_like(p)
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st['step'] += 1
-                m, v, g = st['exp_avg'], st['exp_avg_sq'], p.grad
-                m.mul_(b1).add_(g, alpha=1 - b1)
-                v.mul_(b2).addcmul_(g, g.conj(), value=1 - b2)
-                corr = math.sqrt(1 - b2 ** st['step']) / (1 - b1 ** st['step']) if self.debias else 1
-                w_norm = torch.norm(p).clamp(0, self.clamp_value)
-                upd = m / v.sqrt().add(group['eps'])
-                if group['weight_decay'] != 0:
-                    upd.add_(p, alpha=group['weight_decay'])
-                u_norm = torch.norm(upd)
-                trust = 1 if (w_norm == 0 or u_norm == 0) else w_norm / u_norm
-                st['weight_norm'], st['adam_norm'], st['trust_ratio'] = w_norm, u_norm, trust
-                if self.adam:
-                    trust = 1
-                p.add_(upd, alpha=-group['lr'] * corr * trust)
+                ps.append(p); gs.append(p.grad); ms.append(st['exp_avg']); vs.append(st['exp_avg_sq'])
+                steps.append(int(st['step']))
+            if not ps:
+                continue
+            dev, n = ps[0].device, len(ps)
+            norms = torch.empty(2 * n, device=dev, dtype=torch.float64)
+            info = torch.empty(3 * n, device=dev, dtype=torch.float32)
+            beta1, beta2 = group['betas']
+            with torch.cuda.device(dev):
+                ops.lamb_step_multi(ps, gs, ms, vs, steps, lr=float(group['lr']), beta1=beta1, beta2=beta2, eps=group['eps'],
+                                    weight_decay=group['weight_decay'], clamp_value=self.clamp_value, debias=self.debias,
+                                    adam=self.adam, norms=norms, info=info)
+            for k, p in enumerate(ps):
+                st = self.state[p]
+                st['weight_norm'], st['adam_norm'], st['trust_ratio'] = info[3 * k], info[3 * k + 1], info[3 * k + 2]
+            torch.autograd.graph.increment_version(ps)      # raw-pointer update: see _FusedAdamBase.step
         return loss

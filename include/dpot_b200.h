@@ -418,6 +418,17 @@ DPOT_API int dpot_adam_step_multi_clip(float* const* p, const float* const* g, f
                                        double beta2, double eps, double weight_decay, const int32_t* steps,
                                        int32_t decoupled, double grad_scale, const double* grad_sqnorm, double max_norm,
                                        void* stream);
+/* Lamb.step (utils/optimizer.py:421-499; the `--opt lamb` branch, evaluate.py:135-136) over `count` tensors in two
+   launches per 56 tensors and no host synchronisation: stage 1 updates exp_avg / exp_avg_sq and reduces sum p^2 and
+   sum u^2 per tensor (u = exp_avg / (sqrt(exp_avg_sq) + eps) [+ wd p]) into norms[2*count] (double, zeroed by the
+   call); stage 2 applies p -= lr * bias_correction * trust * u with weight_norm = min(||p||, clamp_value),
+   trust = 1 if either norm is 0 else weight_norm / ||u|| (1 when `adam`), and stores (weight_norm, adam_norm,
+   trust_ratio) per tensor in info[3*count] (may be NULL) -- the reference's state entries.  steps[t] >= 1 is the
+   tensor's step count AFTER the increment (debias: bias_correction = sqrt(1-b2^t)/(1-b1^t), else 1). */
+DPOT_API int dpot_lamb_step_multi(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* n,
+                         int32_t count, double lr, double beta1, double beta2, double eps, double weight_decay,
+                         double clamp_value, const int32_t* steps, int32_t debias, int32_t adam, double* norms, float* info,
+                         void* stream);
 /* global gradient norm: out_sq[0] = sum over `count` tensors of sum g^2 (double accumulation; zeroed by the call).
    Replaces the norm computation of clip_grad_norm_, train_temporal.py:228. */
 DPOT_API int dpot_grad_sqnorm(const float* const* g, const int64_t* n, int32_t count, double* out_sq, void* stream);

@@ -325,6 +325,28 @@ def adam_step(p: np.ndarray, g: np.ndarray, m: np.ndarray, v: np.ndarray, step: 
     return p, m, v
 
 
+def lamb_step(p: np.ndarray, g: np.ndarray, m: np.ndarray, v: np.ndarray, step: int, *, lr: float, beta1: float,
+              beta2: float, eps: float, weight_decay: float, clamp_value: float = 10.0, adam: bool = False,
+              debias: bool = False):
+    """Lamb.step for one parameter, utils/optimizer.py:459-491.  `step` is the 1-based count after the increment (:460).
+    Updates p, m, v in place; returns (weight_norm, adam_norm, trust_ratio) as the reference stores them (:485-487)."""
+    dt = p.dtype.type
+    m *= dt(beta1)
+    m += dt(1 - beta1) * g  # :463
+    v *= dt(beta2)
+    v += dt(1 - beta2) * (g * g)  # :465
+    corr = math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step) if debias else 1  # :468-472
+    step_size = lr * corr  # :475
+    w_norm = dt(min(max(float(np.sqrt(np.sum(p.astype(np.float64) ** 2))), 0.0), clamp_value))  # :474
+    upd = m / (np.sqrt(v) + dt(eps))  # :476
+    if weight_decay != 0:
+        upd = upd + dt(weight_decay) * p  # :477-478
+    u_norm = dt(np.sqrt(np.sum(upd.astype(np.float64) ** 2)))  # :479
+    trust = dt(1) if (w_norm == 0 or u_norm == 0) else dt(w_norm / u_norm)  # :480-483
+    p += dt(-step_size * float(dt(1) if adam else trust)) * upd  # :488-491
+    return w_norm, u_norm, trust
+
+
 # --------------------------------------------------------------------------- #
 # synthetic parameters / inputs (platform-independent: numpy Generator streams)
 # --------------------------------------------------------------------------- #

@@ -208,9 +208,13 @@ def test_optimizer_state_layout_and_errors():
         AdamW([p], lr=-1.0)
     q = torch.nn.Parameter(torch.ones(3))
     lamb = Lamb([q], lr=1e-2)
+    assert lamb.clamp_value == 10 and lamb.adam is False and lamb.debias is False and lamb.param_groups[0]["eps"] == 1e-6
     q.grad = torch.ones(3)
-    lamb.step()
-    assert set(lamb.state[q]) >= {"step", "exp_avg", "exp_avg_sq", "trust_ratio"}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lamb.step()  # fused step only: no CPU / plain-torch fallback
+    for bad in (dict(lr=0.0), dict(eps=-1.0), dict(betas=(1.0, 0.9)), dict(weight_decay=-1), dict(clamp_value=-1.0)):
+        with pytest.raises(ValueError):
+            Lamb([q], **bad)
 
 
 def test_product_does_not_import_oracle():
