@@ -291,6 +291,59 @@ __global__ void __launch_bounds__(256) spatial_mean16_kernel(const __half* __res
   }
 }
 
+// The same with 16-byte loads (E % 8 == 0): a CTA owns 128 channels of one sample, 16 lanes-of-8-channels x 16 row
+// slices; every thread keeps 8 loads of 16 B in flight (the 2-byte loads of the kernel above ran at 2 TB/s on an
+// L2-resident latent: 16.9 us for 33.5 MB at DPOT-S, B = 32).
+__global__ void __launch_bounds__(256) spatial_mean16v_kernel(const __half* __restrict__ a, int n, int E, float* __restrict__ tok,
+                                                              __half* __restrict__ tok16) {
+  __shared__ float red[2][16][128 + 4];
+  const int cg = threadIdx.x & 15, sl = threadIdx.x >> 4;
+  const int e0 = blockIdx.x * 128 + cg * 8, b = blockIdx.y;
+  float sh[8], slo[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[k] = slo[k] = 0.f;
+  if (e0 < E) {
+    const __half* p = a + (int64_t)b * n * 2 * E + e0;
+    auto acc = [&](const uint4& v, float (&d)[8]) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); d[2 * k] += f.x; d[2 * k + 1] += f.y; }
+    };
+    int r = sl;
+    for (; r + 48 < n; r += 64) {
+      uint4 vh[4], vl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        vh[q] = *reinterpret_cast<const uint4*>(p + (int64_t)(r + 16 * q) * 2 * E);
+        vl[q] = *reinterpret_cast<const uint4*>(p + (int64_t)(r + 16 * q) * 2 * E + E);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { acc(vh[q], sh); acc(vl[q], slo); }
+    }
+    for (; r < n; r += 16) {
+      acc(*reinterpret_cast<const uint4*>(p + (int64_t)r * 2 * E), sh);
+      acc(*reinterpret_cast<const uint4*>(p + (int64_t)r * 2 * E + E), slo);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[0][sl][cg * 8 + k] = sh[k]; red[1][sl][cg * 8 + k] = slo[k]; }
+  __syncthreads();
+  const int c = threadIdx.x, e = blockIdx.x * 128 + c;
+  if (c < 128 && e < E) {
+    double hi = 0.0, lo = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { hi += (double)red[0][k][c]; lo += (double)red[1][k][c]; }
+    const float m = (float)((hi + lo * (1.0 / 2048.0)) / (double)n);
+    if (tok) tok[(int64_t)b * E + e] = m;
+    if (tok16) {
+      __half h, l;
+      hl_split(m, h, l);
+      tok16[(int64_t)b * 2 * E + e] = h;
+      tok16[(int64_t)b * 2 * E + E + e] = l;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- input statistics
 constexpr int IS_CMAX = 16;
 __global__ void __launch_bounds__(1024) input_stats_kernel(const float* __restrict__ x, int64_t per_sample, int C,
@@ -544,6 +597,12 @@ extern "C" int dpot_spatial_mean16(const void* a16, int32_t B, int32_t n, int32_
 }
 extern "C" int dpot_spatial_mean16s(const void* a16, int32_t B, int32_t n, int32_t E, float* tok, void* tok16, void* stream) {
   DPOT_REQUIRE(a16 && (tok || tok16) && B > 0 && n > 0 && E > 0, DPOT_E_BADARG, "dpot_spatial_mean16: bad args");
+  if (E % 8 == 0 && reinterpret_cast<uintptr_t>(a16) % 16 == 0) {
+    spatial_mean16v_kernel<<<dim3((unsigned)ceil_div(E, 128), (unsigned)B), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __half*>(a16), n, E, tok, reinterpret_cast<__half*>(tok16));
+    DPOT_LAUNCH_CHECK("spatial_mean16v_kernel");
+    return 0;
+  }
   spatial_mean16_kernel<<<dim3((unsigned)ceil_div(E, 64), (unsigned)B), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const __half*>(a16), n, E, tok, reinterpret_cast<__half*>(tok16));
   DPOT_LAUNCH_CHECK("spatial_mean16_kernel");

@@ -70,8 +70,9 @@ def ar_train_step(model, optimizer, xx: torch.Tensor, yy: torch.Tensor, msk: Opt
         im, _cls = model(xx)
         term = LpLossFn.apply(im, y, msk)
         loss = term if loss is None else loss + term
-        xx = torch.cat((xx[..., T_bundle:, :], im), dim=-2)
         n_ar += 1
+        if t + T_bundle < yy.shape[-2]:      # the window shift (:219) feeds the NEXT forward only: not after the last one
+            xx = torch.cat((xx[..., T_bundle:, :], im), dim=-2)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
     if arena is not None:

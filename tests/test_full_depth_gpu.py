@@ -80,3 +80,42 @@ def test_full_depth_forward_matches_reference(name, B):
     print(f"\nDPOT-{name} full depth ({cfg['depth']} blocks) vs fp64 reference: ours y {e_y:.2e} cls {e_c:.2e} | "
           f"reference fp32 eager y {r_y:.2e} cls {r_c:.2e} | ours vs fp32 eager y {_rel(y, y_ref.double()):.2e}")
     assert e_y < TOL and e_c < TOL, (e_y, e_c)
+
+
+def test_half_mode_against_reference_bf16_autocast():
+    """BASELINE.json config 3 names a bf16 DPOT-M step.  The reference has no reduced-precision code of its own; what a
+    user would run is its DPOTNet under torch.autocast(bfloat16).  This library's 16-bit mode is set_precision("half"):
+    fp16 operands (11-bit significand), one tensor-core MMA per product, fp32 accumulation / epilogues / residual stream.
+    Both against the fp64 reference at full depth: the half mode must be at least as close to it as the autocast run
+    (measured: ~3e-4 vs ~1e-2), and the 1e-5 bar applies to the default fp32-faithful mode only."""
+    import dpot_b200
+    from dpot_b200 import zoo
+    from dpot_b200.models.dpot import DPOTNet
+    RefNet = _reference()
+    cfg = zoo.zoo_cfg("M", **SHAPES["M"])
+    ours = zoo.synthetic_weights_(DPOTNet(**cfg), seed=0)
+    sd = ours.state_dict()
+    x = torch.randn((2, 128, 128, 10, 4), generator=torch.Generator().manual_seed(7)).cuda()
+    with torch.no_grad():
+        torch.set_default_dtype(torch.float64)
+        try:
+            y64, _ = _truth(RefNet, cfg, sd, x)
+        finally:
+            torch.set_default_dtype(torch.float32)
+        ref = RefNet(**cfg)
+        ref.load_state_dict(sd)
+        ref = ref.cuda().eval()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y_bf16, _ = ref(x)
+        del ref
+        ours = ours.cuda().eval()
+        prev = dpot_b200.set_precision("half")
+        try:
+            y_half, _ = ours(x)
+        finally:
+            dpot_b200.set_precision(prev)
+        y_fp32, _ = ours(x)
+    e_half, e_bf16, e_fp32 = _rel(y_half, y64), _rel(y_bf16.float(), y64), _rel(y_fp32, y64)
+    print(f"\nDPOT-M full depth vs fp64 reference: half mode {e_half:.2e} | reference under bf16 autocast {e_bf16:.2e} | "
+          f"fp32-faithful mode {e_fp32:.2e}")
+    assert e_half < e_bf16 and e_half < 2e-3 and e_fp32 < TOL
