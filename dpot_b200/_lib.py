@@ -126,7 +126,7 @@ SIGNATURES = {
     "dpot_afno_fused": (C.c_int, [_p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "dpot_afno_fused_gn2": (C.c_int, [_p, _p, _p, _p, _i32, _f, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _f, _p]),
     "dpot_afno_set_fused": (None, [_i32]),
-    "dpot_afno_set_fused_gn2": (None, [_i32]),
+    "dpot_afno_set_fused_gn2": (C.c_int, [_i32]),
     "dpot_afno_fused_set_trace": (None, [C.c_void_p]),
     "dpot_split_f16_gn": (C.c_int, [_p, _i64, _i64, _i32, _p, _p, _p, _i32, _f, _i32, _p, _i64, _i64, _p]),
     "dpot_afno_fft_inv": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _f, _p]),

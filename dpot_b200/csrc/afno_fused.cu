@@ -452,14 +452,21 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
           }
           fft_reg<16, +1>(zr, zi);
           float* fp = f_u + (int64_t)(2 * pr) * 16 * E + j;
+          // GroupNorm-2 in the kernel: the two output rows go back into this thread's OWN 32 slots of Z (the only ones it
+          // has just read; no other thread touches them) and are normalised from there once the unit's statistics are known
+          float2* const zs0 = Z + ((2 * pr) * 8) * 128 + j;
+          float2* const zs1 = zs0 + 8 * 128;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float v0 = fmaf(zr[q], norm, fmaf(k0[q], sc, sh));
-            const float v1 = fmaf(zi[q], norm, fmaf(k1v[q], sc, sh));
-            fp[(int64_t)q * E] = v0;
-            fp[(int64_t)(16 + q) * E] = v1;
-            s1 += v0 + v1;
-            s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
+          for (int q = 0; q < 16; q += 2) {
+            const float v0a = fmaf(zr[q], norm, fmaf(k0[q], sc, sh)), v0b = fmaf(zr[q + 1], norm, fmaf(k0[q + 1], sc, sh));
+            const float v1a = fmaf(zi[q], norm, fmaf(k1v[q], sc, sh)), v1b = fmaf(zi[q + 1], norm, fmaf(k1v[q + 1], sc, sh));
+            if (P.f) {
+              fp[(int64_t)q * E] = v0a; fp[(int64_t)(q + 1) * E] = v0b;
+              fp[(int64_t)(16 + q) * E] = v1a; fp[(int64_t)(17 + q) * E] = v1b;
+            }
+            if (P.n2) { zs0[(q >> 1) * 128] = make_float2(v0a, v0b); zs1[(q >> 1) * 128] = make_float2(v1a, v1b); }
+            s1 += (v0a + v0b) + (v1a + v1b);
+            s2 = fmaf(v0a, v0a, fmaf(v0b, v0b, fmaf(v1a, v1a, fmaf(v1b, v1b, s2))));
           }
         }
         if (P.stats2 || P.n2) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
@@ -473,7 +480,8 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
         if (P.n2) {
           // GroupNorm-2 + fp16 split of the channel-MLP input in the same launch: a unit covers whole groups (group size
           // 32 / 64 / 128 channels of its 128), so its statistics are complete once the 16 warps have met; every thread
-          // then re-reads the f values it has just written (its own stores: L1 / L2 hits) and writes them normalised.
+          // then takes its 64 values back from shared memory (stashed above) and writes them normalised and split --
+          // f itself need not go to global memory at all (P.f == nullptr: inference, nobody else reads it).
           float* red = reinterpret_cast<float*>(S + 131072);       // the 16 KB of the operand tile beyond Z
           if (lane == 0) { red[2 * warp] = s1; red[2 * warp + 1] = s2; }
           named_bar_sync(1, AF_CTHREADS);
@@ -493,19 +501,27 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
 #pragma unroll 1
           for (int t = 0; t < 2; ++t) {
             const int pr = sl + 4 * t;
-            const float* fp = f_u + (int64_t)(2 * pr) * 16 * E + j;
+            const float2* const zs0 = Z + ((2 * pr) * 8) * 128 + j;
+            const float2* const zs1 = zs0 + 8 * 128;
             __half* np_ = P.n2 + ((int64_t)b * 256 + (2 * pr) * 16) * (2 * (int64_t)E) + ch;
             float v0[16], v1[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) { v0[q] = fp[(int64_t)q * E]; v1[q] = fp[(int64_t)(16 + q) * E]; }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              __half hi, lo;
-              hl_split(fmaf(v0[q], sc2, sh2), hi, lo);
-              np_[(int64_t)q * 2 * E] = hi; np_[(int64_t)q * 2 * E + E] = lo;
-              hl_split(fmaf(v1[q], sc2, sh2), hi, lo);
-              np_[(int64_t)(16 + q) * 2 * E] = hi; np_[(int64_t)(16 + q) * 2 * E + E] = lo;
+            for (int q = 0; q < 16; q += 2) {
+              const float2 a0 = zs0[(q >> 1) * 128], a1 = zs1[(q >> 1) * 128];
+              v0[q] = a0.x; v0[q + 1] = a0.y; v1[q] = a1.x; v1[q + 1] = a1.y;
             }
+            // adjacent lanes own adjacent channels: the even lane stores (hi_j, hi_j+1) into the hi plane, the odd lane
+            // (lo_j-1, lo_j) into the lo plane -- one 4-byte store per value instead of two 2-byte stores
+            uint32_t* const np32 = reinterpret_cast<uint32_t*>((lane & 1) ? np_ + E - 1 : np_);
+            auto put = [&](float v, int row) {
+              __half hi, lo;
+              hl_split(fmaf(v, sc2, sh2), hi, lo);
+              const uint32_t w = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+              const uint32_t pw = __shfl_xor_sync(0xffffffffu, w, 1);
+              np32[(int64_t)row * E] = (lane & 1) ? __byte_perm(pw, w, 0x7632) : __byte_perm(w, pw, 0x5410);   // row stride 2E halves = E words
+            };
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { put(v0[q], q); put(v1[q], 16 + q); }
           }
         }
       }
@@ -629,7 +645,7 @@ extern "C" int dpot_afno_fused_gn2(const float* lat, const double* stats1, const
                                    int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
                                    int32_t act, float* f, double* stats2, float* dbg, void* n2_16, const float* gamma2,
                                    const float* beta2, float eps2, void* stream) {
-  DPOT_REQUIRE(lat && stats1 && gamma1 && beta1 && packed && f, DPOT_E_BADARG, "dpot_afno_fused: null pointer");
+  DPOT_REQUIRE(lat && stats1 && gamma1 && beta1 && packed && (f || n2_16), DPOT_E_BADARG, "dpot_afno_fused: null pointer");
   DPOT_REQUIRE(lat != f, DPOT_E_BADARG, "dpot_afno_fused: in-place operation is not supported (the skip term re-reads the input)");
   DPOT_REQUIRE(B > 0 && dpot_afno_fused_supported(h, E, nb, h, h / 2 + 1, groups), DPOT_E_UNSUPPORTED,
                "dpot_afno_fused: geometry h=%d E=%d nb=%d groups=%d is not served by the fused mixer", h, E, nb, groups);

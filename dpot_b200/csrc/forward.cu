@@ -57,8 +57,9 @@ static int run_tail(const float* Y, const float* w2, const float* b2, const dpot
 // the last latent, like the output head: it runs on a library-owned side stream between a fork event (after the last
 // block) and a join event (end of the forward) -- also under stream capture, where the events become graph edges.
 // One side stream per device: concurrent forwards from SEVERAL host threads on one device are not supported with it.
-int g_fused_gn2 = 0;     // dpot_afno_set_fused_gn2: GroupNorm-2 + split inside the fused mixer.  Measured neutral (the in-kernel
-                         // pass costs the 11 us the separate 12 us kernel took: it sits on the unit's serial path) -> off
+int g_fused_gn2 = 1;     // dpot_afno_set_fused_gn2: GroupNorm-2 + split inside the fused mixer (the unit's f tile stays in shared
+                         // memory, f never goes to global memory): the separate 12 us pass per block is gone, the in-kernel
+                         // pass costs ~8.7 us per launch -> +1.5 % on the rollout (tools/ab_gn2.py)
 constexpr int AF_UNIT_CH = 128;
 int g_cls_tc = 1;        // dpot_set_cls_engine: 1 = the cls head on the f16-split engine, 0 = CUDA-core skinny contractions
 int g_cls_overlap = 0;   // measured (r02t): the side stream takes SMs from the persistent contraction kernels of the output head: -3 %
@@ -115,7 +116,7 @@ static int forward_tc16(const dpot_config* cfg, const dpot_params* prm, const fl
       fused_gn2 = gnref && g_fused_gn2 && AF_UNIT_CH % (d.E / groups) == 0 && (d.E / groups) % 32 == 0;
       if (fused_gn2) {
         DPOT_CALL(dpot_afno_fused_gn2(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, pk + PL.Wfus, act,
-                                      ws + WL.f, nullptr, nullptr, ws + WL.n2, bp.norm2_w, bp.norm2_b, 1e-5f, stream));
+                                      nullptr /* f stays on chip */, nullptr, nullptr, ws + WL.n2, bp.norm2_w, bp.norm2_b, 1e-5f, stream));
       } else {
         DPOT_CUDA(cudaMemsetAsync(st2, 0, sizeof(double) * 2 * groups * B, st));
         DPOT_CALL(dpot_afno_fused(lat, st1, bp.norm1_w, bp.norm1_b, groups, 1e-5f, B, d.h, d.E, d.nb, pk + PL.Wfus, act,
@@ -437,5 +438,5 @@ static int forward_impl(const dpot_config* cfg, const dpot_params* prm, const fl
 
 // 1: the classification head of dpot_forward* runs on a library-owned side stream, concurrently with the output head (default 0)
 extern "C" void dpot_set_cls_overlap(int32_t on) { dpot::g_cls_overlap = on ? 1 : 0; }
-extern "C" void dpot_afno_set_fused_gn2(int32_t on) { dpot::g_fused_gn2 = on ? 1 : 0; }
+extern "C" int dpot_afno_set_fused_gn2(int32_t on) { const int prev = dpot::g_fused_gn2; if (on >= 0) dpot::g_fused_gn2 = on ? 1 : 0; return prev; }
 extern "C" void dpot_set_cls_engine(int32_t tc) { dpot::g_cls_tc = tc ? 1 : 0; }

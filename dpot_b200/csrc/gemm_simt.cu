@@ -249,6 +249,66 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const GemmDe
   }
 }
 
+// M <= 32 rows and K <= 1024 (the classification head at every published width up to 1024): the WHOLE A panel
+// (<= 128 KB) arrives in shared memory by bulk async copies -- one elected thread, one mbarrier, no per-thread staging
+// loop (the slice-by-slice staging of the kernel above exposed the L2 latency twice per launch: 18-21 us per head layer)
+// -- while every warp already has its entire weight row (K / 128 float4 per lane) in flight.
+constexpr int SW_MAXK = 1024, SW_V = SW_MAXK / 128;
+__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_whole_kernel(const GemmDev p) {
+  extern __shared__ __align__(128) float A_s[];          // [32][K], then the mbarrier
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * SK_WARPS + warp, K = p.K;
+  const bool live = n0 < p.N;
+  const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(A_s), bar = a_s + 32u * (uint32_t)K * 4u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t row_bytes = (uint32_t)K * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)p.M) : "memory");
+    for (int i = 0; i < p.M; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(a_s + (uint32_t)i * row_bytes), "l"(p.A + (int64_t)i * p.lda), "r"(row_bytes), "r"(bar) : "memory");
+  }
+  for (int e = p.M * (K / 4) + threadIdx.x; e < 32 * (K / 4); e += SK_WARPS * 32)      // rows M .. 31: zeros
+    reinterpret_cast<float4*>(A_s)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* __restrict__ wrow = p.W + (int64_t)(live ? n0 : 0) * p.ldw;
+  float4 w[SW_V];
+#pragma unroll
+  for (int v = 0; v < SW_V; ++v) {
+    const int k = v * 128 + lane * 4;
+    w[v] = (live && k < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+  }
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float4* ar = reinterpret_cast<const float4*>(A_s + i * K) + lane;
+    float a = 0.f;
+#pragma unroll
+    for (int v = 0; v < SW_V; ++v)
+      if (v * 128 < K) {
+        const float4 x = (v * 128 + lane * 4 < K) ? ar[v * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+        a = fmaf(x.x, w[v].x, fmaf(x.y, w[v].y, fmaf(x.z, w[v].z, fmaf(x.w, w[v].w, a))));
+      }
+    acc[i] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = warp_sum(acc[i]);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mine = (lane == i) ? acc[i] : mine;
+  if (live && lane < p.M) gemm_epilogue_store(p, p.C, p.bias, lane, n0, mine);
+}
+
 }  // namespace
 
 int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st) {
@@ -258,6 +318,18 @@ int gemm_simt_launch(const GemmDev& p, int batch, cudaStream_t st) {
                        (p.lda % 4 == 0) && (p.ldw % 4 == 0) && (p.K % 4 == 0) && (p.sA % 4 == 0) && (p.sW % 4 == 0) &&
                        (!p.a_scale || (reinterpret_cast<uintptr_t>(p.a_scale) % 16 == 0 &&
                                        reinterpret_cast<uintptr_t>(p.a_shift) % 16 == 0));
+  if (p.M <= 32 && batch == 1 && p.a_mode == DPOT_A_PLAIN && p.a_fmt == DPOT_FMT_F32 && !p.a_scale && p.K <= SW_MAXK && p.K % 4 == 0 &&
+      p.lda % 4 == 0 && p.ldw % 4 == 0 && reinterpret_cast<uintptr_t>(p.A) % 16 == 0 && reinterpret_cast<uintptr_t>(p.W) % 16 == 0) {
+    const int smem = 32 * p.K * 4 + 16;
+    static DevOnce attr;
+    if (attr.need()) {
+      DPOT_CUDA(cudaFuncSetAttribute(gemm_skinny_whole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * SW_MAXK * 4 + 16));
+      attr.done();
+    }
+    gemm_skinny_whole_kernel<<<(unsigned)ceil_div(p.N, SK_WARPS), SK_WARPS * 32, smem, st>>>(p);
+    DPOT_LAUNCH_CHECK("gemm_skinny_whole_kernel");
+    return 0;
+  }
   if (p.M <= SK_MAXM && batch == 1 && p.a_mode == DPOT_A_PLAIN) {
     constexpr int smem = 32 * SK_KC * 4;
     static DevOnce attr;

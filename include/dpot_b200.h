@@ -236,16 +236,18 @@ DPOT_API int     dpot_afno_fused(const float* lat, const double* stats1, const f
                                  int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
                                  int32_t act, float* f, double* stats2, float* dbg, void* stream);
 /* The same launch with GroupNorm-2 applied inside: a work unit (sample, channel block of 128) covers whole GroupNorm groups
-   (group size 32 / 64 / 128), so once its 16 warps have met the unit normalises the f values it has just written and stores
-   n2 = GN2(f) as split fp16 (rows [hi E | lo E]) -- the channel MLP's operand, without the separate dpot_split_f16_gn pass
-   (models/dpot.py:175).  n2_16 = NULL: exactly dpot_afno_fused.  stats2 may be NULL. */
+   (group size 32 / 64 / 128), so once its 16 warps have met the unit normalises its f values -- kept in shared memory, each
+   thread's outputs in the slots of the inverse-transform scratch it has just consumed -- and stores n2 = GN2(f) as split
+   fp16 (rows [hi E | lo E]): the channel MLP's operand, without the separate dpot_split_f16_gn pass (models/dpot.py:175).
+   f may then be NULL (inference: nothing else reads it, so it never goes to global memory).  n2_16 = NULL: exactly
+   dpot_afno_fused.  stats2 may be NULL. */
 DPOT_API int     dpot_afno_fused_gn2(const float* lat, const double* stats1, const float* gamma1, const float* beta1,
                                      int32_t groups, float eps, int32_t B, int32_t h, int32_t E, int32_t nb, const float* packed,
                                      int32_t act, float* f, double* stats2, float* dbg, void* n2_16, const float* gamma2,
                                      const float* beta2, float eps2, void* stream);
-/* knob (tests / A-B measurements): 1 = dpot_forward* lets the fused mixer apply GroupNorm-2, 0 = separate pass (default:
-   measured neutral -- the in-kernel pass sits on the unit's serial path and costs what the separate kernel took) */
-DPOT_API void    dpot_afno_set_fused_gn2(int32_t on);
+/* knob (tests / A-B measurements): 1 = dpot_forward* lets the fused mixer apply GroupNorm-2 (default: +1.5 % on the DPOT-S
+   rollout), 0 = separate dpot_split_f16_gn pass, negative = query.  Returns the previous value. */
+DPOT_API int     dpot_afno_set_fused_gn2(int32_t on);
 /* knob (tests / A-B measurements): -1 = fused whenever supported (default), 0 = never */
 DPOT_API void    dpot_afno_set_fused(int32_t mode);
 /* profiling aid: device buffer of 8 int64 per unit of CTA 0 receiving clock64() at the phase boundaries of the fused

@@ -206,6 +206,7 @@ def test_model_forward_with_groupnorm2_inside_the_mixer():
     params = O.make_params(cfg, seed=0)
     x = torch.from_numpy(O.make_input(cfg, 3, seed=1)).cuda()
     outs = []
+    default = lib.dpot_afno_set_fused_gn2(-1)
     for on in (0, 1):
         lib.dpot_afno_set_fused_gn2(on)
         try:
@@ -218,7 +219,7 @@ def test_model_forward_with_groupnorm2_inside_the_mixer():
             torch.cuda.synchronize()
             outs.append((y.cpu().numpy(), cls.cpu().numpy(), lib.dpot_launch_count() - l0))
         finally:
-            lib.dpot_afno_set_fused_gn2(0)
+            lib.dpot_afno_set_fused_gn2(default)
     yo, _ = O.dpot_forward(x.cpu().numpy(), params, cfg)
     assert O.rel_l2(outs[1][0], yo) < 1e-5
     assert O.rel_l2(outs[0][0], outs[1][0]) < 2e-6 and O.rel_l2(outs[0][1], outs[1][1]) < 2e-6
