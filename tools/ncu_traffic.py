@@ -21,11 +21,14 @@ def col(name, r):
     return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1.0)
 
 
-sel = [r for r in data if pat in r[ki]]
+max_us = float(sys.argv[4]) if len(sys.argv) > 4 else 1e30     # e.g. 60: leave out the ConvTranspose contraction (same instantiation, 80 us)
+def _us(r):
+    i = hdr.index("gpu__time_duration.sum")
+    return float(r[i].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[i], 1e-3)
+sel = [r for r in data if pat in r[ki] and _us(r) < max_us]
 if not sel:
     raise SystemExit(f"no launch matching {pat!r} in {path}")
 tot = [col("dram__bytes_read.sum", r) + col("dram__bytes_write.sum", r) for r in sel]
-us = [float(r[hdr.index('gpu__time_duration.sum')].replace(',', '')) for r in sel]
 out = {"kernel": pat, "launches": len(sel), "dram_bytes_per_launch": sum(tot) / len(tot),
        "dram_read_bytes_per_launch": sum(col("dram__bytes_read.sum", r) for r in sel) / len(sel),
        "dram_write_bytes_per_launch": sum(col("dram__bytes_write.sum", r) for r in sel) / len(sel),
