@@ -288,3 +288,31 @@ def test_bench_reference_arm_uses_the_staged_reference():
             assert open(os.path.join(mod.SRC, rel), "rb").read() == open(os.path.join(mod.DST, rel), "rb").read(), rel
     RefNet, RefAdam, RefLoss, _ = mod.import_reference()
     assert RefNet.__module__.endswith("models.dpot") and "dpot_b200" not in RefNet.__module__
+
+
+def test_knobs_and_argument_validation_without_a_gpu():
+    """Entry points that validate before they launch answer on a CPU-only box too: the knobs added in round 2 (chain limit,
+    GroupNorm-2 inside the mixer) keep / report their state, and the chained contraction and the Lamb step reject
+    malformed calls with an error code and a message instead of touching the device."""
+    import ctypes as C
+    import dpot_b200
+    from dpot_b200 import _lib
+    lib = _lib.load()
+    assert dpot_b200.set_chain(1024) == 2048 and dpot_b200.set_chain(2048) == 1024 and lib.dpot_tc16_set_chain(-1) == 2048
+    assert lib.dpot_afno_set_fused_gn2(-1) == 1 and lib.dpot_afno_set_fused_gn2(0) == 1 and lib.dpot_afno_set_fused_gn2(1) == 0
+    with pytest.raises(ValueError):
+        dpot_b200.set_precision("bf16")
+    g = _lib.GemmArgs()
+    fake = 1 << 20                                   # non-null, 16-byte aligned, never dereferenced: validation fails first
+    g.A, g.W, g.C, g.lda, g.ldw, g.ldc = fake, fake, fake, 4096, 4096, 64
+    g.M, g.N, g.K, g.batch = 32, 64, 4096, 1
+    g.a_fmt = g.w_fmt = _lib.FMT_F32                 # fp32 operands: not the engine the chained form serves
+    rc = lib.dpot_gemm_chained(C.byref(g), 2048, fake, 64, None)
+    assert rc != 0 and b"dpot_gemm_chained" in lib.dpot_last_error_string()
+    g.a_fmt = g.w_fmt = _lib.FMT_HL16
+    g.a_lo_off = g.w_lo_off = 4096
+    rc = lib.dpot_gemm_chained(C.byref(g), 2048, None, 64, None)          # needs a scratch buffer
+    assert rc != 0 and b"scratch" in lib.dpot_last_error_string()
+    assert lib.dpot_lamb_step_multi(None, None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-6, 0.0, 10.0, None, 0, 0, None, None, None) == 0
+    assert lib.dpot_lamb_step_multi(None, None, None, None, None, 2, 1e-3, 0.9, 0.999, 1e-6, 0.0, 10.0, None, 0, 0, None, None, None) != 0
+    assert b"dpot_lamb_step_multi" in lib.dpot_last_error_string()
