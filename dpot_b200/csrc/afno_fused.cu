@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) afno_fused_kernel(const AfArgs 
       const int b = u / nb, kap = u % nb;
       const uint32_t par = it & 1u;
       const float* const lat_u = P.lat + (int64_t)b * 256 * E + (int64_t)kap * AF_BS;
-      float* const f_u = P.f + (int64_t)b * 256 * E + (int64_t)kap * AF_BS;
+      float* const f_u = P.f ? P.f + (int64_t)b * 256 * E + (int64_t)kap * AF_BS : nullptr;   // nullptr: f stays on chip (GroupNorm-2 in the kernel)
       const bool tr = P.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
       long long* const trow_t = P.trace + (int64_t)it * 8;
       if (tr) trow_t[0] = clock64();
